@@ -1,0 +1,160 @@
+/*
+ * mixstage_b200 C-ABI  --  B200 (sm_100a) kernels for the Mix-StAGE generator hot path.
+ *
+ * Drop-in boundary: the reference has no native layer at all -- its hot
+ * path is `JointLateClusterSoftStyle4_G.forward` / `Speech2Gesture_D.forward` /
+ * `GAN.forward` calling torch.nn ops (cuDNN/ATen in fp64).  Each entry point below
+ * replaces one ATen op family at the reference call site quoted next to it
+ * (paths relative to /root/reference/src/model/).  The Python host mirror
+ * (mixstage_b200/*.py) binds them with ctypes; INTEGRATION.md shows the binding and
+ * how the classes are installed under the reference's own names.
+ *
+ * Conventions
+ *   - every function returns 0 on success, otherwise a cudaError_t value (or a negative
+ *     MS_E* code for argument errors); nothing is printed, nothing throws.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises.  Functions are re-entrant per device (one process per GPU).
+ *   - activations are channels-last: 1-D (B, L, C) is passed as H=1, W=L.
+ *     2-D is (B, H, W, C).  fp32 everywhere in the `_f32` family; bf16 operands with fp32
+ *     accumulation in the `_bf16` (tcgen05) family.
+ *   - `pdt` arguments give the dtype of caller-owned parameter tensors
+ *     (MS_F32 / MS_F64): the reference keeps fp64 master parameters
+ *     (trainer.py:138 `.double()`), so parameters/grad buffers are read and written in
+ *     the caller's dtype while all arithmetic runs in fp32/bf16.
+ */
+#ifndef MIXSTAGE_B200_H
+#define MIXSTAGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_F32 0
+#define MS_F64 1
+#define MS_BF16 2
+
+#define MS_EINVAL (-1)   /* bad argument (shape/stride/alignment not supported)   */
+#define MS_ENOTSUP (-2)  /* valid request this build cannot serve (e.g. no sm_100) */
+
+/* Geometry of one convolution, NHWC activations.  Replaces the nn.Conv1d/nn.Conv2d
+ * construction in ConvNormRelu (layers.py:58-70): Cin/Cout are TOTAL channel counts
+ * (already multiplied by groups as at layers.py:58-59). */
+typedef struct ms_conv_desc {
+  int32_t B, H, W, Cin, Cout;
+  int32_t kh, kw, sh, sw, ph, pw, groups;
+  int32_t Ho, Wo;
+} ms_conv_desc;
+
+int ms_version(void);
+/* 1 when the current device is compute capability 10.x (tcgen05 path usable). */
+int ms_device_is_sm100(void);
+
+/* ---- weight packing (replaces nothing in the reference: ATen consumes (Cout,Cin/g,kh,kw)
+ * directly; we re-tile once per parameter version) --------------------------------- */
+/* w (Cout, Cin/g, kh, kw) in dtype pdt -> wf[g][tap][c][n] (forward / wgrad layout) and
+ * wt[g][tap][n][c] (dgrad layout), both fp32.  Either output may be NULL. */
+int ms_pack_conv_weight_f32(const void* w, int pdt, const ms_conv_desc* d, float* wf, float* wt, void* stream);
+/* dwf[g][tap][c][n] fp32 -> dw (Cout, Cin/g, kh, kw) in dtype pdt (overwrites). */
+int ms_unpack_conv_wgrad(const float* dwf, const ms_conv_desc* d, void* dw, int pdt, void* stream);
+/* dst[i] = (T_dst) src[i]; dtypes MS_F32/MS_F64/MS_BF16. */
+int ms_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream);
+
+/* ---- convolution as implicit GEMM, fp32 SIMT (conv1d/conv2d call sites:
+ * layers.py:60-70 via :78; speech2gesture.py:76,90; jlcss.py:83; layers.py:459) ------ */
+/* y (B,Ho,Wo,Cout) = conv(x (B,H,W,Cin), wf) + bias (bias nullable; bias in fp32).
+ * act: 0 none, 1 LeakyReLU(slope) applied in the epilogue (speech2gesture.py:76-77). */
+int ms_conv_fwd_f32(const float* x, const float* wf, const float* bias, float* y,
+                    const ms_conv_desc* d, int act, float slope, void* stream);
+/* dx (B,H,W,Cin) = conv_transpose(dy (B,Ho,Wo,Cout), wt)  (aten::convolution_backward, input grad) */
+int ms_conv_dgrad_f32(const float* dy, const float* wt, float* dx, const ms_conv_desc* d, void* stream);
+/* dwf[g][tap][c][n] = sum_pos x[pos+tap] * dy[pos]   (convolution_backward, weight grad).
+ * Overwrites dwf (zeroed internally; split-K partials are combined with fp32 atomics). */
+int ms_conv_wgrad_f32(const float* x, const float* dy, float* dwf, const ms_conv_desc* d, void* stream);
+
+/* ---- BatchNorm (+LeakyReLU) pieces, nn.BatchNorm1d/2d at layers.py:64,70 and
+ * nn.LeakyReLU(0.2) at layers.py:72-73, applied as in ConvNormRelu.forward (:78) ------ */
+/* column sums over rows: sum[c] += x[r,c], sumsq[c] += x[r,c]^2 (double accumulators,
+ * caller zeroes them).  sumsq nullable.  Also used for conv-bias gradients. */
+int ms_col_stats_f32(const float* x, int64_t rows, int C, double* sum, double* sumsq, void* stream);
+/* training: batch mean / biased var from (sum,sumsq,rows) -> scale = gamma*rstd,
+ * shift = beta - mean*scale, save mean/rstd; update running_mean/var in place
+ * (momentum, unbiased var) in dtype pdt.  eval (training=0): scale/shift from the running
+ * statistics, sum/sumsq ignored. */
+int ms_bn_finalize(const double* sum, const double* sumsq, int64_t rows, int C,
+                   const void* gamma, const void* beta, void* running_mean, void* running_var, int pdt,
+                   int training, float momentum, float eps,
+                   float* scale, float* shift, float* mean, float* rstd, void* stream);
+/* y = act(x*scale[c] + shift[c]) over rows x C; act LeakyReLU(slope) when slope != 1.
+ * up2 != 0 fuses UNet1D's `upconv(x) + residual` (layers.py:151): y has 2*L rows per
+ * sequence, y[b,2l+r,:] = act(..)[b,l,:] + res[b,2l+r,:]  (L = rows_per_seq). */
+int ms_bn_act_fwd_f32(const float* x, const float* scale, const float* shift, float slope,
+                      int64_t rows, int C, float* y, const float* res, int up2, int rows_per_seq, void* stream);
+/* backward reductions of act(bn(x)):  dz = dy * (z>0 ? 1 : slope) with z = x*scale+shift,
+ * dbeta[c] += sum dz, dgamma_hat[c] += sum dz * xhat  (xhat = (x-mean)*rstd), doubles,
+ * caller zeroes.  up2: dy has 2*L rows per sequence and the two rows of a pair are summed. */
+int ms_bn_act_bwd_reduce_f32(const float* dy, const float* x, const float* scale, const float* shift,
+                             const float* mean, const float* rstd, float slope, int64_t rows, int C,
+                             int up2, int rows_per_seq, double* dgamma, double* dbeta, void* stream);
+/* dx = scale * (dz - dbeta/rows - xhat*dgamma/rows)  (training) or scale*dz (training=0). */
+int ms_bn_act_bwd_apply_f32(const float* dy, const float* x, const float* scale, const float* shift,
+                            const float* mean, const float* rstd, float slope, int64_t rows, int C,
+                            int up2, int rows_per_seq, const double* dgamma, const double* dbeta,
+                            int training, float* dx, void* stream);
+/* dz = dy * (y > 0 ? 1 : slope) for a plain conv + LeakyReLU (speech2gesture.py:76-77); y is the
+ * activation output. */
+int ms_lrelu_bwd_f32(const float* dy, const float* y, float slope, int64_t n, float* dz, void* stream);
+/* out[i] (dtype pdt) = (T) in[i] for small per-channel vectors (dgamma/dbeta/dbias). */
+int ms_store_param_grad(const double* src, int n, void* dst, int pdt, void* stream);
+
+/* ---- resize / glue ---------------------------------------------------------------- */
+/* torch.nn.functional.interpolate(x, size=(T,1), mode='bilinear') + squeeze (layers.py:197-198):
+ * x (B,Hi,Wi,C) -> y (B,T,C). */
+int ms_bilinear_to_T_fwd_f32(const float* x, int B, int Hi, int Wi, int C, int T, float* y, void* stream);
+int ms_bilinear_to_T_bwd_f32(const float* dy, int B, int Hi, int Wi, int C, int T, float* dx, void* stream);
+/* style embedding + concat (layers.py:659-663, jlcss.py:175-180):
+ * out (rows, C+sd): out[r,:C] = x[r,:], out[r,C:] = emb[idx[r/rep]] ('emb' mode, idx int64)
+ * or soft[r/rep,:] @ emb ('lin' mode, soft (rows/rep, S) fp32).  emb (S, sd) in dtype pdt.
+ * rep = T when the style is constant over the sequence and given per sequence, else 1. */
+int ms_style_concat_fwd_f32(const float* x, int64_t rows, int C, const int64_t* idx, const float* soft,
+                            int rep, const void* emb, int pdt, int S, int sd, float* out, void* stream);
+/* backward: dx[r,:] = dout[r,:C]; demb[s,:] += sum_{r: idx=s} dout[r,C:] (fp32 table, caller
+ * zeroes; 'lin': demb += soft^T dout_style, dsoft[q,:] = sum_{r in q} dout_style[r,:] @ emb^T). */
+int ms_style_concat_bwd_f32(const float* dout, int64_t rows, int C, const int64_t* idx, const float* soft,
+                            int rep, const void* emb, int pdt, int S, int sd,
+                            float* dx, float* demb, float* dsoft, void* stream);
+/* softmax over K + cross-entropy (mean over rows) + argmax (jlcss.py:183-187, :159-165, :203):
+ * score (rows,K) -> soft (rows,K) (nullable), amax (rows) int64 (nullable),
+ * loss_sum += sum_r -log soft[r,target[r/trep]] (double, caller zeroes; nullable with target). */
+int ms_softmax_ce_fwd_f32(const float* score, int64_t rows, int K, const int64_t* target, int trep,
+                          float* soft, int64_t* amax, double* loss_sum, void* stream);
+/* dscore = g_ce/rows * (soft - onehot) + soft * (dsoft - sum_k soft*dsoft); g_ce device scalar
+ * (nullable), dsoft nullable. */
+int ms_softmax_ce_bwd_f32(const float* soft, int64_t rows, int K, const int64_t* target, int trep,
+                          const float* g_ce, const float* dsoft, float* dscore, void* stream);
+/* index_select_outputs (jlcss.py:106-115): out[r,p] = sum_k w[r,k] * z[r,k*P+p]. */
+int ms_mixture_fwd_f32(const float* z, const float* w, int64_t rows, int K, int P, float* out, void* stream);
+int ms_mixture_bwd_f32(const float* dout, const float* z, const float* w, int64_t rows, int K, int P,
+                       float* dz, float* dw, void* stream);
+/* x.mean(-1) of PoseStyleEncoder (layers.py:287): (B,L,C) -> (B,C) and its adjoint. */
+int ms_mean_rows_fwd_f32(const float* x, int B, int L, int C, float* y, void* stream);
+int ms_mean_rows_bwd_f32(const float* dy, int B, int L, int C, float* dx, void* stream);
+
+/* ---- GAN losses (gan.py:47-52, 64-75) ---------------------------------------------- */
+/* velocity: v[b,0,:]=0, v[b,t,:]=x[b,t,:]-x[b,t-1,:]; adjoint in _bwd. */
+int ms_velocity_fwd_f32(const float* x, int B, int T, int P, float* v, void* stream);
+int ms_velocity_bwd_f32(const float* dv, int B, int T, int P, float* dx, void* stream);
+/* L1Loss(reduction='none') then mean: loss_sum += sum |a - b| (b nullable -> constant c);
+ * sgn (nullable) receives sign(a-b) for the backward. */
+int ms_l1_fwd_f32(const float* a, const float* b, float c, int64_t n, double* loss_sum, float* sgn, void* stream);
+/* da = g[0] * sgn / n  (g device scalar) */
+int ms_l1_bwd_f32(const float* sgn, const float* g, int64_t n, float* da, void* stream);
+/* out[0] = (float)(scale * in[0]) : turns a double accumulator into a loss scalar. */
+int ms_scalar_finish(const double* in, double scale, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIXSTAGE_B200_H */

@@ -1,0 +1,106 @@
+"""ctypes binding of libmixstage_b200.so (include/mixstage_b200.h).
+
+There is NO CPU fallback: if the shared library is missing or an entry point fails,
+a RuntimeError is raised."""
+import ctypes
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmixstage_b200.so")
+
+MS_F32, MS_F64, MS_BF16 = 0, 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("B", "H", "W", "Cin", "Cout", "kh", "kw", "sh", "sw", "ph", "pw", "groups", "Ho", "Wo")]
+
+
+_P, _I, _L, _F, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+_CD = ctypes.POINTER(ConvDesc)
+
+# name -> argtypes (mirrors include/mixstage_b200.h; tests/test_capi_symbols.py checks both ways)
+PROTOTYPES = {
+    "ms_version": [],
+    "ms_device_is_sm100": [],
+    "ms_pack_conv_weight_f32": [_P, _I, _CD, _P, _P, _P],
+    "ms_unpack_conv_wgrad": [_P, _CD, _P, _I, _P],
+    "ms_cast": [_P, _I, _P, _I, _L, _P],
+    "ms_conv_fwd_f32": [_P, _P, _P, _P, _CD, _I, _F, _P],
+    "ms_conv_dgrad_f32": [_P, _P, _P, _CD, _P],
+    "ms_conv_wgrad_f32": [_P, _P, _P, _CD, _P],
+    "ms_col_stats_f32": [_P, _L, _I, _P, _P, _P],
+    "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],
+    "ms_bn_act_fwd_f32": [_P, _P, _P, _F, _L, _I, _P, _P, _I, _I, _P],
+    "ms_bn_act_bwd_reduce_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _P],
+    "ms_bn_act_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _I, _P, _P],
+    "ms_lrelu_bwd_f32": [_P, _P, _F, _L, _P, _P],
+    "ms_store_param_grad": [_P, _I, _P, _I, _P],
+    "ms_bilinear_to_T_fwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "ms_bilinear_to_T_bwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "ms_style_concat_fwd_f32": [_P, _L, _I, _P, _P, _I, _P, _I, _I, _I, _P, _P],
+    "ms_style_concat_bwd_f32": [_P, _L, _I, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P],
+    "ms_softmax_ce_fwd_f32": [_P, _L, _I, _P, _I, _P, _P, _P, _P],
+    "ms_softmax_ce_bwd_f32": [_P, _L, _I, _P, _I, _P, _P, _P, _P],
+    "ms_mixture_fwd_f32": [_P, _P, _L, _I, _I, _P, _P],
+    "ms_mixture_bwd_f32": [_P, _P, _P, _L, _I, _I, _P, _P, _P],
+    "ms_mean_rows_fwd_f32": [_P, _I, _I, _I, _P, _P],
+    "ms_mean_rows_bwd_f32": [_P, _I, _I, _I, _P, _P],
+    "ms_velocity_fwd_f32": [_P, _I, _I, _I, _P, _P],
+    "ms_velocity_bwd_f32": [_P, _I, _I, _I, _P, _P],
+    "ms_l1_fwd_f32": [_P, _P, _F, _L, _P, _P, _P],
+    "ms_l1_bwd_f32": [_P, _P, _L, _P, _P],
+    "ms_scalar_finish": [_P, _D, _P, _P],
+}
+
+_LIB = None
+LAUNCHES = 0          # number of C-ABI kernel entry points called (bench.py's gpu_launches claim)
+
+
+class MixStageError(RuntimeError):
+    pass
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise MixStageError(
+                "libmixstage_b200.so is not built (%s). Run `python -m mixstage_b200.build`; "
+                "mixstage_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, args in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        _LIB = lib
+    return _LIB
+
+
+def call(name, *args):
+    """Invoke an entry point; raises on a non-zero status (cudaError_t or MS_E*)."""
+    global LAUNCHES
+    rc = getattr(load(), name)(*args)
+    LAUNCHES += 1
+    if rc != 0:
+        raise MixStageError("%s failed with status %d" % (name, rc))
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt_code(dtype):
+    if dtype == torch.float32:
+        return MS_F32
+    if dtype == torch.float64:
+        return MS_F64
+    if dtype == torch.bfloat16:
+        return MS_BF16
+    raise MixStageError("unsupported dtype %s" % dtype)

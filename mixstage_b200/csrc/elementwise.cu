@@ -1,0 +1,767 @@
+// HBM-bound kernels of the generator hot path: BatchNorm statistics / apply / backward
+// fused with LeakyReLU and the UNet upsample+skip add, weight (un)packing, casts, bilinear
+// time resize, style-embedding gather/scatter fused with the concat, softmax+CE+argmax,
+// softmax-weighted cluster mixture, velocity, L1 reductions.
+//
+// All take channels-last fp32 activations ([rows, C], C contiguous); every warp reads
+// contiguous 128-byte rows (float4 where C % 4 == 0), reductions accumulate in double and
+// use one atomic per block and column.
+#include "common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline int ew_blocks(int64_t work, int per_block = EW_THREADS) {
+  int64_t b = ms_cdiv(work, per_block);
+  int64_t cap = (int64_t)ms_num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ------------------------------------------------------------------ casts / packing
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = (D)(float)s[i];
+}
+template <>
+__global__ void cast_kernel<double, double>(const double* __restrict__ s, double* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+template <>
+__global__ void cast_kernel<float, double>(const float* __restrict__ s, double* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = (double)s[i];
+}
+
+// w (Cout, Cin_g, kh, kw) -> wf[g][tap][c][n], wt[g][tap][n][c]
+__global__ void pack_weight_kernel(const void* __restrict__ w, int pdt, int Cout, int Cin_g, int taps, int groups,
+                                   float* __restrict__ wf, float* __restrict__ wt) {
+  int Cout_g = Cout / groups;
+  int64_t total = (int64_t)Cout * Cin_g * taps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int tap = (int)(i % taps);
+    int64_t t = i / taps;
+    int c = (int)(t % Cin_g);
+    int o = (int)(t / Cin_g);
+    int g = o / Cout_g, n = o - g * Cout_g;
+    float v = ms_ldp(w, pdt, i);
+    if (wf) wf[(((int64_t)g * taps + tap) * Cin_g + c) * Cout_g + n] = v;
+    if (wt) wt[(((int64_t)g * taps + tap) * Cout_g + n) * Cin_g + c] = v;
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int Cout, int Cin_g, int taps, int groups,
+                                    void* __restrict__ dw, int pdt) {
+  int Cout_g = Cout / groups;
+  int64_t total = (int64_t)Cout * Cin_g * taps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int tap = (int)(i % taps);
+    int64_t t = i / taps;
+    int c = (int)(t % Cin_g);
+    int o = (int)(t / Cin_g);
+    int g = o / Cout_g, n = o - g * Cout_g;
+    ms_stp(dw, pdt, i, (double)dwf[(((int64_t)g * taps + tap) * Cin_g + c) * Cout_g + n]);
+  }
+}
+
+__global__ void store_param_grad_kernel(const double* __restrict__ s, int n, void* __restrict__ d, int pdt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ms_stp(d, pdt, i, s[i]);
+}
+
+// ------------------------------------------------------------------ column statistics
+// block = 32 channels x 8 row lanes; grid = (C/32, row chunks)
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ x, int64_t rows, int C,
+                                                        double* __restrict__ sum, double* __restrict__ sumsq) {
+  __shared__ double s1[8][33], s2[8][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int c = blockIdx.x * 32 + tx;
+  int64_t per = ms_cdiv_dev(rows, gridDim.y);
+  int64_t r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float v = __ldg(x + r * C + c);
+      a += v;
+      b += (double)v * v;
+    }
+  s1[ty][tx] = a;
+  s2[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; i++) { a += s1[i][tx]; b += s2[i][tx]; }
+    atomicAdd(sum + c, a);
+    if (sumsq) atomicAdd(sumsq + c, b);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, int64_t rows, int C,
+                                   const void* gamma, const void* beta, void* rmean, void* rvar, int pdt,
+                                   int training, float momentum, float eps,
+                                   float* scale, float* shift, float* mean_o, float* rstd_o) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean, var;
+  if (training) {
+    mean = sum[c] / (double)rows;
+    var = sumsq[c] / (double)rows - mean * mean;
+    if (var < 0.0) var = 0.0;
+    double unb = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
+    double rm = ms_ldp_d(rmean, pdt, c), rv = ms_ldp_d(rvar, pdt, c);
+    ms_stp(rmean, pdt, c, (1.0 - (double)momentum) * rm + (double)momentum * mean);
+    ms_stp(rvar, pdt, c, (1.0 - (double)momentum) * rv + (double)momentum * unb);
+  } else {
+    mean = ms_ldp_d(rmean, pdt, c);
+    var = ms_ldp_d(rvar, pdt, c);
+  }
+  double rstd = 1.0 / sqrt(var + (double)eps);
+  double g = ms_ldp_d(gamma, pdt, c), b = ms_ldp_d(beta, pdt, c);
+  scale[c] = (float)(g * rstd);
+  shift[c] = (float)(b - mean * g * rstd);
+  mean_o[c] = (float)mean;
+  rstd_o[c] = (float)rstd;
+}
+
+// ------------------------------------------------------------------ BN apply + LeakyReLU (+ upsample x2 + skip)
+template <int VEC>
+__global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  float slope, int64_t rows_out, int C, float* __restrict__ y,
+                                  const float* __restrict__ res, int up2, int L) {
+  int Cv = C / VEC;
+  int64_t total = rows_out * Cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t ro = i / Cv;
+    int cv = (int)(i - ro * Cv);
+    int64_t ri = ro;
+    if (up2) {
+      int64_t b = ro / (2 * L);
+      int l2 = (int)(ro - b * 2 * L);
+      ri = b * L + (l2 >> 1);
+    }
+    if (VEC == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x + ri * C) + cv);
+      float4 s = __ldg(reinterpret_cast<const float4*>(scale) + cv);
+      float4 h = __ldg(reinterpret_cast<const float4*>(shift) + cv);
+      float4 o;
+      o.x = fmaf(v.x, s.x, h.x); o.y = fmaf(v.y, s.y, h.y); o.z = fmaf(v.z, s.z, h.z); o.w = fmaf(v.w, s.w, h.w);
+      o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+      o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+      if (res) {
+        float4 r = __ldg(reinterpret_cast<const float4*>(res + ro * C) + cv);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      reinterpret_cast<float4*>(y + ro * C)[cv] = o;
+    } else {
+      float o = fmaf(__ldg(x + ri * C + cv), scale[cv], shift[cv]);
+      o = o > 0.f ? o : o * slope;
+      if (res) o += __ldg(res + ro * C + cv);
+      y[ro * C + cv] = o;
+    }
+  }
+}
+
+__device__ __forceinline__ float dy_at(const float* __restrict__ dy, int64_t r, int c, int C, int up2, int L) {
+  if (!up2) return __ldg(dy + r * C + c);
+  int64_t b = r / L;
+  int l = (int)(r - b * L);
+  int64_t ro = b * 2 * L + 2 * l;
+  return __ldg(dy + ro * C + c) + __ldg(dy + (ro + 1) * C + c);
+}
+
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(
+    const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd, float slope,
+    int64_t rows, int C, int up2, int L, double* __restrict__ dgamma, double* __restrict__ dbeta) {
+  __shared__ double s1[8][33], s2[8][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int c = blockIdx.x * 32 + tx;
+  int64_t per = ms_cdiv_dev(rows, gridDim.y);
+  int64_t r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    float sc = scale[c], sh = shift[c], mu = mean[c], rs = rstd[c];
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float xv = __ldg(x + r * C + c);
+      float z = fmaf(xv, sc, sh);
+      float d = dy_at(dy, r, c, C, up2, L);
+      float dz = z > 0.f ? d : d * slope;
+      a += dz;
+      b += (double)dz * (double)((xv - mu) * rs);
+    }
+  }
+  s1[ty][tx] = a;
+  s2[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; i++) { a += s1[i][tx]; b += s2[i][tx]; }
+    atomicAdd(dbeta + c, a);
+    atomicAdd(dgamma + c, b);
+  }
+}
+
+__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd, float slope,
+                                        int64_t rows, int C, int up2, int L, const double* __restrict__ dgamma,
+                                        const double* __restrict__ dbeta, int training, float* __restrict__ dx) {
+  int64_t total = rows * C;
+  float inv = 1.f / (float)rows;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    float xv = __ldg(x + i);
+    float sc = scale[c];
+    float z = fmaf(xv, sc, shift[c]);
+    float d = dy_at(dy, r, c, C, up2, L);
+    float dz = z > 0.f ? d : d * slope;
+    float o;
+    if (training) {
+      float xh = (xv - mean[c]) * rstd[c];
+      o = sc * (dz - (float)dbeta[c] * inv - xh * (float)dgamma[c] * inv);
+    } else {
+      o = sc * dz;
+    }
+    dx[i] = o;
+  }
+}
+
+__global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope, int64_t n,
+                                 float* __restrict__ dz) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = __ldg(dy + i);
+    dz[i] = __ldg(y + i) > 0.f ? d : d * slope;
+  }
+}
+
+// ------------------------------------------------------------------ bilinear (Hi,Wi) -> (T,1), align_corners=False
+__device__ __forceinline__ void lin_src(int o, int in_size, int out_size, int& i0, int& i1, float& lam) {
+  float scale = (float)in_size / (float)out_size;
+  float src = ((float)o + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  lam = src - (float)i0;
+}
+
+__global__ void bilinear_fwd_kernel(const float* __restrict__ x, int B, int Hi, int Wi, int C, int T, float* __restrict__ y) {
+  int64_t total = (int64_t)B * T * C;
+  int w0, w1;
+  float lw;
+  lin_src(0, Wi, 1, w0, w1, lw);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t2 = i / C;
+    int t = (int)(t2 % T);
+    int b = (int)(t2 / T);
+    int h0, h1;
+    float lh;
+    lin_src(t, Hi, T, h0, h1, lh);
+    const float* xb = x + (size_t)b * Hi * Wi * C;
+    float v00 = __ldg(xb + ((size_t)h0 * Wi + w0) * C + c), v01 = __ldg(xb + ((size_t)h0 * Wi + w1) * C + c);
+    float v10 = __ldg(xb + ((size_t)h1 * Wi + w0) * C + c), v11 = __ldg(xb + ((size_t)h1 * Wi + w1) * C + c);
+    y[i] = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+  }
+}
+
+// deterministic gather form of the adjoint: every input element sums its contributions
+__global__ void bilinear_bwd_kernel(const float* __restrict__ dy, int B, int Hi, int Wi, int C, int T, float* __restrict__ dx) {
+  int64_t total = (int64_t)B * Hi * Wi * C;
+  int w0, w1;
+  float lw;
+  lin_src(0, Wi, 1, w0, w1, lw);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t2 = i / C;
+    int w = (int)(t2 % Wi);
+    t2 /= Wi;
+    int h = (int)(t2 % Hi);
+    int b = (int)(t2 / Hi);
+    float ww = (w == w0 ? 1.f - lw : 0.f) + (w == w1 ? lw : 0.f);
+    float acc = 0.f;
+    if (ww != 0.f) {
+      for (int t = 0; t < T; t++) {
+        int h0, h1;
+        float lh;
+        lin_src(t, Hi, T, h0, h1, lh);
+        float wh = (h == h0 ? 1.f - lh : 0.f) + (h == h1 ? lh : 0.f);
+        if (wh != 0.f) acc += wh * __ldg(dy + ((size_t)b * T + t) * C + c);
+      }
+    }
+    dx[i] = acc * ww;
+  }
+}
+
+// ------------------------------------------------------------------ style embedding + concat
+__global__ void style_concat_fwd_kernel(const float* __restrict__ x, int64_t rows, int C, const int64_t* __restrict__ idx,
+                                        const float* __restrict__ soft, int rep, const void* __restrict__ emb, int pdt,
+                                        int S, int sd, float* __restrict__ out) {
+  int Co = C + sd;
+  int64_t total = rows * Co;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / Co;
+    int c = (int)(i - r * Co);
+    float v;
+    if (c < C) {
+      v = __ldg(x + r * C + c);
+    } else {
+      int j = c - C;
+      int64_t q = r / rep;
+      if (idx) {
+        int64_t s = idx[q];
+        v = (s >= 0 && s < S) ? ms_ldp(emb, pdt, s * sd + j) : 0.f;
+      } else {
+        v = 0.f;
+        for (int s = 0; s < S; s++) v = fmaf(__ldg(soft + q * S + s), ms_ldp(emb, pdt, (int64_t)s * sd + j), v);
+      }
+    }
+    out[i] = v;
+  }
+}
+
+// dx = dout[:, :C]
+__global__ void slice_cols_kernel(const float* __restrict__ dout, int64_t rows, int C, int Co, float* __restrict__ dx) {
+  int64_t total = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C;
+    int c = (int)(i - r * C);
+    dx[i] = __ldg(dout + r * Co + c);
+  }
+}
+
+// scatter-add of the style columns: a block stages a [S][sd] table in shared memory (one smem
+// atomic per element, rows of one sequence share a style so contention is a broadcast add),
+// then one global atomic per table entry and block.  'lin' mode adds soft^T * dstyle instead.
+__global__ void __launch_bounds__(256) style_scatter_kernel(const float* __restrict__ dout, int64_t rows, int C,
+                                                            const int64_t* __restrict__ idx, const float* __restrict__ soft,
+                                                            int rep, int S, int sd, float* __restrict__ demb) {
+  extern __shared__ float tab[];   // S*sd
+  int Co = C + sd;
+  for (int i = threadIdx.x; i < S * sd; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  int64_t per = ms_cdiv_dev(rows, gridDim.x);
+  int64_t r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // one warp per row: lanes over the sd style columns
+  for (int64_t r = r0 + warp; r < r1; r += nw) {
+    int64_t q = r / rep;
+    for (int j = lane; j < sd; j += 32) {
+      float d = __ldg(dout + r * Co + C + j);
+      if (idx) {
+        int64_t s = idx[q];
+        if (s >= 0 && s < S) atomicAdd(&tab[s * sd + j], d);
+      } else {
+        for (int s = 0; s < S; s++) atomicAdd(&tab[s * sd + j], __ldg(soft + q * S + s) * d);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < S * sd; i += blockDim.x)
+    if (tab[i] != 0.f) atomicAdd(demb + i, tab[i]);
+}
+
+// dsoft[q, s] = sum_{r in q} sum_j dstyle[r, j] * emb[s, j]
+__global__ void style_dsoft_kernel(const float* __restrict__ dout, int64_t nq, int C, int rep, const void* __restrict__ emb,
+                                   int pdt, int S, int sd, float* __restrict__ dsoft) {
+  int Co = C + sd;
+  int64_t total = nq * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t q = i / S;
+    int s = (int)(i - q * S);
+    float acc = 0.f;
+    for (int t = 0; t < rep; t++) {
+      const float* d = dout + (q * rep + t) * Co + C;
+      for (int j = 0; j < sd; j++) acc = fmaf(__ldg(d + j), ms_ldp(emb, pdt, (int64_t)s * sd + j), acc);
+    }
+    dsoft[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ softmax + CE + argmax (K <= 64), one thread per row
+constexpr int SM_MAXK = 64;
+
+__global__ void softmax_ce_fwd_kernel(const float* __restrict__ score, int64_t rows, int K, const int64_t* __restrict__ target,
+                                      int trep, float* __restrict__ soft, int64_t* __restrict__ amax, double* __restrict__ loss_sum) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  double loss = 0.0;
+  if (r < rows) {
+    const float* s = score + r * K;
+    float m = s[0];
+    int am = 0;
+    for (int k = 1; k < K; k++) {
+      float v = s[k];
+      if (v > m) { m = v; am = k; }           // first maximum wins, as torch.argmax on ties
+    }
+    float e[SM_MAXK];
+    float z = 0.f;
+    for (int k = 0; k < K; k++) { e[k] = expf(s[k] - m); z += e[k]; }
+    float inv = 1.f / z;
+    if (soft) for (int k = 0; k < K; k++) soft[r * K + k] = e[k] * inv;
+    if (amax) amax[r] = am;
+    if (target && loss_sum) {
+      int64_t t = target[r / trep];
+      if (t >= 0 && t < K) loss = (double)(logf(z) + m - s[t]);
+    }
+  }
+  if (loss_sum) {
+    loss = ms_warp_sum_d(loss);
+    if ((threadIdx.x & 31) == 0 && loss != 0.0) atomicAdd(loss_sum, loss);
+  }
+}
+
+__global__ void softmax_ce_bwd_kernel(const float* __restrict__ soft, int64_t rows, int K, const int64_t* __restrict__ target,
+                                      int trep, const float* __restrict__ g_ce, const float* __restrict__ dsoft,
+                                      float* __restrict__ dscore) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float g = (g_ce && target) ? g_ce[0] / (float)rows : 0.f;
+  int64_t t = target ? target[r / trep] : -1;
+  float dot = 0.f;
+  if (dsoft) for (int k = 0; k < K; k++) dot = fmaf(soft[r * K + k], dsoft[r * K + k], dot);
+  for (int k = 0; k < K; k++) {
+    float p = soft[r * K + k];
+    float v = g * (p - (k == t ? 1.f : 0.f));
+    if (dsoft) v += p * (dsoft[r * K + k] - dot);
+    dscore[r * K + k] = v;
+  }
+}
+
+// ------------------------------------------------------------------ cluster mixture
+__global__ void mixture_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w, int64_t rows, int K, int P,
+                                   float* __restrict__ out) {
+  int64_t total = rows * P;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / P;
+    int p = (int)(i - r * P);
+    float acc = 0.f;
+    for (int k = 0; k < K; k++) acc = fmaf(__ldg(w + r * K + k), __ldg(z + (r * K + k) * P + p), acc);
+    out[i] = acc;
+  }
+}
+
+// one warp per (row, k): dz = w * dout ; dw = <z, dout>
+__global__ void mixture_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ z, const float* __restrict__ w,
+                                   int64_t rows, int K, int P, float* __restrict__ dz, float* __restrict__ dw) {
+  int lane = threadIdx.x & 31;
+  int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < rows * K; i += nwarps) {
+    int64_t r = i / K;
+    float wk = __ldg(w + i);
+    float acc = 0.f;
+    for (int p = lane; p < P; p += 32) {
+      float d = __ldg(dout + r * P + p);
+      acc = fmaf(__ldg(z + i * P + p), d, acc);
+      dz[i * P + p] = wk * d;
+    }
+    acc = ms_warp_sum(acc);
+    if (lane == 0) dw[i] = acc;
+  }
+}
+
+__global__ void mean_rows_fwd_kernel(const float* __restrict__ x, int B, int L, int C, float* __restrict__ y) {
+  int64_t total = (int64_t)B * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = i / C;
+    int c = (int)(i - b * C);
+    float acc = 0.f;
+    for (int l = 0; l < L; l++) acc += __ldg(x + (b * L + l) * C + c);
+    y[i] = acc / (float)L;
+  }
+}
+__global__ void mean_rows_bwd_kernel(const float* __restrict__ dy, int B, int L, int C, float* __restrict__ dx) {
+  int64_t total = (int64_t)B * L * C;
+  float inv = 1.f / (float)L;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t b = i / ((int64_t)L * C);
+    dx[i] = __ldg(dy + b * C + c) * inv;
+  }
+}
+
+// ------------------------------------------------------------------ velocity / L1
+__global__ void velocity_fwd_kernel(const float* __restrict__ x, int B, int T, int P, float* __restrict__ v) {
+  int64_t total = (int64_t)B * T * P;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)((i / P) % T);
+    v[i] = t == 0 ? 0.f : __ldg(x + i) - __ldg(x + i - P);
+  }
+}
+__global__ void velocity_bwd_kernel(const float* __restrict__ dv, int B, int T, int P, float* __restrict__ dx) {
+  int64_t total = (int64_t)B * T * P;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)((i / P) % T);
+    float a = t >= 1 ? __ldg(dv + i) : 0.f;
+    float b = t + 1 < T ? __ldg(dv + i + P) : 0.f;
+    dx[i] = a - b;
+  }
+}
+
+__global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float c, int64_t n,
+                                                     double* __restrict__ loss_sum, float* __restrict__ sgn) {
+  __shared__ double part[8];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = __ldg(a + i) - (b ? __ldg(b + i) : c);
+    acc += fabsf(d);
+    if (sgn) sgn[i] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  }
+  acc = ms_warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); i++) t += part[i];
+    atomicAdd(loss_sum, t);
+  }
+}
+__global__ void l1_bwd_kernel(const float* __restrict__ sgn, const float* __restrict__ g, int64_t n, float* __restrict__ da) {
+  float s = g[0] / (float)n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    da[i] = __ldg(sgn + i) * s;
+}
+__global__ void scalar_finish_kernel(const double* in, double scale, float* out) { out[0] = (float)(in[0] * scale); }
+
+dim3 col_grid(int64_t rows, int C) {
+  int gx = (int)ms_cdiv(C, 32);
+  int64_t want = ms_cdiv((int64_t)ms_num_sms() * 4, gx);
+  int64_t maxy = ms_cdiv(rows, 64);
+  int64_t gy = want < maxy ? want : maxy;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+  return dim3((unsigned)gx, (unsigned)gy);
+}
+
+}  // namespace
+
+#define ST ms_stream(stream)
+
+extern "C" int ms_version(void) { return 100; }
+
+extern "C" int ms_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+extern "C" int ms_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream) {
+  if (!src || !dst || n < 0) return MS_EINVAL;
+  if (n == 0) return 0;
+  int blocks = ew_blocks(n);
+#define CASE(S, SD, D, DD) if (sdt == SD && ddt == DD) { cast_kernel<S, D><<<blocks, EW_THREADS, 0, ST>>>((const S*)src, (D*)dst, n); MS_LAUNCH_CHECK(); return 0; }
+  CASE(float, MS_F32, float, MS_F32)
+  CASE(float, MS_F32, double, MS_F64)
+  CASE(double, MS_F64, float, MS_F32)
+  CASE(double, MS_F64, double, MS_F64)
+  CASE(float, MS_F32, __nv_bfloat16, MS_BF16)
+  CASE(double, MS_F64, __nv_bfloat16, MS_BF16)
+  CASE(__nv_bfloat16, MS_BF16, float, MS_F32)
+  CASE(__nv_bfloat16, MS_BF16, double, MS_F64)
+#undef CASE
+  return MS_EINVAL;
+}
+
+extern "C" int ms_pack_conv_weight_f32(const void* w, int pdt, const ms_conv_desc* d, float* wf, float* wt, void* stream) {
+  if (!w || !d || (!wf && !wt) || d->groups < 1 || d->Cin % d->groups || d->Cout % d->groups) return MS_EINVAL;
+  int64_t total = (int64_t)d->Cout * (d->Cin / d->groups) * d->kh * d->kw;
+  pack_weight_kernel<<<ew_blocks(total), EW_THREADS, 0, ST>>>(w, pdt, d->Cout, d->Cin / d->groups, d->kh * d->kw, d->groups, wf, wt);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_unpack_conv_wgrad(const float* dwf, const ms_conv_desc* d, void* dw, int pdt, void* stream) {
+  if (!dwf || !d || !dw || d->groups < 1) return MS_EINVAL;
+  int64_t total = (int64_t)d->Cout * (d->Cin / d->groups) * d->kh * d->kw;
+  unpack_wgrad_kernel<<<ew_blocks(total), EW_THREADS, 0, ST>>>(dwf, d->Cout, d->Cin / d->groups, d->kh * d->kw, d->groups, dw, pdt);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_store_param_grad(const double* src, int n, void* dst, int pdt, void* stream) {
+  if (!src || !dst || n < 0) return MS_EINVAL;
+  if (n == 0) return 0;
+  store_param_grad_kernel<<<(n + 255) / 256, 256, 0, ST>>>(src, n, dst, pdt);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_col_stats_f32(const float* x, int64_t rows, int C, double* sum, double* sumsq, void* stream) {
+  if (!x || !sum || rows < 1 || C < 1) return MS_EINVAL;
+  col_stats_kernel<<<col_grid(rows, C), 256, 0, ST>>>(x, rows, C, sum, sumsq);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_bn_finalize(const double* sum, const double* sumsq, int64_t rows, int C, const void* gamma, const void* beta,
+                              void* running_mean, void* running_var, int pdt, int training, float momentum, float eps,
+                              float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || !mean || !rstd || C < 1) return MS_EINVAL;
+  if (training && (!sum || !sumsq || rows < 1)) return MS_EINVAL;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sum, sumsq, rows, C, gamma, beta, running_mean, running_var, pdt,
+                                                      training, momentum, eps, scale, shift, mean, rstd);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_bn_act_fwd_f32(const float* x, const float* scale, const float* shift, float slope, int64_t rows, int C,
+                                 float* y, const float* res, int up2, int rows_per_seq, void* stream) {
+  if (!x || !scale || !shift || !y || rows < 1 || C < 1) return MS_EINVAL;
+  if (up2 && (rows_per_seq < 1 || rows % rows_per_seq)) return MS_EINVAL;
+  int64_t rows_out = up2 ? rows * 2 : rows;
+  bool vec = (C % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift | (uintptr_t)res) & 15) == 0);
+  if (vec) bn_act_fwd_kernel<4><<<ew_blocks(rows_out * C / 4), EW_THREADS, 0, ST>>>(x, scale, shift, slope, rows_out, C, y, res, up2, rows_per_seq);
+  else bn_act_fwd_kernel<1><<<ew_blocks(rows_out * C), EW_THREADS, 0, ST>>>(x, scale, shift, slope, rows_out, C, y, res, up2, rows_per_seq);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_bn_act_bwd_reduce_f32(const float* dy, const float* x, const float* scale, const float* shift,
+                                        const float* mean, const float* rstd, float slope, int64_t rows, int C, int up2,
+                                        int rows_per_seq, double* dgamma, double* dbeta, void* stream) {
+  if (!dy || !x || !scale || !shift || !mean || !rstd || !dgamma || !dbeta || rows < 1 || C < 1) return MS_EINVAL;
+  bn_act_bwd_reduce_kernel<<<col_grid(rows, C), 256, 0, ST>>>(dy, x, scale, shift, mean, rstd, slope, rows, C, up2,
+                                                              rows_per_seq, dgamma, dbeta);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_bn_act_bwd_apply_f32(const float* dy, const float* x, const float* scale, const float* shift,
+                                       const float* mean, const float* rstd, float slope, int64_t rows, int C, int up2,
+                                       int rows_per_seq, const double* dgamma, const double* dbeta, int training, float* dx,
+                                       void* stream) {
+  if (!dy || !x || !scale || !shift || !mean || !rstd || !dx || rows < 1 || C < 1) return MS_EINVAL;
+  if (training && (!dgamma || !dbeta)) return MS_EINVAL;
+  bn_act_bwd_apply_kernel<<<ew_blocks(rows * C), EW_THREADS, 0, ST>>>(dy, x, scale, shift, mean, rstd, slope, rows, C, up2,
+                                                                      rows_per_seq, dgamma, dbeta, training, dx);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_lrelu_bwd_f32(const float* dy, const float* y, float slope, int64_t n, float* dz, void* stream) {
+  if (!dy || !y || !dz || n < 1) return MS_EINVAL;
+  lrelu_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, ST>>>(dy, y, slope, n, dz);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_bilinear_to_T_fwd_f32(const float* x, int B, int Hi, int Wi, int C, int T, float* y, void* stream) {
+  if (!x || !y || B < 1 || Hi < 1 || Wi < 1 || C < 1 || T < 1) return MS_EINVAL;
+  bilinear_fwd_kernel<<<ew_blocks((int64_t)B * T * C), EW_THREADS, 0, ST>>>(x, B, Hi, Wi, C, T, y);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_bilinear_to_T_bwd_f32(const float* dy, int B, int Hi, int Wi, int C, int T, float* dx, void* stream) {
+  if (!dy || !dx || B < 1 || Hi < 1 || Wi < 1 || C < 1 || T < 1) return MS_EINVAL;
+  bilinear_bwd_kernel<<<ew_blocks((int64_t)B * Hi * Wi * C), EW_THREADS, 0, ST>>>(dy, B, Hi, Wi, C, T, dx);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_style_concat_fwd_f32(const float* x, int64_t rows, int C, const int64_t* idx, const float* soft, int rep,
+                                       const void* emb, int pdt, int S, int sd, float* out, void* stream) {
+  if (!x || !emb || !out || (!idx && !soft) || rows < 1 || rep < 1 || rows % rep || S < 1 || sd < 1) return MS_EINVAL;
+  style_concat_fwd_kernel<<<ew_blocks(rows * (C + sd)), EW_THREADS, 0, ST>>>(x, rows, C, idx, soft, rep, emb, pdt, S, sd, out);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_style_concat_bwd_f32(const float* dout, int64_t rows, int C, const int64_t* idx, const float* soft, int rep,
+                                       const void* emb, int pdt, int S, int sd, float* dx, float* demb, float* dsoft,
+                                       void* stream) {
+  if (!dout || (!idx && !soft) || rows < 1 || rep < 1 || rows % rep || S < 1 || sd < 1) return MS_EINVAL;
+  if (dx) {
+    slice_cols_kernel<<<ew_blocks(rows * C), EW_THREADS, 0, ST>>>(dout, rows, C, C + sd, dx);
+    MS_LAUNCH_CHECK();
+  }
+  if (demb) {
+    int blocks = (int)ms_cdiv(rows, 256);
+    if (blocks > ms_num_sms() * 2) blocks = ms_num_sms() * 2;
+    style_scatter_kernel<<<blocks, 256, sizeof(float) * S * sd, ST>>>(dout, rows, C, idx, soft, rep, S, sd, demb);
+    MS_LAUNCH_CHECK();
+  }
+  if (dsoft && soft) {
+    style_dsoft_kernel<<<ew_blocks(rows / rep * S), EW_THREADS, 0, ST>>>(dout, rows / rep, C, rep, emb, pdt, S, sd, dsoft);
+    MS_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int ms_softmax_ce_fwd_f32(const float* score, int64_t rows, int K, const int64_t* target, int trep, float* soft,
+                                     int64_t* amax, double* loss_sum, void* stream) {
+  if (!score || rows < 1 || K < 1 || K > SM_MAXK || trep < 1) return MS_EINVAL;
+  softmax_ce_fwd_kernel<<<(unsigned)ms_cdiv(rows, 128), 128, 0, ST>>>(score, rows, K, target, trep, soft, amax, loss_sum);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_softmax_ce_bwd_f32(const float* soft, int64_t rows, int K, const int64_t* target, int trep, const float* g_ce,
+                                     const float* dsoft, float* dscore, void* stream) {
+  if (!soft || !dscore || rows < 1 || K < 1 || trep < 1) return MS_EINVAL;
+  softmax_ce_bwd_kernel<<<(unsigned)ms_cdiv(rows, 128), 128, 0, ST>>>(soft, rows, K, target, trep, g_ce, dsoft, dscore);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_mixture_fwd_f32(const float* z, const float* w, int64_t rows, int K, int P, float* out, void* stream) {
+  if (!z || !w || !out || rows < 1 || K < 1 || P < 1) return MS_EINVAL;
+  mixture_fwd_kernel<<<ew_blocks(rows * P), EW_THREADS, 0, ST>>>(z, w, rows, K, P, out);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_mixture_bwd_f32(const float* dout, const float* z, const float* w, int64_t rows, int K, int P, float* dz,
+                                  float* dw, void* stream) {
+  if (!dout || !z || !w || !dz || !dw || rows < 1) return MS_EINVAL;
+  mixture_bwd_kernel<<<ew_blocks(rows * K * 32), EW_THREADS, 0, ST>>>(dout, z, w, rows, K, P, dz, dw);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_mean_rows_fwd_f32(const float* x, int B, int L, int C, float* y, void* stream) {
+  if (!x || !y || B < 1 || L < 1 || C < 1) return MS_EINVAL;
+  mean_rows_fwd_kernel<<<ew_blocks((int64_t)B * C), EW_THREADS, 0, ST>>>(x, B, L, C, y);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_mean_rows_bwd_f32(const float* dy, int B, int L, int C, float* dx, void* stream) {
+  if (!dy || !dx || B < 1 || L < 1 || C < 1) return MS_EINVAL;
+  mean_rows_bwd_kernel<<<ew_blocks((int64_t)B * L * C), EW_THREADS, 0, ST>>>(dy, B, L, C, dx);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_velocity_fwd_f32(const float* x, int B, int T, int P, float* v, void* stream) {
+  if (!x || !v || B < 1 || T < 1 || P < 1) return MS_EINVAL;
+  velocity_fwd_kernel<<<ew_blocks((int64_t)B * T * P), EW_THREADS, 0, ST>>>(x, B, T, P, v);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_velocity_bwd_f32(const float* dv, int B, int T, int P, float* dx, void* stream) {
+  if (!dv || !dx || B < 1 || T < 1 || P < 1) return MS_EINVAL;
+  velocity_bwd_kernel<<<ew_blocks((int64_t)B * T * P), EW_THREADS, 0, ST>>>(dv, B, T, P, dx);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_l1_fwd_f32(const float* a, const float* b, float c, int64_t n, double* loss_sum, float* sgn, void* stream) {
+  if (!a || !loss_sum || n < 1) return MS_EINVAL;
+  int blocks = ew_blocks(n, 256 * 4);
+  l1_fwd_kernel<<<blocks, 256, 0, ST>>>(a, b, c, n, loss_sum, sgn);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_l1_bwd_f32(const float* sgn, const float* g, int64_t n, float* da, void* stream) {
+  if (!sgn || !g || !da || n < 1) return MS_EINVAL;
+  l1_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, ST>>>(sgn, g, n, da);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_scalar_finish(const double* in, double scale, float* out, void* stream) {
+  if (!in || !out) return MS_EINVAL;
+  scalar_finish_kernel<<<1, 1, 0, ST>>>(in, scale, out);
+  MS_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,110 @@
+"""GAN wrapper, mirror of reference src/model/gan.py (GAN.forward :86-164) with the velocity,
+discriminator and L1 reductions running in the CUDA kernels.  Same constructor and
+``forward(x_audio, y_pose, **kwargs) -> (fake_pose, internal_losses, args)`` contract, same
+host RNG consumption (one ``torch.rand(1)`` per training forward, gan.py:105)."""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class LambdaScheduler:
+    """Stand-in for pycasper.torchUtils.LambdaScheduler (un-vendored; semantics defined in
+    oracle/ref_loader.py: constant lambdas)."""
+
+    def __init__(self, lambdas, **kwargs):
+        self.lambdas = list(lambdas)
+
+    def step(self):
+        return list(self.lambdas)
+
+
+class GAN(nn.Module):
+    def __init__(self, G, D, dg_iter_ratio=1, lambda_D=1, lambda_gan=1, lr=0.0001, criterion='MSELoss', optim='Adam',
+                 joint=False, update_D_prob_flag=True, no_grad=True, **kwargs):
+        super().__init__()
+        self.G = G
+        self.D = D
+        self.D_prob = dg_iter_ratio / (dg_iter_ratio + 1)
+        self.lambda_D = lambda_D
+        self.lambda_gan = lambda_gan
+        self.lambda_scheduler = LambdaScheduler([self.lambda_D, self.lambda_gan], kind='incremental', max_interval=300,
+                                                max_lambda=2)
+        self.G_flag = True
+        self.lr = lr
+        if criterion != 'L1Loss':
+            raise NotImplementedError("mixstage_b200.GAN accelerates criterion='L1Loss' (the reference jobs' -loss)")
+        if joint:
+            raise NotImplementedError("mixstage_b200.GAN: joint=True is outside the accelerated path")
+        self.joint = joint
+        self.input_modalities = kwargs['input_modalities']
+        self.update_D_prob_flag = update_D_prob_flag
+        self.no_grad = no_grad
+        self.force_step = None        # 'G' / 'D' overrides the coin flip (tests, bench)
+
+    def get_velocity(self, x, x_audio=None):
+        return ops.cast(ops.velocity(ops.cast(x, torch.float32).contiguous()), x.dtype)
+
+    def estimate_weights(self, x_audio, y_pose, **kwargs):
+        return torch.ones(y_pose.shape[0]).to(y_pose.device), None
+
+    @staticmethod
+    def _l1(a, b=None, const=0.0, dtype=None):
+        a32 = ops.cast(a, torch.float32).contiguous()
+        b32 = None if b is None else ops.cast(b, torch.float32).contiguous()
+        return ops.cast(ops.l1_mean(a32, b32, const), dtype or a.dtype)
+
+    def _score(self, pose):
+        """D(velocity(pose)) without leaving fp32."""
+        v = ops.velocity(ops.cast(pose, torch.float32).contiguous())
+        s, _ = self.D(v)
+        return s
+
+    def forward(self, x_audio, y_pose, **kwargs):
+        internal_losses = []
+        W, _ = self.estimate_weights(x_audio, y_pose, **kwargs)
+        dt = y_pose.dtype
+        if 'input_modalities' not in kwargs:
+            kwargs['input_modalities'] = self.input_modalities
+        if self.training:
+            self.lambda_D, self.lambda_gan = self.lambda_scheduler.step()
+            coin = torch.rand(1).item()
+            d_step = coin < self.D_prob if self.force_step is None else self.force_step == 'D'
+            if d_step:
+                self.G.eval()
+                with torch.no_grad():
+                    fake_pose, partial_i_loss, *args = self.G(x_audio, y_pose, **kwargs)
+                    args = args[0] if len(args) > 0 else {}
+                self.G.train(self.training)
+                self.fake_flag = True
+                fake_score = self._score(fake_pose.detach())
+                fake_D_loss = self.lambda_D * self._l1(fake_score, None, 0.0, dt)
+                real_score = self._score(y_pose)
+                real_D_loss = self._l1(real_score, None, 1.0, dt)
+                internal_losses.append(real_D_loss)
+                internal_losses.append(fake_D_loss)
+                internal_losses += partial_i_loss
+                self.G_flag = False
+            else:
+                fake_pose, partial_i_loss, *args = self.G(x_audio, y_pose, **kwargs)
+                args = args[0] if len(args) > 0 else {}
+                if self.no_grad:
+                    with torch.no_grad():
+                        fake_score = self._score(fake_pose)
+                else:
+                    fake_score = self._score(fake_pose)
+                G_gan_loss = self.lambda_gan * self._l1(fake_score, None, 1.0, dt)
+                pose_loss = self._l1(fake_pose, y_pose, 0.0, dt)
+                internal_losses.append(pose_loss)
+                internal_losses.append(G_gan_loss)
+                internal_losses += partial_i_loss
+                self.G_flag = True
+        else:
+            fake_pose, partial_i_loss, *args = self.G(x_audio, y_pose, **kwargs)
+            args = args[0] if len(args) > 0 else {}
+            internal_losses.append(self._l1(fake_pose, y_pose, 0.0, dt))
+            internal_losses.append(torch.tensor(0))
+            internal_losses += partial_i_loss
+            self.G_flag = True
+        args.update(dict(W=W))
+        return fake_pose, internal_losses, args

@@ -1,0 +1,197 @@
+"""B200-native drop-in for the reference generator
+(reference: src/model/joint_late_cluster_soft_style.py).
+
+Same class names, constructor kwargs, state_dict layout, ``forward(x, y, time_steps=None,
+**kwargs)`` signature, return value ``(pose (B,T,P), [cluster_CE, id_in*lambda, id_out*lambda])``
+and ``labels_cap_soft`` side attribute.  All arithmetic is hand-written CUDA for sm_100a
+reached through the C-ABI in include/mixstage_b200.h; there is no CPU/PyTorch fallback."""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import MixStageError
+from .layers import (AudioEncoder, ClusterClassify, ConvNormRelu, Curriculum, EmbLin, Group, PlainConv,
+                     PoseEncoder, PoseStyleEncoder, TextEncoder1D, UNet1D)
+from .speech2gesture import Speech2Gesture_D
+
+JointLateClusterSoftStyle4_D = Speech2Gesture_D
+
+
+@contextlib.contextmanager
+def some_grad(module):
+    """Stand-in for pycasper.torchUtils.some_grad (un-vendored, semantics defined in
+    oracle/ref_loader.py): parameters of ``module`` are frozen inside the block while
+    gradients still reach the block's input (reference jlcss.py:198-200)."""
+    saved = [p.requires_grad for p in module.parameters()]
+    for p in module.parameters():
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p, r in zip(module.parameters(), saved):
+            p.requires_grad_(r)
+
+
+class JointLateClusterSoftStyle4_G(nn.Module):
+    '''
+    gives id_in and id_out losses as well
+    Late Fusion with clustering in the input pose
+
+    input_shape audio:  (N, time, frequency)
+    output_shape: (N, time, pose_feats)
+    '''
+
+    def __init__(self, time_steps=64, in_channels=256, out_feats=104, p=0, num_clusters=8, cluster=None,
+                 style_dict={}, style_dim=10, lambda_id=1, train_only=0, softmax=1, argmax=0,
+                 some_grad_flag=False, **kwargs):
+        super().__init__()
+        self.num_clusters = num_clusters
+        self.audio_encoder = AudioEncoder(output_feats=time_steps, p=p)
+        self.style_dict = style_dict
+        self.style_dim = style_dim
+        self.lambda_id = lambda_id
+        self.train_only = train_only
+        self.softmax = softmax
+        self.argmax = argmax
+        self.some_grad_flag = some_grad_flag
+        self.in_channels = in_channels
+        self.out_feats = out_feats
+
+        text_key = None
+        for key in kwargs.get('shape', {}):
+            if key in ['text/w2v', 'text/bert']:
+                text_key = key
+        if text_key:
+            self.text_encoder = TextEncoder1D(output_feats=time_steps, input_channels=kwargs['shape'][text_key][-1], p=p)
+        else:
+            self.text_encoder = TextEncoder1D(output_feats=time_steps, p=p)
+        self.pose_encoder = PoseEncoder(output_feats=time_steps, input_channels=out_feats, p=p)
+        self.unet = UNet1D(input_channels=in_channels, output_channels=in_channels, p=p, groups=1)
+
+        # style
+        S = len(self.style_dict)
+        self.pose_style_encoder = PoseStyleEncoder(input_channels=out_feats, p=p, num_speakers=S)
+        self.style_emb = EmbLin(num_embeddings=S, embedding_dim=self.style_dim)
+        self.style_dec = nn.Sequential(*[ConvNormRelu(in_channels, in_channels, type='1d', leaky=True, downsample=False,
+                                                      p=p, groups=self.style_dim) for _ in range(2)])
+        self.style_dec_gr = Group([self.style_dec], groups=self.style_dim)
+
+        # content: num_clusters parallel sub-decoders as grouped convolutions
+        dec = [ConvNormRelu(self.style_dim + in_channels, in_channels, type='1d', leaky=True, downsample=False,
+                            p=p, groups=self.num_clusters)]
+        dec += [ConvNormRelu(in_channels, in_channels, type='1d', leaky=True, downsample=False, p=p,
+                             groups=self.num_clusters) for _ in range(3)]
+        self.decoder = nn.Sequential(*dec)
+        # every group of decoder.0 reads the SAME 266 channels (reference `cat([x]*K)`, jlcss.py:190):
+        # run it as one dense conv C_in=266 -> C_out=256*K, the repeat is never materialised.
+        self.decoder[0].cfg.groups = 1
+        self.concat_encoder = nn.Sequential(ConvNormRelu(512, 256, type='1d', leaky=True, downsample=False, p=p))
+        self.logits = nn.Conv1d(in_channels * self.num_clusters, out_feats * self.num_clusters, kernel_size=1, stride=1,
+                                groups=self.num_clusters)
+        self._logits = PlainConv(self.logits)
+        self.classify_cluster = ClusterClassify(num_clusters=self.num_clusters, groups=1,
+                                                input_channels=self.style_dim + in_channels)
+        self.eye = nn.Parameter(torch.eye(self.num_clusters, self.num_clusters), requires_grad=False)
+        self.smoothen = ConvNormRelu(out_feats, out_feats, type='1d', leaky=True, downsample=False, p=p)
+        self.cluster = cluster
+        self.thresh = Curriculum(0, 1, 1000)
+        self.labels_cap_soft = None
+        self.style_index = None       # last integer style index used for the embedding ('emb' mode)
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _as_f32_cl(t, B, T):
+        """(B,T,F) caller tensor -> contiguous fp32 (B,T,F)."""
+        return ops.cast(t, torch.float32).contiguous()
+
+    def forward(self, x, y, time_steps=None, **kwargs):
+        internal_losses = []
+        labels = x[-1]                      # cluster labels ride along with the inputs (jlcss.py:119)
+        x = list(x[:-1])
+        ops._need_cuda(y)
+        out_dtype = y.dtype
+        B = y.shape[0]
+
+        # curriculum coin flip: same RNG consumption as the reference (jlcss.py:127)
+        if torch.rand(1).item() > self.thresh.step(self.training) and self.training:
+            T = y.shape[1]
+            h = self.pose_encoder(self._as_f32_cl(y, B, T).view(B, 1, T, y.shape[2]), time_steps)
+        else:
+            feats = []
+            for i, modality in enumerate(kwargs['input_modalities']):
+                kind = modality.split('/')[0]
+                if kind == 'text':
+                    feats.append(self.text_encoder(x[i], time_steps))
+                elif kind == 'audio':
+                    a = x[i]
+                    if a.dim() == 4:           # (B,1,T,F)
+                        a = a.squeeze(1)
+                    Bt, T, F = a.shape
+                    a = self._as_f32_cl(a, Bt, T).view(Bt, T, F, 1)     # NHWC with C=1
+                    feats.append(self.audio_encoder(a, time_steps if time_steps is not None else T))
+            if len(feats) != 1:
+                raise NotImplementedError("mixstage_b200: exactly one (audio) input modality is accelerated")
+            h = feats[0]                      # (B,1,T,256)
+        h = self.unet(h)                      # (B,1,T,256)
+        Bx, _, T, C = h.shape
+
+        style = kwargs['style']
+        flag = (not kwargs['sample_flag']) and (kwargs['description'] == 'train' or not self.train_only)
+        idx = soft_style = None
+        rep = 1
+        if flag:
+            Ty, P = y.shape[1], y.shape[2]
+            y32 = self._as_f32_cl(y, B, Ty).view(B, 1, Ty, P)
+            score = self.pose_style_encoder(y32)                              # (B,S)
+            tgt = style[:, 0].contiguous()
+            sm, id_in_loss, amax = ops.softmax_ce(score, tgt, 1)              # jlcss.py:159-165
+            if self.softmax:
+                if self.argmax:
+                    idx, rep = amax, T
+                else:
+                    soft_style, rep = sm, T
+            else:
+                soft_style, rep = score, T
+        else:
+            if style.dim() == 2:
+                idx = style.reshape(-1).contiguous()
+                rep = (Bx * T) // idx.numel()
+                if idx.numel() * rep != Bx * T:
+                    raise MixStageError("style index shape %s does not tile (B,T)=(%d,%d)" % (tuple(style.shape), Bx, T))
+            elif style.dim() == 3:
+                soft_style = ops.cast(style, torch.float32).contiguous().view(-1, style.shape[-1])
+                rep = (Bx * T) // soft_style.shape[0]
+            else:
+                raise MixStageError("style must be (B,T) int64 or (B,T,S) float")
+            id_in_loss = torch.zeros((), dtype=torch.float32, device=h.device)
+        self.style_index = idx
+        hc = ops.style_concat(h, self.style_emb.emb.weight, idx=idx, soft=soft_style, rep=rep)   # (B,1,T,266)
+
+        # cluster classifier: softmax weights + CE vs k-means labels (jlcss.py:183-187)
+        score_c = self.classify_cluster(hc)                                   # (B,1,T,K)
+        K = self.num_clusters
+        lab = labels.reshape(-1).contiguous()
+        soft_c, ce, _ = ops.softmax_ce(score_c.view(Bx * T, K), lab, 1)
+        internal_losses.append(ops.cast(ce, out_dtype))
+        self.labels_cap_soft = ops.cast(soft_c.view(Bx, T, K), out_dtype)
+
+        # K sub-decoders (grouped) + grouped 1x1 logits + soft mixture (jlcss.py:190-194)
+        d = self.decoder(hc)
+        z = self._logits(self.logits, d)                                      # (B,1,T,K*P)
+        pose = ops.mixture(z.view(Bx * T, K * self.out_feats), soft_c).view(Bx, T, self.out_feats)
+
+        if flag:
+            ctxm = some_grad(self.pose_style_encoder) if self.some_grad_flag else contextlib.nullcontext()
+            with ctxm:
+                score_out = self.pose_style_encoder(pose.view(Bx, 1, T, self.out_feats))
+            _, id_out_loss, _ = ops.softmax_ce(score_out, style[:, 0].contiguous(), 1)
+        else:
+            id_out_loss = torch.zeros((), dtype=torch.float32, device=h.device)
+
+        internal_losses.append(ops.cast(id_in_loss, out_dtype) * self.lambda_id)
+        internal_losses.append(ops.cast(id_out_loss, out_dtype) * self.lambda_id)
+        return ops.cast(pose, out_dtype), internal_losses

@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference layer classes on the generator hot path
+(reference: src/model/layers.py).  Same class names, constructor arguments, parameter
+names and state_dict layout; the arithmetic runs in hand-written CUDA (ops.py).
+
+Internal activation layout is channels-last fp32 (B, H, W, C) with H == 1 for the 1-D
+stacks, so none of the reference's transposes exist here.  ``nn.Conv*``/``nn.BatchNorm*``
+objects are used purely as parameter containers (identical names, shapes, default
+initialisation and ``.double()`` behaviour); their forward is never called."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import MixStageError
+
+
+def num_powers_of_two(x):
+    n = 0
+    while x > 1 and x % 2 == 0:
+        x //= 2
+        n += 1
+    return n
+
+
+class ConvNormRelu(nn.Module):
+    """conv -> BatchNorm -> (Leaky)ReLU, reference layers.py:32-78.  Same ctor contract:
+    default k3/s1, ``downsample`` k4/s2, padding (k-s)//2, channels multiplied by groups."""
+
+    def __init__(self, in_channels, out_channels, type='1d', leaky=False, downsample=False,
+                 kernel_size=None, stride=None, padding=None, p=0, groups=1):
+        super().__init__()
+        if p != 0:
+            raise NotImplementedError("mixstage_b200: dropout p>0 is outside the accelerated path (reference jobs use p=0)")
+        if kernel_size is None and stride is None:
+            kernel_size, stride = (4, 2) if downsample else (3, 1)
+        if padding is None:           # layers.py:46-55
+            if isinstance(kernel_size, int) and isinstance(stride, tuple):
+                padding = tuple(int((kernel_size - st) / 2) for st in stride)
+            elif isinstance(kernel_size, tuple) and isinstance(stride, int):
+                padding = tuple(int((ks - stride) / 2) for ks in kernel_size)
+            elif isinstance(kernel_size, tuple) and isinstance(stride, tuple):
+                padding = tuple(int((ks - st) / 2) for ks, st in zip(kernel_size, kernel_size))
+            else:
+                padding = int((kernel_size - stride) / 2)
+        in_channels, out_channels = in_channels * groups, out_channels * groups
+        if type == '1d':
+            self.conv = nn.Conv1d(in_channels, out_channels, kernel_size, stride, padding, groups=groups)
+            self.norm = nn.BatchNorm1d(out_channels)
+            kh, kw = 1, self.conv.kernel_size[0]
+            sh, sw = 1, self.conv.stride[0]
+            ph, pw = 0, self.conv.padding[0]
+        elif type == '2d':
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, groups=groups)
+            self.norm = nn.BatchNorm2d(out_channels)
+            (kh, kw), (sh, sw), (ph, pw) = self.conv.kernel_size, self.conv.stride, self.conv.padding
+        else:
+            raise ValueError(type)
+        self.cfg = ops.ConvCfg(kh, kw, sh, sw, ph, pw, groups, 0.2 if leaky else 0.0, has_bn=True, act=True)
+        self._packed = ops.PackedWeight()
+
+    def forward(self, x, residual=None, up2=False):
+        """x: channels-last (B, H, W, C) fp32.  With ``up2`` the output is
+        ``upsample2(act(bn(conv(x)))) + residual`` (UNet1D decoder step, layers.py:151)."""
+        n = self.norm
+        return ops.conv_block(x, self.conv.weight, self.conv.bias, n.weight, n.bias, self.cfg, self._packed,
+                              (n.running_mean, n.running_var, n.num_batches_tracked), self.training,
+                              residual=residual, up2=up2)
+
+
+class PlainConv(object):
+    """Helper (not a Module): runs an nn.Conv1d's parameters as conv (+ optional LeakyReLU)."""
+
+    def __init__(self, conv, slope=None):
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        self.cfg = ops.ConvCfg(1, k, 1, s, 0, p, conv.groups, 0.0 if slope is None else slope, has_bn=False,
+                               act=slope is not None)
+        self.packed = ops.PackedWeight()
+
+    def __call__(self, conv, x):
+        return ops.conv_block(x, conv.weight, conv.bias, None, None, self.cfg, self.packed, None, False)
+
+
+def _run(blocks, x):
+    for b in blocks:
+        x = b(x)
+    return x
+
+
+class UNet1D(nn.Module):
+    """reference layers.py:80-157."""
+
+    def __init__(self, input_channels, output_channels, max_depth=5, kernel_size=None, stride=None, p=0, groups=1):
+        super().__init__()
+        self.pre_downsampling_conv = nn.ModuleList([])
+        self.conv1 = nn.ModuleList([])
+        self.conv2 = nn.ModuleList([])
+        self.max_depth = max_depth
+        self.groups = groups
+        kw = dict(type='1d', leaky=True, kernel_size=kernel_size, stride=stride, p=p, groups=groups)
+        self.pre_downsampling_conv.append(ConvNormRelu(input_channels, output_channels, downsample=False, **kw))
+        self.pre_downsampling_conv.append(ConvNormRelu(output_channels, output_channels, downsample=False, **kw))
+        for _ in range(max_depth):
+            self.conv1.append(ConvNormRelu(output_channels, output_channels, downsample=True, **kw))
+        for _ in range(max_depth):
+            self.conv2.append(ConvNormRelu(output_channels, output_channels, downsample=False, **kw))
+
+    def forward(self, x):
+        T = x.shape[2]
+        assert T / (2 ** (self.max_depth - 1)) >= 1, \
+            'Input size is {}. It must be >= {}'.format(T, 2 ** (self.max_depth - 1))
+        assert num_powers_of_two(T) >= self.max_depth, \
+            'Input size is {}. It must be a multiple of 2^(max_depth) = 2^{} = {}'.format(T, self.max_depth, 2 ** self.max_depth)
+        x = _run(self.pre_downsampling_conv, x)
+        residuals = [x]
+        d = self.max_depth
+        # the last down block feeds `upconv(x) + residual` directly (layers.py:150-151): fuse it
+        for i, conv1 in enumerate(self.conv1):
+            if i < d - 1:
+                x = conv1(x)
+                residuals.append(x)
+            else:
+                x = conv1(x, residual=residuals[d - 1], up2=True)
+        for i, conv2 in enumerate(self.conv2):
+            if i < d - 1:
+                x = conv2(x, residual=residuals[d - i - 2], up2=True)     # output already holds next step's input
+            else:
+                x = conv2(x)
+        return x
+
+
+class AudioEncoder(nn.Module):
+    """reference layers.py:159-199.  forward takes (B, T, F, 1) channels-last, returns (B, 1, T, 256)."""
+
+    def __init__(self, output_feats=64, input_channels=1, kernel_size=None, stride=None, p=0, groups=1):
+        super().__init__()
+        kw = dict(type='2d', leaky=True, kernel_size=kernel_size, stride=stride, p=p, groups=groups)
+        self.conv = nn.ModuleList([])
+        for ci, co, down in [(input_channels, 64, False), (64, 64, True), (64, 128, False), (128, 128, True),
+                             (128, 256, False), (256, 256, True), (256, 256, False)]:
+            self.conv.append(ConvNormRelu(ci, co, downsample=down, **kw))
+        self.conv.append(ConvNormRelu(256, 256, type='2d', leaky=True, downsample=False,
+                                      kernel_size=(3, 8), stride=1, p=p, groups=groups))
+
+    def forward(self, x, time_steps=None):
+        if time_steps is None:
+            time_steps = x.shape[1]
+        x = _run(self.conv, x)
+        return ops.bilinear_to_T(x, time_steps)
+
+
+class _SeqEncoder(nn.Module):
+    def __init__(self, input_channels, p=0, groups=1, kernel_size=None, stride=None):
+        super().__init__()
+        kw = dict(type='1d', leaky=True, downsample=False, kernel_size=kernel_size, stride=stride, p=p, groups=groups)
+        chans = [input_channels, 64, 64, 128, 128, 256, 256]
+        self.conv = nn.ModuleList([ConvNormRelu(chans[i], chans[i + 1], **kw) for i in range(6)])
+
+    def forward(self, x, time_steps=None):
+        return _run(self.conv, x)
+
+
+class PoseEncoder(_SeqEncoder):
+    """reference layers.py:201-240."""
+
+    def __init__(self, output_feats=64, input_channels=96, kernel_size=None, stride=None, p=0, groups=1):
+        super().__init__(input_channels, p=p, groups=groups, kernel_size=kernel_size, stride=stride)
+
+
+class TextEncoder1D(_SeqEncoder):
+    """reference layers.py:339-373.  Parameters exist for state_dict compatibility; the text
+    modalities are outside the accelerated path and raise."""
+
+    def __init__(self, output_feats=64, input_channels=300, kernel_size=None, stride=None, p=0, groups=1):
+        super().__init__(input_channels, p=p, groups=groups, kernel_size=kernel_size, stride=stride)
+
+    def forward(self, x, time_steps=None, **kwargs):
+        raise NotImplementedError("mixstage_b200: text modalities are not on the accelerated path")
+
+
+class PoseStyleEncoder(nn.Module):
+    """reference layers.py:246-289.  (B,1,T,P) -> (B,S)."""
+
+    def __init__(self, output_feats=64, input_channels=96, kernel_size=None, stride=None, p=0, groups=1, num_speakers=4):
+        super().__init__()
+        kw = dict(type='1d', leaky=True, kernel_size=kernel_size, stride=stride, p=p, groups=groups)
+        chans = [input_channels, 64, 64, 128, 128, 256, 256, num_speakers]
+        self.conv = nn.ModuleList([ConvNormRelu(chans[0], chans[1], downsample=False, **kw)])
+        for i in range(1, 7):
+            self.conv.append(ConvNormRelu(chans[i], chans[i + 1], downsample=True, **kw))
+
+    def forward(self, x, time_steps=None):
+        x = _run(self.conv, x)
+        B, _, L, C = x.shape
+        return ops.mean_rows(x.view(B, L, C))
+
+
+class ClusterClassify(nn.Module):
+    """reference layers.py:446-467.  (B,1,T,C_in) -> (B,1,T,num_clusters)."""
+
+    def __init__(self, num_clusters=8, kernel_size=None, stride=None, p=0, groups=1, input_channels=256):
+        super().__init__()
+        kw = dict(type='1d', leaky=True, downsample=False, kernel_size=kernel_size, stride=stride, p=p, groups=groups)
+        self.conv = nn.ModuleList([ConvNormRelu(input_channels, 256, **kw)])
+        self.conv += nn.ModuleList([ConvNormRelu(256, 256, **kw) for _ in range(5)])
+        self.logits = nn.Conv1d(256 * groups, num_clusters * groups, kernel_size=1, stride=1, groups=groups)
+        self._logits = PlainConv(self.logits)
+
+    def forward(self, x, time_steps=None):
+        x = _run(self.conv, x)
+        return self._logits(self.logits, x)
+
+
+class EmbLin(nn.Module):
+    """reference layers.py:652-663 -- parameter holder; the lookup is fused with the concat
+    (ops.style_concat)."""
+
+    def __init__(self, num_embeddings, embedding_dim):
+        super().__init__()
+        self.num_embeddings = num_embeddings
+        self.embedding_dim = embedding_dim
+        self.emb = nn.Embedding(num_embeddings, embedding_dim)
+
+
+class Group(nn.Module):
+    """reference layers.py:593-650.  Constructed (aliases style_dec in the state_dict) but never
+    called on the hot path."""
+
+    def __init__(self, models, groups=1, dim=1):
+        super().__init__()
+        if not isinstance(models, list):
+            models = [models]
+        self.models = nn.ModuleList(models)
+        self.groups = groups
+        self.dim = dim
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("mixstage_b200: Group is not on the accelerated path")
+
+
+class Curriculum():
+    """reference layers.py:677-696 (plain host object, not in the state_dict)."""
+
+    def __init__(self, start, end, num_iters):
+        self.start, self.end, self.num_iters = start, end, num_iters
+        self.iters = 0
+        self.diff = (end - start) / num_iters
+        self.value = start
+
+    def step(self, flag=True):
+        if not flag:
+            return self.value
+        if self.iters < self.num_iters:
+            v = self.value
+            self.value += self.diff
+            self.iters += 1
+            return v
+        return self.end

@@ -1,0 +1,323 @@
+"""TEST-ONLY executable specification of the C-ABI (include/mixstage_b200.h) in torch-CPU.
+
+The build container has no GPU.  To exercise the *host logic* of mixstage_b200 (autograd
+wiring, layer order, BatchNorm bookkeeping, state_dict handling, data-parallel plumbing)
+in the `-m "not gpu"` suite, `install()` below replaces `mixstage_b200._lib.call` with
+functions that reinterpret the raw pointers as CPU arrays and compute what each kernel is
+specified to compute.  The product never imports this module and has no CPU fallback;
+the `-m gpu` tests compare the real kernels against the oracle and against these same
+definitions."""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+_NP = {0: (np.float32, 4), 1: (np.float64, 8)}
+
+
+def _arr(p, n, dtype):
+    if p is None or p == 0:
+        return None
+    n = int(n)
+    buf = (ctypes.c_char * (n * np.dtype(dtype).itemsize)).from_address(int(p))
+    return torch.from_numpy(np.frombuffer(buf, dtype=dtype, count=n))
+
+
+def f32(p, n):
+    return _arr(p, n, np.float32)
+
+
+def f64(p, n):
+    return _arr(p, n, np.float64)
+
+
+def i64(p, n):
+    return _arr(p, n, np.int64)
+
+
+def param(p, n, pdt):
+    return _arr(p, n, _NP[pdt][0])
+
+
+def _d(desc):
+    d = desc._obj if hasattr(desc, "_obj") else desc
+    return d
+
+
+def ms_cast(src, sdt, dst, ddt, n, st):
+    if sdt == 2 or ddt == 2:
+        raise NotImplementedError
+    param(dst, n, ddt).copy_(param(src, n, sdt))
+
+
+def ms_pack_conv_weight_f32(w, pdt, desc, wf, wt, st):
+    d = _d(desc)
+    g, taps = d.groups, d.kh * d.kw
+    cg, ng = d.Cin // g, d.Cout // g
+    W = param(w, d.Cout * cg * taps, pdt).float().view(g, ng, cg, taps)
+    if wf:
+        f32(wf, W.numel()).copy_(W.permute(0, 3, 2, 1).reshape(-1))        # [g][tap][c][n]
+    if wt:
+        f32(wt, W.numel()).copy_(W.permute(0, 3, 1, 2).reshape(-1))        # [g][tap][n][c]
+
+
+def ms_unpack_conv_wgrad(dwf, desc, dw, pdt, st):
+    d = _d(desc)
+    g, taps = d.groups, d.kh * d.kw
+    cg, ng = d.Cin // g, d.Cout // g
+    G = f32(dwf, d.Cout * cg * taps).view(g, taps, cg, ng).permute(0, 3, 2, 1).reshape(-1)
+    param(dw, G.numel(), pdt).copy_(G)
+
+
+def _weight_from_wf(wf, d):
+    g, taps = d.groups, d.kh * d.kw
+    cg, ng = d.Cin // g, d.Cout // g
+    return f32(wf, d.Cout * cg * taps).view(g, taps, cg, ng).permute(0, 3, 2, 1).reshape(d.Cout, cg, d.kh, d.kw)
+
+
+def _weight_from_wt(wt, d):
+    g, taps = d.groups, d.kh * d.kw
+    cg, ng = d.Cin // g, d.Cout // g
+    return f32(wt, d.Cout * cg * taps).view(g, taps, ng, cg).permute(0, 2, 3, 1).reshape(d.Cout, cg, d.kh, d.kw)
+
+
+def ms_conv_fwd_f32(x, wf, bias, y, desc, act, slope, st):
+    d = _d(desc)
+    X = f32(x, d.B * d.H * d.W * d.Cin).view(d.B, d.H, d.W, d.Cin).permute(0, 3, 1, 2)
+    Wt = _weight_from_wf(wf, d)
+    b = f32(bias, d.Cout)
+    Y = F.conv2d(X, Wt, b, stride=(d.sh, d.sw), padding=(d.ph, d.pw), groups=d.groups)
+    if act:
+        Y = F.leaky_relu(Y, slope)
+    f32(y, Y.numel()).copy_(Y.permute(0, 2, 3, 1).reshape(-1))
+
+
+def ms_conv_dgrad_f32(dy, wt, dx, desc, st):
+    d = _d(desc)
+    DY = f32(dy, d.B * d.Ho * d.Wo * d.Cout).view(d.B, d.Ho, d.Wo, d.Cout).permute(0, 3, 1, 2)
+    Wt = _weight_from_wt(wt, d)
+    DX = torch.nn.grad.conv2d_input((d.B, d.Cin, d.H, d.W), Wt, DY, stride=(d.sh, d.sw), padding=(d.ph, d.pw),
+                                    groups=d.groups)
+    f32(dx, DX.numel()).copy_(DX.permute(0, 2, 3, 1).reshape(-1))
+
+
+def ms_conv_wgrad_f32(x, dy, dwf, desc, st):
+    d = _d(desc)
+    X = f32(x, d.B * d.H * d.W * d.Cin).view(d.B, d.H, d.W, d.Cin).permute(0, 3, 1, 2)
+    DY = f32(dy, d.B * d.Ho * d.Wo * d.Cout).view(d.B, d.Ho, d.Wo, d.Cout).permute(0, 3, 1, 2)
+    g, taps = d.groups, d.kh * d.kw
+    cg, ng = d.Cin // g, d.Cout // g
+    DW = torch.nn.grad.conv2d_weight(X, (d.Cout, cg, d.kh, d.kw), DY, stride=(d.sh, d.sw), padding=(d.ph, d.pw),
+                                     groups=g)
+    f32(dwf, DW.numel()).copy_(DW.reshape(g, ng, cg, taps).permute(0, 3, 2, 1).reshape(-1))
+
+
+def ms_col_stats_f32(x, rows, C, s, ss, st):
+    X = f32(x, rows * C).view(rows, C).double()
+    f64(s, C).add_(X.sum(0))
+    if ss:
+        f64(ss, C).add_((X * X).sum(0))
+
+
+def ms_bn_finalize(s, ss, rows, C, gamma, beta, rm, rv, pdt, training, momentum, eps, scale, shift, mean, rstd, st):
+    g, b = param(gamma, C, pdt).double(), param(beta, C, pdt).double()
+    RM, RV = param(rm, C, pdt), param(rv, C, pdt)
+    if training:
+        m = f64(s, C) / rows
+        v = (f64(ss, C) / rows - m * m).clamp_min(0)
+        unb = v * (rows / (rows - 1)) if rows > 1 else v
+        RM.copy_(((1 - momentum) * RM.double() + momentum * m).to(RM.dtype))
+        RV.copy_(((1 - momentum) * RV.double() + momentum * unb).to(RV.dtype))
+    else:
+        m, v = RM.double().clone(), RV.double().clone()
+    r = 1.0 / torch.sqrt(v + eps)
+    f32(scale, C).copy_((g * r).float())
+    f32(shift, C).copy_((b - m * g * r).float())
+    f32(mean, C).copy_(m.float())
+    f32(rstd, C).copy_(r.float())
+
+
+def _act(z, slope):
+    return torch.where(z > 0, z, z * slope)
+
+
+def ms_bn_act_fwd_f32(x, scale, shift, slope, rows, C, y, res, up2, L, st):
+    Z = f32(x, rows * C).view(rows, C) * f32(scale, C) + f32(shift, C)
+    A = _act(Z, slope)
+    if up2:
+        A = A.view(rows // L, L, 1, C).expand(rows // L, L, 2, C).reshape(2 * rows, C)
+    if res:
+        A = A + f32(res, A.numel()).view(A.shape)
+    f32(y, A.numel()).copy_(A.reshape(-1))
+
+
+def _dy(dy, rows, C, up2, L):
+    if up2:
+        return f32(dy, 2 * rows * C).view(rows // L, L, 2, C).sum(2).reshape(rows, C)
+    return f32(dy, rows * C).view(rows, C)
+
+
+def ms_bn_act_bwd_reduce_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up2, L, dgamma, dbeta, st):
+    X = f32(x, rows * C).view(rows, C)
+    Z = X * f32(scale, C) + f32(shift, C)
+    D = _dy(dy, rows, C, up2, L)
+    dz = torch.where(Z > 0, D, D * slope)
+    xh = (X - f32(mean, C)) * f32(rstd, C)
+    f64(dgamma, C).add_((dz * xh).double().sum(0))
+    f64(dbeta, C).add_(dz.double().sum(0))
+
+
+def ms_bn_act_bwd_apply_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up2, L, dgamma, dbeta, training, dx, st):
+    X = f32(x, rows * C).view(rows, C)
+    sc = f32(scale, C)
+    Z = X * sc + f32(shift, C)
+    D = _dy(dy, rows, C, up2, L)
+    dz = torch.where(Z > 0, D, D * slope)
+    if training:
+        xh = (X - f32(mean, C)) * f32(rstd, C)
+        o = sc * (dz - f64(dbeta, C).float() / rows - xh * f64(dgamma, C).float() / rows)
+    else:
+        o = sc * dz
+    f32(dx, rows * C).copy_(o.reshape(-1))
+
+
+def ms_lrelu_bwd_f32(dy, y, slope, n, dz, st):
+    D, Y = f32(dy, n), f32(y, n)
+    f32(dz, n).copy_(torch.where(Y > 0, D, D * slope))
+
+
+def ms_store_param_grad(src, n, dst, pdt, st):
+    param(dst, n, pdt).copy_(f64(src, n))
+
+
+def ms_bilinear_to_T_fwd_f32(x, B, Hi, Wi, C, T, y, st):
+    X = f32(x, B * Hi * Wi * C).view(B, Hi, Wi, C).permute(0, 3, 1, 2)
+    Y = F.interpolate(X, size=(T, 1), mode="bilinear").squeeze(-1)          # (B,C,T)
+    f32(y, B * T * C).copy_(Y.permute(0, 2, 1).reshape(-1))
+
+
+def ms_bilinear_to_T_bwd_f32(dy, B, Hi, Wi, C, T, dx, st):
+    DY = f32(dy, B * T * C).view(B, T, C).permute(0, 2, 1)
+    with torch.enable_grad():
+        X = torch.zeros(B, C, Hi, Wi, requires_grad=True)
+        Y = F.interpolate(X, size=(T, 1), mode="bilinear").squeeze(-1)
+        Y.backward(DY)
+    f32(dx, X.numel()).copy_(X.grad.permute(0, 2, 3, 1).reshape(-1))
+
+
+def ms_style_concat_fwd_f32(x, rows, C, idx, soft, rep, emb, pdt, S, sd, out, st):
+    X = f32(x, rows * C).view(rows, C)
+    E = param(emb, S * sd, pdt).float().view(S, sd)
+    if idx:
+        sty = E[i64(idx, rows // rep)]
+    else:
+        sty = f32(soft, rows // rep * S).view(-1, S) @ E
+    sty = sty.repeat_interleave(rep, 0)
+    f32(out, rows * (C + sd)).copy_(torch.cat([X, sty], 1).reshape(-1))
+
+
+def ms_style_concat_bwd_f32(dout, rows, C, idx, soft, rep, emb, pdt, S, sd, dx, demb, dsoft, st):
+    D = f32(dout, rows * (C + sd)).view(rows, C + sd)
+    E = param(emb, S * sd, pdt).float().view(S, sd)
+    ds = D[:, C:]
+    if dx:
+        f32(dx, rows * C).copy_(D[:, :C].reshape(-1))
+    dsq = ds.reshape(rows // rep, rep, sd).sum(1)
+    if demb:
+        de = f32(demb, S * sd).view(S, sd)
+        if idx:
+            de.index_add_(0, i64(idx, rows // rep), dsq)
+        else:
+            de.add_(f32(soft, rows // rep * S).view(-1, S).t() @ dsq)
+    if dsoft and soft:
+        f32(dsoft, rows // rep * S).copy_((dsq @ E.t()).reshape(-1))
+
+
+def ms_softmax_ce_fwd_f32(score, rows, K, target, trep, soft, amax, loss_sum, st):
+    Sx = f32(score, rows * K).view(rows, K)
+    P = torch.softmax(Sx, -1)
+    if soft:
+        f32(soft, rows * K).copy_(P.reshape(-1))
+    if amax:
+        i64(amax, rows).copy_(Sx.argmax(-1))
+    if target and loss_sum:
+        t = i64(target, rows // trep).repeat_interleave(trep)
+        f64(loss_sum, 1).add_(F.cross_entropy(Sx, t, reduction="sum").double())
+
+
+def ms_softmax_ce_bwd_f32(soft, rows, K, target, trep, g_ce, dsoft, dscore, st):
+    P = f32(soft, rows * K).view(rows, K)
+    out = torch.zeros(rows, K)
+    if g_ce and target:
+        t = i64(target, rows // trep).repeat_interleave(trep)
+        out += f32(g_ce, 1)[0] / rows * (P - F.one_hot(t, K).float())
+    if dsoft:
+        DS = f32(dsoft, rows * K).view(rows, K)
+        out += P * (DS - (P * DS).sum(-1, keepdim=True))
+    f32(dscore, rows * K).copy_(out.reshape(-1))
+
+
+def ms_mixture_fwd_f32(z, w, rows, K, P, out, st):
+    Z, Wt = f32(z, rows * K * P).view(rows, K, P), f32(w, rows * K).view(rows, K, 1)
+    f32(out, rows * P).copy_((Z * Wt).sum(1).reshape(-1))
+
+
+def ms_mixture_bwd_f32(dout, z, w, rows, K, P, dz, dw, st):
+    D = f32(dout, rows * P).view(rows, 1, P)
+    Z, Wt = f32(z, rows * K * P).view(rows, K, P), f32(w, rows * K).view(rows, K, 1)
+    f32(dz, rows * K * P).copy_((Wt * D).reshape(-1))
+    f32(dw, rows * K).copy_((Z * D).sum(-1).reshape(-1))
+
+
+def ms_mean_rows_fwd_f32(x, B, L, C, y, st):
+    f32(y, B * C).copy_(f32(x, B * L * C).view(B, L, C).mean(1).reshape(-1))
+
+
+def ms_mean_rows_bwd_f32(dy, B, L, C, dx, st):
+    f32(dx, B * L * C).copy_((f32(dy, B * C).view(B, 1, C) / L).expand(B, L, C).reshape(-1))
+
+
+def ms_velocity_fwd_f32(x, B, T, P, v, st):
+    X = f32(x, B * T * P).view(B, T, P)
+    V = torch.cat([torch.zeros(B, 1, P), X[:, 1:] - X[:, :-1]], 1)
+    f32(v, B * T * P).copy_(V.reshape(-1))
+
+
+def ms_velocity_bwd_f32(dv, B, T, P, dx, st):
+    D = f32(dv, B * T * P).view(B, T, P).clone()
+    D[:, 0] = 0
+    out = D.clone()
+    out[:, :-1] -= D[:, 1:]
+    f32(dx, B * T * P).copy_(out.reshape(-1))
+
+
+def ms_l1_fwd_f32(a, b, c, n, loss_sum, sgn, st):
+    A = f32(a, n)
+    dlt = A - (f32(b, n) if b else c)
+    f64(loss_sum, 1).add_(dlt.abs().double().sum())
+    if sgn:
+        f32(sgn, n).copy_(torch.sign(dlt))
+
+
+def ms_l1_bwd_f32(sgn, g, n, da, st):
+    f32(da, n).copy_(f32(sgn, n) * (f32(g, 1)[0] / n))
+
+
+def ms_scalar_finish(inp, scale, out, st):
+    f32(out, 1).copy_((f64(inp, 1) * scale).float())
+
+
+def install(monkeypatch):
+    """Route mixstage_b200's kernel calls to the CPU specification (tests only)."""
+    from mixstage_b200 import _lib, ops, speech2gesture, joint_late_cluster_soft_style as j
+    table = {k: v for k, v in globals().items() if k.startswith("ms_")}
+
+    def call(name, *args):
+        _lib.LAUNCHES += 1
+        table[name](*args)
+
+    monkeypatch.setattr(_lib, "call", call)
+    monkeypatch.setattr(ops, "call", call)
+    monkeypatch.setattr(ops, "stream", lambda: None)
+    monkeypatch.setattr(ops, "_need_cuda", lambda t: None)

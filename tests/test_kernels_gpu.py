@@ -1,0 +1,213 @@
+"""Kernel-level parity on the GPU: every C-ABI entry point against its torch-CPU
+specification (tests/cpu_emu.py) on the shapes the generator uses,
+including the ragged ones (C_in=1, C_in=266, N=1, N=25, L=1, 3x8 kernel, stride 2)."""
+import numpy as np
+import pytest
+import torch
+
+import cpu_emu
+from mixstage_b200 import _lib, ops
+from mixstage_b200._lib import ConvDesc, ptr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def run_both(name, args):
+    """args: list of python scalars / ConvDesc / (tensor, 'in'|'out'|'inout') tuples.  Runs the CUDA
+    entry point on device copies and the CPU spec on host copies; returns ([gpu outs], [cpu outs])."""
+    gpu_args, cpu_args, outs_g, outs_c = [], [], [], []
+    keep = []
+    for a in args:
+        if isinstance(a, tuple):
+            t, role = a
+            if t is None:
+                gpu_args.append(None)
+                cpu_args.append(None)
+                continue
+            tc = t.clone().contiguous()
+            tg = t.clone().contiguous().to(DEV)
+            keep += [tc, tg]
+            gpu_args.append(ptr(tg))
+            cpu_args.append(ptr(tc))
+            if role != "in":
+                outs_g.append(tg)
+                outs_c.append(tc)
+        else:
+            gpu_args.append(a)
+            cpu_args.append(a)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call(name, *gpu_args, st)
+    getattr(cpu_emu, name)(*cpu_args, None)
+    torch.cuda.synchronize()
+    return [t.cpu() for t in outs_g], outs_c
+
+
+def close(g, c, tol=2e-5):
+    scale = float(c.double().abs().max()) + 1e-30
+    err = float((g.double() - c.double()).abs().max())
+    assert err <= tol * scale + 1e-7, (err, scale)
+
+
+CONVS = [
+    # B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups
+    (2, 16, 64, 1, 64, 3, 3, 1, 1, 1, 1, 1),        # audio_encoder.conv.0
+    (2, 16, 32, 64, 64, 4, 4, 2, 2, 1, 1, 1),       # conv.1 (stride 2)
+    (2, 8, 8, 256, 256, 3, 8, 1, 1, 1, 3, 1),       # conv.7 (3x8, pad (1,3))
+    (3, 1, 64, 256, 256, 3, 1 and 3, 1, 1, 0, 1, 1),  # placeholder replaced below
+]
+CONVS[3] = (3, 1, 64, 256, 256, 1, 3, 1, 1, 0, 1, 1)      # unet / classify k3
+CONVS += [
+    (3, 1, 64, 256, 256, 1, 4, 1, 2, 0, 1, 1),      # unet down k4 s2
+    (2, 1, 2, 256, 25, 1, 4, 1, 2, 0, 1, 1),        # pose_style_encoder.conv.6 (L 2 -> 1, N=25)
+    (2, 1, 64, 266, 2048, 1, 3, 1, 1, 0, 1, 1),     # decoder.0 as dense conv
+    (2, 1, 32, 2048, 2048, 1, 3, 1, 1, 0, 1, 8),    # decoder.1-3 grouped
+    (2, 1, 64, 2048, 768, 1, 1, 1, 1, 0, 0, 8),     # logits grouped 1x1, N=96 per group
+    (2, 1, 64, 256, 8, 1, 1, 1, 1, 0, 0, 1),        # classify logits N=8
+    (2, 1, 15, 256, 1, 1, 4, 1, 1, 0, 0, 1),        # D.logits N=1, p=0
+    (2, 1, 16, 128, 256, 1, 4, 1, 1, 0, 1, 1),      # D.conv3 k4 s1 p1 (16 -> 15)
+    (2, 1, 64, 96, 64, 1, 4, 1, 2, 0, 1, 1),        # D.conv1
+]
+
+
+def _desc(c):
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, g = c
+    return ConvDesc(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, g, ops.conv_out(H, kh, sh, ph), ops.conv_out(W, kw, sw, pw))
+
+
+@pytest.mark.parametrize("c", CONVS)
+def test_conv_fwd_dgrad_wgrad(c):
+    torch.manual_seed(0)
+    d = _desc(c)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, g = c
+    x = torch.randn(B, H, W, Cin)
+    w = torch.randn(Cout, Cin // g, kh, kw, dtype=torch.float64) / (Cin // g * kh * kw) ** 0.5
+    bias = torch.randn(Cout)
+    n = w.numel()
+    (wf, wt), (wf_c, wt_c) = run_both("ms_pack_conv_weight_f32", [(w, "in"), 1, d, (torch.zeros(n), "out"), (torch.zeros(n), "out")])
+    assert torch.equal(wf, wf_c) and torch.equal(wt, wt_c)
+    y = torch.zeros(B, d.Ho, d.Wo, Cout)
+    for act in (0, 1):
+        (yg,), (yc,) = run_both("ms_conv_fwd_f32", [(x, "in"), (wf, "in"), (bias, "in"), (y, "out"), d, act, 0.2])
+        close(yg, yc)
+    dy = torch.randn(B, d.Ho, d.Wo, Cout)
+    (dxg,), (dxc,) = run_both("ms_conv_dgrad_f32", [(dy, "in"), (wt, "in"), (torch.zeros_like(x), "out"), d])
+    close(dxg, dxc)
+    (dwg,), (dwc,) = run_both("ms_conv_wgrad_f32", [(x, "in"), (dy, "in"), (torch.zeros(n), "out"), d])
+    close(dwg, dwc, 5e-5)
+    (g64,), (c64,) = run_both("ms_unpack_conv_wgrad", [(dwc, "in"), d, (torch.zeros(n, dtype=torch.float64), "out"), 1])
+    assert torch.equal(g64, c64)
+
+
+@pytest.mark.parametrize("rows,C,L,up2", [(1024, 256, 64, 0), (64, 256, 2, 1), (32, 25, 1, 0), (2048, 2048, 64, 0), (8192, 64, 64, 0)])
+def test_batchnorm_chain(rows, C, L, up2):
+    torch.manual_seed(1)
+    x = torch.randn(rows, C) * 1.7 + 0.3
+    s, ss = torch.zeros(C, dtype=torch.float64), torch.zeros(C, dtype=torch.float64)
+    (sg, ssg), (sc, ssc) = run_both("ms_col_stats_f32", [(x, "in"), rows, C, (s, "inout"), (ss, "inout")])
+    close(sg, sc, 1e-9)
+    close(ssg, ssc, 1e-9)
+    for pdt, dt in ((0, torch.float32), (1, torch.float64)):
+        gamma, beta = torch.rand(C, dtype=dt) + 0.5, torch.randn(C, dtype=dt) * 0.1
+        rm, rv = torch.randn(C, dtype=dt) * 0.1, torch.rand(C, dtype=dt) + 0.5
+        for training in (1, 0):
+            outs = [(torch.zeros(C), "out") for _ in range(4)]
+            g, c = run_both("ms_bn_finalize", [(sc, "in"), (ssc, "in"), rows, C, (gamma, "in"), (beta, "in"), (rm, "inout"),
+                                               (rv, "inout"), pdt, training, 0.1, 1e-5] + outs)
+            for a, b in zip(g, c):
+                close(a, b, 1e-6)
+    scale, shift, mean, rstd = c[2], c[3], c[4], c[5]
+    res = torch.randn(rows * (2 if up2 else 1), C)
+    y = torch.zeros_like(res)
+    (yg,), (yc,) = run_both("ms_bn_act_fwd_f32", [(x, "in"), (scale, "in"), (shift, "in"), 0.2, rows, C, (y, "out"),
+                                                  (res if up2 else None, "in"), up2, L])
+    close(yg, yc, 1e-6)
+    dy = torch.randn_like(res)
+    z2 = [(torch.zeros(C, dtype=torch.float64), "inout") for _ in range(2)]
+    (dgg, dbg), (dgc, dbc) = run_both("ms_bn_act_bwd_reduce_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
+                                                                     (rstd, "in"), 0.2, rows, C, up2, L] + z2)
+    close(dgg, dgc, 1e-5)
+    close(dbg, dbc, 1e-5)
+    for training in (1, 0):
+        (dxg,), (dxc,) = run_both("ms_bn_act_bwd_apply_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
+                                                                (rstd, "in"), 0.2, rows, C, up2, L, (dgc, "in"), (dbc, "in"),
+                                                                training, (torch.zeros(rows, C), "out")])
+        close(dxg, dxc, 1e-5)
+
+
+def test_small_ops():
+    torch.manual_seed(2)
+    B, T, P, K, S, sd, C = 4, 64, 96, 8, 25, 10, 256
+    # bilinear (8,7)->(64,1) and (32,7)->(256,1)
+    for Hi, Tt in ((8, 64), (32, 256), (3, 64)):
+        x = torch.randn(2, Hi, 7, 64)
+        (yg,), (yc,) = run_both("ms_bilinear_to_T_fwd_f32", [(x, "in"), 2, Hi, 7, 64, Tt, (torch.zeros(2, Tt, 64), "out")])
+        close(yg, yc, 1e-6)
+        dy = torch.randn(2, Tt, 64)
+        (dg,), (dc,) = run_both("ms_bilinear_to_T_bwd_f32", [(dy, "in"), 2, Hi, 7, 64, Tt, (torch.zeros_like(x), "out")])
+        close(dg, dc, 1e-5)
+    # style concat, emb and lin modes, fp64 table
+    rows = B * T
+    x = torch.randn(rows, C)
+    emb = torch.randn(S, sd, dtype=torch.float64)
+    idx = torch.randint(0, S, (B,))
+    soft = torch.softmax(torch.randn(B, S), -1)
+    for (i, s_) in ((idx, None), (None, soft)):
+        (og,), (oc,) = run_both("ms_style_concat_fwd_f32", [(x, "in"), rows, C, (i, "in"), (s_, "in"), T, (emb, "in"), 1, S, sd,
+                                                            (torch.zeros(rows, C + sd), "out")])
+        close(og, oc, 1e-6)
+        dout = torch.randn(rows, C + sd)
+        g, c = run_both("ms_style_concat_bwd_f32", [(dout, "in"), rows, C, (i, "in"), (s_, "in"), T, (emb, "in"), 1, S, sd,
+                                                    (torch.zeros(rows, C), "out"), (torch.zeros(S, sd), "inout"),
+                                                    (torch.zeros(B, S) if s_ is not None else None, "out")])
+        for a, b in zip(g, c):
+            close(a, b, 1e-5)
+    # per-frame style index (rep=1)
+    idx2 = torch.randint(0, S, (rows,))
+    (og,), (oc,) = run_both("ms_style_concat_fwd_f32", [(x, "in"), rows, C, (idx2, "in"), (None, "in"), 1, (emb, "in"), 1, S, sd,
+                                                        (torch.zeros(rows, C + sd), "out")])
+    close(og, oc, 1e-6)
+    # softmax / CE / argmax
+    for Kk, r, trep in ((8, rows, 1), (25, B, 1), (4, 64, 16)):
+        score = torch.randn(r, Kk) * 3
+        tgt = torch.randint(0, Kk, (r // trep,))
+        g, c = run_both("ms_softmax_ce_fwd_f32", [(score, "in"), r, Kk, (tgt, "in"), trep, (torch.zeros(r, Kk), "out"),
+                                                  (torch.zeros(r, dtype=torch.int64), "out"), (torch.zeros(1, dtype=torch.float64), "inout")])
+        close(g[0], c[0], 1e-6)
+        assert torch.equal(g[1], c[1])
+        close(g[2], c[2], 1e-6)
+        gce, dsoft = torch.tensor([0.7]), torch.randn(r, Kk)
+        (dg,), (dc,) = run_both("ms_softmax_ce_bwd_f32", [(c[0], "in"), r, Kk, (tgt, "in"), trep, (gce, "in"), (dsoft, "in"),
+                                                          (torch.zeros(r, Kk), "out")])
+        close(dg, dc, 1e-5)
+    # mixture
+    z, w, dout = torch.randn(rows, K * P), torch.softmax(torch.randn(rows, K), -1), torch.randn(rows, P)
+    (og,), (oc,) = run_both("ms_mixture_fwd_f32", [(z, "in"), (w, "in"), rows, K, P, (torch.zeros(rows, P), "out")])
+    close(og, oc, 1e-6)
+    g, c = run_both("ms_mixture_bwd_f32", [(dout, "in"), (z, "in"), (w, "in"), rows, K, P, (torch.zeros(rows, K * P), "out"),
+                                           (torch.zeros(rows, K), "out")])
+    close(g[0], c[0], 1e-6)
+    close(g[1], c[1], 1e-5)
+    # mean rows, velocity, l1
+    x3 = torch.randn(B, 4, 25)
+    (og,), (oc,) = run_both("ms_mean_rows_fwd_f32", [(x3, "in"), B, 4, 25, (torch.zeros(B, 25), "out")])
+    close(og, oc, 1e-6)
+    (og,), (oc,) = run_both("ms_mean_rows_bwd_f32", [(torch.randn(B, 25), "in"), B, 4, 25, (torch.zeros(B, 4, 25), "out")])
+    close(og, oc, 1e-6)
+    xp = torch.randn(B, T, P)
+    (og,), (oc,) = run_both("ms_velocity_fwd_f32", [(xp, "in"), B, T, P, (torch.zeros(B, T, P), "out")])
+    assert torch.equal(og, oc)
+    (og,), (oc,) = run_both("ms_velocity_bwd_f32", [(xp, "in"), B, T, P, (torch.zeros(B, T, P), "out")])
+    assert torch.equal(og, oc)
+    n = B * T * P
+    for b_, cst in ((torch.randn(n), 0.0), (None, 1.0)):
+        g, c = run_both("ms_l1_fwd_f32", [(xp.reshape(-1), "in"), (b_, "in"), cst, n, (torch.zeros(1, dtype=torch.float64), "inout"),
+                                          (torch.zeros(n), "out")])
+        close(g[0], c[0], 1e-9)
+        assert torch.equal(g[1], c[1])
+    (og,), (oc,) = run_both("ms_l1_bwd_f32", [(c[1], "in"), (torch.tensor([0.3]), "in"), n, (torch.zeros(n), "out")])
+    close(og, oc, 1e-6)
+    # casts
+    src = torch.randn(1000, dtype=torch.float64)
+    (og,), (oc,) = run_both("ms_cast", [(src, "in"), 1, (torch.zeros(1000), "out"), 0, 1000])
+    assert torch.equal(og, oc)

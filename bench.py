@@ -1,0 +1,334 @@
+"""Benchmark of the Mix-StAGE generator hot path on B200 (contract: see the task statement).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1]): full GAN train step of JointLateClusterSoftStyle4_G +
+pose discriminator (gan=1, L1Loss), batch 16 per GPU, 64-frame windows, 4 speakers,
+num_clusters=8, fp64 master parameters and inputs as the reference's trainer keeps them
+(trainer.py:138), synthetic N(0,1) inputs and seeded synthetic weights.  A "step" is one
+training iteration: zero_grad, GAN.forward (generator step on even iterations, discriminator
+step on odd ones -- the reference flips a fair coin, gan.py:105), backward, gradient
+all-reduce when N>1, clip_grad_norm_(1) and Adam(1e-4) (trainer.py:1138-1146).
+Metric: pose sequences (64-frame windows) per second, whole job.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "pose sequences/sec (64-frame windows), GAN train step"
+UNIT = "sequences/s"
+MOD = ["audio/log_mel_400"]
+T = 64
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_train_steps(B, S, steps, warmup, dtype=torch.float64):
+    """Times the oracle's restatement of one reference train step (fwd + bwd + clip + Adam)."""
+    import mixstage_oracle as O
+    from oracle_cases import D_SEED, G_SEED, leafify
+    torch.set_num_threads(os.cpu_count())
+    spec = O.Spec(num_speakers=S)
+    sd = leafify(O.synth_state(O.g_state_shapes(spec), G_SEED, dtype))
+    sdd = leafify(O.synth_state(O.d_state_shapes(spec.out_feats), D_SEED, dtype))
+    audio, pose, labels, style = O.synth_inputs(B, T, spec, dtype=dtype)
+    gleaf = [v for k, v in sd.items() if v.requires_grad and not k.startswith("style_dec_gr.")]
+    dleaf = [v for v in sdd.values() if v.requires_grad]
+    state = {id(v): (torch.zeros_like(v), torch.zeros_like(v)) for v in gleaf + dleaf}
+    nstep = {"G": 0, "D": 0}
+
+    def one(kind):
+        for v in gleaf + dleaf:
+            v.grad = None
+        lg, ld = O.BNLog(), O.BNLog()
+        fake, losses, _ = O.gan_forward(sd, sdd, spec, audio, labels, pose, style, step=kind, log_g=lg, log_d=ld)
+        sum(losses).backward()
+        leaves = gleaf if kind == "G" else dleaf
+        used = [v for v in leaves if v.grad is not None]
+        nstep[kind] += 1
+        with torch.no_grad():
+            O.clip_and_adam(used, [v.grad for v in used], [state[id(v)][0] for v in used],
+                            [state[id(v)][1] for v in used], nstep[kind])
+            for k, v in lg.updates.items():
+                sd[k] = v
+            for k, v in ld.updates.items():
+                sdd[k] = v
+        return float(sum(losses))
+
+    for i in range(warmup):
+        one("G" if i % 2 == 0 else "D")
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one("G" if i % 2 == 0 else "D")
+    dt = time.perf_counter() - t0
+    return dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, S = args.batch, 4
+    steps, warmup = args.steps, args.warmup
+    dt = cpu_train_steps(B, S, steps, warmup)
+    val = steps * B / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: GAN train step (alternating G/D), B=%d, T=64, S=4, K=8, fp64" % B},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d train steps (G/D alternating) after %d warm-up, oracle port of the reference "
+                                   "algorithm (torch CPU fp64, %d threads); the reference is Python and "
+                                   "/root/reference does not exist on the GPU box" % (steps, warmup, os.cpu_count())},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------------
+def conv_flops(name, desc):
+    g = desc.groups
+    if name == "ms_conv_fwd_f32" or name == "ms_conv_wgrad_f32":
+        return 2.0 * desc.B * desc.Ho * desc.Wo * desc.Cout * (desc.Cin // g) * desc.kh * desc.kw
+    if name == "ms_conv_dgrad_f32":
+        return 2.0 * desc.B * desc.Ho * desc.Wo * desc.Cout * (desc.Cin // g) * desc.kh * desc.kw
+    return 0.0
+
+
+def run_cuda(args):
+    import torch.distributed as dist
+    import mixstage_b200 as M
+    import mixstage_oracle as O
+    from mixstage_b200 import _lib, ops, parallel
+    from model_cases import build as build_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B, S = args.batch, 4
+    spec = O.Spec(num_speakers=S)
+    G, D, gan = build_model(spec, T, dev, torch.float64)
+    gan.train()
+    G.thresh.value, G.thresh.iters = 1.0, 1000            # past the curriculum: audio branch
+    fg, fd = parallel.FlatGrads(G), parallel.FlatGrads(D)
+    optG = torch.optim.Adam(G.parameters(), lr=1e-4)
+    optD = torch.optim.Adam(D.parameters(), lr=1e-4)
+    parallel.sync_host_rng(11212)
+
+    # per-rank synthetic shard (weak scaling: B sequences per GPU), pinned host copies for the e2e leg
+    audio, pose, labels, style = O.synth_inputs(B, T, spec, seed=11212 + rank)
+    host = [t.pin_memory() for t in (audio, pose, labels, style)]
+    resident = [t.to(dev) for t in host]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def step(i, batch, read_loss):
+        kind = "G" if i % 2 == 0 else "D"
+        fg.zero()
+        fd.zero()
+        gan.force_step = kind
+        a, y, lab, sty = batch
+        fake, losses, _ = gan([a, lab], y, input_modalities=MOD, style=sty, sample_flag=0, description="train", desc="train")
+        loss = sum(losses)
+        loss.backward()
+        if kind == "G":
+            fg.allreduce_mean()
+            torch.nn.utils.clip_grad_norm_(G.parameters(), 1)
+            optG.step()
+        else:
+            fd.allreduce_mean()
+            torch.nn.utils.clip_grad_norm_(D.parameters(), 1)
+            optD.step()
+        if read_loss:
+            return loss.item()              # D2H read of the step's result
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(nsteps):
+            if e2e:
+                batch = [t.to(dev, non_blocking=True) for t in host]
+                step(i, batch, True)
+            else:
+                step(i, resident, False)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if e2e:
+            ms = max(ms, wall * 1e3)        # the host read-back is part of the step
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(max(args.warmup, 3)):
+        step(i, resident, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.LAUNCHES
+    ms = timed(args.steps, False)
+    launches = _lib.LAUNCHES - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, True)
+
+    # ---- roofline of the dominant kernel family (implicit-GEMM convolutions): one instrumented
+    # step pair with CUDA events around every conv launch on the launch stream
+    records = []
+    orig_call = ops.call
+
+    def timed_call(name, *a):
+        if name.startswith("ms_conv_"):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig_call(name, *a)
+            e1.record()
+            desc = [x for x in a if isinstance(x, _lib.ConvDesc)][0]
+            records.append((name, conv_flops(name, desc), e0, e1))
+        else:
+            orig_call(name, *a)
+
+    ops.call = timed_call
+    try:
+        step(0, resident, False)
+        step(1, resident, False)
+    finally:
+        ops.call = orig_call
+    torch.cuda.synchronize()
+    conv_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in records)
+    conv_fl = sum(f for _, f, _, _ in records)
+    pk, pk_kind = peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+
+    if rank == 0:
+        cpu_steps = 4
+        cpu_dt = cpu_train_steps(B, S, cpu_steps, 1)
+        total = args.steps * B * world
+        line = {
+            "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: GAN train step (G on even, D on odd iterations), B=%d per GPU, T=64, "
+                                   "S=4, K=8, gan=1, L1Loss, fp64 master params/inputs, fp32 CUDA arithmetic" % B,
+                       "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2": "no explicit flush: per-step working set (fp64 params + packed fp32 weights + grads + "
+                             "Adam state ~0.9 GB) exceeds the 126 MB L2"},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+            "gpu_launches": launches,
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "kernel": "conv_gemm_simt (fwd+dgrad+wgrad, %d launches per G+D step pair, fp32 CUDA cores)" % len(records),
+                         "peak_source": "%s bf16 sustained" % pk_kind},
+            "cpu_baseline": {"value": cpu_steps * B / cpu_dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d train steps (G/D alternating) B=%d after 1 warm-up, oracle port, torch CPU fp64" % (cpu_steps, B)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=16, help="sequences per GPU")
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

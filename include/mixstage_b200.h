@@ -74,6 +74,45 @@ int ms_conv_dgrad_f32(const float* dy, const float* wt, float* dx, const ms_conv
  * Overwrites dwf (zeroed internally; split-K partials are combined with fp32 atomics). */
 int ms_conv_wgrad_f32(const float* x, const float* dy, float* dwf, const ms_conv_desc* d, void* stream);
 
+/* ---- implicit-GEMM convolution on tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM,
+ * operands staged by TMA).  Same call sites as the fp32 family above; this is the fast path
+ * ("precision=bf16").  One descriptor type serves the forward pass and the input gradient:
+ *
+ *   out[b,h,w, off[q] + n] = sum_t sum_c A5[base[q] + taps[q][t].chan + c, w + taps.dw, taps.par, h + taps.dh, b]
+ *                                        * Wp[q*class_n + n][t][c]          (+ bias | * scale + shift, LeakyReLU)
+ *
+ * A5 is the bf16 activation seen as a 5-D tensor (channel, w-like, h-parity, h-like, batch) with
+ * element strides a_strides; reads outside it are zero (the convolution's padding).  Wp is the
+ * re-tiled weight [classes*class_n][ntaps][cchunks*64] bf16 (ms_pack_igemm_weight_bf16).
+ * box = {64, bw, 1, bh, bb} with bw*bh*bb = 128 rows per tile.  Requires sm_100. */
+#define MS_IGEMM_MAX_CLASSES 16
+#define MS_IGEMM_MAX_TAPS 48
+typedef struct ms_igemm_desc {
+  int32_t a_dims[5];
+  int64_t a_strides[5];
+  int32_t box[5];
+  int32_t out_dims[3];      /* w-like, h-like, batch extents of the output */
+  int64_t out_strides[3];   /* element strides of the output for (w, h, b)  */
+  int32_t num_classes, class_n, block_n;
+  int32_t ntaps, cchunks, shared_taps;
+  int32_t a_chan_base[MS_IGEMM_MAX_CLASSES];
+  int64_t out_off[MS_IGEMM_MAX_CLASSES];
+  int16_t taps[MS_IGEMM_MAX_TAPS][4];   /* chan offset, w shift, h-parity coordinate, h shift */
+  int32_t out_dtype;        /* MS_F32 or MS_BF16 */
+  int32_t epilogue;         /* 0: + bias (nullable); 1: * scale[n] + shift[n] then LeakyReLU(slope) */
+  float slope;
+} ms_igemm_desc;
+int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                  const float* shift, void* out, void* stream);
+/* Re-tile a conv weight (Cout, Cin/g, kh*kw) of dtype pdt into Wp (bf16).
+ * mode 0 (forward):  Wp[q*class_n + r][t][c] = w[q*class_n + r][c][srctap[t]]            (c < Cin/g, else 0)
+ * mode 1 (dgrad):    Wp[q*class_n + r][t][n] = w[g*Cout/g + n][r][srctap[q*ntaps + t]]   (n < Cout/g, r < Cin/g, else 0)
+ *                    with g = q when groups > 1 (classes are groups) and g = 0 otherwise (classes are parities).
+ * srctap_host: HOST array of ntaps (mode 0) or num_classes*ntaps (mode 1) source tap indices. */
+int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int taps_total, int groups, int mode,
+                              int num_classes, int class_n, int ntaps, int kpad, const int16_t* srctap_host,
+                              void* wp, void* stream);
+
 /* ---- BatchNorm (+LeakyReLU) pieces, nn.BatchNorm1d/2d at layers.py:64,70 and
  * nn.LeakyReLU(0.2) at layers.py:72-73, applied as in ConvNormRelu.forward (:78) ------ */
 /* column sums over rows: sum[c] += x[r,c], sumsq[c] += x[r,c]^2 (double accumulators,

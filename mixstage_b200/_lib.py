@@ -18,8 +18,26 @@ class ConvDesc(ctypes.Structure):
                 ("B", "H", "W", "Cin", "Cout", "kh", "kw", "sh", "sw", "ph", "pw", "groups", "Ho", "Wo")]
 
 
+MAX_CLASSES, MAX_TAPS = 16, 48
+
+
+class IgemmDesc(ctypes.Structure):
+    """ms_igemm_desc (include/mixstage_b200.h)."""
+    _fields_ = [
+        ("a_dims", ctypes.c_int32 * 5), ("a_strides", ctypes.c_int64 * 5), ("box", ctypes.c_int32 * 5),
+        ("out_dims", ctypes.c_int32 * 3), ("out_strides", ctypes.c_int64 * 3),
+        ("num_classes", ctypes.c_int32), ("class_n", ctypes.c_int32), ("block_n", ctypes.c_int32),
+        ("ntaps", ctypes.c_int32), ("cchunks", ctypes.c_int32), ("shared_taps", ctypes.c_int32),
+        ("a_chan_base", ctypes.c_int32 * MAX_CLASSES), ("out_off", ctypes.c_int64 * MAX_CLASSES),
+        ("taps", (ctypes.c_int16 * 4) * MAX_TAPS),
+        ("out_dtype", ctypes.c_int32), ("epilogue", ctypes.c_int32), ("slope", ctypes.c_float),
+    ]
+
+
 _P, _I, _L, _F, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 _CD = ctypes.POINTER(ConvDesc)
+_GD = ctypes.POINTER(IgemmDesc)
+_S16 = ctypes.POINTER(ctypes.c_int16)
 
 # name -> argtypes (mirrors include/mixstage_b200.h; tests/test_capi_symbols.py checks both ways)
 PROTOTYPES = {
@@ -31,6 +49,8 @@ PROTOTYPES = {
     "ms_conv_fwd_f32": [_P, _P, _P, _P, _CD, _I, _F, _P],
     "ms_conv_dgrad_f32": [_P, _P, _P, _CD, _P],
     "ms_conv_wgrad_f32": [_P, _P, _P, _CD, _P],
+    "ms_igemm_bf16": [_GD, _P, _P, _P, _P, _P, _P, _P],
+    "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P],
     "ms_col_stats_f32": [_P, _L, _I, _P, _P, _P],
     "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],
     "ms_bn_act_fwd_f32": [_P, _P, _P, _F, _L, _I, _P, _P, _I, _I, _P],

@@ -1,0 +1,394 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands fed by TMA.
+//
+//   out[row, n] = sum_{tap} sum_{c} A[row shifted by tap, c] * W[n, tap, c]       (bf16 x bf16 -> fp32)
+//
+// * A is a channels-last bf16 activation tensor seen through a 5-D TMA tensor map
+//   (channel, w-like, h-parity, h-like, batch).  Each k-step loads one 128-row x 64-channel box
+//   whose start coordinate is the tile origin plus the tap's shift; rows that fall outside the
+//   tensor (the convolution's zero padding, ragged batch tails, channel tails) are zero-filled
+//   by the TMA unit, so im2col is never materialised and padding costs nothing.  Stride-2
+//   convolutions use a space-to-depth *view* of the same memory ((B,L,C) == (B,L/2,2C)), so the
+//   strided taps are plain boxes as well.
+// * W is the weight re-tiled once per parameter version to [n][tap][c] (K-major bf16).
+// * 128 x block_n fp32 accumulator in TMEM; UMMA 128 x block_n x 16, cta_group::1.
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+//   (tcgen05.ld, bias / BN scale-shift / LeakyReLU, fp32 or bf16 stores).  4-stage smem ring with
+//   full/empty mbarriers; tcgen05.commit releases stages and signals the epilogue.
+// * "Classes" generalise groups and stride parities: every class owns class_n output columns, a
+//   channel base in A, an output offset and (optionally) its own tap table.  Grouped sub-decoders
+//   are classes with a shared tap table; the input gradient of a stride-2 convolution is a
+//   stride-1 problem with one class per output parity.
+//
+// The same kernel serves forward and input-gradient (descriptors differ); see ms_igemm_desc.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;            // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr uint32_t SPIN_LIMIT = 1u << 22;   // bounded mbarrier spins: trap instead of hanging the GPU
+
+struct IgemmParams {
+  int ntaps, cchunks, shared_taps;
+  int num_classes, class_n, block_n, n_tiles_per_class;
+  int box_w, box_h, box_b;
+  int tiles_w, tiles_h, tiles_b;
+  int out_w, out_h, out_b;
+  long long os_w, os_h, os_b;           // output element strides
+  int a_chan_base[MS_IGEMM_MAX_CLASSES];
+  long long out_off[MS_IGEMM_MAX_CLASSES];
+  short taps[MS_IGEMM_MAX_TAPS][4];     // chan_off, d_w, d_par, d_h
+  int out_dtype, epilogue;
+  float slope;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, 128-byte swizzle: 8-row atoms of 1024 B, SBO = 1024 B, LBO unused (=1), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ IgemmParams p, const float* __restrict__ bias, const float* __restrict__ scale,
+                const float* __restrict__ shift, void* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int mt = blockIdx.x;
+  const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+  const int th = mt % p.tiles_h; mt /= p.tiles_h;
+  const int tb = mt;
+  const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = tb * p.box_b;
+  const int cls = blockIdx.y / p.n_tiles_per_class;
+  const int nt = blockIdx.y - cls * p.n_tiles_per_class;
+  const int n0 = nt * p.block_n;                       // column offset inside the class
+  const int num_k = p.ntaps * p.cchunks;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int tap_base = p.shared_taps ? 0 : cls * p.ntaps;
+      const int chan_base = p.a_chan_base[cls];
+      const int wrow = cls * p.class_n + n0;
+      for (int ks = 0; ks < num_k; ks++) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap = ks / p.cchunks, cc = ks - tap * p.cchunks;
+        const short* t = p.taps[tap_base + tap];
+        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + b_stage_bytes);
+        tma_load_5d(&map_a, &full_bar[s], smem_a + (size_t)s * A_STAGE_BYTES, chan_base + t[0] + cc * BLOCK_K, w0 + t[1],
+                    t[2], h0 + t[3], b0);
+        tma_load_2d(&map_w, &full_bar[s], smem_b + (size_t)s * b_stage_bytes, ks * BLOCK_K, wrow);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      for (int ks = 0; ks < num_k; ks++) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + (size_t)s * A_STAGE_BYTES));
+        const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + (size_t)s * b_stage_bytes));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+          // advance 16 bf16 = 32 B inside the swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);            // stage reusable once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);             // accumulator complete
+    }
+  } else {
+    // ================= epilogue: 4 warps, one TMEM lane quadrant each =================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                       // tile row == TMEM lane
+    const int wi = r % p.box_w;
+    const int hi = (r / p.box_w) % p.box_h;
+    const int bi = r / (p.box_w * p.box_h);
+    const int ow = w0 + wi, oh = h0 + hi, ob = b0 + bi;
+    const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
+    const long long row_off = (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + p.out_off[cls] + n0;
+    const int ncol = cls * p.class_n + n0;             // global column (bias / scale index)
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (valid && (n0 + c0) < p.class_n) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          float x = __uint_as_float(v[j]);
+          if (p.epilogue == 1) {
+            x = fmaf(x, __ldg(scale + ncol + c0 + j), __ldg(shift + ncol + c0 + j));
+            x = x > 0.f ? x : x * p.slope;
+          } else if (bias) {
+            x += __ldg(bias + ncol + c0 + j);
+          }
+          f[j] = x;
+        }
+        if (p.out_dtype == MS_F32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row_off + c0);
+#pragma unroll
+          for (int j = 0; j < 4; j++) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + row_off + c0);
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct PackParams {
+  int Cout, Cin_g, taps_total, groups, mode, num_classes, class_n, ntaps, kpad;
+  short srctap[MS_IGEMM_MAX_TAPS];
+};
+
+__global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, PackParams q, __nv_bfloat16* __restrict__ wp) {
+  const long long total = (long long)q.num_classes * q.class_n * q.ntaps * q.kpad;
+  const int Cout_g = q.Cout / q.groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int kc = (int)(i % q.kpad);
+    long long t2 = i / q.kpad;
+    int t = (int)(t2 % q.ntaps);
+    long long row = t2 / q.ntaps;
+    int cls = (int)(row / q.class_n), r = (int)(row - (long long)cls * q.class_n);
+    float v = 0.f;
+    if (q.mode == 0) {
+      long long o = row;                    // global output channel
+      if (o < q.Cout && kc < q.Cin_g) v = ms_ldp(w, pdt, (o * q.Cin_g + kc) * q.taps_total + q.srctap[t]);
+    } else {
+      int g = q.groups > 1 ? cls : 0;
+      if (kc < Cout_g && r < q.Cin_g)
+        v = ms_ldp(w, pdt, ((long long)(g * Cout_g + kc) * q.Cin_g + r) * q.taps_total + q.srctap[cls * q.ntaps + t]);
+    }
+    wp[i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace
+
+extern "C" int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int taps_total, int groups, int mode,
+                                         int num_classes, int class_n, int ntaps, int kpad, const int16_t* srctap_host,
+                                         void* wp, void* stream) {
+  if (!w || !wp || !srctap_host || groups < 1 || num_classes < 1 || ntaps < 1) return MS_EINVAL;
+  const int nsrc = mode == 0 ? ntaps : num_classes * ntaps;
+  if (nsrc > MS_IGEMM_MAX_TAPS || kpad % 64) return MS_EINVAL;
+  PackParams q;
+  q.Cout = Cout; q.Cin_g = Cin_g; q.taps_total = taps_total; q.groups = groups; q.mode = mode;
+  q.num_classes = num_classes; q.class_n = class_n; q.ntaps = ntaps; q.kpad = kpad;
+  for (int i = 0; i < MS_IGEMM_MAX_TAPS; i++) q.srctap[i] = i < nsrc ? srctap_host[i] : 0;
+  const long long total = (long long)num_classes * class_n * ntaps * kpad;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_igemm_weight_kernel<<<(unsigned)blocks, 256, 0, ms_stream(stream)>>>(w, pdt, q, reinterpret_cast<__nv_bfloat16*>(wp));
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                             const float* shift, void* out, void* stream) {
+  if (!d || !a || !w || !out) return MS_EINVAL;
+  if (d->num_classes < 1 || d->num_classes > MS_IGEMM_MAX_CLASSES) return MS_EINVAL;
+  if (d->ntaps < 1 || d->cchunks < 1) return MS_EINVAL;
+  const int tap_rows = d->shared_taps ? d->ntaps : d->ntaps * d->num_classes;
+  if (tap_rows > MS_IGEMM_MAX_TAPS) return MS_EINVAL;
+  if (d->block_n < 16 || d->block_n > 256 || d->block_n % 16) return MS_EINVAL;
+  if (d->class_n % 16 || d->class_n < 16) return MS_EINVAL;
+  if (d->box[0] != BLOCK_K || d->box[2] != 1 || d->box[1] * d->box[3] * d->box[4] != BLOCK_M) return MS_EINVAL;
+  if (d->epilogue == 1 && (!scale || !shift)) return MS_EINVAL;
+  if (d->out_dtype != MS_F32 && d->out_dtype != MS_BF16) return MS_EINVAL;
+  if (((uintptr_t)a & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15)) return MS_EINVAL;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MS_ENOTSUP;
+
+  CUtensorMap map_a, map_w;
+  {
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+    for (int i = 0; i < 5; i++) { dims[i] = (cuuint64_t)d->a_dims[i]; box[i] = (cuuint32_t)d->box[i]; }
+    for (int i = 1; i < 5; i++) {
+      strides[i - 1] = (cuuint64_t)d->a_strides[i] * 2;
+      if (strides[i - 1] % 16) return MS_EINVAL;
+    }
+    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MS_EINVAL;
+  }
+  {
+    const long long ktot = (long long)d->ntaps * d->cchunks * BLOCK_K;
+    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)((long long)d->num_classes * d->class_n)};
+    cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)d->block_n}, es[2] = {1, 1};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return MS_EINVAL;
+  }
+  IgemmParams p;
+  p.ntaps = d->ntaps; p.cchunks = d->cchunks; p.shared_taps = d->shared_taps;
+  p.num_classes = d->num_classes; p.class_n = d->class_n; p.block_n = d->block_n;
+  p.n_tiles_per_class = (d->class_n + d->block_n - 1) / d->block_n;
+  p.box_w = d->box[1]; p.box_h = d->box[3]; p.box_b = d->box[4];
+  p.out_w = d->out_dims[0]; p.out_h = d->out_dims[1]; p.out_b = d->out_dims[2];
+  p.tiles_w = (p.out_w + p.box_w - 1) / p.box_w;
+  p.tiles_h = (p.out_h + p.box_h - 1) / p.box_h;
+  p.tiles_b = (p.out_b + p.box_b - 1) / p.box_b;
+  p.os_w = d->out_strides[0]; p.os_h = d->out_strides[1]; p.os_b = d->out_strides[2];
+  for (int i = 0; i < MS_IGEMM_MAX_CLASSES; i++) { p.a_chan_base[i] = d->a_chan_base[i]; p.out_off[i] = d->out_off[i]; }
+  for (int i = 0; i < MS_IGEMM_MAX_TAPS; i++)
+    for (int j = 0; j < 4; j++) p.taps[i][j] = d->taps[i][j];
+  p.out_dtype = d->out_dtype; p.epilogue = d->epilogue; p.slope = d->slope;
+  // vector stores need 16-byte aligned rows
+  const int esz = d->out_dtype == MS_F32 ? 4 : 2;
+  if ((p.os_w * esz) % 16 || (p.os_h * esz) % 16 || (p.os_b * esz) % 16) return MS_EINVAL;
+  for (int i = 0; i < d->num_classes; i++)
+    if ((p.out_off[i] * esz) % 16) return MS_EINVAL;
+
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)d->block_n * BLOCK_K * 2) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_b), (unsigned)(p.n_tiles_per_class * d->num_classes));
+  igemm_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, p, bias, scale, shift, out);
+  MS_LAUNCH_CHECK();
+  return 0;
+}

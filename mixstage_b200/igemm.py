@@ -1,0 +1,185 @@
+"""Host-side descriptors for the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu, ms_igemm_bf16).
+
+A convolution (forward) or its input gradient is described by
+  * a 5-D view (channel, w-like, h-parity, h-like, batch) of the bf16 activation,
+  * a tap table: per tap the channel offset, w shift, h-parity coordinate and h shift of the box,
+  * "classes" of output columns (conv groups, or output parities of a strided conv's input gradient),
+  * the weight re-tiling recipe (which source tap feeds each (class, tap)).
+Everything here is pure Python on small integers; tests/test_igemm_desc_cpu.py checks the
+descriptors against F.conv2d through the CPU specification of the kernel."""
+from __future__ import annotations
+
+import ctypes
+
+from ._lib import MS_BF16, MS_F32, MixStageError
+
+from ._lib import IgemmDesc, MAX_CLASSES, MAX_TAPS      # noqa: E402
+
+BLOCK_M, BLOCK_K = 128, 64
+
+
+def _pow2ceil(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+def _boxes(Wo, Ho, rows=BLOCK_M):
+    bw = min(rows, _pow2ceil(Wo))
+    bh = min(rows // bw, _pow2ceil(Ho))
+    bb = rows // (bw * bh)
+    return bw, bh, bb
+
+
+class Plan:
+    """A filled descriptor plus the weight re-tiling recipe that goes with it."""
+
+    def __init__(self, desc, mode, srctap, kpad, wp_rows):
+        self.desc = desc
+        self.mode = mode              # 0 forward, 1 dgrad
+        self.srctap = srctap          # list[int]
+        self.kpad = kpad
+        self.wp_rows = wp_rows        # num_classes * class_n
+        self.srctap_c = (ctypes.c_int16 * len(srctap))(*srctap)
+
+    @property
+    def wp_numel(self):
+        return self.wp_rows * self.desc.ntaps * self.kpad
+
+
+def fwd_supported(Cin, Cout, groups, sh, sw, H, W, a_row_stride=None):
+    cg, ng = Cin // groups, Cout // groups
+    if (a_row_stride or Cin) % 8 or ng % 16 or ng < 16:
+        return False
+    if sh not in (1, 2) or sw not in (1, 2):
+        return False
+    if (sh == 2 and H % 2) or (sw == 2 and W % 2):
+        return False
+    if groups > MAX_CLASSES:
+        return False
+    return True
+
+
+def dgrad_supported(Cin, Cout, groups, sh, sw, H, W, kh, kw):
+    cg, ng = Cin // groups, Cout // groups
+    if Cout % 8 or cg % 16 or cg < 16:
+        return False
+    if sh not in (1, 2) or sw not in (1, 2):
+        return False
+    if (sh == 2 and (H % 2 or kh % 2)) or (sw == 2 and (W % 2 or kw % 2)):
+        return False
+    if groups > 1 and (sh != 1 or sw != 1):
+        return False
+    if groups > MAX_CLASSES:
+        return False
+    return True
+
+
+def _split(e, s):
+    """input coordinate offset e (in input pixels) -> (shift in s-strided units, parity)."""
+    if s == 1:
+        return e, 0
+    return e // 2, e % 2          # floor semantics
+
+
+def make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo, out_dtype=MS_F32, epilogue=0, slope=1.0,
+             a_row_stride=None):
+    """Forward conv: A = x (B,H,W,Cin[row stride a_row_stride]) bf16, out (B,Ho,Wo,Cout)."""
+    if not fwd_supported(Cin, Cout, groups, sh, sw, H, W, a_row_stride):
+        raise MixStageError("igemm forward: unsupported geometry")
+    C = a_row_stride or Cin        # elements between consecutive pixels
+    cg, ng = Cin // groups, Cout // groups
+    d = IgemmDesc()
+    Wd, Hd = W // sw, H // sh
+    d.a_dims[:] = [Cin * sw if sw == 2 else Cin, Wd, sh, Hd, B]
+    if sw == 2:
+        d.a_dims[0] = C + Cin      # parity 1 channels start at +C; valid extent C + Cin
+    row = C * W                    # elements per image row
+    d.a_strides[:] = [1, C * sw, row, row * sh, row * H]
+    taps, srctap = [], []
+    for th in range(kh):
+        fh, par_h = _split(th - ph, sh)
+        for tw in range(kw):
+            fw, par_w = _split(tw - pw, sw)
+            taps.append((par_w * C, fw, par_h, fh))
+            srctap.append(th * kw + tw)
+    ntaps = len(taps)
+    if ntaps > MAX_TAPS:
+        raise MixStageError("too many taps")
+    for i, t in enumerate(taps):
+        d.taps[i][:] = t
+    d.ntaps, d.shared_taps = ntaps, 1
+    d.cchunks = (cg + BLOCK_K - 1) // BLOCK_K
+    d.num_classes, d.class_n = groups, ng
+    d.block_n = min(256, ng)
+    for g in range(groups):
+        d.a_chan_base[g] = g * cg
+        d.out_off[g] = g * ng
+    d.out_dims[:] = [Wo, Ho, B]
+    d.out_strides[:] = [Cout, Wo * Cout, Ho * Wo * Cout]
+    bw, bh, bb = _boxes(Wo, Ho)
+    d.box[:] = [BLOCK_K, bw, 1, bh, bb]
+    d.out_dtype, d.epilogue, d.slope = out_dtype, epilogue, slope
+    return Plan(d, 0, srctap, d.cchunks * BLOCK_K, groups * ng)
+
+
+def make_dgrad(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo, out_row_stride=None):
+    """Input gradient: A = dz (B,Ho,Wo,Cout) bf16, out = dx (B,H,W,out_row_stride) fp32.
+    With groups == 1 and out_row_stride > Cin the extra columns are produced as zeros
+    (their weight rows are zero), e.g. the 266 -> 272 channel padding of the style concat."""
+    Co = out_row_stride or Cin
+    if groups == 1 and Co != Cin:
+        Cin_eff = Co
+    else:
+        Cin_eff = Cin
+    if not dgrad_supported(Cin_eff, Cout, groups, sh, sw, H, W, kh, kw):
+        raise MixStageError("igemm dgrad: unsupported geometry")
+    cg, ng = Cin_eff // groups, Cout // groups
+    d = IgemmDesc()
+    d.a_dims[:] = [Cout, Wo, 1, Ho, B]
+    d.a_strides[:] = [1, Cout, Cout * Wo, Cout * Wo, Cout * Wo * Ho]
+
+    def dim_taps(k, s, p):
+        """per output parity r: list of (source tap j, shift of the dz coordinate)."""
+        out = []
+        for r in range(s):
+            lst = [(j, (r + p - j) // s) for j in range(k) if (r + p - j) % s == 0]
+            out.append(lst)
+        return out
+
+    th_l, tw_l = dim_taps(kh, sh, ph), dim_taps(kw, sw, pw)
+    nt = len(th_l[0]) * len(tw_l[0])
+    for lst in th_l:
+        assert len(lst) == len(th_l[0])
+    for lst in tw_l:
+        assert len(lst) == len(tw_l[0])
+    parity_classes = [(rh, rw) for rh in range(sh) for rw in range(sw)]
+    if groups > 1:
+        classes = [(g, 0, 0) for g in range(groups)]
+    else:
+        classes = [(0, rh, rw) for rh, rw in parity_classes]
+    if len(classes) > MAX_CLASSES or (1 if groups > 1 else len(classes)) * nt > MAX_TAPS:
+        raise MixStageError("igemm dgrad: tap table too large")
+    srctap = []
+    shared = 1 if groups > 1 else 0
+    rows = []
+    for qi, (g, rh, rw) in enumerate(classes):
+        tl = [(jh * kw + jw, dw_, dh_) for (jh, dh_) in th_l[rh] for (jw, dw_) in tw_l[rw]]
+        for ti, (src, dw_, dh_) in enumerate(tl):
+            srctap.append(src)
+            if not shared or qi == 0:
+                d.taps[(0 if shared else qi * nt) + ti][:] = (0, dw_, 0, dh_)
+        d.a_chan_base[qi] = g * ng
+        d.out_off[qi] = g * cg + rh * W * Co + rw * Co
+    d.ntaps, d.shared_taps = nt, shared
+    d.cchunks = (ng + BLOCK_K - 1) // BLOCK_K
+    d.num_classes, d.class_n = len(classes), cg
+    d.block_n = min(256, cg)
+    Wd, Hd = W // sw, H // sh
+    d.out_dims[:] = [Wd, Hd, B]
+    d.out_strides[:] = [Co * sw, Co * W * sh, Co * W * H]
+    bw, bh, bb = _boxes(Wd, Hd)
+    d.box[:] = [BLOCK_K, bw, 1, bh, bb]
+    d.out_dtype, d.epilogue, d.slope = MS_F32, 0, 1.0
+    return Plan(d, 1, srctap, d.cchunks * BLOCK_K, len(classes) * cg)

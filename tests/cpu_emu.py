@@ -308,6 +308,69 @@ def ms_scalar_finish(inp, scale, out, st):
     f32(out, 1).copy_((f64(inp, 1) * scale).float())
 
 
+def bf16(p, n):
+    if p is None or p == 0:
+        return None
+    buf = (ctypes.c_char * (int(n) * 2)).from_address(int(p))
+    return torch.frombuffer(buf, dtype=torch.bfloat16, count=int(n))
+
+
+def ms_pack_igemm_weight_bf16(w, pdt, Cout, Cin_g, taps_total, groups, mode, num_classes, class_n, ntaps, kpad,
+                              srctap, wp, st):
+    Wsrc = param(w, Cout * Cin_g * taps_total, pdt).float().view(Cout, Cin_g, taps_total)
+    out = torch.zeros(num_classes * class_n, ntaps, kpad)
+    Cout_g = Cout // groups
+    for q in range(num_classes):
+        for t in range(ntaps):
+            if mode == 0:
+                rows = slice(q * class_n, min((q + 1) * class_n, Cout))
+                n = rows.stop - rows.start
+                if n > 0:
+                    out[q * class_n:q * class_n + n, t, :Cin_g] = Wsrc[rows, :, srctap[t]]
+            else:
+                g = q if groups > 1 else 0
+                src = Wsrc[g * Cout_g:(g + 1) * Cout_g, :, srctap[q * ntaps + t]]      # (Cout_g, Cin_g)
+                out[q * class_n:q * class_n + Cin_g, t, :Cout_g] = src.t()
+    bf16(wp, out.numel()).copy_(out.reshape(-1).to(torch.bfloat16))
+
+
+def ms_igemm_bf16(desc, a, w, bias, scale, shift, out, st):
+    d = _d(desc)
+    dims, strides = list(d.a_dims), list(d.a_strides)
+    extent = 1 + sum((dims[i] - 1) * strides[i] for i in range(5))
+    A = bf16(a, extent).float()
+    A5 = torch.as_strided(A, [dims[4], dims[3], dims[2], dims[1], dims[0]],
+                          [strides[4], strides[3], strides[2], strides[1], strides[0]])   # (b, h, par, w, c)
+    Wo, Ho, Bo = d.out_dims
+    kpad = d.cchunks * 64
+    Wp = bf16(w, d.num_classes * d.class_n * d.ntaps * kpad).float().view(d.num_classes * d.class_n, d.ntaps, kpad)
+    osw, osh, osb = d.out_strides
+    out_extent = 1 + (Wo - 1) * osw + (Ho - 1) * osh + (Bo - 1) * osb + max(d.out_off[q] for q in range(d.num_classes)) + d.class_n - 1
+    O = f32(out, out_extent) if d.out_dtype == 0 else bf16(out, out_extent)
+    PADW = PADH = 16
+    Ap = torch.zeros(dims[4], dims[3] + 2 * PADH + Ho, dims[2], dims[1] + 2 * PADW + Wo, dims[0] + kpad + 64)
+    Ap[:, PADH:PADH + dims[3], :, PADW:PADW + dims[1], :dims[0]] = A5
+    for q in range(d.num_classes):
+        acc = torch.zeros(Bo, Ho, Wo, d.class_n)
+        for t in range(d.ntaps):
+            tt = d.taps[(0 if d.shared_taps else q * d.ntaps) + t]
+            c0 = d.a_chan_base[q] + tt[0]
+            hs, ws = PADH + tt[3], PADW + tt[1]
+            bb = min(Bo, dims[4])
+            sl = torch.zeros(Bo, Ho, Wo, kpad)
+            sl[:bb] = Ap[:bb, hs:hs + Ho, tt[2], ws:ws + Wo, c0:c0 + kpad]
+            acc += sl @ Wp[q * d.class_n:(q + 1) * d.class_n, t].t()
+        cols = slice(q * d.class_n, (q + 1) * d.class_n)
+        if d.epilogue == 1:
+            acc = acc * f32(scale, d.num_classes * d.class_n)[cols] + f32(shift, d.num_classes * d.class_n)[cols]
+            acc = torch.where(acc > 0, acc, acc * d.slope)
+        elif bias:
+            acc = acc + f32(bias, d.num_classes * d.class_n)[cols]
+        idx = (torch.arange(Bo).view(-1, 1, 1, 1) * osb + torch.arange(Ho).view(1, -1, 1, 1) * osh
+               + torch.arange(Wo).view(1, 1, -1, 1) * osw + d.out_off[q] + torch.arange(d.class_n).view(1, 1, 1, -1))
+        O[idx.reshape(-1)] = acc.reshape(-1).to(O.dtype)
+
+
 def install(monkeypatch):
     """Route mixstage_b200's kernel calls to the CPU specification (tests only)."""
     from mixstage_b200 import _lib, ops, speech2gesture, joint_late_cluster_soft_style as j

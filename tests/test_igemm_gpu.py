@@ -1,0 +1,76 @@
+"""tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu) on the GPU against its CPU specification and
+against F.conv2d, over the generator's geometries: forward and input gradient, stride 1/2, 1-D/2-D,
+grouped, ragged channel counts, both output dtypes and both epilogues."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cpu_emu
+from mixstage_b200 import _lib, igemm
+from mixstage_b200._lib import ptr
+from test_igemm_desc_cpu import GEOMS, _conv_out
+
+pytestmark = pytest.mark.gpu
+
+BIG = [
+    (16, 1, 64, 256, 256, 1, 3, 1, 1, 0, 1, 1),      # the most repeated GEMM (M=1024, N=256, K=768)
+    (16, 1, 64, 2048, 2048, 1, 3, 1, 1, 0, 1, 8),    # decoder.1-3
+    (4, 64, 64, 64, 64, 4, 4, 2, 2, 1, 1, 1),        # audio_encoder.conv.1
+    (4, 8, 8, 256, 256, 3, 8, 1, 1, 1, 3, 1),        # audio_encoder.conv.7
+    (16, 1, 2, 256, 256, 1, 3, 1, 1, 0, 1, 1),       # unet bottom: 32 rows in a 128-row tile
+    (130, 1, 2, 256, 256, 1, 3, 1, 1, 0, 1, 1),      # ragged batch tail
+]
+
+
+def _sync_ok():
+    torch.cuda.synchronize()
+
+
+def _gpu_igemm(plan, a, w_src, mode, Cout, Cin_g, taps_total, groups, bias=None, scale=None, shift=None, out=None):
+    st = torch.cuda.current_stream().cuda_stream
+    wp = torch.zeros(plan.wp_numel, dtype=torch.bfloat16, device="cuda")
+    d = plan.desc
+    _lib.call("ms_pack_igemm_weight_bf16", ptr(w_src), _lib.dt_code(w_src.dtype), Cout, Cin_g, taps_total, groups, mode,
+              d.num_classes, d.class_n, d.ntaps, plan.kpad, plan.srctap_c, ptr(wp), st)
+    _lib.call("ms_igemm_bf16", d, ptr(a), ptr(wp), ptr(bias), ptr(scale), ptr(shift), ptr(out), st)
+    torch.cuda.synchronize()
+    return wp
+
+
+@pytest.mark.parametrize("g", GEOMS + BIG)
+def test_igemm_fwd_dgrad(g):
+    torch.manual_seed(0)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups = g
+    Ho, Wo = _conv_out(H, kh, sh, ph), _conv_out(W, kw, sw, pw)
+    x = torch.randn(B, H, W, Cin).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin // groups, kh, kw, dtype=torch.float64) / (Cin // groups * kh * kw) ** 0.5)
+    w = w.to(torch.bfloat16).double()
+    bias = torch.randn(Cout)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w, bias.double(), stride=(sh, sw), padding=(ph, pw), groups=groups).permute(0, 2, 3, 1)
+    plan = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda")
+    wp = _gpu_igemm(plan, x.cuda(), w.cuda(), 0, Cout, Cin // groups, kh * kw, groups, bias=bias.cuda(), out=out)
+    # weight re-tiling is bit-exact vs the spec
+    wp_c = torch.zeros(plan.wp_numel, dtype=torch.bfloat16)
+    cpu_emu.ms_pack_igemm_weight_bf16(ptr(w), 1, Cout, Cin // groups, kh * kw, groups, 0, plan.desc.num_classes,
+                                      plan.desc.class_n, plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp_c), None)
+    assert torch.equal(wp.cpu(), wp_c)
+    err = float((out.cpu().double() - ref).abs().max())
+    assert err < 1e-3 * float(ref.abs().max()), (err, float(ref.abs().max()))
+    # fused scale/shift + LeakyReLU epilogue with bf16 output
+    scale, shift = torch.rand(Cout) + 0.5, torch.randn(Cout) * 0.1
+    plan2 = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo, out_dtype=_lib.MS_BF16, epilogue=1, slope=0.2)
+    out2 = torch.zeros((B, Ho, Wo, Cout), dtype=torch.bfloat16, device="cuda")
+    _gpu_igemm(plan2, x.cuda(), w.cuda(), 0, Cout, Cin // groups, kh * kw, groups, scale=scale.cuda(), shift=shift.cuda(), out=out2)
+    ref2 = F.leaky_relu((ref - bias.double()) * scale.double() + shift.double(), 0.2)
+    err2 = float((out2.cpu().double() - ref2).abs().max())
+    assert err2 < 1e-2 * float(ref2.abs().max()), (err2,)
+    # input gradient
+    dz = torch.randn(B, Ho, Wo, Cout).to(torch.bfloat16)
+    dref = torch.nn.grad.conv2d_input((B, Cin, H, W), w, dz.double().permute(0, 3, 1, 2), stride=(sh, sw), padding=(ph, pw),
+                                      groups=groups).permute(0, 2, 3, 1)
+    plan3 = igemm.make_dgrad(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
+    dx = torch.full((B, H, W, Cin), float("nan"), device="cuda")
+    _gpu_igemm(plan3, dz.cuda(), w.cuda(), 1, Cout, Cin // groups, kh * kw, groups, out=dx)
+    err3 = float((dx.cpu().double() - dref).abs().max())
+    assert err3 < 1e-3 * float(dref.abs().max()), (err3, float(dref.abs().max()))

@@ -113,6 +113,15 @@ int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int t
                               int num_classes, int class_n, int ntaps, int kpad, const int16_t* srctap_host,
                               void* wp, void* stream);
 
+/* Weight gradient on tcgen05 (aten::convolution_backward, weight grad): with d the FORWARD descriptor,
+ *   dwp[q*class_n + n][t][c] = sum_{b,h,w} dz[b,h,w, off[q] + n] * A5[base[q] + taps[t].chan + c, w + dw, par, h + dh, b]
+ * x and dz are bf16 (dz has the forward output's shape), dwp is fp32 [classes*class_n][ntaps][cchunks*64]
+ * (overwritten; split-K partials are reduced with fp32 atomics).  Both operands are MN-major UMMA operands. */
+int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* dz, float* dwp, void* stream);
+/* dwp (forward tiling, one source tap per tap) -> dw (Cout, Cin/g, taps) in dtype pdt. */
+int ms_unpack_igemm_wgrad(const float* dwp, int Cout, int Cin_g, int taps_total, int ntaps, int kpad, void* dw, int pdt,
+                          void* stream);
+
 /* ---- BatchNorm (+LeakyReLU) pieces, nn.BatchNorm1d/2d at layers.py:64,70 and
  * nn.LeakyReLU(0.2) at layers.py:72-73, applied as in ConvNormRelu.forward (:78) ------ */
 /* column sums over rows: sum[c] += x[r,c], sumsq[c] += x[r,c]^2 (double accumulators,

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "ms_conv_wgrad_f32": [_P, _P, _P, _CD, _P],
     "ms_igemm_bf16": [_GD, _P, _P, _P, _P, _P, _P, _P],
     "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P],
+    "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],
+    "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "ms_col_stats_f32": [_P, _L, _I, _P, _P, _P],
     "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],
     "ms_bn_act_fwd_f32": [_P, _P, _P, _F, _L, _I, _P, _P, _I, _I, _P],

@@ -274,6 +274,172 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient:  dWp[q*class_n + n][t][c] = sum_rows dZ[row, off[q] + n] * X[row shifted by tap t, base[q] + c]
+// Both operands are activations whose contraction index (the pixel row) is the slow index in
+// memory, so they are fed as MN-major UMMA operands: a TMA box of 64 pixel rows x 64 channels
+// lands as 64 swizzled 128-byte rows = the canonical MN-major SWIZZLE_128B layout (8-row atoms,
+// SBO = 1024 B between 8-pixel groups, LBO = 8192 B between 64-channel chunks).  One CTA owns a
+// (class, tap, 128 x Nc) tile of dWp and a slice of the pixel rows (split-K); partial tiles are
+// combined with fp32 reductions in L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_ROWS = 64;                       // pixel rows per k-step
+constexpr uint32_t WG_CHUNK_BYTES = WG_ROWS * 64 * 2;   // 8 KB: 64 rows x 64 channels bf16
+constexpr int WG_STAGES = 4;
+
+struct WgradParams {
+  int ntaps, cchunks, shared_taps, num_classes, class_n;
+  int box_w, box_h, box_b, tiles_w, tiles_h, tiles_b;
+  int n_tiles, c_tiles, kpad, split;
+  int a_chan_base[MS_IGEMM_MAX_CLASSES];
+  int z_chan_base[MS_IGEMM_MAX_CLASSES];
+  short taps[MS_IGEMM_MAX_TAPS][4];
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;      // LBO: next 64-channel chunk
+  d |= (uint64_t)(1024 >> 4) << 32;      // SBO: next group of 8 pixel rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z,
+                const __grid_constant__ WgradParams p, float* __restrict__ dwp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[WG_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[WG_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int cls = blockIdx.z / p.ntaps, tap = blockIdx.z - cls * p.ntaps;
+  const int nt = blockIdx.y / p.c_tiles, ct = blockIdx.y - nt * p.c_tiles;
+  const int n0 = nt * 128, c0 = ct * 256;
+  const int nc = min(256, p.kpad - c0);                 // columns of this tile (multiple of 64)
+  const int xchunks = nc / 64;
+  const uint32_t stage_bytes = (2 + xchunks) * WG_CHUNK_BYTES;
+  const int total_rt = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int per = (total_rt + p.split - 1) / p.split;
+  const int rt_beg = blockIdx.x * per, rt_end = min(total_rt, rt_beg + per);
+  const int num_k = max(0, rt_end - rt_beg);
+  uint8_t* smem_a = smem;                                // [stage][2 chunks]
+  uint8_t* smem_b = smem + WG_STAGES * 2 * WG_CHUNK_BYTES;   // [stage][4 chunks]
+  uint32_t tmem_cols = 64;
+  while (tmem_cols < (uint32_t)nc) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_z)) : "memory");
+    for (int s = 0; s < WG_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const short* t = p.taps[(p.shared_taps ? 0 : cls * p.ntaps) + tap];
+        const int xc = p.a_chan_base[cls] + t[0] + c0;
+        const int zc = p.z_chan_base[cls] + n0;
+        for (int ks = 0; ks < num_k; ks++) {
+          const int s = ks % WG_STAGES;
+          const uint32_t ph = (uint32_t)(ks / WG_STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          int rt = rt_beg + ks;
+          const int tw = rt % p.tiles_w; rt /= p.tiles_w;
+          const int th = rt % p.tiles_h; rt /= p.tiles_h;
+          const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = rt * p.box_b;
+          mbar_expect_tx(&full_bar[s], stage_bytes);
+          uint8_t* sa = smem_a + (size_t)s * 2 * WG_CHUNK_BYTES;
+          uint8_t* sb = smem_b + (size_t)s * 4 * WG_CHUNK_BYTES;
+          tma_load_5d(&map_z, &full_bar[s], sa, zc, w0, 0, h0, b0);
+          tma_load_5d(&map_z, &full_bar[s], sa + WG_CHUNK_BYTES, zc + 64, w0, 0, h0, b0);
+          for (int i = 0; i < xchunks; i++)
+            tma_load_5d(&map_x, &full_bar[s], sb + (size_t)i * WG_CHUNK_BYTES, xc + 64 * i, w0 + t[1], t[2], h0 + t[3], b0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // D=f32, A=B=bf16, both MN-major (bits 15/16), N = nc, M = 128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        for (int ks = 0; ks < num_k; ks++) {
+          const int s = ks % WG_STAGES;
+          const uint32_t ph = (uint32_t)(ks / WG_STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_mnmajor_sw128_desc(smem_u32(smem_a + (size_t)s * 2 * WG_CHUNK_BYTES));
+          const uint64_t db = make_mnmajor_sw128_desc(smem_u32(smem_b + (size_t)s * 4 * WG_CHUNK_BYTES));
+#pragma unroll
+          for (int k = 0; k < WG_ROWS / UMMA_K; k++) {
+            // 16 pixel rows = 2 atoms of 1024 B: +2048 B = +128 in the (addr >> 4) field
+            umma_bf16(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar);
+      }
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;                     // n index inside the tile
+      const bool valid = (n0 + r) < p.class_n;
+      float* dst_row = dwp + ((size_t)(cls * p.class_n + n0 + r) * p.ntaps + tap) * p.kpad + c0;
+      mbar_wait(&tmem_full_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int cc = 0; cc < nc; cc += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)cc, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (valid) {
+          if (p.split > 1) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) atomicAdd(dst_row + cc + j, __uint_as_float(v[j]));
+          } else {
+            float4* d4 = reinterpret_cast<float4*>(dst_row + cc);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3]));
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// dWp[row][t][c] fp32 -> dw (Cout, Cin_g, taps_total) in dtype pdt (inverse of the forward re-tiling)
+__global__ void unpack_igemm_wgrad_kernel(const float* __restrict__ dwp, int Cout, int Cin_g, int taps_total, int ntaps, int kpad,
+                                          void* __restrict__ dw, int pdt) {
+  const long long total = (long long)Cout * Cin_g * taps_total;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int tap = (int)(i % taps_total);
+    long long t2 = i / taps_total;
+    int c = (int)(t2 % Cin_g);
+    long long o = t2 / Cin_g;
+    ms_stp(dw, pdt, i, (double)dwp[(o * ntaps + tap) * kpad + c]);
+  }
+}
+
 struct PackParams {
   int Cout, Cin_g, taps_total, groups, mode, num_classes, class_n, ntaps, kpad;
   short srctap[MS_IGEMM_MAX_TAPS];
@@ -389,6 +555,83 @@ extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* 
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_b), (unsigned)(p.n_tiles_per_class * d->num_classes));
   igemm_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, p, bias, scale, shift, out);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+static int encode_5d(EncodeTiledFn enc, CUtensorMap* m, const void* base, const int32_t* dims, const int64_t* strides_el,
+                     const int* box) {
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; i++) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; }
+  for (int i = 1; i < 5; i++) {
+    st[i - 1] = (cuuint64_t)strides_el[i] * 2;
+    if (st[i - 1] % 16) return MS_EINVAL;
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MS_EINVAL;
+}
+
+extern "C" int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* dz, float* dwp, void* stream) {
+  if (!d || !x || !dz || !dwp) return MS_EINVAL;
+  if (d->num_classes < 1 || d->num_classes > MS_IGEMM_MAX_CLASSES || d->ntaps < 1 || d->cchunks < 1) return MS_EINVAL;
+  if (((uintptr_t)x & 15) || ((uintptr_t)dz & 15) || ((uintptr_t)dwp & 15)) return MS_EINVAL;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MS_ENOTSUP;
+  WgradParams p;
+  p.ntaps = d->ntaps; p.cchunks = d->cchunks; p.shared_taps = d->shared_taps;
+  p.num_classes = d->num_classes; p.class_n = d->class_n;
+  // 64-row boxes: halve the outermost non-unit dimension of the forward (128-row) box
+  int bw = d->box[1], bh = d->box[3], bb = d->box[4];
+  if (bb > 1) bb /= 2; else if (bh > 1) bh /= 2; else bw /= 2;
+  if (bw * bh * bb != WG_ROWS) return MS_EINVAL;
+  p.box_w = bw; p.box_h = bh; p.box_b = bb;
+  const int Wo = d->out_dims[0], Ho = d->out_dims[1], Bo = d->out_dims[2];
+  p.tiles_w = (Wo + bw - 1) / bw; p.tiles_h = (Ho + bh - 1) / bh; p.tiles_b = (Bo + bb - 1) / bb;
+  p.kpad = d->cchunks * BLOCK_K;
+  p.n_tiles = (d->class_n + 127) / 128;
+  p.c_tiles = (p.kpad + 255) / 256;
+  for (int i = 0; i < MS_IGEMM_MAX_CLASSES; i++) { p.a_chan_base[i] = d->a_chan_base[i]; p.z_chan_base[i] = (int)d->out_off[i]; }
+  for (int i = 0; i < MS_IGEMM_MAX_TAPS; i++)
+    for (int j = 0; j < 4; j++) p.taps[i][j] = d->taps[i][j];
+  const long long total_rt = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  const long long tiles = (long long)p.n_tiles * p.c_tiles * d->num_classes * d->ntaps;
+  long long split = (2LL * ms_num_sms() + tiles - 1) / tiles;
+  if (split > total_rt) split = total_rt;
+  if (split < 1) split = 1;
+  p.split = (int)split;
+
+  CUtensorMap map_x, map_z;
+  int box[5] = {64, bw, 1, bh, bb};
+  int rc = encode_5d(enc, &map_x, x, d->a_dims, d->a_strides, box);
+  if (rc) return rc;
+  const int32_t zdims[5] = {(int32_t)d->out_strides[0], Wo, 1, Ho, Bo};
+  const int64_t zstr[5] = {1, d->out_strides[0], d->out_strides[1], d->out_strides[1], d->out_strides[2]};
+  rc = encode_5d(enc, &map_z, dz, zdims, zstr, box);
+  if (rc) return rc;
+
+  const size_t wbytes = sizeof(float) * (size_t)d->num_classes * d->class_n * d->ntaps * p.kpad;
+  if (p.split > 1) MS_CUDA(cudaMemsetAsync(dwp, 0, wbytes, ms_stream(stream)));
+  const size_t smem = (size_t)WG_STAGES * 6 * WG_CHUNK_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)p.split, (unsigned)(p.n_tiles * p.c_tiles), (unsigned)(d->num_classes * d->ntaps));
+  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_x, map_z, p, dwp);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_unpack_igemm_wgrad(const float* dwp, int Cout, int Cin_g, int taps_total, int ntaps, int kpad, void* dw,
+                                     int pdt, void* stream) {
+  if (!dwp || !dw || ntaps != taps_total) return MS_EINVAL;
+  const long long total = (long long)Cout * Cin_g * taps_total;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_igemm_wgrad_kernel<<<(unsigned)blocks, 256, 0, ms_stream(stream)>>>(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt);
   MS_LAUNCH_CHECK();
   return 0;
 }

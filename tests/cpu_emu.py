@@ -371,6 +371,37 @@ def ms_igemm_bf16(desc, a, w, bias, scale, shift, out, st):
         O[idx.reshape(-1)] = acc.reshape(-1).to(O.dtype)
 
 
+def ms_wgrad_bf16(desc, x, dz, dwp, st):
+    d = _d(desc)
+    dims, strides = list(d.a_dims), list(d.a_strides)
+    extent = 1 + sum((dims[i] - 1) * strides[i] for i in range(5))
+    A5 = torch.as_strided(bf16(x, extent).float(), [dims[4], dims[3], dims[2], dims[1], dims[0]],
+                          [strides[4], strides[3], strides[2], strides[1], strides[0]])
+    Wo, Ho, Bo = d.out_dims
+    Ct = d.out_strides[0]
+    Z = bf16(dz, Bo * Ho * Wo * Ct).float().view(Bo, Ho, Wo, Ct)
+    kpad = d.cchunks * 64
+    PADW = PADH = 16
+    Ap = torch.zeros(dims[4], dims[3] + 2 * PADH + Ho, dims[2], dims[1] + 2 * PADW + Wo, dims[0] + kpad + 64)
+    Ap[:, PADH:PADH + dims[3], :, PADW:PADW + dims[1], :dims[0]] = A5
+    out = f32(dwp, d.num_classes * d.class_n * d.ntaps * kpad).view(d.num_classes * d.class_n, d.ntaps, kpad)
+    for q in range(d.num_classes):
+        zq = Z[..., d.out_off[q]:d.out_off[q] + d.class_n].reshape(-1, d.class_n)
+        for t in range(d.ntaps):
+            tt = d.taps[(0 if d.shared_taps else q * d.ntaps) + t]
+            c0 = d.a_chan_base[q] + tt[0]
+            hs, ws = PADH + tt[3], PADW + tt[1]
+            bb = min(Bo, dims[4])
+            sl = torch.zeros(Bo, Ho, Wo, kpad)
+            sl[:bb] = Ap[:bb, hs:hs + Ho, tt[2], ws:ws + Wo, c0:c0 + kpad]
+            out[q * d.class_n:(q + 1) * d.class_n, t] = zq.t() @ sl.reshape(-1, kpad)
+
+
+def ms_unpack_igemm_wgrad(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, st):
+    G = f32(dwp, Cout * ntaps * kpad).view(Cout, ntaps, kpad)[:, :, :Cin_g].permute(0, 2, 1).reshape(-1)
+    param(dw, G.numel(), pdt).copy_(G)
+
+
 def install(monkeypatch):
     """Route mixstage_b200's kernel calls to the CPU specification (tests only)."""
     from mixstage_b200 import _lib, ops, speech2gesture, joint_late_cluster_soft_style as j

@@ -55,6 +55,15 @@ def test_fwd_and_dgrad_descriptors_match_conv2d(g):
     dx = torch.full((B, H, W, Cin), float("nan"))
     cpu_emu.ms_igemm_bf16(plan.desc, ptr(dz), ptr(wp), None, None, None, ptr(dx), None)
     assert float((dx - dref).abs().max()) < 2e-4 * float(dref.abs().max())
+    # weight gradient (uses the forward descriptor)
+    wref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (Cout, Cin // groups, kh, kw), dz.float().permute(0, 3, 1, 2),
+                                       stride=(sh, sw), padding=(ph, pw), groups=groups)
+    plan = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
+    dwp = torch.full((plan.wp_numel,), float("nan"))
+    cpu_emu.ms_wgrad_bf16(plan.desc, ptr(x), ptr(dz), ptr(dwp), None)
+    dw = torch.zeros(Cout, Cin // groups, kh, kw)
+    cpu_emu.ms_unpack_igemm_wgrad(ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 0, None)
+    assert float((dw - wref).abs().max()) < 2e-4 * float(wref.abs().max())
 
 
 def test_padded_channel_rows_266():

@@ -74,3 +74,23 @@ def test_igemm_fwd_dgrad(g):
     _gpu_igemm(plan3, dz.cuda(), w.cuda(), 1, Cout, Cin // groups, kh * kw, groups, out=dx)
     err3 = float((dx.cpu().double() - dref).abs().max())
     assert err3 < 1e-3 * float(dref.abs().max()), (err3, float(dref.abs().max()))
+
+
+@pytest.mark.parametrize("g", GEOMS + BIG)
+def test_wgrad_tc(g):
+    torch.manual_seed(3)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups = g
+    Ho, Wo = _conv_out(H, kh, sh, ph), _conv_out(W, kw, sw, pw)
+    x = torch.randn(B, H, W, Cin).to(torch.bfloat16)
+    dz = torch.randn(B, Ho, Wo, Cout).to(torch.bfloat16)
+    wref = torch.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), (Cout, Cin // groups, kh, kw), dz.double().permute(0, 3, 1, 2),
+                                       stride=(sh, sw), padding=(ph, pw), groups=groups)
+    plan = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
+    st = torch.cuda.current_stream().cuda_stream
+    dwp = torch.full((plan.wp_numel,), float("nan"), device="cuda")
+    _lib.call("ms_wgrad_bf16", plan.desc, ptr(x.cuda()), ptr(dz.cuda()), ptr(dwp), st)
+    dw = torch.zeros(Cout, Cin // groups, kh, kw, dtype=torch.float64, device="cuda")
+    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 1, st)
+    torch.cuda.synchronize()
+    err = float((dw.cpu() - wref).abs().max())
+    assert err < 1e-3 * float(wref.abs().max()), (err, float(wref.abs().max()))

@@ -35,6 +35,7 @@ extern "C" {
 #define MS_F32 0
 #define MS_F64 1
 #define MS_BF16 2
+#define MS_BF16X2 3      /* split-bf16: a hi plane and a lo plane, v ~= hi + lo (~16 mantissa bits) */
 
 #define MS_EINVAL (-1)   /* bad argument (shape/stride/alignment not supported)   */
 #define MS_ENOTSUP (-2)  /* valid request this build cannot serve (e.g. no sm_100) */
@@ -98,9 +99,16 @@ typedef struct ms_igemm_desc {
   int32_t a_chan_base[MS_IGEMM_MAX_CLASSES];
   int64_t out_off[MS_IGEMM_MAX_CLASSES];
   int16_t taps[MS_IGEMM_MAX_TAPS][4];   /* chan offset, w shift, h-parity coordinate, h shift */
-  int32_t out_dtype;        /* MS_F32 or MS_BF16 */
-  int32_t epilogue;         /* 0: + bias (nullable); 1: * scale[n] + shift[n] then LeakyReLU(slope) */
+  int32_t out_dtype;        /* MS_F32, MS_BF16 or MS_BF16X2 (hi plane at out, lo plane at out + out_plane_stride) */
+  int32_t epilogue;         /* 0: + bias (nullable); 1: * scale[n] + shift[n] then LeakyReLU(slope);
+                               2: + bias (nullable) then LeakyReLU(slope) */
   float slope;
+  /* Split-bf16 operands ("bf16x3", ~fp32 accuracy on the bf16 tensor pipe): planes == 2 means A and Wp each
+   * come as a hi plane and a lo plane (lo at + *_plane_stride elements) and every k-step is issued three
+   * times: hi*hi + hi*lo + lo*hi.  planes == 1: plain bf16 operands.  For ms_wgrad_bf16 the dz operand's
+   * lo plane sits at dz + out_plane_stride. */
+  int32_t planes;
+  int64_t a_plane_stride, w_plane_stride, out_plane_stride;
 } ms_igemm_desc;
 int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
                   const float* shift, void* out, void* stream);
@@ -108,10 +116,11 @@ int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const fl
  * mode 0 (forward):  Wp[q*class_n + r][t][c] = w[q*class_n + r][c][srctap[t]]            (c < Cin/g, else 0)
  * mode 1 (dgrad):    Wp[q*class_n + r][t][n] = w[g*Cout/g + n][r][srctap[q*ntaps + t]]   (n < Cout/g, r < Cin/g, else 0)
  *                    with g = q when groups > 1 (classes are groups) and g = 0 otherwise (classes are parities).
- * srctap_host: HOST array of ntaps (mode 0) or num_classes*ntaps (mode 1) source tap indices. */
+ * srctap_host: HOST array of ntaps (mode 0) or num_classes*ntaps (mode 1) source tap indices.
+ * wp_lo (nullable): lo plane for the split-bf16 mode, bf16(w - float(wp)). */
 int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int taps_total, int groups, int mode,
                               int num_classes, int class_n, int ntaps, int kpad, const int16_t* srctap_host,
-                              void* wp, void* stream);
+                              void* wp, void* wp_lo, void* stream);
 
 /* Weight gradient on tcgen05 (aten::convolution_backward, weight grad): with d the FORWARD descriptor,
  *   dwp[q*class_n + n][t][c] = sum_{b,h,w} dz[b,h,w, off[q] + n] * A5[base[q] + taps[t].chan + c, w + dw, par, h + dh, b]
@@ -130,16 +139,24 @@ int ms_col_stats_f32(const float* x, int64_t rows, int C, double* sum, double* s
 /* training: batch mean / biased var from (sum,sumsq,rows) -> scale = gamma*rstd,
  * shift = beta - mean*scale, save mean/rstd; update running_mean/var in place
  * (momentum, unbiased var) in dtype pdt.  eval (training=0): scale/shift from the running
- * statistics, sum/sumsq ignored. */
+ * statistics, sum/sumsq ignored.  conv_bias (nullable, dtype pdt): bias of the producing convolution when
+ * the GEMM output x was stored WITHOUT it (tensor-core path): batch-stat BN cancels a per-channel constant,
+ * so it only enters the running-mean update (training) or the shift (eval). */
 int ms_bn_finalize(const double* sum, const double* sumsq, int64_t rows, int C,
-                   const void* gamma, const void* beta, void* running_mean, void* running_var, int pdt,
+                   const void* gamma, const void* beta, const void* conv_bias, void* running_mean, void* running_var, int pdt,
                    int training, float momentum, float eps,
                    float* scale, float* shift, float* mean, float* rstd, void* stream);
 /* y = act(x*scale[c] + shift[c]) over rows x C; act LeakyReLU(slope) when slope != 1.
  * up2 != 0 fuses UNet1D's `upconv(x) + residual` (layers.py:151): y has 2*L rows per
  * sequence, y[b,2l+r,:] = act(..)[b,l,:] + res[b,2l+r,:]  (L = rows_per_seq). */
 int ms_bn_act_fwd_f32(const float* x, const float* scale, const float* shift, float slope,
-                      int64_t rows, int C, float* y, const float* res, int up2, int rows_per_seq, void* stream);
+                      int64_t rows, int C, float* y, const float* res, int up2, int rows_per_seq,
+                      void* planes, int pfmt, int64_t pstride, void* stream);
+/* "planes": optional second output of the activation as bf16 tensor-core operand planes, same element
+ * order as y: pfmt MS_BF16 (one plane) or MS_BF16X2 (hi plane, then lo = bf16(v - hi) at + pstride elements).
+ * y may be NULL when only the planes are wanted. */
+/* x (rows, C) fp32 -> planes with row stride row_stride >= C (pad columns zero). */
+int ms_to_planes(const float* x, int64_t rows, int C, int row_stride, void* planes, int pfmt, int64_t pstride, void* stream);
 /* backward reductions of act(bn(x)):  dz = dy * (z>0 ? 1 : slope) with z = x*scale+shift,
  * dbeta[c] += sum dz, dgamma_hat[c] += sum dz * xhat  (xhat = (x-mean)*rstd), doubles,
  * caller zeroes.  up2: dy has 2*L rows per sequence and the two rows of a pair are summed. */
@@ -150,10 +167,11 @@ int ms_bn_act_bwd_reduce_f32(const float* dy, const float* x, const float* scale
 int ms_bn_act_bwd_apply_f32(const float* dy, const float* x, const float* scale, const float* shift,
                             const float* mean, const float* rstd, float slope, int64_t rows, int C,
                             int up2, int rows_per_seq, const double* dgamma, const double* dbeta,
-                            int training, float* dx, void* stream);
+                            int training, float* dx, void* planes, int pfmt, int64_t pstride, void* stream);
 /* dz = dy * (y > 0 ? 1 : slope) for a plain conv + LeakyReLU (speech2gesture.py:76-77); y is the
  * activation output. */
-int ms_lrelu_bwd_f32(const float* dy, const float* y, float slope, int64_t n, float* dz, void* stream);
+int ms_lrelu_bwd_f32(const float* dy, const float* y, float slope, int64_t n, float* dz, void* planes, int pfmt,
+                     int64_t pstride, void* stream);
 /* out[i] (dtype pdt) = (T) in[i] for small per-channel vectors (dgamma/dbeta/dbias). */
 int ms_store_param_grad(const double* src, int n, void* dst, int pdt, void* stream);
 

@@ -9,9 +9,10 @@ from .gan import GAN                                              # noqa: F401
 from .joint_late_cluster_soft_style import (JointLateClusterSoftStyle4_D,      # noqa: F401
                                             JointLateClusterSoftStyle4_G)
 from .speech2gesture import Speech2Gesture_D                      # noqa: F401
+from .ops import get_precision, precision_scope, set_precision    # noqa: F401
 
 __all__ = ["JointLateClusterSoftStyle4_G", "JointLateClusterSoftStyle4_D", "Speech2Gesture_D", "GAN",
-           "install", "MixStageError"]
+           "install", "MixStageError", "set_precision", "get_precision", "precision_scope"]
 
 
 def install(namespace=None):

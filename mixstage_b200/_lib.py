@@ -10,7 +10,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmixstage_b200.so")
 
-MS_F32, MS_F64, MS_BF16 = 0, 1, 2
+MS_F32, MS_F64, MS_BF16, MS_BF16X2 = 0, 1, 2, 3
 
 
 class ConvDesc(ctypes.Structure):
@@ -31,6 +31,8 @@ class IgemmDesc(ctypes.Structure):
         ("a_chan_base", ctypes.c_int32 * MAX_CLASSES), ("out_off", ctypes.c_int64 * MAX_CLASSES),
         ("taps", (ctypes.c_int16 * 4) * MAX_TAPS),
         ("out_dtype", ctypes.c_int32), ("epilogue", ctypes.c_int32), ("slope", ctypes.c_float),
+        ("planes", ctypes.c_int32),
+        ("a_plane_stride", ctypes.c_int64), ("w_plane_stride", ctypes.c_int64), ("out_plane_stride", ctypes.c_int64),
     ]
 
 
@@ -50,15 +52,16 @@ PROTOTYPES = {
     "ms_conv_dgrad_f32": [_P, _P, _P, _CD, _P],
     "ms_conv_wgrad_f32": [_P, _P, _P, _CD, _P],
     "ms_igemm_bf16": [_GD, _P, _P, _P, _P, _P, _P, _P],
-    "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P],
+    "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P, _P],
     "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],
     "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
     "ms_col_stats_f32": [_P, _L, _I, _P, _P, _P],
-    "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],
-    "ms_bn_act_fwd_f32": [_P, _P, _P, _F, _L, _I, _P, _P, _I, _I, _P],
+    "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],
+    "ms_bn_act_fwd_f32": [_P, _P, _P, _F, _L, _I, _P, _P, _I, _I, _P, _I, _L, _P],
+    "ms_to_planes": [_P, _L, _I, _I, _P, _I, _L, _P],
     "ms_bn_act_bwd_reduce_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _P],
-    "ms_bn_act_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _I, _P, _P],
-    "ms_lrelu_bwd_f32": [_P, _P, _F, _L, _P, _P],
+    "ms_bn_act_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _I, _P, _P, _I, _L, _P],
+    "ms_lrelu_bwd_f32": [_P, _P, _F, _L, _P, _P, _I, _L, _P],
     "ms_store_param_grad": [_P, _I, _P, _I, _P],
     "ms_bilinear_to_T_fwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ms_bilinear_to_T_bwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],

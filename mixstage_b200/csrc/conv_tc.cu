@@ -45,6 +45,8 @@ struct IgemmParams {
   short taps[MS_IGEMM_MAX_TAPS][4];     // chan_off, d_w, d_par, d_h
   int out_dtype, epilogue;
   float slope;
+  int npass;                            // 1: bf16 operands; 3: split-bf16 (hi*hi + hi*lo + lo*hi)
+  long long out_plane_stride;           // MS_BF16X2 output: elements between the hi and lo planes
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,6 +120,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
                 const __grid_constant__ IgemmParams p, const float* __restrict__ bias, const float* __restrict__ scale,
                 const float* __restrict__ shift, void* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -142,7 +145,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int cls = blockIdx.y / p.n_tiles_per_class;
   const int nt = blockIdx.y - cls * p.n_tiles_per_class;
   const int n0 = nt * p.block_n;                       // column offset inside the class
-  const int num_k = p.ntaps * p.cchunks;
+  const int num_k = p.ntaps * p.cchunks * p.npass;
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
@@ -150,6 +153,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    if (p.npass > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
+    }
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -173,12 +180,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int s = ks % STAGES;
         const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap = ks / p.cchunks, cc = ks - tap * p.cchunks;
+        // split-bf16: three passes per (tap, channel chunk): hi*hi, hi*lo, lo*hi
+        const int kk = ks / p.npass, pass = ks - kk * p.npass;
+        const int tap = kk / p.cchunks, cc = kk - tap * p.cchunks;
         const short* t = p.taps[tap_base + tap];
         mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + b_stage_bytes);
-        tma_load_5d(&map_a, &full_bar[s], smem_a + (size_t)s * A_STAGE_BYTES, chan_base + t[0] + cc * BLOCK_K, w0 + t[1],
-                    t[2], h0 + t[3], b0);
-        tma_load_2d(&map_w, &full_bar[s], smem_b + (size_t)s * b_stage_bytes, ks * BLOCK_K, wrow);
+        tma_load_5d(pass == 2 ? &map_a_lo : &map_a, &full_bar[s], smem_a + (size_t)s * A_STAGE_BYTES,
+                    chan_base + t[0] + cc * BLOCK_K, w0 + t[1], t[2], h0 + t[3], b0);
+        tma_load_2d(pass == 1 ? &map_w_lo : &map_w, &full_bar[s], smem_b + (size_t)s * b_stage_bytes, kk * BLOCK_K, wrow);
       }
     }
   } else if (warp == 1) {
@@ -228,8 +237,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (p.epilogue == 1) {
             x = fmaf(x, __ldg(scale + ncol + c0 + j), __ldg(shift + ncol + c0 + j));
             x = x > 0.f ? x : x * p.slope;
-          } else if (bias) {
-            x += __ldg(bias + ncol + c0 + j);
+          } else {
+            if (bias) x += __ldg(bias + ncol + c0 + j);
+            if (p.epilogue == 2) x = x > 0.f ? x : x * p.slope;
           }
           f[j] = x;
         }
@@ -244,9 +254,23 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           for (int j = 0; j < 8; j++) {
             __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
             w[j] = *reinterpret_cast<uint32_t*>(&h2);
+            if (p.out_dtype == MS_BF16X2) {          // residuals for the lo plane
+              f[2 * j] -= __bfloat162float(h2.x);
+              f[2 * j + 1] -= __bfloat162float(h2.y);
+            }
           }
           dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
           dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          if (p.out_dtype == MS_BF16X2) {
+            dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + p.out_plane_stride + row_off + c0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              w[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
         }
       }
     }
@@ -290,7 +314,7 @@ constexpr int WG_STAGES = 4;
 struct WgradParams {
   int ntaps, cchunks, shared_taps, num_classes, class_n;
   int box_w, box_h, box_b, tiles_w, tiles_h, tiles_b;
-  int n_tiles, c_tiles, kpad, split;
+  int n_tiles, c_tiles, kpad, split, npass;
   int a_chan_base[MS_IGEMM_MAX_CLASSES];
   int z_chan_base[MS_IGEMM_MAX_CLASSES];
   short taps[MS_IGEMM_MAX_TAPS][4];
@@ -308,6 +332,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z,
+                const __grid_constant__ CUtensorMap map_x_lo, const __grid_constant__ CUtensorMap map_z_lo,
                 const __grid_constant__ WgradParams p, float* __restrict__ dwp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -326,7 +351,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   const int total_rt = p.tiles_w * p.tiles_h * p.tiles_b;
   const int per = (total_rt + p.split - 1) / p.split;
   const int rt_beg = blockIdx.x * per, rt_end = min(total_rt, rt_beg + per);
-  const int num_k = max(0, rt_end - rt_beg);
+  const int num_k = max(0, rt_end - rt_beg) * p.npass;
   uint8_t* smem_a = smem;                                // [stage][2 chunks]
   uint8_t* smem_b = smem + WG_STAGES * 2 * WG_CHUNK_BYTES;   // [stage][4 chunks]
   uint32_t tmem_cols = 64;
@@ -358,17 +383,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
           const int s = ks % WG_STAGES;
           const uint32_t ph = (uint32_t)(ks / WG_STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          int rt = rt_beg + ks;
+          const int pass = ks % p.npass;              // split-bf16: x_hi*z_hi, x_hi*z_lo, x_lo*z_hi
+          int rt = rt_beg + ks / p.npass;
+          const CUtensorMap* mz = pass == 1 ? &map_z_lo : &map_z;
+          const CUtensorMap* mx = pass == 2 ? &map_x_lo : &map_x;
           const int tw = rt % p.tiles_w; rt /= p.tiles_w;
           const int th = rt % p.tiles_h; rt /= p.tiles_h;
           const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = rt * p.box_b;
           mbar_expect_tx(&full_bar[s], stage_bytes);
           uint8_t* sa = smem_a + (size_t)s * 2 * WG_CHUNK_BYTES;
           uint8_t* sb = smem_b + (size_t)s * 4 * WG_CHUNK_BYTES;
-          tma_load_5d(&map_z, &full_bar[s], sa, zc, w0, 0, h0, b0);
-          tma_load_5d(&map_z, &full_bar[s], sa + WG_CHUNK_BYTES, zc + 64, w0, 0, h0, b0);
+          tma_load_5d(mz, &full_bar[s], sa, zc, w0, 0, h0, b0);
+          tma_load_5d(mz, &full_bar[s], sa + WG_CHUNK_BYTES, zc + 64, w0, 0, h0, b0);
           for (int i = 0; i < xchunks; i++)
-            tma_load_5d(&map_x, &full_bar[s], sb + (size_t)i * WG_CHUNK_BYTES, xc + 64 * i, w0 + t[1], t[2], h0 + t[3], b0);
+            tma_load_5d(mx, &full_bar[s], sb + (size_t)i * WG_CHUNK_BYTES, xc + 64 * i, w0 + t[1], t[2], h0 + t[3], b0);
         }
       }
     } else if (warp == 1) {
@@ -445,7 +473,8 @@ struct PackParams {
   short srctap[MS_IGEMM_MAX_TAPS];
 };
 
-__global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, PackParams q, __nv_bfloat16* __restrict__ wp) {
+__global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, PackParams q, __nv_bfloat16* __restrict__ wp,
+                                         __nv_bfloat16* __restrict__ wp_lo) {
   const long long total = (long long)q.num_classes * q.class_n * q.ntaps * q.kpad;
   const int Cout_g = q.Cout / q.groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -463,7 +492,9 @@ __global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, Pa
       if (kc < Cout_g && r < q.Cin_g)
         v = ms_ldp(w, pdt, ((long long)(g * Cout_g + kc) * q.Cin_g + r) * q.taps_total + q.srctap[cls * q.ntaps + t]);
     }
-    wp[i] = __float2bfloat16(v);
+    __nv_bfloat16 h = __float2bfloat16(v);
+    wp[i] = h;
+    if (wp_lo) wp_lo[i] = __float2bfloat16(v - __bfloat162float(h));
   }
 }
 
@@ -471,7 +502,7 @@ __global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, Pa
 
 extern "C" int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int taps_total, int groups, int mode,
                                          int num_classes, int class_n, int ntaps, int kpad, const int16_t* srctap_host,
-                                         void* wp, void* stream) {
+                                         void* wp, void* wp_lo, void* stream) {
   if (!w || !wp || !srctap_host || groups < 1 || num_classes < 1 || ntaps < 1) return MS_EINVAL;
   const int nsrc = mode == 0 ? ntaps : num_classes * ntaps;
   if (nsrc > MS_IGEMM_MAX_TAPS || kpad % 64) return MS_EINVAL;
@@ -482,7 +513,8 @@ extern "C" int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int C
   const long long total = (long long)num_classes * class_n * ntaps * kpad;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_igemm_weight_kernel<<<(unsigned)blocks, 256, 0, ms_stream(stream)>>>(w, pdt, q, reinterpret_cast<__nv_bfloat16*>(wp));
+  pack_igemm_weight_kernel<<<(unsigned)blocks, 256, 0, ms_stream(stream)>>>(w, pdt, q, reinterpret_cast<__nv_bfloat16*>(wp),
+                                                                               reinterpret_cast<__nv_bfloat16*>(wp_lo));
   MS_LAUNCH_CHECK();
   return 0;
 }
@@ -498,36 +530,49 @@ extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* 
   if (d->class_n % 16 || d->class_n < 16) return MS_EINVAL;
   if (d->box[0] != BLOCK_K || d->box[2] != 1 || d->box[1] * d->box[3] * d->box[4] != BLOCK_M) return MS_EINVAL;
   if (d->epilogue == 1 && (!scale || !shift)) return MS_EINVAL;
-  if (d->out_dtype != MS_F32 && d->out_dtype != MS_BF16) return MS_EINVAL;
+  if (d->epilogue < 0 || d->epilogue > 2) return MS_EINVAL;
+  if (d->out_dtype != MS_F32 && d->out_dtype != MS_BF16 && d->out_dtype != MS_BF16X2) return MS_EINVAL;
+  if (d->out_dtype == MS_BF16X2 && (d->out_plane_stride <= 0 || (d->out_plane_stride * 2) % 16)) return MS_EINVAL;
   if (((uintptr_t)a & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15)) return MS_EINVAL;
   EncodeTiledFn enc = get_encode();
   if (!enc) return MS_ENOTSUP;
 
-  CUtensorMap map_a, map_w;
-  {
-    cuuint64_t dims[5], strides[4];
-    cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
-    for (int i = 0; i < 5; i++) { dims[i] = (cuuint64_t)d->a_dims[i]; box[i] = (cuuint32_t)d->box[i]; }
-    for (int i = 1; i < 5; i++) {
-      strides[i - 1] = (cuuint64_t)d->a_strides[i] * 2;
-      if (strides[i - 1] % 16) return MS_EINVAL;
+  const int planes = d->planes == 2 ? 2 : 1;
+  if (d->planes != 1 && d->planes != 2) return MS_EINVAL;
+  if (planes == 2 && ((d->a_plane_stride * 2) % 16 || (d->w_plane_stride * 2) % 16 || d->a_plane_stride <= 0 || d->w_plane_stride <= 0))
+    return MS_EINVAL;
+  CUtensorMap map_a, map_w, map_a_lo, map_w_lo;
+  for (int pl = 0; pl < planes; pl++) {
+    const __nv_bfloat16* ap = reinterpret_cast<const __nv_bfloat16*>(a) + (pl ? d->a_plane_stride : 0);
+    const __nv_bfloat16* wq = reinterpret_cast<const __nv_bfloat16*>(w) + (pl ? d->w_plane_stride : 0);
+    {
+      cuuint64_t dims[5], strides[4];
+      cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+      for (int i = 0; i < 5; i++) { dims[i] = (cuuint64_t)d->a_dims[i]; box[i] = (cuuint32_t)d->box[i]; }
+      for (int i = 1; i < 5; i++) {
+        strides[i - 1] = (cuuint64_t)d->a_strides[i] * 2;
+        if (strides[i - 1] % 16) return MS_EINVAL;
+      }
+      CUresult r = enc(pl ? &map_a_lo : &map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(ap), dims, strides,
+                       box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return MS_EINVAL;
     }
-    CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return MS_EINVAL;
+    {
+      const long long ktot = (long long)d->ntaps * d->cchunks * BLOCK_K;
+      cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)((long long)d->num_classes * d->class_n)};
+      cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+      cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)d->block_n}, es[2] = {1, 1};
+      CUresult r = enc(pl ? &map_w_lo : &map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wq), dims, strides,
+                       box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return MS_EINVAL;
+    }
   }
-  {
-    const long long ktot = (long long)d->ntaps * d->cchunks * BLOCK_K;
-    cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)((long long)d->num_classes * d->class_n)};
-    cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)d->block_n}, es[2] = {1, 1};
-    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return MS_EINVAL;
-  }
+  if (planes == 1) { map_a_lo = map_a; map_w_lo = map_w; }
   IgemmParams p;
+  p.npass = planes == 2 ? 3 : 1;
+  p.out_plane_stride = d->out_plane_stride;
   p.ntaps = d->ntaps; p.cchunks = d->cchunks; p.shared_taps = d->shared_taps;
   p.num_classes = d->num_classes; p.class_n = d->class_n; p.block_n = d->block_n;
   p.n_tiles_per_class = (d->class_n + d->block_n - 1) / d->block_n;
@@ -554,7 +599,7 @@ extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* 
     attr_set = true;
   }
   dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_b), (unsigned)(p.n_tiles_per_class * d->num_classes));
-  igemm_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, p, bias, scale, shift, out);
+  igemm_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
   MS_LAUNCH_CHECK();
   return 0;
 }
@@ -601,15 +646,27 @@ extern "C" int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* 
   if (split > total_rt) split = total_rt;
   if (split < 1) split = 1;
   p.split = (int)split;
+  if (d->planes != 1 && d->planes != 2) return MS_EINVAL;
+  p.npass = d->planes == 2 ? 3 : 1;
+  if (d->planes == 2 && (d->a_plane_stride <= 0 || d->out_plane_stride <= 0 || (d->a_plane_stride * 2) % 16 || (d->out_plane_stride * 2) % 16))
+    return MS_EINVAL;
 
-  CUtensorMap map_x, map_z;
+  CUtensorMap map_x, map_z, map_x_lo, map_z_lo;
   int box[5] = {64, bw, 1, bh, bb};
-  int rc = encode_5d(enc, &map_x, x, d->a_dims, d->a_strides, box);
-  if (rc) return rc;
   const int32_t zdims[5] = {(int32_t)d->out_strides[0], Wo, 1, Ho, Bo};
   const int64_t zstr[5] = {1, d->out_strides[0], d->out_strides[1], d->out_strides[1], d->out_strides[2]};
+  int rc = encode_5d(enc, &map_x, x, d->a_dims, d->a_strides, box);
+  if (rc) return rc;
   rc = encode_5d(enc, &map_z, dz, zdims, zstr, box);
   if (rc) return rc;
+  if (d->planes == 2) {
+    rc = encode_5d(enc, &map_x_lo, reinterpret_cast<const __nv_bfloat16*>(x) + d->a_plane_stride, d->a_dims, d->a_strides, box);
+    if (rc) return rc;
+    rc = encode_5d(enc, &map_z_lo, reinterpret_cast<const __nv_bfloat16*>(dz) + d->out_plane_stride, zdims, zstr, box);
+    if (rc) return rc;
+  } else {
+    map_x_lo = map_x; map_z_lo = map_z;
+  }
 
   const size_t wbytes = sizeof(float) * (size_t)d->num_classes * d->class_n * d->ntaps * p.kpad;
   if (p.split > 1) MS_CUDA(cudaMemsetAsync(dwp, 0, wbytes, ms_stream(stream)));
@@ -620,7 +677,7 @@ extern "C" int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* 
     attr_set = true;
   }
   dim3 grid((unsigned)p.split, (unsigned)(p.n_tiles * p.c_tiles), (unsigned)(d->num_classes * d->ntaps));
-  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_x, map_z, p, dwp);
+  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_x, map_z, map_x_lo, map_z_lo, p, dwp);
   MS_LAUNCH_CHECK();
   return 0;
 }

@@ -99,22 +99,24 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, int64_t rows, int C,
-                                   const void* gamma, const void* beta, void* rmean, void* rvar, int pdt,
+                                   const void* gamma, const void* beta, const void* cbias, void* rmean, void* rvar, int pdt,
                                    int training, float momentum, float eps,
                                    float* scale, float* shift, float* mean_o, float* rstd_o) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double mean, var;
+  // cbias: bias of the producing convolution when the statistics were taken on the bias-free GEMM output
+  double cb = cbias ? ms_ldp_d(cbias, pdt, c) : 0.0;
   if (training) {
     mean = sum[c] / (double)rows;
     var = sumsq[c] / (double)rows - mean * mean;
     if (var < 0.0) var = 0.0;
     double unb = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
     double rm = ms_ldp_d(rmean, pdt, c), rv = ms_ldp_d(rvar, pdt, c);
-    ms_stp(rmean, pdt, c, (1.0 - (double)momentum) * rm + (double)momentum * mean);
+    ms_stp(rmean, pdt, c, (1.0 - (double)momentum) * rm + (double)momentum * (mean + cb));
     ms_stp(rvar, pdt, c, (1.0 - (double)momentum) * rv + (double)momentum * unb);
   } else {
-    mean = ms_ldp_d(rmean, pdt, c);
+    mean = ms_ldp_d(rmean, pdt, c) - cb;
     var = ms_ldp_d(rvar, pdt, c);
   }
   double rstd = 1.0 / sqrt(var + (double)eps);
@@ -126,10 +128,35 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 }
 
 // ------------------------------------------------------------------ BN apply + LeakyReLU (+ upsample x2 + skip)
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// hi plane always; lo plane (residual of the bf16 rounding) when fmt == MS_BF16X2.  i = element index (multiple of 4)
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ pl, int fmt, int64_t ps, int64_t i, float4 o) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(pl + i) = u;
+  if (fmt == MS_BF16X2) {
+    uint2 v;
+    v.x = pack_bf162(o.x - __bfloat162float(h0.x), o.y - __bfloat162float(h0.y));
+    v.y = pack_bf162(o.z - __bfloat162float(h1.x), o.w - __bfloat162float(h1.y));
+    *reinterpret_cast<uint2*>(pl + ps + i) = v;
+  }
+}
+__device__ __forceinline__ void store_planes1(__nv_bfloat16* __restrict__ pl, int fmt, int64_t ps, int64_t i, float o) {
+  __nv_bfloat16 h = __float2bfloat16_rn(o);
+  pl[i] = h;
+  if (fmt == MS_BF16X2) pl[ps + i] = __float2bfloat16_rn(o - __bfloat162float(h));
+}
+
 template <int VEC>
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                   float slope, int64_t rows_out, int C, float* __restrict__ y,
-                                  const float* __restrict__ res, int up2, int L) {
+                                  const float* __restrict__ res, int up2, int L,
+                                  __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride) {
   int Cv = C / VEC;
   int64_t total = rows_out * Cv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -153,12 +180,14 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __re
         float4 r = __ldg(reinterpret_cast<const float4*>(res + ro * C) + cv);
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
-      reinterpret_cast<float4*>(y + ro * C)[cv] = o;
+      if (y) reinterpret_cast<float4*>(y + ro * C)[cv] = o;
+      if (planes) store_planes4(planes, pfmt, pstride, ro * C + 4 * cv, o);
     } else {
       float o = fmaf(__ldg(x + ri * C + cv), scale[cv], shift[cv]);
       o = o > 0.f ? o : o * slope;
       if (res) o += __ldg(res + ro * C + cv);
-      y[ro * C + cv] = o;
+      if (y) y[ro * C + cv] = o;
+      if (planes) store_planes1(planes, pfmt, pstride, ro * C + cv, o);
     }
   }
 }
@@ -207,7 +236,8 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dy, const floa
                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                         const float* __restrict__ mean, const float* __restrict__ rstd, float slope,
                                         int64_t rows, int C, int up2, int L, const double* __restrict__ dgamma,
-                                        const double* __restrict__ dbeta, int training, float* __restrict__ dx) {
+                                        const double* __restrict__ dbeta, int training, float* __restrict__ dx,
+                                        __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride) {
   int64_t total = rows * C;
   float inv = 1.f / (float)rows;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -225,15 +255,35 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dy, const floa
     } else {
       o = sc * dz;
     }
-    dx[i] = o;
+    if (dx) dx[i] = o;
+    if (planes) store_planes1(planes, pfmt, pstride, i, o);
   }
 }
 
+// x (rows, C) fp32 -> bf16 planes with row stride rs >= C (pad columns zero-filled)
+__global__ void to_planes_kernel(const float* __restrict__ x, int64_t rows, int C, int rs, __nv_bfloat16* __restrict__ planes,
+                                 int pfmt, int64_t pstride) {
+  int64_t total = rows * rs;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / rs;
+    int c = (int)(i - r * rs);
+    float v = c < C ? __ldg(x + r * C + c) : 0.f;
+    store_planes1(planes, pfmt, pstride, i, v);
+  }
+}
+__global__ void to_planes4_kernel(const float* __restrict__ x, int64_t n4, __nv_bfloat16* __restrict__ planes, int pfmt,
+                                  int64_t pstride) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+    store_planes4(planes, pfmt, pstride, 4 * i, __ldg(reinterpret_cast<const float4*>(x) + i));
+}
+
 __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope, int64_t n,
-                                 float* __restrict__ dz) {
+                                 float* __restrict__ dz, __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float d = __ldg(dy + i);
-    dz[i] = __ldg(y + i) > 0.f ? d : d * slope;
+    float o = __ldg(y + i) > 0.f ? d : d * slope;
+    if (dz) dz[i] = o;
+    if (planes) store_planes1(planes, pfmt, pstride, i, o);
   }
 }
 
@@ -598,24 +648,48 @@ extern "C" int ms_col_stats_f32(const float* x, int64_t rows, int C, double* sum
 }
 
 extern "C" int ms_bn_finalize(const double* sum, const double* sumsq, int64_t rows, int C, const void* gamma, const void* beta,
-                              void* running_mean, void* running_var, int pdt, int training, float momentum, float eps,
-                              float* scale, float* shift, float* mean, float* rstd, void* stream) {
+                              const void* conv_bias, void* running_mean, void* running_var, int pdt, int training,
+                              float momentum, float eps, float* scale, float* shift, float* mean, float* rstd, void* stream) {
   if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || !mean || !rstd || C < 1) return MS_EINVAL;
   if (training && (!sum || !sumsq || rows < 1)) return MS_EINVAL;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sum, sumsq, rows, C, gamma, beta, running_mean, running_var, pdt,
-                                                      training, momentum, eps, scale, shift, mean, rstd);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sum, sumsq, rows, C, gamma, beta, conv_bias, running_mean, running_var,
+                                                      pdt, training, momentum, eps, scale, shift, mean, rstd);
   MS_LAUNCH_CHECK();
   return 0;
 }
 
+static bool planes_ok(const void* planes, int pfmt, int64_t pstride) {
+  if (!planes) return true;
+  if (pfmt != MS_BF16 && pfmt != MS_BF16X2) return false;
+  if (pfmt == MS_BF16X2 && (pstride <= 0 || pstride % 8)) return false;
+  return ((uintptr_t)planes & 15) == 0;
+}
+
 extern "C" int ms_bn_act_fwd_f32(const float* x, const float* scale, const float* shift, float slope, int64_t rows, int C,
-                                 float* y, const float* res, int up2, int rows_per_seq, void* stream) {
-  if (!x || !scale || !shift || !y || rows < 1 || C < 1) return MS_EINVAL;
+                                 float* y, const float* res, int up2, int rows_per_seq, void* planes, int pfmt,
+                                 int64_t pstride, void* stream) {
+  if (!x || !scale || !shift || (!y && !planes) || rows < 1 || C < 1) return MS_EINVAL;
   if (up2 && (rows_per_seq < 1 || rows % rows_per_seq)) return MS_EINVAL;
+  if (!planes_ok(planes, pfmt, pstride)) return MS_EINVAL;
   int64_t rows_out = up2 ? rows * 2 : rows;
+  __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(planes);
   bool vec = (C % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift | (uintptr_t)res) & 15) == 0);
-  if (vec) bn_act_fwd_kernel<4><<<ew_blocks(rows_out * C / 4), EW_THREADS, 0, ST>>>(x, scale, shift, slope, rows_out, C, y, res, up2, rows_per_seq);
-  else bn_act_fwd_kernel<1><<<ew_blocks(rows_out * C), EW_THREADS, 0, ST>>>(x, scale, shift, slope, rows_out, C, y, res, up2, rows_per_seq);
+  if (vec) bn_act_fwd_kernel<4><<<ew_blocks(rows_out * C / 4), EW_THREADS, 0, ST>>>(x, scale, shift, slope, rows_out, C, y, res, up2, rows_per_seq, pl, pfmt, pstride);
+  else bn_act_fwd_kernel<1><<<ew_blocks(rows_out * C), EW_THREADS, 0, ST>>>(x, scale, shift, slope, rows_out, C, y, res, up2, rows_per_seq, pl, pfmt, pstride);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_to_planes(const float* x, int64_t rows, int C, int row_stride, void* planes, int pfmt, int64_t pstride,
+                            void* stream) {
+  if (!x || !planes || rows < 1 || C < 1 || row_stride < C) return MS_EINVAL;
+  if (!planes_ok(planes, pfmt, pstride)) return MS_EINVAL;
+  __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(planes);
+  int64_t n = rows * C;
+  if (row_stride == C && n % 4 == 0 && ((uintptr_t)x & 15) == 0)
+    to_planes4_kernel<<<ew_blocks(n / 4), EW_THREADS, 0, ST>>>(x, n / 4, pl, pfmt, pstride);
+  else
+    to_planes_kernel<<<ew_blocks(rows * row_stride), EW_THREADS, 0, ST>>>(x, rows, C, row_stride, pl, pfmt, pstride);
   MS_LAUNCH_CHECK();
   return 0;
 }
@@ -633,18 +707,22 @@ extern "C" int ms_bn_act_bwd_reduce_f32(const float* dy, const float* x, const f
 extern "C" int ms_bn_act_bwd_apply_f32(const float* dy, const float* x, const float* scale, const float* shift,
                                        const float* mean, const float* rstd, float slope, int64_t rows, int C, int up2,
                                        int rows_per_seq, const double* dgamma, const double* dbeta, int training, float* dx,
-                                       void* stream) {
-  if (!dy || !x || !scale || !shift || !mean || !rstd || !dx || rows < 1 || C < 1) return MS_EINVAL;
+                                       void* planes, int pfmt, int64_t pstride, void* stream) {
+  if (!dy || !x || !scale || !shift || !mean || !rstd || (!dx && !planes) || rows < 1 || C < 1) return MS_EINVAL;
   if (training && (!dgamma || !dbeta)) return MS_EINVAL;
+  if (!planes_ok(planes, pfmt, pstride)) return MS_EINVAL;
   bn_act_bwd_apply_kernel<<<ew_blocks(rows * C), EW_THREADS, 0, ST>>>(dy, x, scale, shift, mean, rstd, slope, rows, C, up2,
-                                                                      rows_per_seq, dgamma, dbeta, training, dx);
+                                                                      rows_per_seq, dgamma, dbeta, training, dx,
+                                                                      reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride);
   MS_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ms_lrelu_bwd_f32(const float* dy, const float* y, float slope, int64_t n, float* dz, void* stream) {
-  if (!dy || !y || !dz || n < 1) return MS_EINVAL;
-  lrelu_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, ST>>>(dy, y, slope, n, dz);
+extern "C" int ms_lrelu_bwd_f32(const float* dy, const float* y, float slope, int64_t n, float* dz, void* planes, int pfmt,
+                                int64_t pstride, void* stream) {
+  if (!dy || !y || (!dz && !planes) || n < 1) return MS_EINVAL;
+  if (!planes_ok(planes, pfmt, pstride)) return MS_EINVAL;
+  lrelu_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, ST>>>(dy, y, slope, n, dz, reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride);
   MS_LAUNCH_CHECK();
   return 0;
 }

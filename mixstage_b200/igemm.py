@@ -121,6 +121,7 @@ def make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo, out_dty
     bw, bh, bb = _boxes(Wo, Ho)
     d.box[:] = [BLOCK_K, bw, 1, bh, bb]
     d.out_dtype, d.epilogue, d.slope = out_dtype, epilogue, slope
+    d.planes = 1
     return Plan(d, 0, srctap, d.cchunks * BLOCK_K, groups * ng)
 
 
@@ -182,4 +183,25 @@ def make_dgrad(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo, out_r
     bw, bh, bb = _boxes(Wd, Hd)
     d.box[:] = [BLOCK_K, bw, 1, bh, bb]
     d.out_dtype, d.epilogue, d.slope = MS_F32, 0, 1.0
+    d.planes = 1
     return Plan(d, 1, srctap, d.cchunks * BLOCK_K, len(classes) * cg)
+
+
+def pick_block_n(d, sms=148):
+    """Output-column tile: the widest tile that still fills the machine, else the narrowest (latency-bound layers)."""
+    tiles_m = 1
+    for dim, box in ((d.out_dims[0], d.box[1]), (d.out_dims[1], d.box[3]), (d.out_dims[2], d.box[4])):
+        tiles_m *= (dim + box - 1) // box
+    cands = [min(256, d.class_n)] + [b for b in (128, 64, 32) if b < min(256, d.class_n)]
+    for bn in cands:
+        if tiles_m * d.num_classes * ((d.class_n + bn - 1) // bn) >= sms:
+            return bn
+    return cands[-1]
+
+
+def set_planes(plan, split, a_plane_stride=0, w_plane_stride=0, out_plane_stride=0):
+    """Operand format of a plan: split=False plain bf16, split=True split-bf16 (hi/lo planes, 3 MMA passes)."""
+    d = plan.desc
+    d.planes = 2 if split else 1
+    d.a_plane_stride, d.w_plane_stride, d.out_plane_stride = a_plane_stride, w_plane_stride, out_plane_stride
+    return plan

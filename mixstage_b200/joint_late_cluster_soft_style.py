@@ -101,6 +101,8 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         self.thresh = Curriculum(0, 1, 1000)
         self.labels_cap_soft = None
         self.style_index = None       # last integer style index used for the embedding ('emb' mode)
+        # arithmetic of the convolutions: None = process default (ops.set_precision), else "fp32" | "bf16x3" | "bf16"
+        self.precision = kwargs.get('precision', None)
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -109,6 +111,10 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         return ops.cast(t, torch.float32).contiguous()
 
     def forward(self, x, y, time_steps=None, **kwargs):
+        with ops.precision_scope(self.precision):
+            return self._forward(x, y, time_steps, **kwargs)
+
+    def _forward(self, x, y, time_steps=None, **kwargs):
         internal_losses = []
         labels = x[-1]                      # cluster labels ride along with the inputs (jlcss.py:119)
         x = list(x[:-1])

@@ -8,10 +8,91 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
-from ._lib import ConvDesc, MixStageError, call, dt_code, ptr, stream
+from . import _lib, igemm
+from ._lib import MS_BF16, MS_BF16X2, ConvDesc, MixStageError, call, dt_code, ptr, stream
 
 LEAKY_SLOPE = 0.2
+
+# ---------------------------------------------------------------------------- precision
+# "fp32"   : every convolution on the exact-fp32 CUDA-core kernels (csrc/conv_simt.cu)
+# "bf16x3" : tcgen05 tensor cores with split-bf16 operands (hi + lo planes, 3 MMA passes, fp32 accumulate):
+#            ~16 mantissa bits per operand, meets the fp32 parity tolerance
+# "bf16"   : tcgen05 tensor cores with plain bf16 operands, fp32 accumulate (the fast mode)
+PRECISIONS = ("fp32", "bf16x3", "bf16")
+_precision = "fp32"
+FORCE_REPACK = False        # set while a CUDA graph is being captured: weights change without a version bump
+
+
+def set_precision(p):
+    global _precision
+    if p not in PRECISIONS:
+        raise MixStageError("precision must be one of %s" % (PRECISIONS,))
+    _precision = p
+
+
+def get_precision():
+    return _precision
+
+
+class precision_scope:
+    """with precision_scope("bf16x3"): ...   (None keeps the current setting)"""
+
+    def __init__(self, p):
+        self.p, self.old = p, None
+
+    def __enter__(self):
+        if self.p is not None:
+            self.old = get_precision()
+            set_precision(self.p)
+
+    def __exit__(self, *a):
+        if self.old is not None:
+            set_precision(self.old)
+
+
+def _fmt(precision):
+    return MS_BF16X2 if precision == "bf16x3" else MS_BF16
+
+
+class Planes:
+    """bf16 tensor-core operand planes of an activation: hi plane [rows*rs] and, in split mode, the lo plane
+    (residual of the bf16 rounding) `ps` elements later.  rs = row stride in elements (channels padded to 8)."""
+    __slots__ = ("t", "fmt", "rs", "ps")
+
+    def __init__(self, t, fmt, rs, ps):
+        self.t, self.fmt, self.rs, self.ps = t, fmt, rs, ps
+
+
+def alloc_planes(rows, rs, fmt, device):
+    ps = (rows * rs + 7) // 8 * 8
+    t = torch.empty((2 if fmt == MS_BF16X2 else 1) * ps, dtype=torch.bfloat16, device=device)
+    return Planes(t, fmt, rs, ps)
+
+
+def pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def planes_of(x, fmt, rs):
+    """Planes of a channels-last fp32 activation: the producer's side output when it made one, else a cast."""
+    pl = getattr(x, "_ms_planes", None)
+    if pl is not None and pl.fmt == fmt and pl.rs == rs:
+        return pl
+    x = _f32c(x)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    pl = alloc_planes(rows, rs, fmt, x.device)
+    call("ms_to_planes", ptr(x), rows, C, rs, ptr(pl.t), fmt, pl.ps, stream())
+    try:
+        x._ms_planes = pl         # a second consumer of the same tensor object reuses the cast
+    except AttributeError:
+        pass
+    return pl
+
+
+def attach_planes(y, pl):
+    y._ms_planes = pl
+    return y
 
 
 def _need_cuda(t):
@@ -74,7 +155,7 @@ class PackedWeight:
 
     def get(self, weight, desc):
         key = (weight.data_ptr(), weight._version, weight.dtype, weight.device)
-        if key != self.key:
+        if key != self.key or FORCE_REPACK:
             w = weight.detach()
             if not w.is_contiguous():
                 w = w.contiguous()
@@ -86,11 +167,53 @@ class PackedWeight:
             self.key = key
         return self.wf, self.wt
 
+    # ---- tensor-core path: cached descriptors per input shape, packed bf16 (hi[, lo]) weights per version
+    def tc_plans(self, x_shape, Cout, cfg, rs, need_dgrad):
+        key = (tuple(x_shape), Cout, rs, need_dgrad)
+        pl = getattr(self, "_plans", None)
+        if pl is None:
+            pl = self._plans = {}
+        if key not in pl:
+            B, H, W, Cin = x_shape
+            Ho, Wo = conv_out(H, cfg.kh, cfg.sh, cfg.ph), conv_out(W, cfg.kw, cfg.sw, cfg.pw)
+            geo = (B, H, W, Cin, Cout, cfg.kh, cfg.kw, cfg.sh, cfg.sw, cfg.ph, cfg.pw, cfg.groups, Ho, Wo)
+            pf = igemm.make_fwd(*geo, a_row_stride=rs if rs != Cin else None)
+            pd = igemm.make_dgrad(*geo, out_row_stride=rs if rs != Cin else None) if need_dgrad else None
+            for p_ in (pf, pd):
+                if p_ is not None:
+                    p_.desc.block_n = igemm.pick_block_n(p_.desc)
+            pl[key] = (pf, pd)
+        return pl[key]
+
+    def get_tc(self, weight, plan, fmt, groups):
+        """Packed weight planes for `plan` (forward or dgrad tiling).  Returns (tensor, plane stride)."""
+        slot = "_tcw%d" % plan.mode
+        key = (weight.data_ptr(), weight._version, weight.dtype, weight.device, fmt, plan.wp_numel, tuple(plan.srctap))
+        cur = getattr(self, slot, None)
+        if cur is not None and cur[0] == key and not FORCE_REPACK:
+            return cur[1], cur[2]
+        w = weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        ps = (plan.wp_numel + 7) // 8 * 8
+        if cur is not None and cur[1].numel() == (2 if fmt == MS_BF16X2 else 1) * ps and cur[1].device == w.device:
+            buf = cur[1]
+        else:
+            buf = torch.empty((2 if fmt == MS_BF16X2 else 1) * ps, dtype=torch.bfloat16, device=w.device)
+        d = plan.desc
+        Cout, Cin_g = w.shape[0], w.shape[1]
+        taps_total = w.shape[2] * w.shape[3]
+        lo = buf.data_ptr() + 2 * ps if fmt == MS_BF16X2 else None
+        call("ms_pack_igemm_weight_bf16", ptr(w), dt_code(w.dtype), Cout, Cin_g, taps_total, groups, plan.mode,
+             d.num_classes, d.class_n, d.ntaps, plan.kpad, plan.srctap_c, ptr(buf), lo, stream())
+        setattr(self, slot, (key, buf, ps))
+        return buf, ps
+
     def get_bias(self, bias):
         if bias is None:
             return None
         key = (bias.data_ptr(), bias._version, bias.dtype, bias.device)
-        if key != self.bias_key:
+        if key != self.bias_key or FORCE_REPACK:
             self.bias = cast_raw(bias.detach(), torch.float32)
             self.bias_key = key
         return self.bias
@@ -113,7 +236,8 @@ class _ConvBlock(torch.autograd.Function):
     """y = act(bn(conv(x) + b)) [+ upsample2(y) + residual].  x: (B,H,W,Cin) fp32 channels-last."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2):
+    def forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2, precision="fp32",
+                carrier=None):
         _need_cuda(x)
         x = _f32c(x)
         B, H, W, Cin = x.shape
@@ -121,6 +245,10 @@ class _ConvBlock(torch.autograd.Function):
         desc = make_desc(x.shape, Cout, cfg.kh, cfg.kw, cfg.sh, cfg.sw, cfg.ph, cfg.pw, cfg.groups)
         if weight.shape[1] * cfg.groups != Cin:
             raise MixStageError("conv: input has %d channels, weight expects %d" % (Cin, weight.shape[1] * cfg.groups))
+        ctx.tc = False
+        if precision != "fp32" and tc_eligible(cfg, B, H, W, Cin, Cout, ctx.needs_input_grad[0]):
+            return _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2,
+                               desc, _fmt(precision), carrier)
         wf, wt = packed.get(weight, desc)
         b32 = packed.get_bias(bias)
         st = stream()
@@ -142,7 +270,7 @@ class _ConvBlock(torch.autograd.Function):
             call("ms_col_stats_f32", ptr(z), rows, Cout, ptr(stats[0]), ptr(stats[1]), st)
         ss = torch.empty(4, Cout, dtype=torch.float32, device=dev)     # scale, shift, mean, rstd
         call("ms_bn_finalize", ptr(stats[0]) if training else None, ptr(stats[1]) if training else None, rows, Cout,
-             ptr(gamma), ptr(beta), ptr(rm), ptr(rv), dt_code(gamma.dtype), 1 if training else 0,
+             ptr(gamma), ptr(beta), None, ptr(rm), ptr(rv), dt_code(gamma.dtype), 1 if training else 0,
              cfg.momentum, cfg.eps, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), st)
         if training:
             nbt.add_(1)
@@ -158,13 +286,15 @@ class _ConvBlock(torch.autograd.Function):
             y = torch.empty_like(z)
             res = None
         call("ms_bn_act_fwd_f32", ptr(z), ptr(ss[0]), ptr(ss[1]), slope, rows, Cout, ptr(y), ptr(res),
-             1 if up2 else 0, desc.Wo, st)
+             1 if up2 else 0, desc.Wo, None, 0, 0, st)
         ctx.gamma_dtype = gamma.dtype
         ctx.save_for_backward(x, z, ss)
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        if ctx.tc:
+            return _tc_backward(ctx, dy)
         cfg, desc, st = ctx.cfg, ctx.desc, stream()
         rows, Cout = ctx.rows, ctx.Cout
         dy = dy.contiguous()
@@ -180,7 +310,8 @@ class _ConvBlock(torch.autograd.Function):
                      rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), st)
             dz = torch.empty_like(z)
             call("ms_bn_act_bwd_apply_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
-                 rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), 1 if ctx.training else 0, ptr(dz), st)
+                 rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), 1 if ctx.training else 0, ptr(dz),
+                 None, 0, 0, st)
             if need_g:
                 dgamma = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
                 call("ms_store_param_grad", ptr(red[0]), Cout, ptr(dgamma), dt_code(ctx.gamma_dtype), st)
@@ -193,7 +324,7 @@ class _ConvBlock(torch.autograd.Function):
             x, z = ctx.saved_tensors
             if cfg.act:
                 dz = torch.empty_like(z)
-                call("ms_lrelu_bwd_f32", ptr(dy), ptr(z), cfg.slope, z.numel(), ptr(dz), st)
+                call("ms_lrelu_bwd_f32", ptr(dy), ptr(z), cfg.slope, z.numel(), ptr(dz), None, 0, 0, st)
             else:
                 dz = dy
         wdt, bdt = ctx.param_dtypes
@@ -215,14 +346,176 @@ class _ConvBlock(torch.autograd.Function):
         if need_x:
             dx = torch.empty_like(x)
             call("ms_conv_dgrad_f32", ptr(dz), ptr(ctx.wt), ptr(dx), desc, st)
-        return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None
+        return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None, None
 
 
-def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, residual=None, up2=False):
+def tc_eligible(cfg, B, H, W, Cin, Cout, need_dgrad):
+    """Geometries the tcgen05 implicit-GEMM kernels take; the rest (C_in = 1, N < 16, ...) stay on the
+    CUDA-core kernels."""
+    rs = pad8(Cin)
+    if cfg.groups > 1 and rs != Cin:
+        return False
+    if not igemm.fwd_supported(Cin, Cout, cfg.groups, cfg.sh, cfg.sw, H, W, rs):
+        return False
+    if cfg.kh * cfg.kw > igemm.MAX_TAPS:
+        return False
+    if need_dgrad:
+        if not igemm.dgrad_supported(rs if cfg.groups == 1 else Cin, Cout, cfg.groups, cfg.sh, cfg.sw, H, W, cfg.kh, cfg.kw):
+            return False
+    elif Cout % 8:
+        return False
+    return True
+
+
+def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2, desc, fmt, carrier):
+    """Tensor-core variant of the block: z = igemm(x planes, W planes) in fp32 (conv bias folded into the BN
+    finalize), then the same statistics / normalise kernels; the activation leaves both as fp32 (autograd,
+    residual adds, non-GEMM consumers) and as bf16 operand planes for the next GEMM."""
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    st, dev = stream(), x.device
+    rs = pad8(Cin)
+    need_dx = ctx.needs_input_grad[0]
+    split = fmt == MS_BF16X2
+    xp = planes_of(x, fmt, rs)
+    pf, pd = packed.tc_plans(x.shape, Cout, cfg, rs, need_dx)
+    wp, wps = packed.get_tc(weight, pf, fmt, cfg.groups)
+    rows = B * desc.Ho * desc.Wo
+    z = torch.empty((B, desc.Ho, desc.Wo, Cout), dtype=torch.float32, device=dev)
+    d = pf.desc
+    igemm.set_planes(pf, split, xp.ps, wps, 0)
+    d.out_dtype = _lib.MS_F32
+    fuse_act = (not cfg.has_bn) and cfg.act
+    d.epilogue, d.slope = (2 if fuse_act else 0), cfg.slope
+    b32 = None if cfg.has_bn else packed.get_bias(bias)
+    call("ms_igemm_bf16", d, ptr(xp.t), ptr(wp), ptr(b32), None, None, ptr(z), st)
+    ctx.tc, ctx.fmt = True, fmt
+    ctx.cfg, ctx.desc, ctx.training, ctx.up2 = cfg, desc, training, up2
+    ctx.rows, ctx.Cout, ctx.rs = rows, Cout, rs
+    ctx.plans = (pf, pd)
+    ctx.wt = packed.get_tc(weight, pd, fmt, cfg.groups) if pd is not None else None
+    ctx.x_shape, ctx.xp_meta = tuple(x.shape), (xp.rs, xp.ps)
+    ctx.param_dtypes = (weight.dtype, None if bias is None else bias.dtype)
+    ctx.has_res = residual is not None
+    if not cfg.has_bn:
+        ctx.save_for_backward(xp.t, z)
+        return z
+    rm, rv, nbt = bn_buffers
+    stats = torch.zeros(2, Cout, dtype=torch.float64, device=dev) if training else None
+    if training:
+        call("ms_col_stats_f32", ptr(z), rows, Cout, ptr(stats[0]), ptr(stats[1]), st)
+    ss = torch.empty(4, Cout, dtype=torch.float32, device=dev)
+    call("ms_bn_finalize", ptr(stats[0]) if training else None, ptr(stats[1]) if training else None, rows, Cout,
+         ptr(gamma), ptr(beta), ptr(bias), ptr(rm), ptr(rv), dt_code(gamma.dtype), 1 if training else 0,
+         cfg.momentum, cfg.eps, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), st)
+    if bias is not None and bias.dtype != gamma.dtype:
+        raise MixStageError("conv bias and BatchNorm parameters must share a dtype")
+    if training:
+        nbt.add_(1)
+    slope = cfg.slope if cfg.act else 1.0
+    if up2:
+        if desc.Ho != 1:
+            raise MixStageError("upsample+skip fusion is 1-D only")
+        y = torch.empty((B, 1, 2 * desc.Wo, Cout), dtype=torch.float32, device=dev)
+        res = _f32c(residual)
+        if res.shape != y.shape:
+            raise MixStageError("skip tensor shape %s != %s" % (tuple(res.shape), tuple(y.shape)))
+    else:
+        y = torch.empty_like(z)
+        res = None
+    yp = alloc_planes(y.numel() // Cout, pad8(Cout), fmt, dev) if Cout % 8 == 0 else None
+    call("ms_bn_act_fwd_f32", ptr(z), ptr(ss[0]), ptr(ss[1]), slope, rows, Cout, ptr(y), ptr(res),
+         1 if up2 else 0, desc.Wo, ptr(yp.t) if yp else None, fmt, yp.ps if yp else 0, st)
+    ctx.gamma_dtype = gamma.dtype
+    ctx.save_for_backward(xp.t, z, ss)
+    if yp is not None and carrier is not None:
+        carrier.planes = yp           # attached to the output by conv_block (autograd returns a fresh tensor object)
+    return y
+
+
+def _tc_backward(ctx, dy):
+    cfg, desc, st, fmt = ctx.cfg, ctx.desc, stream(), ctx.fmt
+    rows, Cout = ctx.rows, ctx.Cout
+    dy = dy.contiguous()
+    dev = dy.device
+    need_x, need_w, need_b, need_g, need_be, need_res = ctx.needs_input_grad[:6]
+    dgamma = dbeta = dres = dbias = dw = dx = None
+    split = fmt == MS_BF16X2
+    dzp = alloc_planes(rows, Cout, fmt, dev)
+    wdt, bdt = ctx.param_dtypes
+    if cfg.has_bn:
+        xpt, z, ss = ctx.saved_tensors
+        slope = cfg.slope if cfg.act else 1.0
+        red = torch.zeros(2, Cout, dtype=torch.float64, device=dev)
+        if ctx.training or need_g or need_be:
+            call("ms_bn_act_bwd_reduce_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
+                 rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), st)
+        need_f32 = need_b and bdt is not None and not ctx.training
+        dz = torch.empty_like(z) if need_f32 else None
+        call("ms_bn_act_bwd_apply_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
+             rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), 1 if ctx.training else 0, ptr(dz),
+             ptr(dzp.t), fmt, dzp.ps, st)
+        if need_g:
+            dgamma = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
+            call("ms_store_param_grad", ptr(red[0]), Cout, ptr(dgamma), dt_code(ctx.gamma_dtype), st)
+        if need_be:
+            dbeta = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
+            call("ms_store_param_grad", ptr(red[1]), Cout, ptr(dbeta), dt_code(ctx.gamma_dtype), st)
+        if ctx.has_res and need_res:
+            dres = dy
+    else:
+        xpt, z = ctx.saved_tensors
+        if cfg.act:
+            dz = torch.empty_like(z)
+            call("ms_lrelu_bwd_f32", ptr(dy), ptr(z), cfg.slope, z.numel(), ptr(dz), ptr(dzp.t), fmt, dzp.ps, st)
+        else:
+            dz = dy
+            call("ms_to_planes", ptr(dy), rows, Cout, Cout, ptr(dzp.t), fmt, dzp.ps, st)
+    if need_b and bdt is not None:
+        if cfg.has_bn and ctx.training:
+            dbias = torch.zeros(Cout, dtype=bdt, device=dev)     # batch-stat BN removes any per-channel constant
+        else:
+            acc = torch.zeros(Cout, dtype=torch.float64, device=dev)
+            call("ms_col_stats_f32", ptr(dz), rows, Cout, ptr(acc), None, st)
+            dbias = torch.empty(Cout, dtype=bdt, device=dev)
+            call("ms_store_param_grad", ptr(acc), Cout, ptr(dbias), dt_code(bdt), st)
+    pf, pd = ctx.plans
+    xrs, xps = ctx.xp_meta
+    B, H, W, Cin = ctx.x_shape
+    Cin_g = Cin // cfg.groups
+    if need_w:
+        igemm.set_planes(pf, split, xps, 0, dzp.ps)
+        dwp = torch.empty(pf.wp_numel, dtype=torch.float32, device=dev)
+        call("ms_wgrad_bf16", pf.desc, ptr(xpt), ptr(dzp.t), ptr(dwp), st)
+        dw = torch.empty((Cout, Cin_g, cfg.kh, cfg.kw), dtype=wdt, device=dev)
+        call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin_g, cfg.kh * cfg.kw, pf.desc.ntaps, pf.kpad, ptr(dw), dt_code(wdt), st)
+    if need_x:
+        wt, wtps = ctx.wt
+        igemm.set_planes(pd, split, dzp.ps, wtps, 0)
+        dxf = torch.empty((B, H, W, xrs), dtype=torch.float32, device=dev)
+        call("ms_igemm_bf16", pd.desc, ptr(dzp.t), ptr(wt), None, None, None, ptr(dxf), st)
+        dx = dxf if xrs == Cin else dxf[..., :Cin]
+    return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None, None
+
+
+def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, residual=None, up2=False, precision=None):
     """weight is the caller's parameter in its own layout/dtype: (Cout, Cin/g, k) or (Cout, Cin/g, kh, kw)."""
     if weight.dim() == 3:
         weight = weight.unsqueeze(2)        # view: (Cout, Cin/g, 1, k); autograd maps the grad back
-    return _ConvBlock.apply(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2)
+    carrier = _Carrier()
+    y = _ConvBlock.apply(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2,
+                         (precision or _precision), carrier)
+    if carrier.planes is not None:
+        y._ms_planes = carrier.planes
+    return y
+
+
+class _Carrier:
+    """Hands the bf16 operand planes produced inside an autograd node to the tensor object the caller receives."""
+    __slots__ = ("planes",)
+
+    def __init__(self):
+        self.planes = None
 
 
 # ---------------------------------------------------------------------------- bilinear time resize

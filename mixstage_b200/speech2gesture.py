@@ -32,9 +32,14 @@ class Speech2Gesture_D(nn.Module):
                                 groups=groups)
         self._conv1 = PlainConv(self.conv1[0], slope=0.2)
         self._logits = PlainConv(self.logits)
+        self.precision = kwargs.get('precision', None)
 
     def forward(self, x):
         """x: (B, T, P) in the caller's dtype -> (scores (B, L'), [])."""
+        with ops.precision_scope(self.precision):
+            return self._forward(x)
+
+    def _forward(self, x):
         ops._need_cuda(x)
         dtype = x.dtype
         B, T, P = x.shape

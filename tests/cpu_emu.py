@@ -120,17 +120,18 @@ def ms_col_stats_f32(x, rows, C, s, ss, st):
         f64(ss, C).add_((X * X).sum(0))
 
 
-def ms_bn_finalize(s, ss, rows, C, gamma, beta, rm, rv, pdt, training, momentum, eps, scale, shift, mean, rstd, st):
+def ms_bn_finalize(s, ss, rows, C, gamma, beta, cbias, rm, rv, pdt, training, momentum, eps, scale, shift, mean, rstd, st):
     g, b = param(gamma, C, pdt).double(), param(beta, C, pdt).double()
     RM, RV = param(rm, C, pdt), param(rv, C, pdt)
+    cb = param(cbias, C, pdt).double() if cbias else torch.zeros(C, dtype=torch.float64)
     if training:
         m = f64(s, C) / rows
         v = (f64(ss, C) / rows - m * m).clamp_min(0)
         unb = v * (rows / (rows - 1)) if rows > 1 else v
-        RM.copy_(((1 - momentum) * RM.double() + momentum * m).to(RM.dtype))
+        RM.copy_(((1 - momentum) * RM.double() + momentum * (m + cb)).to(RM.dtype))
         RV.copy_(((1 - momentum) * RV.double() + momentum * unb).to(RV.dtype))
     else:
-        m, v = RM.double().clone(), RV.double().clone()
+        m, v = RM.double().clone() - cb, RV.double().clone()
     r = 1.0 / torch.sqrt(v + eps)
     f32(scale, C).copy_((g * r).float())
     f32(shift, C).copy_((b - m * g * r).float())
@@ -142,14 +143,36 @@ def _act(z, slope):
     return torch.where(z > 0, z, z * slope)
 
 
-def ms_bn_act_fwd_f32(x, scale, shift, slope, rows, C, y, res, up2, L, st):
+def _store_planes(planes, pfmt, pstride, v):
+    """v: flat fp32 tensor -> hi plane at planes[0:n], lo plane (MS_BF16X2) at planes[pstride:pstride+n]."""
+    if not planes:
+        return
+    n = v.numel()
+    hi = v.to(torch.bfloat16)
+    if pfmt == 3:
+        buf = bf16(planes, pstride + n)
+        buf[:n].copy_(hi)
+        buf[pstride:pstride + n].copy_((v - hi.float()).to(torch.bfloat16))
+    else:
+        bf16(planes, n).copy_(hi)
+
+
+def ms_bn_act_fwd_f32(x, scale, shift, slope, rows, C, y, res, up2, L, planes, pfmt, pstride, st):
     Z = f32(x, rows * C).view(rows, C) * f32(scale, C) + f32(shift, C)
     A = _act(Z, slope)
     if up2:
         A = A.view(rows // L, L, 1, C).expand(rows // L, L, 2, C).reshape(2 * rows, C)
     if res:
         A = A + f32(res, A.numel()).view(A.shape)
-    f32(y, A.numel()).copy_(A.reshape(-1))
+    if y:
+        f32(y, A.numel()).copy_(A.reshape(-1))
+    _store_planes(planes, pfmt, pstride, A.reshape(-1))
+
+
+def ms_to_planes(x, rows, C, rs, planes, pfmt, pstride, st):
+    X = torch.zeros(rows, rs)
+    X[:, :C] = f32(x, rows * C).view(rows, C)
+    _store_planes(planes, pfmt, pstride, X.reshape(-1))
 
 
 def _dy(dy, rows, C, up2, L):
@@ -168,7 +191,8 @@ def ms_bn_act_bwd_reduce_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up
     f64(dbeta, C).add_(dz.double().sum(0))
 
 
-def ms_bn_act_bwd_apply_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up2, L, dgamma, dbeta, training, dx, st):
+def ms_bn_act_bwd_apply_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up2, L, dgamma, dbeta, training, dx,
+                            planes, pfmt, pstride, st):
     X = f32(x, rows * C).view(rows, C)
     sc = f32(scale, C)
     Z = X * sc + f32(shift, C)
@@ -179,12 +203,17 @@ def ms_bn_act_bwd_apply_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up2
         o = sc * (dz - f64(dbeta, C).float() / rows - xh * f64(dgamma, C).float() / rows)
     else:
         o = sc * dz
-    f32(dx, rows * C).copy_(o.reshape(-1))
+    if dx:
+        f32(dx, rows * C).copy_(o.reshape(-1))
+    _store_planes(planes, pfmt, pstride, o.reshape(-1))
 
 
-def ms_lrelu_bwd_f32(dy, y, slope, n, dz, st):
+def ms_lrelu_bwd_f32(dy, y, slope, n, dz, planes, pfmt, pstride, st):
     D, Y = f32(dy, n), f32(y, n)
-    f32(dz, n).copy_(torch.where(Y > 0, D, D * slope))
+    o = torch.where(Y > 0, D, D * slope)
+    if dz:
+        f32(dz, n).copy_(o)
+    _store_planes(planes, pfmt, pstride, o)
 
 
 def ms_store_param_grad(src, n, dst, pdt, st):
@@ -316,7 +345,7 @@ def bf16(p, n):
 
 
 def ms_pack_igemm_weight_bf16(w, pdt, Cout, Cin_g, taps_total, groups, mode, num_classes, class_n, ntaps, kpad,
-                              srctap, wp, st):
+                              srctap, wp, wp_lo, st):
     Wsrc = param(w, Cout * Cin_g * taps_total, pdt).float().view(Cout, Cin_g, taps_total)
     out = torch.zeros(num_classes * class_n, ntaps, kpad)
     Cout_g = Cout // groups
@@ -331,70 +360,86 @@ def ms_pack_igemm_weight_bf16(w, pdt, Cout, Cin_g, taps_total, groups, mode, num
                 g = q if groups > 1 else 0
                 src = Wsrc[g * Cout_g:(g + 1) * Cout_g, :, srctap[q * ntaps + t]]      # (Cout_g, Cin_g)
                 out[q * class_n:q * class_n + Cin_g, t, :Cout_g] = src.t()
-    bf16(wp, out.numel()).copy_(out.reshape(-1).to(torch.bfloat16))
+    hi = out.reshape(-1).to(torch.bfloat16)
+    bf16(wp, out.numel()).copy_(hi)
+    if wp_lo:
+        bf16(wp_lo, out.numel()).copy_((out.reshape(-1) - hi.float()).to(torch.bfloat16))
+
+
+def _padded_a(a, d, kpad, Ho, Wo, PADH=16, PADW=16):
+    dims, strides = list(d.a_dims), list(d.a_strides)
+    extent = 1 + sum((dims[i] - 1) * strides[i] for i in range(5))
+    A5 = torch.as_strided(bf16(a, extent).float(), [dims[4], dims[3], dims[2], dims[1], dims[0]],
+                          [strides[4], strides[3], strides[2], strides[1], strides[0]])   # (b, h, par, w, c)
+    Ap = torch.zeros(dims[4], dims[3] + 2 * PADH + Ho, dims[2], dims[1] + 2 * PADW + Wo, dims[0] + kpad + 64)
+    Ap[:, PADH:PADH + dims[3], :, PADW:PADW + dims[1], :dims[0]] = A5
+    return Ap
+
+
+def _tap_slice(Ap, d, q, t, kpad, Bo, Ho, Wo, PADH=16, PADW=16):
+    tt = d.taps[(0 if d.shared_taps else q * d.ntaps) + t]
+    c0 = d.a_chan_base[q] + tt[0]
+    hs, ws = PADH + tt[3], PADW + tt[1]
+    bb = min(Bo, d.a_dims[4])
+    sl = torch.zeros(Bo, Ho, Wo, kpad)
+    sl[:bb] = Ap[:bb, hs:hs + Ho, tt[2], ws:ws + Wo, c0:c0 + kpad]
+    return sl
 
 
 def ms_igemm_bf16(desc, a, w, bias, scale, shift, out, st):
     d = _d(desc)
-    dims, strides = list(d.a_dims), list(d.a_strides)
-    extent = 1 + sum((dims[i] - 1) * strides[i] for i in range(5))
-    A = bf16(a, extent).float()
-    A5 = torch.as_strided(A, [dims[4], dims[3], dims[2], dims[1], dims[0]],
-                          [strides[4], strides[3], strides[2], strides[1], strides[0]])   # (b, h, par, w, c)
     Wo, Ho, Bo = d.out_dims
     kpad = d.cchunks * 64
-    Wp = bf16(w, d.num_classes * d.class_n * d.ntaps * kpad).float().view(d.num_classes * d.class_n, d.ntaps, kpad)
+    nw = d.num_classes * d.class_n * d.ntaps * kpad
+    planes = 2 if d.planes == 2 else 1
+    Ap = [_padded_a(a + 2 * d.a_plane_stride * i, d, kpad, Ho, Wo) for i in range(planes)]
+    Wp = [bf16(w + 2 * d.w_plane_stride * i, nw).float().view(d.num_classes * d.class_n, d.ntaps, kpad) for i in range(planes)]
+    passes = [(0, 0), (0, 1), (1, 0)] if planes == 2 else [(0, 0)]
     osw, osh, osb = d.out_strides
     out_extent = 1 + (Wo - 1) * osw + (Ho - 1) * osh + (Bo - 1) * osb + max(d.out_off[q] for q in range(d.num_classes)) + d.class_n - 1
     O = f32(out, out_extent) if d.out_dtype == 0 else bf16(out, out_extent)
-    PADW = PADH = 16
-    Ap = torch.zeros(dims[4], dims[3] + 2 * PADH + Ho, dims[2], dims[1] + 2 * PADW + Wo, dims[0] + kpad + 64)
-    Ap[:, PADH:PADH + dims[3], :, PADW:PADW + dims[1], :dims[0]] = A5
+    Olo = bf16(out + 2 * d.out_plane_stride, out_extent) if d.out_dtype == 3 else None
     for q in range(d.num_classes):
         acc = torch.zeros(Bo, Ho, Wo, d.class_n)
         for t in range(d.ntaps):
-            tt = d.taps[(0 if d.shared_taps else q * d.ntaps) + t]
-            c0 = d.a_chan_base[q] + tt[0]
-            hs, ws = PADH + tt[3], PADW + tt[1]
-            bb = min(Bo, dims[4])
-            sl = torch.zeros(Bo, Ho, Wo, kpad)
-            sl[:bb] = Ap[:bb, hs:hs + Ho, tt[2], ws:ws + Wo, c0:c0 + kpad]
-            acc += sl @ Wp[q * d.class_n:(q + 1) * d.class_n, t].t()
+            for pa, pw in passes:
+                sl = _tap_slice(Ap[pa], d, q, t, kpad, Bo, Ho, Wo)
+                acc += sl @ Wp[pw][q * d.class_n:(q + 1) * d.class_n, t].t()
         cols = slice(q * d.class_n, (q + 1) * d.class_n)
         if d.epilogue == 1:
             acc = acc * f32(scale, d.num_classes * d.class_n)[cols] + f32(shift, d.num_classes * d.class_n)[cols]
             acc = torch.where(acc > 0, acc, acc * d.slope)
-        elif bias:
-            acc = acc + f32(bias, d.num_classes * d.class_n)[cols]
+        else:
+            if bias:
+                acc = acc + f32(bias, d.num_classes * d.class_n)[cols]
+            if d.epilogue == 2:
+                acc = torch.where(acc > 0, acc, acc * d.slope)
         idx = (torch.arange(Bo).view(-1, 1, 1, 1) * osb + torch.arange(Ho).view(1, -1, 1, 1) * osh
                + torch.arange(Wo).view(1, 1, -1, 1) * osw + d.out_off[q] + torch.arange(d.class_n).view(1, 1, 1, -1))
-        O[idx.reshape(-1)] = acc.reshape(-1).to(O.dtype)
+        v = acc.reshape(-1)
+        O[idx.reshape(-1)] = v.to(O.dtype)
+        if Olo is not None:
+            Olo[idx.reshape(-1)] = (v - v.to(torch.bfloat16).float()).to(torch.bfloat16)
 
 
 def ms_wgrad_bf16(desc, x, dz, dwp, st):
     d = _d(desc)
-    dims, strides = list(d.a_dims), list(d.a_strides)
-    extent = 1 + sum((dims[i] - 1) * strides[i] for i in range(5))
-    A5 = torch.as_strided(bf16(x, extent).float(), [dims[4], dims[3], dims[2], dims[1], dims[0]],
-                          [strides[4], strides[3], strides[2], strides[1], strides[0]])
     Wo, Ho, Bo = d.out_dims
     Ct = d.out_strides[0]
-    Z = bf16(dz, Bo * Ho * Wo * Ct).float().view(Bo, Ho, Wo, Ct)
     kpad = d.cchunks * 64
-    PADW = PADH = 16
-    Ap = torch.zeros(dims[4], dims[3] + 2 * PADH + Ho, dims[2], dims[1] + 2 * PADW + Wo, dims[0] + kpad + 64)
-    Ap[:, PADH:PADH + dims[3], :, PADW:PADW + dims[1], :dims[0]] = A5
+    planes = 2 if d.planes == 2 else 1
+    Ap = [_padded_a(x + 2 * d.a_plane_stride * i, d, kpad, Ho, Wo) for i in range(planes)]
+    Z = [bf16(dz + 2 * d.out_plane_stride * i, Bo * Ho * Wo * Ct).float().view(Bo, Ho, Wo, Ct) for i in range(planes)]
+    passes = [(0, 0), (0, 1), (1, 0)] if planes == 2 else [(0, 0)]      # (x plane, dz plane)
     out = f32(dwp, d.num_classes * d.class_n * d.ntaps * kpad).view(d.num_classes * d.class_n, d.ntaps, kpad)
     for q in range(d.num_classes):
-        zq = Z[..., d.out_off[q]:d.out_off[q] + d.class_n].reshape(-1, d.class_n)
         for t in range(d.ntaps):
-            tt = d.taps[(0 if d.shared_taps else q * d.ntaps) + t]
-            c0 = d.a_chan_base[q] + tt[0]
-            hs, ws = PADH + tt[3], PADW + tt[1]
-            bb = min(Bo, dims[4])
-            sl = torch.zeros(Bo, Ho, Wo, kpad)
-            sl[:bb] = Ap[:bb, hs:hs + Ho, tt[2], ws:ws + Wo, c0:c0 + kpad]
-            out[q * d.class_n:(q + 1) * d.class_n, t] = zq.t() @ sl.reshape(-1, kpad)
+            acc = torch.zeros(d.class_n, kpad)
+            for px, pz in passes:
+                zq = Z[pz][..., d.out_off[q]:d.out_off[q] + d.class_n].reshape(-1, d.class_n)
+                sl = _tap_slice(Ap[px], d, q, t, kpad, Bo, Ho, Wo)
+                acc += zq.t() @ sl.reshape(-1, kpad)
+            out[q * d.class_n:(q + 1) * d.class_n, t] = acc
 
 
 def ms_unpack_igemm_wgrad(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, st):

@@ -23,9 +23,19 @@ def build(spec, T, device, dtype=torch.float64):
     return G, D, gan
 
 
-def run_case(name, device, dtype=torch.float64):
+def run_case(name, device, dtype=torch.float64, precision="fp32"):
     """Runs case `name` through the mixstage_b200 classes exactly as the reference's trainer
     would (GAN.forward / G.forward); returns a dict comparable with oracle_cases.run_oracle."""
+    from mixstage_b200 import ops
+    old = ops.get_precision()
+    ops.set_precision(precision)
+    try:
+        return _run_case(name, device, dtype)
+    finally:
+        ops.set_precision(old)
+
+
+def _run_case(name, device, dtype):
     spec, B, T, kind, kw = CASES[name]
     G, D, gan = build(spec, T, device, dtype)
     audio, pose, labels, style = O.synth_inputs(B, T, spec, dtype=dtype)

@@ -40,7 +40,7 @@ def test_fwd_and_dgrad_descriptors_match_conv2d(g):
     plan = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
     wp = torch.zeros(plan.wp_numel, dtype=torch.bfloat16)
     cpu_emu.ms_pack_igemm_weight_bf16(ptr(w), 0, Cout, Cin // groups, kh * kw, groups, 0, plan.desc.num_classes,
-                                      plan.desc.class_n, plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp), None)
+                                      plan.desc.class_n, plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp), None, None)
     out = torch.full((B, Ho, Wo, Cout), float("nan"))
     cpu_emu.ms_igemm_bf16(plan.desc, ptr(x), ptr(wp), ptr(bias), None, None, ptr(out), None)
     assert float((out - ref).abs().max()) < 2e-4 * float(ref.abs().max())
@@ -51,7 +51,7 @@ def test_fwd_and_dgrad_descriptors_match_conv2d(g):
     plan = igemm.make_dgrad(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
     wp = torch.zeros(plan.wp_numel, dtype=torch.bfloat16)
     cpu_emu.ms_pack_igemm_weight_bf16(ptr(w), 0, Cout, Cin // groups, kh * kw, groups, 1, plan.desc.num_classes,
-                                      plan.desc.class_n, plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp), None)
+                                      plan.desc.class_n, plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp), None, None)
     dx = torch.full((B, H, W, Cin), float("nan"))
     cpu_emu.ms_igemm_bf16(plan.desc, ptr(dz), ptr(wp), None, None, None, ptr(dx), None)
     assert float((dx - dref).abs().max()) < 2e-4 * float(dref.abs().max())
@@ -76,7 +76,7 @@ def test_padded_channel_rows_266():
     ref = F.conv2d(x[..., :Cin].float().permute(0, 3, 1, 2), w, None, padding=(0, 1)).permute(0, 2, 3, 1)
     plan = igemm.make_fwd(B, 1, L, Cin, Cout, 1, 3, 1, 1, 0, 1, 1, 1, L, a_row_stride=Cp)
     wp = torch.zeros(plan.wp_numel, dtype=torch.bfloat16)
-    cpu_emu.ms_pack_igemm_weight_bf16(ptr(w), 0, Cout, Cin, 3, 1, 0, 1, Cout, 3, plan.kpad, plan.srctap, ptr(wp), None)
+    cpu_emu.ms_pack_igemm_weight_bf16(ptr(w), 0, Cout, Cin, 3, 1, 0, 1, Cout, 3, plan.kpad, plan.srctap, ptr(wp), None, None)
     out = torch.zeros(B, 1, L, Cout)
     cpu_emu.ms_igemm_bf16(plan.desc, ptr(x), ptr(wp), None, None, None, ptr(out), None)
     assert float((out - ref).abs().max()) < 2e-4 * float(ref.abs().max())
@@ -85,7 +85,7 @@ def test_padded_channel_rows_266():
     plan = igemm.make_dgrad(B, 1, L, Cin, Cout, 1, 3, 1, 1, 0, 1, 1, 1, L, out_row_stride=Cp)
     wp = torch.zeros(plan.wp_numel, dtype=torch.bfloat16)
     cpu_emu.ms_pack_igemm_weight_bf16(ptr(w), 0, Cout, Cin, 3, 1, 1, plan.desc.num_classes, plan.desc.class_n,
-                                      plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp), None)
+                                      plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp), None, None)
     dx = torch.full((B, 1, L, Cp), float("nan"))
     cpu_emu.ms_igemm_bf16(plan.desc, ptr(dz), ptr(wp), None, None, None, ptr(dx), None)
     assert float((dx[..., :Cin] - dref).abs().max()) < 2e-4 * float(dref.abs().max())

@@ -31,7 +31,7 @@ def _gpu_igemm(plan, a, w_src, mode, Cout, Cin_g, taps_total, groups, bias=None,
     wp = torch.zeros(plan.wp_numel, dtype=torch.bfloat16, device="cuda")
     d = plan.desc
     _lib.call("ms_pack_igemm_weight_bf16", ptr(w_src), _lib.dt_code(w_src.dtype), Cout, Cin_g, taps_total, groups, mode,
-              d.num_classes, d.class_n, d.ntaps, plan.kpad, plan.srctap_c, ptr(wp), st)
+              d.num_classes, d.class_n, d.ntaps, plan.kpad, plan.srctap_c, ptr(wp), None, st)
     _lib.call("ms_igemm_bf16", d, ptr(a), ptr(wp), ptr(bias), ptr(scale), ptr(shift), ptr(out), st)
     torch.cuda.synchronize()
     return wp
@@ -53,7 +53,7 @@ def test_igemm_fwd_dgrad(g):
     # weight re-tiling is bit-exact vs the spec
     wp_c = torch.zeros(plan.wp_numel, dtype=torch.bfloat16)
     cpu_emu.ms_pack_igemm_weight_bf16(ptr(w), 1, Cout, Cin // groups, kh * kw, groups, 0, plan.desc.num_classes,
-                                      plan.desc.class_n, plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp_c), None)
+                                      plan.desc.class_n, plan.desc.ntaps, plan.kpad, plan.srctap, ptr(wp_c), None, None)
     assert torch.equal(wp.cpu(), wp_c)
     err = float((out.cpu().double() - ref).abs().max())
     assert err < 1e-3 * float(ref.abs().max()), (err, float(ref.abs().max()))
@@ -88,9 +88,80 @@ def test_wgrad_tc(g):
     plan = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
     st = torch.cuda.current_stream().cuda_stream
     dwp = torch.full((plan.wp_numel,), float("nan"), device="cuda")
-    _lib.call("ms_wgrad_bf16", plan.desc, ptr(x.cuda()), ptr(dz.cuda()), ptr(dwp), st)
+    xg, dzg = x.cuda(), dz.cuda()          # keep the device copies alive across the launch
+    _lib.call("ms_wgrad_bf16", plan.desc, ptr(xg), ptr(dzg), ptr(dwp), st)
     dw = torch.zeros(Cout, Cin // groups, kh, kw, dtype=torch.float64, device="cuda")
     _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 1, st)
     torch.cuda.synchronize()
     err = float((dw.cpu() - wref).abs().max())
     assert err < 1e-3 * float(wref.abs().max()), (err, float(wref.abs().max()))
+
+
+SPLIT = [GEOMS[0], GEOMS[1], GEOMS[3], GEOMS[6], GEOMS[9], BIG[1], BIG[3], BIG[4]]
+
+
+def _planes(t, rs=None):
+    """fp32 (…, C) CUDA tensor -> (hi/lo planes tensor, plane stride) via ms_to_planes."""
+    C = t.shape[-1]
+    rs = rs or C
+    rows = t.numel() // C
+    ps = (rows * rs + 7) // 8 * 8
+    pl = torch.zeros(2 * ps, dtype=torch.bfloat16, device="cuda")
+    _lib.call("ms_to_planes", ptr(t), rows, C, rs, ptr(pl), 3, ps, torch.cuda.current_stream().cuda_stream)
+    return pl, ps
+
+
+@pytest.mark.parametrize("g", SPLIT)
+def test_split_bf16_fwd_dgrad_wgrad(g):
+    """bf16x3: hi/lo operand planes, three MMA passes -> ~fp32 accuracy (error bound 3e-5 of the output scale)."""
+    torch.manual_seed(5)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups = g
+    Ho, Wo = _conv_out(H, kh, sh, ph), _conv_out(W, kw, sw, pw)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(B, H, W, Cin)
+    w = torch.randn(Cout, Cin // groups, kh, kw, dtype=torch.float64) / (Cin // groups * kh * kw) ** 0.5
+    dz = torch.randn(B, Ho, Wo, Cout)
+    xd, wd, dzd = x.double().permute(0, 3, 1, 2), w, dz.double().permute(0, 3, 1, 2)
+    ref = F.conv2d(xd, wd, None, stride=(sh, sw), padding=(ph, pw), groups=groups).permute(0, 2, 3, 1)
+    dref = torch.nn.grad.conv2d_input((B, Cin, H, W), wd, dzd, stride=(sh, sw), padding=(ph, pw), groups=groups).permute(0, 2, 3, 1)
+    wref = torch.nn.grad.conv2d_weight(xd, (Cout, Cin // groups, kh, kw), dzd, stride=(sh, sw), padding=(ph, pw), groups=groups)
+    xg, wg, dzg = x.cuda(), w.cuda(), dz.cuda()
+    xp, xps = _planes(xg)
+    dzp, dzps = _planes(dzg)
+
+    def packed(plan, mode):
+        ps = (plan.wp_numel + 7) // 8 * 8
+        wp = torch.zeros(2 * ps, dtype=torch.bfloat16, device="cuda")
+        d = plan.desc
+        _lib.call("ms_pack_igemm_weight_bf16", ptr(wg), 1, Cout, Cin // groups, kh * kw, groups, mode, d.num_classes, d.class_n,
+                  d.ntaps, plan.kpad, plan.srctap_c, ptr(wp), wp.data_ptr() + 2 * ps, st)
+        return wp, ps
+
+    pf = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
+    pf.desc.block_n = igemm.pick_block_n(pf.desc)
+    wp, wps = packed(pf, 0)
+    igemm.set_planes(pf, True, xps, wps, 0)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda")
+    _lib.call("ms_igemm_bf16", pf.desc, ptr(xp), ptr(wp), None, None, None, ptr(out), st)
+    torch.cuda.synchronize()
+    err = float((out.cpu().double() - ref).abs().max())
+    assert err < 3e-5 * float(ref.abs().max()), (err, float(ref.abs().max()))
+
+    pd = igemm.make_dgrad(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
+    pd.desc.block_n = igemm.pick_block_n(pd.desc)
+    wt, wtps = packed(pd, 1)
+    igemm.set_planes(pd, True, dzps, wtps, 0)
+    dx = torch.full((B, H, W, Cin), float("nan"), device="cuda")
+    _lib.call("ms_igemm_bf16", pd.desc, ptr(dzp), ptr(wt), None, None, None, ptr(dx), st)
+    torch.cuda.synchronize()
+    err = float((dx.cpu().double() - dref).abs().max())
+    assert err < 3e-5 * float(dref.abs().max()), (err, float(dref.abs().max()))
+
+    igemm.set_planes(pf, True, xps, 0, dzps)
+    dwp = torch.full((pf.wp_numel,), float("nan"), device="cuda")
+    _lib.call("ms_wgrad_bf16", pf.desc, ptr(xp), ptr(dzp), ptr(dwp), st)
+    dw = torch.zeros(Cout, Cin // groups, kh, kw, dtype=torch.float64, device="cuda")
+    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, pf.desc.ntaps, pf.kpad, ptr(dw), 1, st)
+    torch.cuda.synchronize()
+    err = float((dw.cpu() - wref).abs().max())
+    assert err < 3e-5 * float(wref.abs().max()), (err, float(wref.abs().max()))

@@ -110,18 +110,46 @@ def test_batchnorm_chain(rows, C, L, up2):
     for pdt, dt in ((0, torch.float32), (1, torch.float64)):
         gamma, beta = torch.rand(C, dtype=dt) + 0.5, torch.randn(C, dtype=dt) * 0.1
         rm, rv = torch.randn(C, dtype=dt) * 0.1, torch.rand(C, dtype=dt) + 0.5
+        cbias = torch.randn(C, dtype=dt) * 0.2
         for training in (1, 0):
-            outs = [(torch.zeros(C), "out") for _ in range(4)]
-            g, c = run_both("ms_bn_finalize", [(sc, "in"), (ssc, "in"), rows, C, (gamma, "in"), (beta, "in"), (rm, "inout"),
-                                               (rv, "inout"), pdt, training, 0.1, 1e-5] + outs)
-            for a, b in zip(g, c):
-                close(a, b, 1e-6)
+            for cb in (None, cbias):
+                outs = [(torch.zeros(C), "out") for _ in range(4)]
+                g, c = run_both("ms_bn_finalize", [(sc, "in"), (ssc, "in"), rows, C, (gamma, "in"), (beta, "in"), (cb, "in"),
+                                                   (rm, "inout"), (rv, "inout"), pdt, training, 0.1, 1e-5] + outs)
+                for a, b in zip(g, c):
+                    close(a, b, 1e-6)
+    outs = [(torch.zeros(C), "out") for _ in range(4)]
+    g, c = run_both("ms_bn_finalize", [(sc, "in"), (ssc, "in"), rows, C, (gamma, "in"), (beta, "in"), (None, "in"),
+                                       (rm, "inout"), (rv, "inout"), 1, 1, 0.1, 1e-5] + outs)
     scale, shift, mean, rstd = c[2], c[3], c[4], c[5]
     res = torch.randn(rows * (2 if up2 else 1), C)
     y = torch.zeros_like(res)
     (yg,), (yc,) = run_both("ms_bn_act_fwd_f32", [(x, "in"), (scale, "in"), (shift, "in"), 0.2, rows, C, (y, "out"),
-                                                  (res if up2 else None, "in"), up2, L])
+                                                  (res if up2 else None, "in"), up2, L, (None, "in"), 0, 0])
     close(yg, yc, 1e-6)
+    # bf16 operand planes as a second output (single plane and hi/lo split): bit-exact vs the specification
+    n = y.numel()
+    ps = (n + 7) // 8 * 8
+    for pfmt in (2, 3):
+        pl = torch.zeros(2 * ps, dtype=torch.bfloat16)
+        (yg2, pg), (yc2, pc) = run_both("ms_bn_act_fwd_f32", [(x, "in"), (scale, "in"), (shift, "in"), 0.2, rows, C, (y, "out"),
+                                                              (res if up2 else None, "in"), up2, L, (pl, "out"), pfmt, ps])
+        hi_g, hi_c = pg[:n].float(), pc[:n].float()
+        assert float((hi_g - yg2.reshape(-1)).abs().max()) <= 2 ** -8 * float(yg2.abs().max())
+        if pfmt == 3:
+            rec = hi_g + pg[ps:ps + n].float()
+            assert float((rec - yg2.reshape(-1)).abs().max()) <= 2 ** -15 * float(yg2.abs().max())
+        close(hi_g, hi_c, 1e-2)
+    if C % 8 == 0:
+        pl = torch.zeros(2 * ps, dtype=torch.bfloat16)
+        (pg,), (pc,) = run_both("ms_to_planes", [(res, "in"), res.shape[0], C, C, (pl, "out"), 3, ps])
+        assert torch.equal(pg, pc)
+        rs = C + 8
+        ps2 = res.shape[0] * rs
+        pl = torch.full((2 * ps2,), 7.0, dtype=torch.bfloat16)
+        (pg,), (pc,) = run_both("ms_to_planes", [(res, "in"), res.shape[0], C, rs, (pl, "out"), 3, ps2])
+        assert torch.equal(pg, pc)
+        assert float(pg[:ps2].view(-1, rs)[:, C:].abs().max()) == 0.0
     dy = torch.randn_like(res)
     z2 = [(torch.zeros(C, dtype=torch.float64), "inout") for _ in range(2)]
     (dgg, dbg), (dgc, dbc) = run_both("ms_bn_act_bwd_reduce_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
@@ -131,8 +159,15 @@ def test_batchnorm_chain(rows, C, L, up2):
     for training in (1, 0):
         (dxg,), (dxc,) = run_both("ms_bn_act_bwd_apply_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
                                                                 (rstd, "in"), 0.2, rows, C, up2, L, (dgc, "in"), (dbc, "in"),
-                                                                training, (torch.zeros(rows, C), "out")])
+                                                                training, (torch.zeros(rows, C), "out"), (None, "in"), 0, 0])
         close(dxg, dxc, 1e-5)
+        psd = (rows * C + 7) // 8 * 8
+        (dxg2, pg), (dxc2, pc) = run_both("ms_bn_act_bwd_apply_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
+                                                                       (rstd, "in"), 0.2, rows, C, up2, L, (dgc, "in"), (dbc, "in"),
+                                                                       training, (torch.zeros(rows, C), "out"),
+                                                                       (torch.zeros(2 * psd, dtype=torch.bfloat16), "out"), 3, psd])
+        rec = pg[:rows * C].float() + pg[psd:psd + rows * C].float()
+        assert float((rec - dxg2.reshape(-1)).abs().max()) <= 2 ** -15 * float(dxg2.abs().max()) + 1e-30
 
 
 def test_small_ops():

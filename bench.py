@@ -183,42 +183,30 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    ops.set_precision(args.precision)
 
     B, S = args.batch, 4
     spec = O.Spec(num_speakers=S)
     G, D, gan = build_model(spec, T, dev, torch.float64)
     gan.train()
     G.thresh.value, G.thresh.iters = 1.0, 1000            # past the curriculum: audio branch
-    fg, fd = parallel.FlatGrads(G), parallel.FlatGrads(D)
-    optG = torch.optim.Adam(G.parameters(), lr=1e-4)
-    optD = torch.optim.Adam(D.parameters(), lr=1e-4)
     parallel.sync_host_rng(11212)
+    # the repo's public train-step API: zero_grad + GAN.forward + backward + (all-reduce) + clip + Adam,
+    # replayed from CUDA graphs (mixstage_b200/train_step.py)
+    ts = M.TrainStep(gan, lr=1e-4, max_norm=1.0, use_graphs=not args.no_graphs)
 
     # per-rank synthetic shard (weak scaling: B sequences per GPU), pinned host copies for the e2e leg
     audio, pose, labels, style = O.synth_inputs(B, T, spec, seed=11212 + rank)
-    host = [t.pin_memory() for t in (audio, pose, labels, style)]
+    host = [t.pin_memory() for t in (audio, labels, pose, style)]
     resident = [t.to(dev) for t in host]
     h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = 5 * 8
 
     def step(i, batch, read_loss):
         kind = "G" if i % 2 == 0 else "D"
-        fg.zero()
-        fd.zero()
-        gan.force_step = kind
-        a, y, lab, sty = batch
-        fake, losses, _ = gan([a, lab], y, input_modalities=MOD, style=sty, sample_flag=0, description="train", desc="train")
-        loss = sum(losses)
-        loss.backward()
-        if kind == "G":
-            fg.allreduce_mean()
-            torch.nn.utils.clip_grad_norm_(G.parameters(), 1)
-            optG.step()
-        else:
-            fd.allreduce_mean()
-            torch.nn.utils.clip_grad_norm_(D.parameters(), 1)
-            optD.step()
+        fake, losses = ts.step(*batch, kind=kind)           # batch: host (pinned) or device tensors -> static buffers
         if read_loss:
-            return loss.item()              # D2H read of the step's result
+            return losses.cpu()             # D2H read of the step's five losses (synchronises)
         return None
 
     def barrier():
@@ -232,11 +220,7 @@ def run_cuda(args):
         t0 = time.perf_counter()
         e0.record()
         for i in range(nsteps):
-            if e2e:
-                batch = [t.to(dev, non_blocking=True) for t in host]
-                step(i, batch, True)
-            else:
-                step(i, resident, False)
+            step(i, host if e2e else resident, e2e)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -248,14 +232,14 @@ def run_cuda(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 4)):
         step(i, resident, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.LAUNCHES
+    l0 = _lib.LAUNCHES + ts.launched
     ms = timed(args.steps, False)
-    launches = _lib.LAUNCHES - l0
+    launches = _lib.LAUNCHES + ts.launched - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(args.steps, True)
 
@@ -265,25 +249,35 @@ def run_cuda(args):
     orig_call = ops.call
 
     def timed_call(name, *a):
-        if name.startswith("ms_conv_"):
+        if name.startswith("ms_conv_") or name in ("ms_igemm_bf16", "ms_wgrad_bf16"):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             orig_call(name, *a)
             e1.record()
-            desc = [x for x in a if isinstance(x, _lib.ConvDesc)][0]
-            records.append((name, conv_flops(name, desc), e0, e1))
+            if name.startswith("ms_conv_"):
+                desc = [x for x in a if isinstance(x, _lib.ConvDesc)][0]
+                fl = conv_flops(name, desc)
+            else:
+                fl = ops.last_gemm_flops
+            records.append((name, fl, e0, e1))
         else:
             orig_call(name, *a)
 
     ops.call = timed_call
+    graphs_on = ts.use_graphs
+    ts.use_graphs = False                    # the instrumented pair runs the same body eagerly
     try:
         step(0, resident, False)
         step(1, resident, False)
     finally:
         ops.call = orig_call
+        ts.use_graphs = graphs_on
     torch.cuda.synchronize()
-    conv_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in records)
-    conv_fl = sum(f for _, f, _, _ in records)
+    tc = [r for r in records if not r[0].startswith("ms_conv_")]
+    dom = tc if tc else records                         # dominant kernel family: the tcgen05 implicit GEMMs when in use
+    conv_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in dom)
+    conv_fl = sum(f for _, f, _, _ in dom)
+    all_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in records)
     pk, pk_kind = peaks()
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     achieved_tf = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -295,18 +289,24 @@ def run_cuda(args):
         line = {
             "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 operands, f32 accumulate)",
+                                           "bf16": "bf16 (f32 accumulate)"}[args.precision], "data": "synthetic",
             "config": {"workload": "configs[1]: GAN train step (G on even, D on odd iterations), B=%d per GPU, T=64, "
-                                   "S=4, K=8, gan=1, L1Loss, fp64 master params/inputs, fp32 CUDA arithmetic" % B,
+                                   "S=4, K=8, gan=1, L1Loss, fp64 master params/inputs, precision=%s, %s" % (
+                                       B, args.precision, "CUDA-graph replay" if ts.use_graphs else "eager launches"),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "no explicit flush: per-step working set (fp64 params + packed fp32 weights + grads + "
                              "Adam state ~0.9 GB) exceeds the 126 MB L2"},
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "mixstage_b200.TrainStep.step(pinned host batch) + losses.cpu()"},
             "gpu_launches": launches,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,
-                         "kernel": "conv_gemm_simt (fwd+dgrad+wgrad, %d launches per G+D step pair, fp32 CUDA cores)" % len(records),
+                         "kernel": ("igemm_tc_kernel + wgrad_tc_kernel (tcgen05 implicit GEMM: fwd+dgrad+wgrad, %d launches "
+                                    "per G+D step pair; algorithmic FLOPs, split-bf16 issues 3x the MMAs)" % len(dom)) if tc else
+                                   "conv_gemm_simt (fwd+dgrad+wgrad, %d launches per G+D step pair, fp32 CUDA cores)" % len(dom),
+                         "gemm_ms_per_step_pair": conv_ms, "all_conv_ms_per_step_pair": all_ms,
                          "peak_source": "%s bf16 sustained" % pk_kind},
             "cpu_baseline": {"value": cpu_steps * B / cpu_dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": "%d train steps (G/D alternating) B=%d after 1 warm-up, oracle port, torch CPU fp64" % (cpu_steps, B)},
@@ -323,6 +323,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--batch", type=int, default=16, help="sequences per GPU")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

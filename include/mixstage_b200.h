@@ -220,6 +220,17 @@ int ms_l1_bwd_f32(const float* sgn, const float* g, int64_t n, float* da, void* 
 /* out[0] = (float)(scale * in[0]) : turns a double accumulator into a loss scalar. */
 int ms_scalar_finish(const double* in, double scale, float* out, void* stream);
 
+/* ---- fused clip_grad_norm_(params, max_norm) + Adam.step() over flat buffers (trainer.py:1138-1146, :262-287).
+ * All parameters of one sub-network live in ONE contiguous buffer of dtype dt (MS_F32 / MS_F64), likewise
+ * gradients and the two Adam moments. */
+/* acc[0] = sum g[i]^2 (zeroed internally); step (nullable, device int64) is incremented by one. */
+int ms_grad_sqnorm(const void* g, int dt, int64_t n, double* acc, int64_t* step, void* stream);
+/* coef = min(1, max_norm / (sqrt(sqnorm[0]) + 1e-6)) (max_norm <= 0: no clipping); t = step[0] (already advanced);
+ * m = b1 m + (1-b1) g c; v = b2 v + (1-b2) (g c)^2; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps). */
+int ms_clip_adam(void* p, const void* g, void* m, void* v, int dt, int64_t n, const double* sqnorm, const int64_t* step,
+                 double lr, double beta1, double beta2, double eps, double max_norm, const double* lr_dev, void* stream);
+/* lr_dev (nullable, device double): overrides lr, so a captured CUDA graph follows a learning-rate schedule. */
+
 #ifdef __cplusplus
 }
 #endif

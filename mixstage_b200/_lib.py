@@ -78,6 +78,8 @@ PROTOTYPES = {
     "ms_l1_fwd_f32": [_P, _P, _F, _L, _P, _P, _P],
     "ms_l1_bwd_f32": [_P, _P, _L, _P, _P],
     "ms_scalar_finish": [_P, _D, _P, _P],
+    "ms_grad_sqnorm": [_P, _I, _L, _P, _P, _P],
+    "ms_clip_adam": [_P, _P, _P, _P, _I, _L, _P, _P, _D, _D, _D, _D, _D, _P, _P],
 }
 
 _LIB = None

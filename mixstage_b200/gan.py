@@ -46,7 +46,7 @@ class GAN(nn.Module):
         return ops.cast(ops.velocity(ops.cast(x, torch.float32).contiguous()), x.dtype)
 
     def estimate_weights(self, x_audio, y_pose, **kwargs):
-        return torch.ones(y_pose.shape[0]).to(y_pose.device), None
+        return torch.ones(y_pose.shape[0], device=y_pose.device), None
 
     @staticmethod
     def _l1(a, b=None, const=0.0, dtype=None):
@@ -68,8 +68,10 @@ class GAN(nn.Module):
             kwargs['input_modalities'] = self.input_modalities
         if self.training:
             self.lambda_D, self.lambda_gan = self.lambda_scheduler.step()
-            coin = torch.rand(1).item()
-            d_step = coin < self.D_prob if self.force_step is None else self.force_step == 'D'
+            if self.force_step is None:
+                d_step = torch.rand(1).item() < self.D_prob          # gan.py:105
+            else:
+                d_step = self.force_step == 'D'                      # the caller (tests, TrainStep) drew the coin
             if d_step:
                 self.G.eval()
                 with torch.no_grad():

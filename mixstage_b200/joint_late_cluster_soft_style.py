@@ -122,8 +122,14 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         out_dtype = y.dtype
         B = y.shape[0]
 
-        # curriculum coin flip: same RNG consumption as the reference (jlcss.py:127)
-        if torch.rand(1).item() > self.thresh.step(self.training) and self.training:
+        # curriculum coin flip: same RNG consumption as the reference (jlcss.py:127).  TrainStep draws it itself
+        # (the branch is baked into a captured CUDA graph) and passes the outcome through force_branch.
+        fb = getattr(self, 'force_branch', None)
+        if fb is not None:
+            use_pose = fb == 'pose'
+        else:
+            use_pose = torch.rand(1).item() > self.thresh.step(self.training) and self.training
+        if use_pose:
             T = y.shape[1]
             h = self.pose_encoder(self._as_f32_cl(y, B, T).view(B, 1, T, y.shape[2]), time_steps)
         else:

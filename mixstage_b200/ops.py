@@ -21,6 +21,8 @@ LEAKY_SLOPE = 0.2
 PRECISIONS = ("fp32", "bf16x3", "bf16")
 _precision = "fp32"
 FORCE_REPACK = False        # set while a CUDA graph is being captured: weights change without a version bump
+_weight_epoch = 0            # bumped when parameters change without a torch version bump (graph replays)
+last_gemm_flops = 0.0       # algorithmic FLOPs (2*MAC, unpadded) of the GEMM launch that follows; read by bench.py
 
 
 def set_precision(p):
@@ -32,6 +34,12 @@ def set_precision(p):
 
 def get_precision():
     return _precision
+
+
+def bump_weight_epoch():
+    """Invalidate every packed-weight cache: parameters were updated by a replayed CUDA graph."""
+    global _weight_epoch
+    _weight_epoch += 1
 
 
 class precision_scope:
@@ -154,7 +162,7 @@ class PackedWeight:
         self.bias_key = None
 
     def get(self, weight, desc):
-        key = (weight.data_ptr(), weight._version, weight.dtype, weight.device)
+        key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype, weight.device)
         if key != self.key or FORCE_REPACK:
             w = weight.detach()
             if not w.is_contiguous():
@@ -188,7 +196,8 @@ class PackedWeight:
     def get_tc(self, weight, plan, fmt, groups):
         """Packed weight planes for `plan` (forward or dgrad tiling).  Returns (tensor, plane stride)."""
         slot = "_tcw%d" % plan.mode
-        key = (weight.data_ptr(), weight._version, weight.dtype, weight.device, fmt, plan.wp_numel, tuple(plan.srctap))
+        key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype, weight.device, fmt, plan.wp_numel,
+               tuple(plan.srctap))
         cur = getattr(self, slot, None)
         if cur is not None and cur[0] == key and not FORCE_REPACK:
             return cur[1], cur[2]
@@ -212,7 +221,7 @@ class PackedWeight:
     def get_bias(self, bias):
         if bias is None:
             return None
-        key = (bias.data_ptr(), bias._version, bias.dtype, bias.device)
+        key = (bias.data_ptr(), bias._version, _weight_epoch, bias.dtype, bias.device)
         if key != self.bias_key or FORCE_REPACK:
             self.bias = cast_raw(bias.detach(), torch.float32)
             self.bias_key = key
@@ -388,6 +397,8 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     fuse_act = (not cfg.has_bn) and cfg.act
     d.epilogue, d.slope = (2 if fuse_act else 0), cfg.slope
     b32 = None if cfg.has_bn else packed.get_bias(bias)
+    global last_gemm_flops
+    last_gemm_flops = ctx.flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
     call("ms_igemm_bf16", d, ptr(xp.t), ptr(wp), ptr(b32), None, None, ptr(z), st)
     ctx.tc, ctx.fmt = True, fmt
     ctx.cfg, ctx.desc, ctx.training, ctx.up2 = cfg, desc, training, up2
@@ -483,6 +494,8 @@ def _tc_backward(ctx, dy):
     xrs, xps = ctx.xp_meta
     B, H, W, Cin = ctx.x_shape
     Cin_g = Cin // cfg.groups
+    global last_gemm_flops
+    last_gemm_flops = ctx.flops
     if need_w:
         igemm.set_planes(pf, split, xps, 0, dzp.ps)
         dwp = torch.empty(pf.wp_numel, dtype=torch.float32, device=dev)

@@ -1,0 +1,218 @@
+"""The hot loop body of the reference's trainer as ONE call, replayed from CUDA graphs.
+
+Reference: `TrainerLateClusterStyleGAN` runs, per batch (src/model/trainer.py:590-675),
+    zero_grad (:1104-1107) -> forward_pass = GAN.forward (:1158-1165, gan.py:86-164) -> calculate_loss = sum of the five
+    internal losses (:1268-1285) -> optimize: backward, clip_grad_norm_(params, 1), G_optim.step() or D_optim.step()
+    (:1138-1146; Adam lr 1e-4, :262-287).
+`TrainStep.step(audio, labels, pose, style)` is that body.  At batch 16 the step is ~600 dependent microsecond-scale
+kernels, so the host (Python, autograd bookkeeping, launches) -- not the GPU -- bounds the eager version.  Here the whole
+body (packing of the updated weights, forward, backward, gradient all-reduce when data-parallel, fused clip + Adam over
+flat buffers) is captured once per (step kind, curriculum branch) into a CUDA graph and replayed; the host only copies the
+batch into static buffers, draws the same two coin flips the reference draws (gan.py:105, jlcss.py:127) and launches one
+graph.
+
+Parameters of G and of D are re-homed into one flat buffer each (the nn.Parameter objects become views, `state_dict` is
+unchanged), with flat gradient / Adam-moment buffers beside them: the optimiser is two kernels (csrc/optimizer.cu) and the
+data-parallel exchange one all-reduce per sub-network with no pack/unpack copies.  Gradients of parameters a step does not
+touch stay zero, which reproduces the reference's torch-1.5 `zero_grad()` (zero-fill, not None) + Adam behaviour.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import MixStageError, call, dt_code, ptr, stream
+
+ALIGN = 4       # parameter offsets in elements: 16-byte aligned for fp32, 32-byte for fp64
+
+
+class FlatState:
+    """Flat parameter / gradient / Adam-moment buffers of one sub-network."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("module has no trainable parameters")
+        p0 = self.params[0]
+        self.dtype, self.device = p0.dtype, p0.device
+        if self.dtype not in (torch.float32, torch.float64):
+            raise MixStageError("TrainStep supports fp32 / fp64 master parameters")
+        off, self.offsets = 0, []
+        for p in self.params:
+            if p.dtype != self.dtype or p.device != self.device:
+                raise ValueError("all parameters must share dtype/device")
+            self.offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        mk = lambda: torch.zeros(self.numel, dtype=self.dtype, device=self.device)       # noqa: E731
+        self.p, self.g, self.m, self.v = mk(), mk(), mk(), mk()
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            self.p[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.p[o:o + n].view(p.shape)
+            p.grad = self.g[o:o + n].view(p.shape)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.sqnorm = torch.zeros(1, dtype=torch.float64, device=self.device)
+
+    def zero_grad(self):
+        self.g.zero_()
+        for p, o in zip(self.params, self.offsets):      # re-attach if someone dropped .grad (zero_grad(set_to_none))
+            if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + o * self.g.element_size():
+                p.grad = self.g[o:o + p.numel()].view(p.shape)
+
+    def allreduce_mean(self, group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        ws = dist.get_world_size(group)
+        if ws == 1:
+            return
+        self.g.div_(ws)
+        dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=group)
+
+    def clip_adam(self, lr, lr_dev, betas, eps, max_norm):
+        st = stream()
+        dt = dt_code(self.dtype)
+        call("ms_grad_sqnorm", ptr(self.g), dt, self.numel, ptr(self.sqnorm), ptr(self.step_count), st)
+        call("ms_clip_adam", ptr(self.p), ptr(self.g), ptr(self.m), ptr(self.v), dt, self.numel, ptr(self.sqnorm),
+             ptr(self.step_count), float(lr), float(betas[0]), float(betas[1]), float(eps), float(max_norm), ptr(lr_dev), st)
+
+
+class TrainStep:
+    """gan: mixstage_b200.GAN already on its device/dtype (`.to(device).double()` as the reference's trainer does,
+    trainer.py:138).  Do not call `.to()/.double()` on the model afterwards: parameters are views of flat buffers."""
+
+    def __init__(self, gan, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, use_graphs=True, group=None,
+                 input_modalities=("audio/log_mel_400",), description="train"):
+        self.gan, self.G, self.D = gan, gan.G, gan.D
+        self.fG, self.fD = FlatState(self.G), FlatState(self.D)
+        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        dev = self.fG.device
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float64, device=dev)
+        self.use_graphs = bool(use_graphs) and dev.type == "cuda"
+        self.group = group
+        self.mod = list(input_modalities)
+        self.description = description
+        self.graphs = {}
+        self.kernels_per_graph = {}
+        self.launched = 0            # C-ABI kernel launches executed through graph replays
+        self.static = None
+        self.losses = None
+        self.fake = None
+        self.last_kind = None
+        self.replays = 0
+        self.warmup_iters = 2
+
+    # ------------------------------------------------------------------ host-side decisions
+    def set_lr(self, lr):
+        """ExponentialLR etc. (trainer.py:311-313): the captured graphs read the rate from device memory."""
+        self.lr = lr
+        self.lr_dev.fill_(float(lr))
+
+    def _decide(self, kind):
+        """Same draws, in the same order, as the reference: D/G coin (gan.py:105), then the curriculum draw inside
+        G.forward (jlcss.py:127; consumed in eval mode too)."""
+        gan, G = self.gan, self.G
+        coin = torch.rand(1).item()
+        if kind is None:
+            kind = "D" if coin < gan.D_prob else "G"
+        u = torch.rand(1).item()
+        if kind == "G":
+            use_pose = u > G.thresh.step(True)
+        else:
+            G.thresh.step(False)
+            use_pose = False
+        return kind, bool(use_pose)
+
+    # ------------------------------------------------------------------ the step body (eager, and what gets captured)
+    def _body(self, kind, use_pose, audio, labels, pose, style):
+        gan, G = self.gan, self.G
+        self.fG.zero_grad()
+        self.fD.zero_grad()
+        gan.force_step = kind
+        G.force_branch = "pose" if use_pose else "audio"
+        try:
+            fake, losses, _ = gan([audio, labels], pose, input_modalities=self.mod, style=style, sample_flag=0,
+                                  description=self.description, desc=self.description)
+        finally:
+            G.force_branch = None
+        loss = sum(losses)
+        loss.backward()
+        f = self.fG if kind == "G" else self.fD
+        f.allreduce_mean(self.group)
+        f.clip_adam(self.lr, self.lr_dev, self.betas, self.eps, self.max_norm)
+        return fake.detach(), torch.stack([l.detach().to(fake.dtype) for l in losses])
+
+    def _capture(self, key, batch):
+        kind, use_pose = key
+        dev = self.fG.device
+        if self.static is None:
+            self.static = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in batch]
+        for s, t in zip(self.static, batch):
+            s.copy_(t, non_blocking=True)
+        # eager warm-up on a side stream (allocator + lazy kernel attributes), with parameters / moments / BN buffers
+        # restored afterwards so that capture does not advance the training state
+        snap = self._snapshot()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup_iters):
+                self._body(kind, use_pose, *self.static)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        ops.FORCE_REPACK = True
+        l0 = _lib.LAUNCHES
+        try:
+            with torch.cuda.graph(g):
+                fake, losses = self._body(kind, use_pose, *self.static)
+        finally:
+            ops.FORCE_REPACK = False
+        self.kernels_per_graph[key] = _lib.LAUNCHES - l0      # C-ABI launches recorded in this graph
+        torch.cuda.synchronize(dev)
+        self._restore(snap)
+        self.graphs[key] = (g, fake, losses)
+
+    def _snapshot(self):
+        bufs = [b for m in (self.G, self.D) for b in m.buffers()]
+        st = [self.fG, self.fD]
+        return ([b.clone() for b in bufs], bufs,
+                [(f.p.clone(), f.m.clone(), f.v.clone(), f.step_count.clone()) for f in st], st)
+
+    def _restore(self, snap):
+        saved, bufs, fs, st = snap
+        for b, s in zip(bufs, saved):
+            b.copy_(s)
+        for f, (p, m, v, c) in zip(st, fs):
+            f.p.copy_(p)
+            f.m.copy_(m)
+            f.v.copy_(v)
+            f.step_count.copy_(c)
+        ops.bump_weight_epoch()
+
+    def step(self, audio, labels, pose, style, kind=None):
+        """One training iteration.  Returns (fake_pose, losses (5,)) as device tensors that stay valid until the next
+        call: [pose L1, G_gan, cluster CE, id_in, id_out] for a G-step, [real_D, fake_D, ...] for a D-step (gan.py)."""
+        kind, use_pose = self._decide(kind)
+        self.last_kind = kind
+        self.gan.train()
+        batch = (audio, labels, pose, style)
+        if not self.use_graphs:
+            dev = self.fG.device
+            batch = [t.to(dev, non_blocking=True) for t in batch]
+            self.fake, self.losses = self._body(kind, use_pose, *batch)
+            ops.bump_weight_epoch()
+            return self.fake, self.losses
+        key = (kind, use_pose)
+        if key not in self.graphs:
+            self._capture(key, batch)
+        for s, t in zip(self.static, batch):
+            if s.shape != t.shape or s.dtype != t.dtype:
+                raise MixStageError("TrainStep: batch shape/dtype changed (%s vs %s); build a new TrainStep" % (tuple(t.shape), tuple(s.shape)))
+            s.copy_(t, non_blocking=True)
+        g, self.fake, self.losses = self.graphs[key]
+        g.replay()
+        self.replays += 1
+        self.launched += self.kernels_per_graph[key]
+        ops.bump_weight_epoch()
+        return self.fake, self.losses

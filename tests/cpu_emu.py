@@ -447,6 +447,29 @@ def ms_unpack_igemm_wgrad(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, st
     param(dw, G.numel(), pdt).copy_(G)
 
 
+def ms_grad_sqnorm(g, dt, n, acc, step, st):
+    G = param(g, n, dt).double()
+    f64(acc, 1).copy_((G * G).sum().reshape(1))
+    if step:
+        i64(step, 1).add_(1)
+
+
+def ms_clip_adam(p, g, m, v, dt, n, sqnorm, step, lr, b1, b2, eps, max_norm, lr_dev, st):
+    if lr_dev:
+        lr = float(f64(lr_dev, 1)[0])
+    P, G, M, V = (param(t, n, dt) for t in (p, g, m, v))
+    total = float(f64(sqnorm, 1)[0]) ** 0.5
+    coef = min(1.0, max_norm / (total + 1e-6)) if max_norm > 0 else 1.0
+    t = int(i64(step, 1)[0])
+    gd = G.double() * coef
+    md = b1 * M.double() + (1 - b1) * gd
+    vd = b2 * V.double() + (1 - b2) * gd * gd
+    denom = vd.sqrt() / (1 - b2 ** t) ** 0.5 + eps
+    M.copy_(md.to(M.dtype))
+    V.copy_(vd.to(V.dtype))
+    P.copy_((P.double() - lr / (1 - b1 ** t) * md / denom).to(P.dtype))
+
+
 def install(monkeypatch):
     """Route mixstage_b200's kernel calls to the CPU specification (tests only)."""
     from mixstage_b200 import _lib, ops, speech2gesture, joint_late_cluster_soft_style as j

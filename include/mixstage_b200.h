@@ -58,8 +58,10 @@ int ms_device_is_sm100(void);
 /* w (Cout, Cin/g, kh, kw) in dtype pdt -> wf[g][tap][c][n] (forward / wgrad layout) and
  * wt[g][tap][n][c] (dgrad layout), both fp32.  Either output may be NULL. */
 int ms_pack_conv_weight_f32(const void* w, int pdt, const ms_conv_desc* d, float* wf, float* wt, void* stream);
-/* dwf[g][tap][c][n] fp32 -> dw (Cout, Cin/g, kh, kw) in dtype pdt (overwrites). */
-int ms_unpack_conv_wgrad(const float* dwf, const ms_conv_desc* d, void* dw, int pdt, void* stream);
+/* dwf[g][tap][c][n] fp32 -> dw (Cout, Cin/g, kh, kw) in dtype pdt. */
+int ms_unpack_conv_wgrad(const float* dwf, const ms_conv_desc* d, void* dw, int pdt, int accumulate, void* stream);
+/* accumulate != 0 (here and below): dw += ... instead of dw = ..., so a train step can write parameter gradients
+ * straight into its flat, pre-zeroed gradient buffer (no per-tensor accumulation kernels afterwards). */
 /* dst[i] = (T_dst) src[i]; dtypes MS_F32/MS_F64/MS_BF16. */
 int ms_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream);
 
@@ -109,6 +111,14 @@ typedef struct ms_igemm_desc {
    * lo plane sits at dz + out_plane_stride. */
   int32_t planes;
   int64_t a_plane_stride, w_plane_stride, out_plane_stride;
+  /* Split-K for launches whose tile count cannot fill the 148 SMs (batch-16 layers, K up to 6144).
+   * ms_igemm_bf16: split_k > 1 slices the k-steps of every tile over gridDim.z; partial tiles are combined with fp32
+   *   vector reductions into `out`, which is zero-filled first (out_numel fp32 elements; MS_F32 output, epilogue 0 only).
+   * ms_wgrad_bf16: split_k slices the pixel rows; slice s writes its partial dWp at dwp + s * wp_numel (the caller
+   *   allocates split_k partials; ms_unpack_igemm_wgrad sums them).  0/1 = no split. */
+  int32_t split_k;
+  int64_t out_numel;
+  int32_t wgrad_c_tile;     /* ms_wgrad_bf16: input-channel columns per CTA tile (64/128/192/256; 0 = 256) */
 } ms_igemm_desc;
 int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
                   const float* shift, void* out, void* stream);
@@ -125,11 +135,11 @@ int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int t
 /* Weight gradient on tcgen05 (aten::convolution_backward, weight grad): with d the FORWARD descriptor,
  *   dwp[q*class_n + n][t][c] = sum_{b,h,w} dz[b,h,w, off[q] + n] * A5[base[q] + taps[t].chan + c, w + dw, par, h + dh, b]
  * x and dz are bf16 (dz has the forward output's shape), dwp is fp32 [classes*class_n][ntaps][cchunks*64]
- * (overwritten; split-K partials are reduced with fp32 atomics).  Both operands are MN-major UMMA operands. */
+ * per split-K slice (see split_k above; every partial is fully overwritten).  Both operands are MN-major UMMA operands. */
 int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* dz, float* dwp, void* stream);
-/* dwp (forward tiling, one source tap per tap) -> dw (Cout, Cin/g, taps) in dtype pdt. */
+/* sum of the nsplit partial dwp (forward tiling, one source tap per tap) -> dw (Cout, Cin/g, taps) in dtype pdt. */
 int ms_unpack_igemm_wgrad(const float* dwp, int Cout, int Cin_g, int taps_total, int ntaps, int kpad, void* dw, int pdt,
-                          void* stream);
+                          int nsplit, int accumulate, void* stream);
 
 /* ---- BatchNorm (+LeakyReLU) pieces, nn.BatchNorm1d/2d at layers.py:64,70 and
  * nn.LeakyReLU(0.2) at layers.py:72-73, applied as in ConvNormRelu.forward (:78) ------ */
@@ -146,6 +156,13 @@ int ms_bn_finalize(const double* sum, const double* sumsq, int64_t rows, int C,
                    const void* gamma, const void* beta, const void* conv_bias, void* running_mean, void* running_var, int pdt,
                    int training, float momentum, float eps,
                    float* scale, float* shift, float* mean, float* rstd, void* stream);
+/* Training-mode statistics and finalize in ONE launch: column sums as ms_col_stats_f32 (sum/sumsq/ticket zeroed by
+ * the caller; ticket = 4 bytes), then the block that finishes last runs the training branch of ms_bn_finalize for every
+ * channel and adds 1 to num_batches_tracked (nullable, device int64). */
+int ms_bn_stats_finalize(const float* x, int64_t rows, int C, double* sum, double* sumsq, void* ticket,
+                         const void* gamma, const void* beta, const void* conv_bias, void* running_mean, void* running_var,
+                         int64_t* num_batches_tracked, int pdt, float momentum, float eps,
+                         float* scale, float* shift, float* mean, float* rstd, void* stream);
 /* y = act(x*scale[c] + shift[c]) over rows x C; act LeakyReLU(slope) when slope != 1.
  * up2 != 0 fuses UNet1D's `upconv(x) + residual` (layers.py:151): y has 2*L rows per
  * sequence, y[b,2l+r,:] = act(..)[b,l,:] + res[b,2l+r,:]  (L = rows_per_seq). */
@@ -167,13 +184,15 @@ int ms_bn_act_bwd_reduce_f32(const float* dy, const float* x, const float* scale
 int ms_bn_act_bwd_apply_f32(const float* dy, const float* x, const float* scale, const float* shift,
                             const float* mean, const float* rstd, float slope, int64_t rows, int C,
                             int up2, int rows_per_seq, const double* dgamma, const double* dbeta,
-                            int training, float* dx, void* planes, int pfmt, int64_t pstride, void* stream);
+                            int training, float* dx, void* planes, int pfmt, int64_t pstride,
+                            void* grad_gamma, void* grad_beta, int gdt, void* stream);
+/* grad_gamma / grad_beta (nullable, dtype gdt): the affine parameters' gradient buffers, += dgamma / dbeta. */
 /* dz = dy * (y > 0 ? 1 : slope) for a plain conv + LeakyReLU (speech2gesture.py:76-77); y is the
  * activation output. */
 int ms_lrelu_bwd_f32(const float* dy, const float* y, float slope, int64_t n, float* dz, void* planes, int pfmt,
                      int64_t pstride, void* stream);
 /* out[i] (dtype pdt) = (T) in[i] for small per-channel vectors (dgamma/dbeta/dbias). */
-int ms_store_param_grad(const double* src, int n, void* dst, int pdt, void* stream);
+int ms_store_param_grad(const double* src, int n, void* dst, int pdt, int accumulate, void* stream);
 
 /* ---- resize / glue ---------------------------------------------------------------- */
 /* torch.nn.functional.interpolate(x, size=(T,1), mode='bilinear') + squeeze (layers.py:197-198):

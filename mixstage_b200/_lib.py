@@ -33,6 +33,7 @@ class IgemmDesc(ctypes.Structure):
         ("out_dtype", ctypes.c_int32), ("epilogue", ctypes.c_int32), ("slope", ctypes.c_float),
         ("planes", ctypes.c_int32),
         ("a_plane_stride", ctypes.c_int64), ("w_plane_stride", ctypes.c_int64), ("out_plane_stride", ctypes.c_int64),
+        ("split_k", ctypes.c_int32), ("out_numel", ctypes.c_int64), ("wgrad_c_tile", ctypes.c_int32),
     ]
 
 
@@ -46,7 +47,7 @@ PROTOTYPES = {
     "ms_version": [],
     "ms_device_is_sm100": [],
     "ms_pack_conv_weight_f32": [_P, _I, _CD, _P, _P, _P],
-    "ms_unpack_conv_wgrad": [_P, _CD, _P, _I, _P],
+    "ms_unpack_conv_wgrad": [_P, _CD, _P, _I, _I, _P],
     "ms_cast": [_P, _I, _P, _I, _L, _P],
     "ms_conv_fwd_f32": [_P, _P, _P, _P, _CD, _I, _F, _P],
     "ms_conv_dgrad_f32": [_P, _P, _P, _CD, _P],
@@ -54,15 +55,16 @@ PROTOTYPES = {
     "ms_igemm_bf16": [_GD, _P, _P, _P, _P, _P, _P, _P],
     "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P, _P],
     "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],
-    "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "ms_col_stats_f32": [_P, _L, _I, _P, _P, _P],
     "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],
     "ms_bn_act_fwd_f32": [_P, _P, _P, _F, _L, _I, _P, _P, _I, _I, _P, _I, _L, _P],
     "ms_to_planes": [_P, _L, _I, _I, _P, _I, _L, _P],
     "ms_bn_act_bwd_reduce_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _P],
-    "ms_bn_act_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _I, _P, _P, _I, _L, _P],
+    "ms_bn_act_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _I, _P, _P, _I, _L, _P, _P, _I, _P],
+    "ms_bn_stats_finalize": [_P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P],
     "ms_lrelu_bwd_f32": [_P, _P, _F, _L, _P, _P, _I, _L, _P],
-    "ms_store_param_grad": [_P, _I, _P, _I, _P],
+    "ms_store_param_grad": [_P, _I, _P, _I, _I, _P],
     "ms_bilinear_to_T_fwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ms_bilinear_to_T_bwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ms_style_concat_fwd_f32": [_P, _L, _I, _P, _P, _I, _P, _I, _I, _I, _P, _P],

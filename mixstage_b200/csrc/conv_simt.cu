@@ -8,6 +8,12 @@
 // the grouped 1x1 `logits` conv (joint_late_cluster_soft_style.py:83,193).
 #include "common.cuh"
 
+// csrc/conv_small.cu: layers that are not GEMM-shaped (N <= 32 output channels, or C_in = 1).  1 = launched there.
+int ms_small_conv_fwd(const float* x, const float* wf, const float* bias, float* y, const ms_conv_desc* d, int act,
+                      float slope, cudaStream_t st);
+int ms_small_conv_dgrad(const float* dy, const float* wt, float* dx, const ms_conv_desc* d, cudaStream_t st);
+int ms_small_conv_wgrad(const float* x, const float* dy, float* dwf, const ms_conv_desc* d, cudaStream_t st);
+
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
@@ -158,6 +164,7 @@ bool valid(const ms_conv_desc* d) {
 extern "C" int ms_conv_fwd_f32(const float* x, const float* wf, const float* bias, float* y,
                                const ms_conv_desc* d, int act, float slope, void* stream) {
   if (!valid(d) || !x || !wf || !y) return MS_EINVAL;
+  if (int r = ms_small_conv_fwd(x, wf, bias, y, d, act, slope, ms_stream(stream))) return r == 1 ? 0 : MS_EINVAL;
   ConvP p = make_p(d);
   int M = d->B * d->Ho * d->Wo, N = p.Cout_g, K = p.taps * p.Cin_g;
   dim3 grid((unsigned)ms_cdiv(M, BM), (unsigned)ms_cdiv(N, BN), (unsigned)d->groups);
@@ -168,6 +175,7 @@ extern "C" int ms_conv_fwd_f32(const float* x, const float* wf, const float* bia
 
 extern "C" int ms_conv_dgrad_f32(const float* dy, const float* wt, float* dx, const ms_conv_desc* d, void* stream) {
   if (!valid(d) || !dy || !wt || !dx) return MS_EINVAL;
+  if (int r = ms_small_conv_dgrad(dy, wt, dx, d, ms_stream(stream))) return r == 1 ? 0 : MS_EINVAL;
   ConvP p = make_p(d);
   int M = d->B * d->H * d->W, N = p.Cin_g, K = p.taps * p.Cout_g;
   dim3 grid((unsigned)ms_cdiv(M, BM), (unsigned)ms_cdiv(N, BN), (unsigned)d->groups);
@@ -178,6 +186,7 @@ extern "C" int ms_conv_dgrad_f32(const float* dy, const float* wt, float* dx, co
 
 extern "C" int ms_conv_wgrad_f32(const float* x, const float* dy, float* dwf, const ms_conv_desc* d, void* stream) {
   if (!valid(d) || !x || !dy || !dwf) return MS_EINVAL;
+  if (int r = ms_small_conv_wgrad(x, dy, dwf, d, ms_stream(stream))) return r == 1 ? 0 : MS_EINVAL;
   ConvP p = make_p(d);
   int M = p.taps * p.Cin_g, N = p.Cout_g, K = d->B * d->Ho * d->Wo;
   int64_t tiles = ms_cdiv(M, BM) * ms_cdiv(N, BN) * d->groups;

@@ -28,7 +28,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;            // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 12;        // smem ring depth is chosen per launch: as many stages as fit in 227 KB
 constexpr int NUM_THREADS = 192;
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr uint32_t SPIN_LIMIT = 1u << 22;   // bounded mbarrier spins: trap instead of hanging the GPU
@@ -47,6 +47,8 @@ struct IgemmParams {
   float slope;
   int npass;                            // 1: bf16 operands; 3: split-bf16 (hi*hi + hi*lo + lo*hi)
   long long out_plane_stride;           // MS_BF16X2 output: elements between the hi and lo planes
+  int stages;                           // smem ring depth (2..MAX_STAGES)
+  int split_k;                          // > 1: gridDim.z CTAs share the k-steps of a tile, fp32 vector reductions into out
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,9 +130,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
   uint8_t* smem_a = smem;
+  const int STAGES = p.stages;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
 
@@ -145,7 +148,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int cls = blockIdx.y / p.n_tiles_per_class;
   const int nt = blockIdx.y - cls * p.n_tiles_per_class;
   const int n0 = nt * p.block_n;                       // column offset inside the class
-  const int num_k = p.ntaps * p.cchunks * p.npass;
+  // k-steps of this CTA: all of them, or one contiguous slice when the tile is split over gridDim.z
+  const int num_k_total = p.ntaps * p.cchunks * p.npass;
+  const int k_per = (num_k_total + p.split_k - 1) / p.split_k;
+  const int k_beg = (int)blockIdx.z * k_per;
+  const int num_k = max(0, min(num_k_total, k_beg + k_per) - k_beg);
 
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
@@ -181,7 +188,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const uint32_t ph = (uint32_t)(ks / STAGES) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         // split-bf16: three passes per (tap, channel chunk): hi*hi, hi*lo, lo*hi
-        const int kk = ks / p.npass, pass = ks - kk * p.npass;
+        const int kg = k_beg + ks;
+        const int kk = kg / p.npass, pass = kg - kk * p.npass;
         const int tap = kk / p.cchunks, cc = kk - tap * p.cchunks;
         const short* t = p.taps[tap_base + tap];
         mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + b_stage_bytes);
@@ -225,11 +233,24 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool lead = blockIdx.z == 0;                  // split-K: the first slice adds the bias
     for (int c0 = 0; c0 < p.block_n; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(taddr + (uint32_t)c0, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (valid && (n0 + c0) < p.class_n) {
+      if (valid && (n0 + c0) < p.class_n && p.split_k > 1) {
+        float* dst = reinterpret_cast<float*>(out) + row_off + c0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float a = __uint_as_float(v[4 * j]), b = __uint_as_float(v[4 * j + 1]), c = __uint_as_float(v[4 * j + 2]),
+                d = __uint_as_float(v[4 * j + 3]);
+          if (bias && lead) {
+            a += __ldg(bias + ncol + c0 + 4 * j); b += __ldg(bias + ncol + c0 + 4 * j + 1);
+            c += __ldg(bias + ncol + c0 + 4 * j + 2); d += __ldg(bias + ncol + c0 + 4 * j + 3);
+          }
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+        }
+      } else if (valid && (n0 + c0) < p.class_n) {
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -315,6 +336,8 @@ struct WgradParams {
   int ntaps, cchunks, shared_taps, num_classes, class_n;
   int box_w, box_h, box_b, tiles_w, tiles_h, tiles_b;
   int n_tiles, c_tiles, kpad, split, npass;
+  int c_tile;                            // x-channel columns per CTA tile: 64, 128, 192 or 256
+  long long wp_numel;
   int a_chan_base[MS_IGEMM_MAX_CLASSES];
   int z_chan_base[MS_IGEMM_MAX_CLASSES];
   short taps[MS_IGEMM_MAX_TAPS][4];
@@ -344,8 +367,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
   const int cls = blockIdx.z / p.ntaps, tap = blockIdx.z - cls * p.ntaps;
   const int nt = blockIdx.y / p.c_tiles, ct = blockIdx.y - nt * p.c_tiles;
-  const int n0 = nt * 128, c0 = ct * 256;
-  const int nc = min(256, p.kpad - c0);                 // columns of this tile (multiple of 64)
+  const int n0 = nt * 128, c0 = ct * p.c_tile;
+  const int nc = min(p.c_tile, p.kpad - c0);            // columns of this tile (multiple of 64)
   const int xchunks = nc / 64;
   const uint32_t stage_bytes = (2 + xchunks) * WG_CHUNK_BYTES;
   const int total_rt = p.tiles_w * p.tiles_h * p.tiles_b;
@@ -424,7 +447,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       const int q = warp & 3;
       const int r = q * 32 + lane;                     // n index inside the tile
       const bool valid = (n0 + r) < p.class_n;
-      float* dst_row = dwp + ((size_t)(cls * p.class_n + n0 + r) * p.ntaps + tap) * p.kpad + c0;
+      // split-K partials: slice blockIdx.x writes its own copy of dWp (summed by ms_unpack_igemm_wgrad)
+      float* dst_row = dwp + (size_t)blockIdx.x * p.wp_numel + ((size_t)(cls * p.class_n + n0 + r) * p.ntaps + tap) * p.kpad + c0;
       mbar_wait(&tmem_full_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -433,16 +457,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         tmem_ld16(taddr + (uint32_t)cc, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (valid) {
-          if (p.split > 1) {
+          float4* d4 = reinterpret_cast<float4*>(dst_row + cc);
 #pragma unroll
-            for (int j = 0; j < 16; j++) atomicAdd(dst_row + cc + j, __uint_as_float(v[j]));
-          } else {
-            float4* d4 = reinterpret_cast<float4*>(dst_row + cc);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                  __uint_as_float(v[4 * j + 3]));
-          }
+          for (int j = 0; j < 4; j++)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -457,14 +476,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
 // dWp[row][t][c] fp32 -> dw (Cout, Cin_g, taps_total) in dtype pdt (inverse of the forward re-tiling)
 __global__ void unpack_igemm_wgrad_kernel(const float* __restrict__ dwp, int Cout, int Cin_g, int taps_total, int ntaps, int kpad,
-                                          void* __restrict__ dw, int pdt) {
+                                          void* __restrict__ dw, int pdt, int nsplit, long long wp_numel, int accumulate) {
   const long long total = (long long)Cout * Cin_g * taps_total;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int tap = (int)(i % taps_total);
     long long t2 = i / taps_total;
     int c = (int)(t2 % Cin_g);
     long long o = t2 / Cin_g;
-    ms_stp(dw, pdt, i, (double)dwp[(o * ntaps + tap) * kpad + c]);
+    const float* src = dwp + (o * ntaps + tap) * kpad + c;
+    double acc = accumulate ? ms_ldp_d(dw, pdt, i) : 0.0;
+    for (int sidx = 0; sidx < nsplit; sidx++) acc += (double)src[(long long)sidx * wp_numel];
+    ms_stp(dw, pdt, i, acc);
   }
 }
 
@@ -592,13 +614,37 @@ extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* 
   for (int i = 0; i < d->num_classes; i++)
     if ((p.out_off[i] * esz) % 16) return MS_EINVAL;
 
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)d->block_n * BLOCK_K * 2) + 1024;
+  const size_t stage_bytes = A_STAGE_BYTES + (size_t)d->block_n * BLOCK_K * 2;
+  const int num_k_total = d->ntaps * d->cchunks * p.npass;
+  // split-K: slices of k-steps reduced with fp32 vector reductions into a zero-filled fp32 output
+  int split = d->split_k > 1 ? d->split_k : 1;
+  if (split > 1) {
+    if (d->out_dtype != MS_F32 || d->epilogue != 0 || d->out_numel <= 0) return MS_EINVAL;
+    if (split > num_k_total) split = num_k_total;
+    const int per = (num_k_total + split - 1) / split;
+    split = (num_k_total + per - 1) / per;            // every slice owns at least one k-step
+  }
+  p.split_k = split;
+  const int k_per_cta = (num_k_total + split - 1) / split;
+  int stages = (int)((227 * 1024 - 4096) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > k_per_cta) stages = k_per_cta < 2 ? 2 : k_per_cta;
+  {
+    // more CTAs than SMs: keep the ring under half of the shared memory so that two CTAs are co-resident
+    const long long ctas = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * d->num_classes * split;
+    const int half = (int)((113 * 1024 - 2048) / stage_bytes);
+    if (ctas > ms_num_sms() && half >= 3 && stages > half) stages = half;
+  }
+  if (stages < 2) return MS_EINVAL;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     MS_CUDA(cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_set = true;
   }
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_b), (unsigned)(p.n_tiles_per_class * d->num_classes));
+  if (split > 1) MS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)d->out_numel, ms_stream(stream)));
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * p.tiles_b), (unsigned)(p.n_tiles_per_class * d->num_classes), (unsigned)split);
   igemm_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
   MS_LAUNCH_CHECK();
   return 0;
@@ -636,16 +682,20 @@ extern "C" int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* 
   p.tiles_w = (Wo + bw - 1) / bw; p.tiles_h = (Ho + bh - 1) / bh; p.tiles_b = (Bo + bb - 1) / bb;
   p.kpad = d->cchunks * BLOCK_K;
   p.n_tiles = (d->class_n + 127) / 128;
-  p.c_tiles = (p.kpad + 255) / 256;
+  p.c_tile = d->wgrad_c_tile > 0 ? d->wgrad_c_tile : 256;
+  if (p.c_tile % 64 || p.c_tile > 256) return MS_EINVAL;
+  p.c_tiles = (p.kpad + p.c_tile - 1) / p.c_tile;
   for (int i = 0; i < MS_IGEMM_MAX_CLASSES; i++) { p.a_chan_base[i] = d->a_chan_base[i]; p.z_chan_base[i] = (int)d->out_off[i]; }
   for (int i = 0; i < MS_IGEMM_MAX_TAPS; i++)
     for (int j = 0; j < 4; j++) p.taps[i][j] = d->taps[i][j];
   const long long total_rt = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
-  const long long tiles = (long long)p.n_tiles * p.c_tiles * d->num_classes * d->ntaps;
-  long long split = (2LL * ms_num_sms() + tiles - 1) / tiles;
+  long long split = d->split_k > 1 ? d->split_k : 1;
   if (split > total_rt) split = total_rt;
-  if (split < 1) split = 1;
+  const long long per = (total_rt + split - 1) / split;
+  split = (total_rt + per - 1) / per;                 // every slice owns at least one row tile
+  if (split != (d->split_k > 1 ? d->split_k : 1)) return MS_EINVAL;   // the caller sized dwp for exactly split_k partials
   p.split = (int)split;
+  p.wp_numel = (long long)d->num_classes * d->class_n * d->ntaps * p.kpad;
   if (d->planes != 1 && d->planes != 2) return MS_EINVAL;
   p.npass = d->planes == 2 ? 3 : 1;
   if (d->planes == 2 && (d->a_plane_stride <= 0 || d->out_plane_stride <= 0 || (d->a_plane_stride * 2) % 16 || (d->out_plane_stride * 2) % 16))
@@ -668,8 +718,6 @@ extern "C" int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* 
     map_x_lo = map_x; map_z_lo = map_z;
   }
 
-  const size_t wbytes = sizeof(float) * (size_t)d->num_classes * d->class_n * d->ntaps * p.kpad;
-  if (p.split > 1) MS_CUDA(cudaMemsetAsync(dwp, 0, wbytes, ms_stream(stream)));
   const size_t smem = (size_t)WG_STAGES * 6 * WG_CHUNK_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -683,12 +731,13 @@ extern "C" int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* 
 }
 
 extern "C" int ms_unpack_igemm_wgrad(const float* dwp, int Cout, int Cin_g, int taps_total, int ntaps, int kpad, void* dw,
-                                     int pdt, void* stream) {
-  if (!dwp || !dw || ntaps != taps_total) return MS_EINVAL;
+                                     int pdt, int nsplit, int accumulate, void* stream) {
+  if (!dwp || !dw || ntaps != taps_total || nsplit < 1) return MS_EINVAL;
   const long long total = (long long)Cout * Cin_g * taps_total;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_igemm_wgrad_kernel<<<(unsigned)blocks, 256, 0, ms_stream(stream)>>>(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt);
+  unpack_igemm_wgrad_kernel<<<(unsigned)blocks, 256, 0, ms_stream(stream)>>>(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, nsplit,
+                                                                             (long long)Cout * ntaps * kpad, accumulate);
   MS_LAUNCH_CHECK();
   return 0;
 }

@@ -53,7 +53,7 @@ __global__ void pack_weight_kernel(const void* __restrict__ w, int pdt, int Cout
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int Cout, int Cin_g, int taps, int groups,
-                                    void* __restrict__ dw, int pdt) {
+                                    void* __restrict__ dw, int pdt, int accumulate) {
   int Cout_g = Cout / groups;
   int64_t total = (int64_t)Cout * Cin_g * taps;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -62,13 +62,13 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwf, int Cout, int
     int c = (int)(t % Cin_g);
     int o = (int)(t / Cin_g);
     int g = o / Cout_g, n = o - g * Cout_g;
-    ms_stp(dw, pdt, i, (double)dwf[(((int64_t)g * taps + tap) * Cin_g + c) * Cout_g + n]);
+    ms_stp(dw, pdt, i, (double)dwf[(((int64_t)g * taps + tap) * Cin_g + c) * Cout_g + n] + (accumulate ? ms_ldp_d(dw, pdt, i) : 0.0));
   }
 }
 
-__global__ void store_param_grad_kernel(const double* __restrict__ s, int n, void* __restrict__ d, int pdt) {
+__global__ void store_param_grad_kernel(const double* __restrict__ s, int n, void* __restrict__ d, int pdt, int accumulate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) ms_stp(d, pdt, i, s[i]);
+  if (i < n) ms_stp(d, pdt, i, s[i] + (accumulate ? ms_ldp_d(d, pdt, i) : 0.0));
 }
 
 // ------------------------------------------------------------------ column statistics
@@ -96,6 +96,65 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
     atomicAdd(sum + c, a);
     if (sumsq) atomicAdd(sumsq + c, b);
   }
+}
+
+__device__ __forceinline__ void bn_finalize_one(int c, double sum, double sumsq, int64_t rows, const void* gamma, const void* beta,
+                                                const void* cbias, void* rmean, void* rvar, int pdt, float momentum, float eps,
+                                                float* scale, float* shift, float* mean_o, float* rstd_o) {
+  double cb = cbias ? ms_ldp_d(cbias, pdt, c) : 0.0;
+  double mean = sum / (double)rows;
+  double var = sumsq / (double)rows - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double unb = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
+  double rm = ms_ldp_d(rmean, pdt, c), rv = ms_ldp_d(rvar, pdt, c);
+  ms_stp(rmean, pdt, c, (1.0 - (double)momentum) * rm + (double)momentum * (mean + cb));
+  ms_stp(rvar, pdt, c, (1.0 - (double)momentum) * rv + (double)momentum * unb);
+  double rstd = 1.0 / sqrt(var + (double)eps);
+  double g = ms_ldp_d(gamma, pdt, c), b = ms_ldp_d(beta, pdt, c);
+  scale[c] = (float)(g * rstd);
+  shift[c] = (float)(b - mean * g * rstd);
+  mean_o[c] = (float)mean;
+  rstd_o[c] = (float)rstd;
+}
+
+// column statistics and, in the block that finishes last, the training-mode finalize of every channel
+// (one launch instead of statistics + finalize + counter increment)
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(
+    const float* __restrict__ x, int64_t rows, int C, double* __restrict__ sum, double* __restrict__ sumsq,
+    unsigned int* __restrict__ ticket, const void* gamma, const void* beta, const void* cbias, void* rmean, void* rvar,
+    long long* nbt, int pdt, float momentum, float eps, float* scale, float* shift, float* mean_o, float* rstd_o) {
+  __shared__ double s1[8][33], s2[8][33];
+  __shared__ unsigned int last;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int c = blockIdx.x * 32 + tx;
+  int64_t per = ms_cdiv_dev(rows, gridDim.y);
+  int64_t r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float v = __ldg(x + r * C + c);
+      a += v;
+      b += (double)v * v;
+    }
+  s1[ty][tx] = a;
+  s2[ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; i++) { a += s1[i][tx]; b += s2[i][tx]; }
+    atomicAdd(sum + c, a);
+    atomicAdd(sumsq + c, b);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x)
+    bn_finalize_one(ch, __ldcg(sum + ch), __ldcg(sumsq + ch), rows, gamma, beta, cbias, rmean, rvar, pdt, momentum, eps, scale,
+                    shift, mean_o, rstd_o);
+  if (threadIdx.x == 0 && nbt) nbt[0] += 1;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, int64_t rows, int C,
@@ -237,12 +296,17 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dy, const floa
                                         const float* __restrict__ mean, const float* __restrict__ rstd, float slope,
                                         int64_t rows, int C, int up2, int L, const double* __restrict__ dgamma,
                                         const double* __restrict__ dbeta, int training, float* __restrict__ dx,
-                                        __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride) {
+                                        __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride,
+                                        void* __restrict__ ggamma, void* __restrict__ gbeta, int gdt) {
   int64_t total = rows * C;
   float inv = 1.f / (float)rows;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / C;
     int c = (int)(i - r * C);
+    if (r == 0) {          // the thread of row 0 also accumulates the affine-parameter gradients of its channel
+      if (ggamma) ms_stp(ggamma, gdt, c, ms_ldp_d(ggamma, gdt, c) + dgamma[c]);
+      if (gbeta) ms_stp(gbeta, gdt, c, ms_ldp_d(gbeta, gdt, c) + dbeta[c]);
+    }
     float xv = __ldg(x + i);
     float sc = scale[c];
     float z = fmaf(xv, sc, shift[c]);
@@ -624,18 +688,18 @@ extern "C" int ms_pack_conv_weight_f32(const void* w, int pdt, const ms_conv_des
   return 0;
 }
 
-extern "C" int ms_unpack_conv_wgrad(const float* dwf, const ms_conv_desc* d, void* dw, int pdt, void* stream) {
+extern "C" int ms_unpack_conv_wgrad(const float* dwf, const ms_conv_desc* d, void* dw, int pdt, int accumulate, void* stream) {
   if (!dwf || !d || !dw || d->groups < 1) return MS_EINVAL;
   int64_t total = (int64_t)d->Cout * (d->Cin / d->groups) * d->kh * d->kw;
-  unpack_wgrad_kernel<<<ew_blocks(total), EW_THREADS, 0, ST>>>(dwf, d->Cout, d->Cin / d->groups, d->kh * d->kw, d->groups, dw, pdt);
+  unpack_wgrad_kernel<<<ew_blocks(total), EW_THREADS, 0, ST>>>(dwf, d->Cout, d->Cin / d->groups, d->kh * d->kw, d->groups, dw, pdt, accumulate);
   MS_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int ms_store_param_grad(const double* src, int n, void* dst, int pdt, void* stream) {
+extern "C" int ms_store_param_grad(const double* src, int n, void* dst, int pdt, int accumulate, void* stream) {
   if (!src || !dst || n < 0) return MS_EINVAL;
   if (n == 0) return 0;
-  store_param_grad_kernel<<<(n + 255) / 256, 256, 0, ST>>>(src, n, dst, pdt);
+  store_param_grad_kernel<<<(n + 255) / 256, 256, 0, ST>>>(src, n, dst, pdt, accumulate);
   MS_LAUNCH_CHECK();
   return 0;
 }
@@ -663,6 +727,20 @@ static bool planes_ok(const void* planes, int pfmt, int64_t pstride) {
   if (pfmt != MS_BF16 && pfmt != MS_BF16X2) return false;
   if (pfmt == MS_BF16X2 && (pstride <= 0 || pstride % 8)) return false;
   return ((uintptr_t)planes & 15) == 0;
+}
+
+extern "C" int ms_bn_stats_finalize(const float* x, int64_t rows, int C, double* sum, double* sumsq, void* ticket,
+                                    const void* gamma, const void* beta, const void* conv_bias, void* running_mean,
+                                    void* running_var, int64_t* num_batches_tracked, int pdt, float momentum, float eps,
+                                    float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  if (!x || !sum || !sumsq || !ticket || !gamma || !beta || !running_mean || !running_var || !scale || !shift || !mean || !rstd)
+    return MS_EINVAL;
+  if (rows < 1 || C < 1) return MS_EINVAL;
+  bn_stats_finalize_kernel<<<col_grid(rows, C), 256, 0, ST>>>(x, rows, C, sum, sumsq, (unsigned int*)ticket, gamma, beta, conv_bias,
+                                                              running_mean, running_var, (long long*)num_batches_tracked, pdt,
+                                                              momentum, eps, scale, shift, mean, rstd);
+  MS_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int ms_bn_act_fwd_f32(const float* x, const float* scale, const float* shift, float slope, int64_t rows, int C,
@@ -707,13 +785,16 @@ extern "C" int ms_bn_act_bwd_reduce_f32(const float* dy, const float* x, const f
 extern "C" int ms_bn_act_bwd_apply_f32(const float* dy, const float* x, const float* scale, const float* shift,
                                        const float* mean, const float* rstd, float slope, int64_t rows, int C, int up2,
                                        int rows_per_seq, const double* dgamma, const double* dbeta, int training, float* dx,
-                                       void* planes, int pfmt, int64_t pstride, void* stream) {
+                                       void* planes, int pfmt, int64_t pstride, void* grad_gamma, void* grad_beta, int gdt,
+                                       void* stream) {
   if (!dy || !x || !scale || !shift || !mean || !rstd || (!dx && !planes) || rows < 1 || C < 1) return MS_EINVAL;
   if (training && (!dgamma || !dbeta)) return MS_EINVAL;
+  if ((grad_gamma || grad_beta) && (!dgamma || !dbeta || (gdt != MS_F32 && gdt != MS_F64))) return MS_EINVAL;
   if (!planes_ok(planes, pfmt, pstride)) return MS_EINVAL;
   bn_act_bwd_apply_kernel<<<ew_blocks(rows * C), EW_THREADS, 0, ST>>>(dy, x, scale, shift, mean, rstd, slope, rows, C, up2,
                                                                       rows_per_seq, dgamma, dbeta, training, dx,
-                                                                      reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride);
+                                                                      reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride,
+                                                                      grad_gamma, grad_beta, gdt);
   MS_LAUNCH_CHECK();
   return 0;
 }

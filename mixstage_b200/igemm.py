@@ -187,16 +187,64 @@ def make_dgrad(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo, out_r
     return Plan(d, 1, srctap, d.cchunks * BLOCK_K, len(classes) * cg)
 
 
-def pick_block_n(d, sms=148):
-    """Output-column tile: the widest tile that still fills the machine, else the narrowest (latency-bound layers)."""
+def pick_block_n(d, npass=1, sms=148):
+    """Output-column tile.  Wide tiles re-read the activation box least (A is 16 KB per k-step whatever the tile
+    width), so: the widest tile that fills the machine on its own; else the widest tile for which split-K
+    (slices of >= 4 k-steps) still reaches ~one CTA per SM; else the narrowest."""
     tiles_m = 1
     for dim, box in ((d.out_dims[0], d.box[1]), (d.out_dims[1], d.box[3]), (d.out_dims[2], d.box[4])):
         tiles_m *= (dim + box - 1) // box
     cands = [min(256, d.class_n)] + [b for b in (128, 64, 32) if b < min(256, d.class_n)]
+    num_k = d.ntaps * d.cchunks * npass
     for bn in cands:
-        if tiles_m * d.num_classes * ((d.class_n + bn - 1) // bn) >= sms:
+        ctas = tiles_m * d.num_classes * ((d.class_n + bn - 1) // bn)
+        if ctas >= sms or ctas * max(1, num_k // 4) >= (3 * sms) // 4:
             return bn
     return cands[-1]
+
+
+def _tiles_m(d, box=None):
+    bw, bh, bb = box or (d.box[1], d.box[3], d.box[4])
+    return ((d.out_dims[0] + bw - 1) // bw) * ((d.out_dims[1] + bh - 1) // bh) * ((d.out_dims[2] + bb - 1) // bb)
+
+
+def _normalise_split(total, split):
+    split = max(1, min(split, total))
+    per = (total + split - 1) // split
+    return (total + per - 1) // per
+
+
+def igemm_split(d, npass, sms=148):
+    """Split-K factor of a forward / input-gradient launch: slices of >= 4 k-steps until ~one CTA per SM."""
+    ctas = _tiles_m(d) * d.num_classes * ((d.class_n + d.block_n - 1) // d.block_n)
+    num_k = d.ntaps * d.cchunks * npass
+    if ctas * 2 > sms or num_k < 8:
+        return 1
+    return _normalise_split(num_k, min(sms // ctas, num_k // 4))          # one wave: at most one CTA per SM
+
+
+def wgrad_split(d, sms=148):
+    """(split, c_tile) of a weight-gradient launch.  Tiles are (128 output channels) x (c_tile input channels) per
+    (class, tap); the 64-pixel-row tiles are sliced `split` ways and every slice writes its own partial dWp, so the
+    policy is: the tile width that reaches ~one CTA per SM with the fewest partials."""
+    bw, bh, bb = d.box[1], d.box[3], d.box[4]
+    if bb > 1:
+        bb //= 2
+    elif bh > 1:
+        bh //= 2
+    else:
+        bw //= 2
+    total_rt = _tiles_m(d, (bw, bh, bb))
+    kpad = d.cchunks * BLOCK_K
+    best = None
+    for c_tile in (256, 128, 64):
+        if c_tile > kpad and c_tile != 64 and kpad <= c_tile // 2:
+            continue
+        tiles = ((d.class_n + 127) // 128) * ((kpad + c_tile - 1) // c_tile) * d.num_classes * d.ntaps
+        split = _normalise_split(total_rt, (sms * 3 // 4 + tiles - 1) // tiles)
+        if best is None or split < best[0]:
+            best = (split, c_tile)
+    return best
 
 
 def set_planes(plan, split, a_plane_stride=0, w_plane_stride=0, out_plane_stride=0):

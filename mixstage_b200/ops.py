@@ -58,6 +58,60 @@ class precision_scope:
             set_precision(self.old)
 
 
+# ---------------------------------------------------------------------------- step-scoped scratch
+class _Arena:
+    """Zero-initialised fp64 accumulators (BatchNorm sums, reduction slots, tickets) carved from ONE buffer that the
+    train step clears with a single memset, instead of one torch.zeros launch per layer.  Outside a step
+    (`active` False) every request falls back to torch.zeros."""
+
+    def __init__(self):
+        self.buf, self.keep = None, []
+        self.off = self.used = self.need = 0
+        self.active = False
+
+    def begin(self, device):
+        if self.buf is None or self.buf.device != device or self.buf.numel() < self.need:
+            if self.buf is not None:
+                self.keep.append(self.buf)          # captured graphs may still point into the old buffer
+            self.buf = torch.zeros(max(self.need, 1 << 15), dtype=torch.float64, device=device)
+        else:
+            self.buf.zero_()
+        self.off = self.used = 0
+        self.active = True
+
+    def end(self):
+        self.need = max(self.need, self.used)
+        self.active = False
+
+    def take(self, shape, device):
+        n = 1
+        for d_ in shape:
+            n *= d_
+        n_al = (n + 1) // 2 * 2
+        self.used += n_al
+        if not self.active or self.buf.device != device or self.off + n_al > self.buf.numel():
+            return torch.zeros(shape, dtype=torch.float64, device=device)
+        t = self.buf[self.off:self.off + n].view(shape)
+        self.off += n_al
+        return t
+
+
+arena = _Arena()
+# When True (set by TrainStep around its body) parameter gradients are accumulated by the kernels straight into the
+# parameters' existing .grad buffers (views of the flat gradient buffer) and autograd receives None for them.
+DIRECT_GRADS = False
+
+
+def _sink(p):
+    """The .grad buffer of parameter p when direct accumulation applies, else None."""
+    if not DIRECT_GRADS or p is None or not p.requires_grad:
+        return None
+    g = p.grad
+    if g is None or not g.is_contiguous() or g.dtype != p.dtype:
+        return None
+    return g
+
+
 def _fmt(precision):
     return MS_BF16X2 if precision == "bf16x3" else MS_BF16
 
@@ -176,8 +230,8 @@ class PackedWeight:
         return self.wf, self.wt
 
     # ---- tensor-core path: cached descriptors per input shape, packed bf16 (hi[, lo]) weights per version
-    def tc_plans(self, x_shape, Cout, cfg, rs, need_dgrad):
-        key = (tuple(x_shape), Cout, rs, need_dgrad)
+    def tc_plans(self, x_shape, Cout, cfg, rs, need_dgrad, npass=1):
+        key = (tuple(x_shape), Cout, rs, need_dgrad, npass)
         pl = getattr(self, "_plans", None)
         if pl is None:
             pl = self._plans = {}
@@ -189,7 +243,7 @@ class PackedWeight:
             pd = igemm.make_dgrad(*geo, out_row_stride=rs if rs != Cin else None) if need_dgrad else None
             for p_ in (pf, pd):
                 if p_ is not None:
-                    p_.desc.block_n = igemm.pick_block_n(p_.desc)
+                    p_.desc.block_n = igemm.pick_block_n(p_.desc, npass)
             pl[key] = (pf, pd)
         return pl[key]
 
@@ -241,6 +295,100 @@ class ConvCfg:
         self.eps = 1e-5
 
 
+# ---- pieces shared by the CUDA-core and tensor-core variants of the block
+def _bn_scale_shift(z, rows, Cout, gamma, beta, cbias, bn_buffers, training, cfg):
+    """Batch statistics + finalize (training: one fused launch that also advances num_batches_tracked) or the
+    running-statistics fold (eval).  Returns ss = [scale, shift, mean, rstd] (4, Cout) fp32."""
+    rm, rv, nbt = bn_buffers
+    st, dev = stream(), z.device
+    ss = torch.empty(4, Cout, dtype=torch.float32, device=dev)
+    pdt = dt_code(gamma.dtype)
+    if cbias is not None and cbias.dtype != gamma.dtype:
+        raise MixStageError("conv bias and BatchNorm parameters must share a dtype")
+    if training:
+        acc = arena.take((2 * Cout + 2,), dev)                 # sum, sumsq, ticket
+        base = acc.data_ptr()
+        call("ms_bn_stats_finalize", ptr(z), rows, Cout, base, base + 8 * Cout, base + 16 * Cout, ptr(gamma), ptr(beta),
+             ptr(cbias), ptr(rm), ptr(rv), ptr(nbt), pdt, cfg.momentum, cfg.eps, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]),
+             ptr(ss[3]), st)
+    else:
+        call("ms_bn_finalize", None, None, rows, Cout, ptr(gamma), ptr(beta), ptr(cbias), ptr(rm), ptr(rv), pdt, 0,
+             cfg.momentum, cfg.eps, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), st)
+    return ss
+
+
+def _bn_act(z, ss, cfg, rows, Cout, desc, residual, up2, fmt, want_planes):
+    """y = act(z*scale + shift) [upsampled x2 + residual], as fp32 and (optionally) as bf16 operand planes."""
+    B = z.shape[0]
+    dev = z.device
+    slope = cfg.slope if cfg.act else 1.0
+    if up2:
+        if desc.Ho != 1:
+            raise MixStageError("upsample+skip fusion is 1-D only")
+        y = torch.empty((B, 1, 2 * desc.Wo, Cout), dtype=torch.float32, device=dev)
+        res = _f32c(residual)
+        if res.shape != y.shape:
+            raise MixStageError("skip tensor shape %s != %s" % (tuple(res.shape), tuple(y.shape)))
+    else:
+        y = torch.empty_like(z)
+        res = None
+    yp = alloc_planes(y.numel() // Cout, Cout, fmt, dev) if (want_planes and Cout % 8 == 0) else None
+    call("ms_bn_act_fwd_f32", ptr(z), ptr(ss[0]), ptr(ss[1]), slope, rows, Cout, ptr(y), ptr(res),
+         1 if up2 else 0, desc.Wo, ptr(yp.t) if yp else None, yp.fmt if yp else 0, yp.ps if yp else 0, stream())
+    return y, yp
+
+
+def _bn_act_backward(ctx, dy, z, ss, want_f32, dzp):
+    """dz = d(act(bn(z)))/dz . dy as fp32 (want_f32) and/or planes (dzp); affine-parameter gradients go to their
+    sinks when direct accumulation is on, else come back as tensors.  Returns (dz, dgamma, dbeta)."""
+    cfg, desc, rows, Cout = ctx.cfg, ctx.desc, ctx.rows, ctx.Cout
+    st, dev = stream(), dy.device
+    need_g, need_be = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+    slope = cfg.slope if cfg.act else 1.0
+    red = arena.take((2, Cout), dev)
+    if ctx.training or need_g or need_be:
+        call("ms_bn_act_bwd_reduce_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
+             rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), st)
+    sg = ctx.sinks[2] if need_g else None
+    sb = ctx.sinks[3] if need_be else None
+    direct = sg is not None and sb is not None and need_g and need_be
+    dz = torch.empty_like(z) if want_f32 else None
+    call("ms_bn_act_bwd_apply_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
+         rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), 1 if ctx.training else 0, ptr(dz),
+         ptr(dzp.t) if dzp else None, dzp.fmt if dzp else 0, dzp.ps if dzp else 0,
+         ptr(sg) if direct else None, ptr(sb) if direct else None, dt_code(ctx.gamma_dtype), st)
+    dgamma = dbeta = None
+    if not direct:
+        if need_g:
+            dgamma = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
+            call("ms_store_param_grad", ptr(red[0]), Cout, ptr(dgamma), dt_code(ctx.gamma_dtype), 0, st)
+        if need_be:
+            dbeta = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
+            call("ms_store_param_grad", ptr(red[1]), Cout, ptr(dbeta), dt_code(ctx.gamma_dtype), 0, st)
+    return dz, dgamma, dbeta
+
+
+def _bias_grad(ctx, dz):
+    """d(bias): identically zero under batch-statistics BatchNorm (any per-channel constant is removed), else the
+    column sums of dz.  Returns a tensor for autograd, or None after accumulating into the sink."""
+    cfg, rows, Cout = ctx.cfg, ctx.rows, ctx.Cout
+    bdt = ctx.param_dtypes[1]
+    if not ctx.needs_input_grad[2] or bdt is None:
+        return None
+    sink = ctx.sinks[1]
+    dev = dz.device if dz is not None else None
+    if cfg.has_bn and ctx.training:
+        return None if sink is not None else torch.zeros(Cout, dtype=bdt, device=ctx.dev)
+    acc = arena.take((Cout,), dev)
+    call("ms_col_stats_f32", ptr(dz), rows, Cout, ptr(acc), None, stream())
+    if sink is not None:
+        call("ms_store_param_grad", ptr(acc), Cout, ptr(sink), dt_code(bdt), 1, stream())
+        return None
+    dbias = torch.empty(Cout, dtype=bdt, device=dev)
+    call("ms_store_param_grad", ptr(acc), Cout, ptr(dbias), dt_code(bdt), 0, stream())
+    return dbias
+
+
 class _ConvBlock(torch.autograd.Function):
     """y = act(bn(conv(x) + b)) [+ upsample2(y) + residual].  x: (B,H,W,Cin) fp32 channels-last."""
 
@@ -255,6 +403,8 @@ class _ConvBlock(torch.autograd.Function):
         if weight.shape[1] * cfg.groups != Cin:
             raise MixStageError("conv: input has %d channels, weight expects %d" % (Cin, weight.shape[1] * cfg.groups))
         ctx.tc = False
+        ctx.sinks = carrier.sinks if carrier is not None else (None, None, None, None)
+        ctx.dev = x.device
         if precision != "fp32" and tc_eligible(cfg, B, H, W, Cin, Cout, ctx.needs_input_grad[0]):
             return _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2,
                                desc, _fmt(precision), carrier)
@@ -273,29 +423,11 @@ class _ConvBlock(torch.autograd.Function):
         if not cfg.has_bn:
             ctx.save_for_backward(x, z)
             return z
-        rm, rv, nbt = bn_buffers
-        stats = torch.zeros(2, Cout, dtype=torch.float64, device=dev) if training else None
-        if training:
-            call("ms_col_stats_f32", ptr(z), rows, Cout, ptr(stats[0]), ptr(stats[1]), st)
-        ss = torch.empty(4, Cout, dtype=torch.float32, device=dev)     # scale, shift, mean, rstd
-        call("ms_bn_finalize", ptr(stats[0]) if training else None, ptr(stats[1]) if training else None, rows, Cout,
-             ptr(gamma), ptr(beta), None, ptr(rm), ptr(rv), dt_code(gamma.dtype), 1 if training else 0,
-             cfg.momentum, cfg.eps, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), st)
-        if training:
-            nbt.add_(1)
-        slope = cfg.slope if cfg.act else 1.0
-        if up2:
-            if desc.Ho != 1:
-                raise MixStageError("upsample+skip fusion is 1-D only")
-            y = torch.empty((B, 1, 2 * desc.Wo, Cout), dtype=torch.float32, device=dev)
-            res = _f32c(residual)
-            if res.shape != y.shape:
-                raise MixStageError("skip tensor shape %s != %s" % (tuple(res.shape), tuple(y.shape)))
-        else:
-            y = torch.empty_like(z)
-            res = None
-        call("ms_bn_act_fwd_f32", ptr(z), ptr(ss[0]), ptr(ss[1]), slope, rows, Cout, ptr(y), ptr(res),
-             1 if up2 else 0, desc.Wo, None, 0, 0, st)
+        ss = _bn_scale_shift(z, rows, Cout, gamma, beta, None, bn_buffers, training, cfg)
+        tc_next = precision != "fp32" and carrier is not None         # the consumer may be a tensor-core layer
+        y, yp = _bn_act(z, ss, cfg, rows, Cout, desc, residual, up2, _fmt(precision), tc_next)
+        if yp is not None:
+            carrier.planes = yp
         ctx.gamma_dtype = gamma.dtype
         ctx.save_for_backward(x, z, ss)
         return y
@@ -309,24 +441,10 @@ class _ConvBlock(torch.autograd.Function):
         dy = dy.contiguous()
         dev = dy.device
         need_x, need_w, need_b, need_g, need_be, need_res = ctx.needs_input_grad[:6]
-        dgamma = dbeta = dres = dbias = dw = dx = None
+        dgamma = dbeta = dres = dw = dx = None
         if cfg.has_bn:
             x, z, ss = ctx.saved_tensors
-            slope = cfg.slope if cfg.act else 1.0
-            red = torch.zeros(2, Cout, dtype=torch.float64, device=dev)
-            if ctx.training or need_g or need_be:
-                call("ms_bn_act_bwd_reduce_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
-                     rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), st)
-            dz = torch.empty_like(z)
-            call("ms_bn_act_bwd_apply_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
-                 rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), 1 if ctx.training else 0, ptr(dz),
-                 None, 0, 0, st)
-            if need_g:
-                dgamma = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
-                call("ms_store_param_grad", ptr(red[0]), Cout, ptr(dgamma), dt_code(ctx.gamma_dtype), st)
-            if need_be:
-                dbeta = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
-                call("ms_store_param_grad", ptr(red[1]), Cout, ptr(dbeta), dt_code(ctx.gamma_dtype), st)
+            dz, dgamma, dbeta = _bn_act_backward(ctx, dy, z, ss, True, None)
             if ctx.has_res and need_res:
                 dres = dy
         else:
@@ -336,22 +454,18 @@ class _ConvBlock(torch.autograd.Function):
                 call("ms_lrelu_bwd_f32", ptr(dy), ptr(z), cfg.slope, z.numel(), ptr(dz), None, 0, 0, st)
             else:
                 dz = dy
-        wdt, bdt = ctx.param_dtypes
-        if need_b and bdt is not None:
-            if cfg.has_bn and ctx.training:
-                # batch-stat BN removes any per-channel constant: d(bias) is identically zero
-                dbias = torch.zeros(Cout, dtype=bdt, device=dev)
-            else:
-                acc = torch.zeros(Cout, dtype=torch.float64, device=dev)
-                call("ms_col_stats_f32", ptr(dz), rows, Cout, ptr(acc), None, st)
-                dbias = torch.empty(Cout, dtype=bdt, device=dev)
-                call("ms_store_param_grad", ptr(acc), Cout, ptr(dbias), dt_code(bdt), st)
+        dbias = _bias_grad(ctx, dz)
+        wdt = ctx.param_dtypes[0]
         if need_w:
             n = Cout * (desc.Cin // desc.groups) * desc.kh * desc.kw
             dwf = torch.empty(n, dtype=torch.float32, device=dev)
             call("ms_conv_wgrad_f32", ptr(x), ptr(dz), ptr(dwf), desc, st)
-            dw = torch.empty((Cout, desc.Cin // desc.groups, desc.kh, desc.kw), dtype=wdt, device=dev)
-            call("ms_unpack_conv_wgrad", ptr(dwf), desc, ptr(dw), dt_code(wdt), st)
+            sink = ctx.sinks[0]
+            if sink is not None:
+                call("ms_unpack_conv_wgrad", ptr(dwf), desc, ptr(sink), dt_code(wdt), 1, st)
+            else:
+                dw = torch.empty((Cout, desc.Cin // desc.groups, desc.kh, desc.kw), dtype=wdt, device=dev)
+                call("ms_unpack_conv_wgrad", ptr(dwf), desc, ptr(dw), dt_code(wdt), 0, st)
         if need_x:
             dx = torch.empty_like(x)
             call("ms_conv_dgrad_f32", ptr(dz), ptr(ctx.wt), ptr(dx), desc, st)
@@ -364,6 +478,8 @@ def tc_eligible(cfg, B, H, W, Cin, Cout, need_dgrad):
     rs = pad8(Cin)
     if cfg.groups > 1 and rs != Cin:
         return False
+    if Cin // cfg.groups < 8:
+        return False            # C_in = 1 (audio_encoder.conv.0): direct kernel in csrc/conv_small.cu
     if not igemm.fwd_supported(Cin, Cout, cfg.groups, cfg.sh, cfg.sw, H, W, rs):
         return False
     if cfg.kh * cfg.kw > igemm.MAX_TAPS:
@@ -387,7 +503,7 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     need_dx = ctx.needs_input_grad[0]
     split = fmt == MS_BF16X2
     xp = planes_of(x, fmt, rs)
-    pf, pd = packed.tc_plans(x.shape, Cout, cfg, rs, need_dx)
+    pf, pd = packed.tc_plans(x.shape, Cout, cfg, rs, need_dx, 3 if split else 1)
     wp, wps = packed.get_tc(weight, pf, fmt, cfg.groups)
     rows = B * desc.Ho * desc.Wo
     z = torch.empty((B, desc.Ho, desc.Wo, Cout), dtype=torch.float32, device=dev)
@@ -397,6 +513,8 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     fuse_act = (not cfg.has_bn) and cfg.act
     d.epilogue, d.slope = (2 if fuse_act else 0), cfg.slope
     b32 = None if cfg.has_bn else packed.get_bias(bias)
+    d.split_k = 1 if fuse_act else igemm.igemm_split(d, 3 if split else 1)
+    d.out_numel = z.numel()
     global last_gemm_flops
     last_gemm_flops = ctx.flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
     call("ms_igemm_bf16", d, ptr(xp.t), ptr(wp), ptr(b32), None, None, ptr(z), st)
@@ -411,32 +529,8 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     if not cfg.has_bn:
         ctx.save_for_backward(xp.t, z)
         return z
-    rm, rv, nbt = bn_buffers
-    stats = torch.zeros(2, Cout, dtype=torch.float64, device=dev) if training else None
-    if training:
-        call("ms_col_stats_f32", ptr(z), rows, Cout, ptr(stats[0]), ptr(stats[1]), st)
-    ss = torch.empty(4, Cout, dtype=torch.float32, device=dev)
-    call("ms_bn_finalize", ptr(stats[0]) if training else None, ptr(stats[1]) if training else None, rows, Cout,
-         ptr(gamma), ptr(beta), ptr(bias), ptr(rm), ptr(rv), dt_code(gamma.dtype), 1 if training else 0,
-         cfg.momentum, cfg.eps, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), st)
-    if bias is not None and bias.dtype != gamma.dtype:
-        raise MixStageError("conv bias and BatchNorm parameters must share a dtype")
-    if training:
-        nbt.add_(1)
-    slope = cfg.slope if cfg.act else 1.0
-    if up2:
-        if desc.Ho != 1:
-            raise MixStageError("upsample+skip fusion is 1-D only")
-        y = torch.empty((B, 1, 2 * desc.Wo, Cout), dtype=torch.float32, device=dev)
-        res = _f32c(residual)
-        if res.shape != y.shape:
-            raise MixStageError("skip tensor shape %s != %s" % (tuple(res.shape), tuple(y.shape)))
-    else:
-        y = torch.empty_like(z)
-        res = None
-    yp = alloc_planes(y.numel() // Cout, pad8(Cout), fmt, dev) if Cout % 8 == 0 else None
-    call("ms_bn_act_fwd_f32", ptr(z), ptr(ss[0]), ptr(ss[1]), slope, rows, Cout, ptr(y), ptr(res),
-         1 if up2 else 0, desc.Wo, ptr(yp.t) if yp else None, fmt, yp.ps if yp else 0, st)
+    ss = _bn_scale_shift(z, rows, Cout, gamma, beta, bias, bn_buffers, training, cfg)
+    y, yp = _bn_act(z, ss, cfg, rows, Cout, desc, residual, up2, fmt, True)
     ctx.gamma_dtype = gamma.dtype
     ctx.save_for_backward(xp.t, z, ss)
     if yp is not None and carrier is not None:
@@ -456,22 +550,8 @@ def _tc_backward(ctx, dy):
     wdt, bdt = ctx.param_dtypes
     if cfg.has_bn:
         xpt, z, ss = ctx.saved_tensors
-        slope = cfg.slope if cfg.act else 1.0
-        red = torch.zeros(2, Cout, dtype=torch.float64, device=dev)
-        if ctx.training or need_g or need_be:
-            call("ms_bn_act_bwd_reduce_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
-                 rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), st)
         need_f32 = need_b and bdt is not None and not ctx.training
-        dz = torch.empty_like(z) if need_f32 else None
-        call("ms_bn_act_bwd_apply_f32", ptr(dy), ptr(z), ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), slope,
-             rows, Cout, 1 if ctx.up2 else 0, desc.Wo, ptr(red[0]), ptr(red[1]), 1 if ctx.training else 0, ptr(dz),
-             ptr(dzp.t), fmt, dzp.ps, st)
-        if need_g:
-            dgamma = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
-            call("ms_store_param_grad", ptr(red[0]), Cout, ptr(dgamma), dt_code(ctx.gamma_dtype), st)
-        if need_be:
-            dbeta = torch.empty(Cout, dtype=ctx.gamma_dtype, device=dev)
-            call("ms_store_param_grad", ptr(red[1]), Cout, ptr(dbeta), dt_code(ctx.gamma_dtype), st)
+        dz, dgamma, dbeta = _bn_act_backward(ctx, dy, z, ss, need_f32, dzp)
         if ctx.has_res and need_res:
             dres = dy
     else:
@@ -482,14 +562,7 @@ def _tc_backward(ctx, dy):
         else:
             dz = dy
             call("ms_to_planes", ptr(dy), rows, Cout, Cout, ptr(dzp.t), fmt, dzp.ps, st)
-    if need_b and bdt is not None:
-        if cfg.has_bn and ctx.training:
-            dbias = torch.zeros(Cout, dtype=bdt, device=dev)     # batch-stat BN removes any per-channel constant
-        else:
-            acc = torch.zeros(Cout, dtype=torch.float64, device=dev)
-            call("ms_col_stats_f32", ptr(dz), rows, Cout, ptr(acc), None, st)
-            dbias = torch.empty(Cout, dtype=bdt, device=dev)
-            call("ms_store_param_grad", ptr(acc), Cout, ptr(dbias), dt_code(bdt), st)
+    dbias = _bias_grad(ctx, dz)
     pf, pd = ctx.plans
     xrs, xps = ctx.xp_meta
     B, H, W, Cin = ctx.x_shape
@@ -498,14 +571,24 @@ def _tc_backward(ctx, dy):
     last_gemm_flops = ctx.flops
     if need_w:
         igemm.set_planes(pf, split, xps, 0, dzp.ps)
-        dwp = torch.empty(pf.wp_numel, dtype=torch.float32, device=dev)
+        nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc)
+        pf.desc.split_k = nsplit
+        dwp = torch.empty(nsplit * pf.wp_numel, dtype=torch.float32, device=dev)     # one partial per row slice
         call("ms_wgrad_bf16", pf.desc, ptr(xpt), ptr(dzp.t), ptr(dwp), st)
-        dw = torch.empty((Cout, Cin_g, cfg.kh, cfg.kw), dtype=wdt, device=dev)
-        call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin_g, cfg.kh * cfg.kw, pf.desc.ntaps, pf.kpad, ptr(dw), dt_code(wdt), st)
+        sink = ctx.sinks[0]
+        if sink is not None:
+            call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin_g, cfg.kh * cfg.kw, pf.desc.ntaps, pf.kpad, ptr(sink),
+                 dt_code(wdt), nsplit, 1, st)
+        else:
+            dw = torch.empty((Cout, Cin_g, cfg.kh, cfg.kw), dtype=wdt, device=dev)
+            call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin_g, cfg.kh * cfg.kw, pf.desc.ntaps, pf.kpad, ptr(dw),
+                 dt_code(wdt), nsplit, 0, st)
     if need_x:
         wt, wtps = ctx.wt
         igemm.set_planes(pd, split, dzp.ps, wtps, 0)
         dxf = torch.empty((B, H, W, xrs), dtype=torch.float32, device=dev)
+        pd.desc.split_k = igemm.igemm_split(pd.desc, 3 if split else 1)
+        pd.desc.out_numel = dxf.numel()
         call("ms_igemm_bf16", pd.desc, ptr(dzp.t), ptr(wt), None, None, None, ptr(dxf), st)
         dx = dxf if xrs == Cin else dxf[..., :Cin]
     return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None, None
@@ -513,9 +596,10 @@ def _tc_backward(ctx, dy):
 
 def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, residual=None, up2=False, precision=None):
     """weight is the caller's parameter in its own layout/dtype: (Cout, Cin/g, k) or (Cout, Cin/g, kh, kw)."""
+    carrier = _Carrier()
+    carrier.sinks = (_sink(weight), _sink(bias), _sink(gamma), _sink(beta))
     if weight.dim() == 3:
         weight = weight.unsqueeze(2)        # view: (Cout, Cin/g, 1, k); autograd maps the grad back
-    carrier = _Carrier()
     y = _ConvBlock.apply(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2,
                          (precision or _precision), carrier)
     if carrier.planes is not None:
@@ -525,10 +609,11 @@ def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, 
 
 class _Carrier:
     """Hands the bf16 operand planes produced inside an autograd node to the tensor object the caller receives."""
-    __slots__ = ("planes",)
+    __slots__ = ("planes", "sinks")
 
     def __init__(self):
         self.planes = None
+        self.sinks = (None, None, None, None)     # .grad buffers of (weight, bias, gamma, beta) for direct accumulation
 
 
 # ---------------------------------------------------------------------------- bilinear time resize

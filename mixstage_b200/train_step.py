@@ -131,13 +131,19 @@ class TrainStep:
         self.fD.zero_grad()
         gan.force_step = kind
         G.force_branch = "pose" if use_pose else "audio"
+        # kernels accumulate parameter gradients straight into the flat buffers and draw their fp64 accumulators from
+        # one arena cleared by a single memset (ops.py)
+        ops.arena.begin(self.fG.device)
+        ops.DIRECT_GRADS = True
         try:
             fake, losses, _ = gan([audio, labels], pose, input_modalities=self.mod, style=style, sample_flag=0,
                                   description=self.description, desc=self.description)
+            loss = sum(losses)
+            loss.backward()
         finally:
             G.force_branch = None
-        loss = sum(losses)
-        loss.backward()
+            ops.DIRECT_GRADS = False
+            ops.arena.end()
         f = self.fG if kind == "G" else self.fD
         f.allreduce_mean(self.group)
         f.clip_adam(self.lr, self.lr_dev, self.betas, self.eps, self.max_norm)

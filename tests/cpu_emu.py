@@ -62,12 +62,17 @@ def ms_pack_conv_weight_f32(w, pdt, desc, wf, wt, st):
         f32(wt, W.numel()).copy_(W.permute(0, 3, 1, 2).reshape(-1))        # [g][tap][n][c]
 
 
-def ms_unpack_conv_wgrad(dwf, desc, dw, pdt, st):
+def _store(dst, n, pdt, val, accumulate):
+    D = param(dst, n, pdt)
+    D.copy_((val.double() + (D.double() if accumulate else 0.0)).to(D.dtype))
+
+
+def ms_unpack_conv_wgrad(dwf, desc, dw, pdt, accumulate, st):
     d = _d(desc)
     g, taps = d.groups, d.kh * d.kw
     cg, ng = d.Cin // g, d.Cout // g
     G = f32(dwf, d.Cout * cg * taps).view(g, taps, cg, ng).permute(0, 3, 2, 1).reshape(-1)
-    param(dw, G.numel(), pdt).copy_(G)
+    _store(dw, G.numel(), pdt, G, accumulate)
 
 
 def _weight_from_wf(wf, d):
@@ -139,6 +144,14 @@ def ms_bn_finalize(s, ss, rows, C, gamma, beta, cbias, rm, rv, pdt, training, mo
     f32(rstd, C).copy_(r.float())
 
 
+def ms_bn_stats_finalize(x, rows, C, s, ss, ticket, gamma, beta, cbias, rm, rv, nbt, pdt, momentum, eps, scale, shift,
+                         mean, rstd, st):
+    ms_col_stats_f32(x, rows, C, s, ss, st)
+    ms_bn_finalize(s, ss, rows, C, gamma, beta, cbias, rm, rv, pdt, 1, momentum, eps, scale, shift, mean, rstd, st)
+    if nbt:
+        i64(nbt, 1).add_(1)
+
+
 def _act(z, slope):
     return torch.where(z > 0, z, z * slope)
 
@@ -192,7 +205,11 @@ def ms_bn_act_bwd_reduce_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up
 
 
 def ms_bn_act_bwd_apply_f32(dy, x, scale, shift, mean, rstd, slope, rows, C, up2, L, dgamma, dbeta, training, dx,
-                            planes, pfmt, pstride, st):
+                            planes, pfmt, pstride, ggamma, gbeta, gdt, st):
+    if ggamma:
+        _store(ggamma, C, gdt, f64(dgamma, C), True)
+    if gbeta:
+        _store(gbeta, C, gdt, f64(dbeta, C), True)
     X = f32(x, rows * C).view(rows, C)
     sc = f32(scale, C)
     Z = X * sc + f32(shift, C)
@@ -216,8 +233,8 @@ def ms_lrelu_bwd_f32(dy, y, slope, n, dz, planes, pfmt, pstride, st):
     _store_planes(planes, pfmt, pstride, o)
 
 
-def ms_store_param_grad(src, n, dst, pdt, st):
-    param(dst, n, pdt).copy_(f64(src, n))
+def ms_store_param_grad(src, n, dst, pdt, accumulate, st):
+    _store(dst, n, pdt, f64(src, n), accumulate)
 
 
 def ms_bilinear_to_T_fwd_f32(x, B, Hi, Wi, C, T, y, st):
@@ -431,7 +448,11 @@ def ms_wgrad_bf16(desc, x, dz, dwp, st):
     Ap = [_padded_a(x + 2 * d.a_plane_stride * i, d, kpad, Ho, Wo) for i in range(planes)]
     Z = [bf16(dz + 2 * d.out_plane_stride * i, Bo * Ho * Wo * Ct).float().view(Bo, Ho, Wo, Ct) for i in range(planes)]
     passes = [(0, 0), (0, 1), (1, 0)] if planes == 2 else [(0, 0)]      # (x plane, dz plane)
-    out = f32(dwp, d.num_classes * d.class_n * d.ntaps * kpad).view(d.num_classes * d.class_n, d.ntaps, kpad)
+    nsplit = max(1, d.split_k)
+    wpn = d.num_classes * d.class_n * d.ntaps * kpad
+    allp = f32(dwp, nsplit * wpn).view(nsplit, d.num_classes * d.class_n, d.ntaps, kpad)
+    allp.zero_()                      # the specification puts the whole sum in partial 0 (any split of the rows is valid)
+    out = allp[0]
     for q in range(d.num_classes):
         for t in range(d.ntaps):
             acc = torch.zeros(d.class_n, kpad)
@@ -442,9 +463,9 @@ def ms_wgrad_bf16(desc, x, dz, dwp, st):
             out[q * d.class_n:(q + 1) * d.class_n, t] = acc
 
 
-def ms_unpack_igemm_wgrad(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, st):
-    G = f32(dwp, Cout * ntaps * kpad).view(Cout, ntaps, kpad)[:, :, :Cin_g].permute(0, 2, 1).reshape(-1)
-    param(dw, G.numel(), pdt).copy_(G)
+def ms_unpack_igemm_wgrad(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, nsplit, accumulate, st):
+    G = f32(dwp, nsplit * Cout * ntaps * kpad).view(nsplit, Cout, ntaps, kpad).sum(0)[:, :, :Cin_g].permute(0, 2, 1).reshape(-1)
+    _store(dw, G.numel(), pdt, G, accumulate)
 
 
 def ms_grad_sqnorm(g, dt, n, acc, step, st):

@@ -62,7 +62,7 @@ def test_fwd_and_dgrad_descriptors_match_conv2d(g):
     dwp = torch.full((plan.wp_numel,), float("nan"))
     cpu_emu.ms_wgrad_bf16(plan.desc, ptr(x), ptr(dz), ptr(dwp), None)
     dw = torch.zeros(Cout, Cin // groups, kh, kw)
-    cpu_emu.ms_unpack_igemm_wgrad(ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 0, None)
+    cpu_emu.ms_unpack_igemm_wgrad(ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 0, 1, 0, None)
     assert float((dw - wref).abs().max()) < 2e-4 * float(wref.abs().max())
 
 

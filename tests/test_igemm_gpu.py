@@ -91,7 +91,7 @@ def test_wgrad_tc(g):
     xg, dzg = x.cuda(), dz.cuda()          # keep the device copies alive across the launch
     _lib.call("ms_wgrad_bf16", plan.desc, ptr(xg), ptr(dzg), ptr(dwp), st)
     dw = torch.zeros(Cout, Cin // groups, kh, kw, dtype=torch.float64, device="cuda")
-    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 1, st)
+    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 1, 1, 0, st)
     torch.cuda.synchronize()
     err = float((dw.cpu() - wref).abs().max())
     assert err < 1e-3 * float(wref.abs().max()), (err, float(wref.abs().max()))
@@ -138,30 +138,34 @@ def test_split_bf16_fwd_dgrad_wgrad(g):
         return wp, ps
 
     pf = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
-    pf.desc.block_n = igemm.pick_block_n(pf.desc)
+    pf.desc.block_n = igemm.pick_block_n(pf.desc, 3)
     wp, wps = packed(pf, 0)
     igemm.set_planes(pf, True, xps, wps, 0)
     out = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda")
+    pf.desc.split_k, pf.desc.out_numel = igemm.igemm_split(pf.desc, 3), out.numel()      # split-K where the grid is small
     _lib.call("ms_igemm_bf16", pf.desc, ptr(xp), ptr(wp), None, None, None, ptr(out), st)
     torch.cuda.synchronize()
     err = float((out.cpu().double() - ref).abs().max())
     assert err < 3e-5 * float(ref.abs().max()), (err, float(ref.abs().max()))
 
     pd = igemm.make_dgrad(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo)
-    pd.desc.block_n = igemm.pick_block_n(pd.desc)
+    pd.desc.block_n = igemm.pick_block_n(pd.desc, 3)
     wt, wtps = packed(pd, 1)
     igemm.set_planes(pd, True, dzps, wtps, 0)
     dx = torch.full((B, H, W, Cin), float("nan"), device="cuda")
+    pd.desc.split_k, pd.desc.out_numel = igemm.igemm_split(pd.desc, 3), dx.numel()
     _lib.call("ms_igemm_bf16", pd.desc, ptr(dzp), ptr(wt), None, None, None, ptr(dx), st)
     torch.cuda.synchronize()
     err = float((dx.cpu().double() - dref).abs().max())
     assert err < 3e-5 * float(dref.abs().max()), (err, float(dref.abs().max()))
 
     igemm.set_planes(pf, True, xps, 0, dzps)
-    dwp = torch.full((pf.wp_numel,), float("nan"), device="cuda")
+    nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc)
+    pf.desc.split_k = nsplit
+    dwp = torch.full((nsplit * pf.wp_numel,), float("nan"), device="cuda")
     _lib.call("ms_wgrad_bf16", pf.desc, ptr(xp), ptr(dzp), ptr(dwp), st)
     dw = torch.zeros(Cout, Cin // groups, kh, kw, dtype=torch.float64, device="cuda")
-    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, pf.desc.ntaps, pf.kpad, ptr(dw), 1, st)
+    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, pf.desc.ntaps, pf.kpad, ptr(dw), 1, nsplit, 0, st)
     torch.cuda.synchronize()
     err = float((dw.cpu() - wref).abs().max())
     assert err < 3e-5 * float(wref.abs().max()), (err, float(wref.abs().max()))

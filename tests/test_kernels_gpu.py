@@ -95,7 +95,10 @@ def test_conv_fwd_dgrad_wgrad(c):
     close(dxg, dxc)
     (dwg,), (dwc,) = run_both("ms_conv_wgrad_f32", [(x, "in"), (dy, "in"), (torch.zeros(n), "out"), d])
     close(dwg, dwc, 5e-5)
-    (g64,), (c64,) = run_both("ms_unpack_conv_wgrad", [(dwc, "in"), d, (torch.zeros(n, dtype=torch.float64), "out"), 1])
+    (g64,), (c64,) = run_both("ms_unpack_conv_wgrad", [(dwc, "in"), d, (torch.zeros(n, dtype=torch.float64), "out"), 1, 0])
+    (g64a,), (c64a,) = run_both("ms_unpack_conv_wgrad", [(dwc, "in"), d, (torch.ones(n, dtype=torch.float64), "inout"), 1, 1])
+    close(g64a, c64a, 1e-9)
+    close(g64a - 1.0, c64, 1e-6)
     assert torch.equal(g64, c64)
 
 
@@ -122,6 +125,17 @@ def test_batchnorm_chain(rows, C, L, up2):
     g, c = run_both("ms_bn_finalize", [(sc, "in"), (ssc, "in"), rows, C, (gamma, "in"), (beta, "in"), (None, "in"),
                                        (rm, "inout"), (rv, "inout"), 1, 1, 0.1, 1e-5] + outs)
     scale, shift, mean, rstd = c[2], c[3], c[4], c[5]
+    # statistics + finalize + batch counter in one launch == the two-kernel sequence
+    s0, ss0 = torch.zeros(C, dtype=torch.float64), torch.zeros(C, dtype=torch.float64)
+    outs = [(torch.zeros(C), "out") for _ in range(4)]
+    g2, c2 = run_both("ms_bn_stats_finalize", [(x, "in"), rows, C, (s0, "inout"), (ss0, "inout"), (torch.zeros(2, dtype=torch.int32), "inout"),
+                                               (gamma, "in"), (beta, "in"), (cbias, "in"), (rm, "inout"), (rv, "inout"),
+                                               (torch.full((1,), 5, dtype=torch.int64), "inout"), 1, 0.1, 1e-5] + outs)
+    assert int(g2[5]) == 6
+    for a, b in zip(g2[6:], c2[6:]):
+        close(a, b, 1e-6)
+    close(g2[3], c2[3], 1e-6)
+    close(g2[4], c2[4], 1e-6)
     res = torch.randn(rows * (2 if up2 else 1), C)
     y = torch.zeros_like(res)
     (yg,), (yc,) = run_both("ms_bn_act_fwd_f32", [(x, "in"), (scale, "in"), (shift, "in"), 0.2, rows, C, (y, "out"),
@@ -159,13 +173,19 @@ def test_batchnorm_chain(rows, C, L, up2):
     for training in (1, 0):
         (dxg,), (dxc,) = run_both("ms_bn_act_bwd_apply_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
                                                                 (rstd, "in"), 0.2, rows, C, up2, L, (dgc, "in"), (dbc, "in"),
-                                                                training, (torch.zeros(rows, C), "out"), (None, "in"), 0, 0])
+                                                                training, (torch.zeros(rows, C), "out"), (None, "in"), 0, 0,
+                                                                (None, "in"), (None, "in"), 0])
         close(dxg, dxc, 1e-5)
         psd = (rows * C + 7) // 8 * 8
-        (dxg2, pg), (dxc2, pc) = run_both("ms_bn_act_bwd_apply_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
+        (dxg2, pg, gg, gb), (dxc2, pc, cg_, cb_) = run_both("ms_bn_act_bwd_apply_f32", [(dy, "in"), (x, "in"), (scale, "in"), (shift, "in"), (mean, "in"),
                                                                        (rstd, "in"), 0.2, rows, C, up2, L, (dgc, "in"), (dbc, "in"),
                                                                        training, (torch.zeros(rows, C), "out"),
-                                                                       (torch.zeros(2 * psd, dtype=torch.bfloat16), "out"), 3, psd])
+                                                                       (torch.zeros(2 * psd, dtype=torch.bfloat16), "out"), 3, psd,
+                                                                       (torch.ones(C, dtype=torch.float64), "inout"),
+                                                                       (torch.ones(C, dtype=torch.float64), "inout"), 1])
+        close(gg, 1.0 + dgc, 1e-9)           # affine-parameter gradients accumulated into their buffers
+        close(gb, 1.0 + dbc, 1e-9)
+        close(gg, cg_, 1e-9)
         rec = pg[:rows * C].float() + pg[psd:psd + rows * C].float()
         assert float((rec - dxg2.reshape(-1)).abs().max()) <= 2 ** -15 * float(dxg2.abs().max()) + 1e-30
 

@@ -29,18 +29,25 @@ def test_graph_replay_equals_eager(precision):
         _, Ge, De, tse, _ = _mk(precision, False)
         kinds = ["G", "D", "G", "G", "D", "D"]
         for it, kind in enumerate(kinds):
+            # same starting state for both (Adam's sign-like first updates make free-running trajectories diverge
+            # chaotically from 1e-7 differences, see test_train_step_cpu.py): copy eager -> graphed before each step
+            with torch.no_grad():
+                for fa, fb in ((tsg.fG, tse.fG), (tsg.fD, tse.fD)):
+                    for name in ("p", "m", "v", "step_count"):
+                        getattr(fa, name).copy_(getattr(fb, name))
+                for (ma, mb) in ((Gg, Ge), (Dg, De)):
+                    for ba, bb in zip(ma.buffers(), mb.buffers()):
+                        ba.copy_(bb)
             fg, lg = tsg.step(*batch, kind=kind)
             fe, le = tse.step(*batch, kind=kind)
             torch.cuda.synchronize()
-            # identical kernels; only fp32 atomics (split-K weight gradients) reorder.  Later steps inherit Adam's
-            # sign-like first updates of near-zero gradients, amplified by batch-stat BN (see test_train_step_cpu.py)
-            tol = 1e-5 if it == 0 else 2e-2
-            assert float((fg - fe).norm() / fe.norm()) < tol, (it, kind)
-            assert torch.allclose(lg, le, rtol=max(tol, 1e-4), atol=1e-5), (it, kind, lg, le)
+            # identical kernels; only fp32 reductions (split-K tiles) reorder
+            assert float((fg - fe).norm() / fe.norm()) < 1e-4, (it, kind)
+            assert torch.allclose(lg, le, rtol=1e-4, atol=1e-5), (it, kind, lg, le)
+            diff = (tsg.fG.p - tse.fG.p).abs() if kind == "G" else (tsg.fD.p - tse.fD.p).abs()
+            assert float((diff > 2e-5).double().mean()) < 2e-3, (it, kind)
         assert tsg.replays == len(kinds) and len(tsg.graphs) == 2
         assert int(tsg.fG.step_count) == 3 and int(tsg.fD.step_count) == 3
-        diff = (tsg.fG.p - tse.fG.p).abs()
-        assert float((diff > 5e-5).double().mean()) < 2e-2
         for (k, a), (_, b) in zip(Gg.state_dict().items(), Ge.state_dict().items()):
             if k.endswith("num_batches_tracked"):
                 assert int(a) == int(b), k

@@ -48,7 +48,7 @@ def run(name, mode):
     xg, dzg = x.cuda(), dz.cuda()
     _lib.call("ms_wgrad_bf16", plan.desc, ptr(xg), ptr(dzg), ptr(dwp), st)
     dw = torch.zeros(Cout, Cin // groups, kh, kw, dtype=torch.float64, device="cuda")
-    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 1, st)
+    _lib.call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin // groups, kh * kw, plan.desc.ntaps, plan.kpad, ptr(dw), 1, 1, 0, st)
     torch.cuda.synchronize()
     dw = dw.cpu()
     err = (dw - wref).abs()

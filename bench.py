@@ -316,16 +316,210 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------
+# CUDA arm, BASELINE configs[2]: batched inference sweep (sample_all_styles over S speakers)
+# --------------------------------------------------------------------------------------------
+def run_infer(args):
+    """One step = the reference's sampling inner loop for one batch (trainer.py:791-794 with update_kwargs :1367-1386):
+    B windows pushed through G.forward once per target style ((style + shift) % S), eval mode, no_grad.  Sequences per
+    step = B * S.  Sharded over ranks with no collective."""
+    import torch.distributed as dist
+    import mixstage_b200 as M
+    import mixstage_oracle as O
+    from mixstage_b200 import _lib, ops
+    from model_cases import build as build_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    prec = args.precision or "bf16"
+    ops.set_precision(prec)
+    B, S = args.batch or 1024, 4
+    spec = O.Spec(num_speakers=S)
+    G, D, gan = build_model(spec, T, dev, torch.float64)
+    G.eval()
+    G.thresh.value, G.thresh.iters = 1.0, 1000
+
+    # two alternating per-rank batches: consecutive steps never see the same audio tensor, so the style-sweep cache
+    # (encoder output reused across the S styles of ONE batch) cannot carry work from one step to the next
+    hosts, residents = [], []
+    for j in range(2):
+        audio, pose, labels, style = O.synth_inputs(B, T, spec, seed=11212 + 2 * rank + j)
+        h = [t.pin_memory() for t in (audio, labels, pose, style)]
+        hosts.append(h)
+        residents.append([t.to(dev) for t in h])
+    h2d = sum(t.numel() * t.element_size() for t in hosts[0])
+    out_host = torch.empty((S, B, T, spec.out_feats), dtype=torch.float64).pin_memory()
+    d2h = out_host.numel() * out_host.element_size()
+
+    def step(i, e2e):
+        if e2e:
+            audio, labels, pose, style = [t.to(dev, non_blocking=True) for t in hosts[i % 2]]
+        else:
+            audio, labels, pose, style = residents[i % 2]
+        with torch.no_grad():
+            for shift in range(S):
+                st = (style + shift) % S
+                out, _ = G([audio, labels], pose, input_modalities=MOD, style=st, sample_flag=1, description="test")
+                if e2e:
+                    out_host[shift].copy_(out, non_blocking=True)
+        if e2e:
+            torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(nsteps):
+            step(i, e2e)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if e2e:
+            ms = max(ms, wall * 1e3)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(max(args.warmup, 3)):
+        step(i, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, hits0 = _lib.LAUNCHES, G.encoder_cache_hits
+    ms = timed(args.steps, False)
+    launches = _lib.LAUNCHES - l0
+    hits = G.encoder_cache_hits - hits0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, True)
+
+    # roofline of the dominant kernel family: CUDA events around every tcgen05 launch of one instrumented step
+    records = []
+    orig_call = ops.call
+
+    def timed_call(name, *a):
+        if name in ("ms_igemm_bf16_fused", "ms_igemm_bf16"):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig_call(name, *a)
+            e1.record()
+            records.append((name, ops.last_gemm_flops, e0, e1))
+        else:
+            orig_call(name, *a)
+
+    ops.call = timed_call
+    try:
+        step(args.steps, False)
+    finally:
+        ops.call = orig_call
+    torch.cuda.synchronize()
+    gemm_ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in records)
+    gemm_fl = sum(f for _, f, _, _ in records)
+    pk, pk_kind = peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    achieved_tf = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    if rank == 0:
+        total = args.steps * B * S * world
+        cpu_b = 16
+        cpu_dt = cpu_infer_sweep(cpu_b, S, 2, 1)
+        line = {
+            "metric": "pose sequences/sec (64-frame windows), inference style sweep", "value": total / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 operands, f32 accumulate)", "bf16": "bf16 (f32 accumulate)"}[prec],
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: inference sweep, B=%d windows per GPU x S=%d target styles per step "
+                                   "(sample_all_styles), T=64, K=8, eval mode, fp64 parameters/inputs/outputs, precision=%s, "
+                                   "encoder+UNet computed once per batch and reused across styles" % (B, S, prec),
+                       "global_batch": B * world, "parallelism": "dp%d (no collective)" % world,
+                       "l2": "two alternating input batches; per-step activations (>1 GB at B=1024) exceed the 126 MB L2"},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "G.forward per style on a pinned host batch + pose outputs copied back to pinned host memory"},
+            "gpu_launches": launches, "encoder_cache_hits": hits,
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
+            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "kernel": "igemm_tc_kernel, fused inference epilogue (%d launches per step; algorithmic FLOPs%s)" % (
+                             len(records), ", split-bf16 issues 3x the MMAs" if prec == "bf16x3" else ""),
+                         "gemm_ms_per_step": gemm_ms, "peak_source": "%s bf16 sustained" % pk_kind},
+            "cpu_baseline": {"value": 2 * cpu_b * S / cpu_dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": "2 sweeps of B=%d x S=%d styles after 1 warm-up, oracle port (torch CPU fp64), encoder "
+                                       "recomputed per style as the reference does" % (cpu_b, S)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_infer_sweep(B, S, steps, warmup, dtype=torch.float64):
+    """Times the oracle's restatement of the reference sampling loop: S full forwards per batch."""
+    import mixstage_oracle as O
+    from oracle_cases import G_SEED
+    torch.set_num_threads(os.cpu_count())
+    spec = O.Spec(num_speakers=S)
+    sd = O.synth_state(O.g_state_shapes(spec), G_SEED, dtype)
+    audio, pose, labels, style = O.synth_inputs(B, T, spec, dtype=dtype)
+
+    def one():
+        with torch.no_grad():
+            for shift in range(S):
+                O.g_forward(sd, spec, audio, labels, pose, (style + shift) % S, training=False, sample_flag=1, description="test")
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    return time.perf_counter() - t0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--batch", type=int, default=16, help="sequences per GPU")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default 16 train, 1024 infer)")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train: BASELINE configs[1] GAN train step (default); infer: configs[2] style-sweep inference")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "bf16"], help="default bf16x3 train, bf16 infer")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
+    if args.workload == "infer" and args.impl == "cuda":
+        return run_infer(args)
+    if args.workload == "infer":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        B, S = args.batch or 16, 4
+        dt = cpu_infer_sweep(B, S, args.steps, args.warmup)
+        val = args.steps * B * S / dt
+        print(json.dumps({
+            "impl": "reference", "metric": "pose sequences/sec (64-frame windows), inference style sweep", "value": val,
+            "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[2]: inference sweep, B=%d x S=%d styles per step, T=64, K=8, fp64" % (B, S)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d sweeps after %d warm-up, oracle port (torch CPU fp64, %d threads)" % (
+                                 args.steps, args.warmup, os.cpu_count())},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    args.batch = args.batch or 16
+    args.precision = args.precision or "bf16x3"
     if args.impl == "reference":
         run_reference(args)
     else:

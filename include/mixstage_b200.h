@@ -77,6 +77,14 @@ int ms_conv_dgrad_f32(const float* dy, const float* wt, float* dx, const ms_conv
  * Overwrites dwf (zeroed internally; split-K partials are combined with fp32 atomics). */
 int ms_conv_wgrad_f32(const float* x, const float* dy, float* dwf, const ms_conv_desc* d, void* stream);
 
+/* Inference form of the C_in = 1 convolution (audio_encoder.conv.0, layers.py:167: 3x3 over the (T, F) log-mel image,
+ * K = 9 -- HBM-bound, not tensor-core work) with the eval-mode BatchNorm folded to scale/shift (conv bias inside shift)
+ * and LeakyReLU(slope) applied in the same pass: v = act(conv(x) * scale[n] + shift[n]) written as fp32 (y, nullable)
+ * and/or as the next layer's bf16 operand planes (nullable; pfmt MS_BF16 | MS_BF16X2, lo plane at + pstride).
+ * wf is the [tap][0][n] fp32 tiling of ms_pack_conv_weight_f32.  Cout % 8 == 0. */
+int ms_conv_cin1_bnact(const float* x, const float* wf, const float* scale, const float* shift, float slope,
+                       const ms_conv_desc* d, float* y, void* planes, int pfmt, int64_t pstride, void* stream);
+
 /* ---- implicit-GEMM convolution on tcgen05 tensor cores (bf16 operands, fp32 accumulate in TMEM,
  * operands staged by TMA).  Same call sites as the fp32 family above; this is the fast path
  * ("precision=bf16").  One descriptor type serves the forward pass and the input gradient:
@@ -122,6 +130,16 @@ typedef struct ms_igemm_desc {
 } ms_igemm_desc;
 int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
                   const float* shift, void* out, void* stream);
+/* Inference form of the same launch (eval-mode ConvNormRelu, layers.py:78 with the BatchNorm folded to scale/shift):
+ * the epilogue result goes out as the NEXT layer's operand planes (`out`, d->out_dtype MS_BF16 / MS_BF16X2) and, when
+ * out_f32 is not NULL, also as fp32 at the same element offsets -- no fp32 round trip through HBM between layers.
+ * up2 != 0 fuses UNet1D's `upconv(x) + residual` (layers.py:150-151, 1-D only): GEMM row (b, w) produces output rows
+ * (b, 2w) and (b, 2w+1) of a tensor with 2*out_dims[0] rows per sequence (out_strides[2] is the stride of the
+ * UN-doubled tensor), each plus the residual row read from `res` (bf16 planes laid out like that output; res_planes 1|2,
+ * lo plane at + res_pstride elements).  split_k must be <= 1. */
+int ms_igemm_bf16_fused(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                        const float* shift, void* out, float* out_f32, const void* res, int res_planes,
+                        int64_t res_pstride, int up2, void* stream);
 /* Re-tile a conv weight (Cout, Cin/g, kh*kw) of dtype pdt into Wp (bf16).
  * mode 0 (forward):  Wp[q*class_n + r][t][c] = w[q*class_n + r][c][srctap[t]]            (c < Cin/g, else 0)
  * mode 1 (dgrad):    Wp[q*class_n + r][t][n] = w[g*Cout/g + n][r][srctap[q*ntaps + t]]   (n < Cout/g, r < Cin/g, else 0)
@@ -131,6 +149,18 @@ int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const fl
 int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int taps_total, int groups, int mode,
                               int num_classes, int class_n, int ntaps, int kpad, const int16_t* srctap_host,
                               void* wp, void* wp_lo, void* stream);
+
+/* The same re-tiling for MANY weights in one launch: table_dev is a DEVICE array of n_entries records (arguments of
+ * ms_pack_igemm_weight_bf16, srctap inline).  Used by the train step to refresh every packed weight of the sub-network
+ * that the optimiser just updated. */
+typedef struct ms_pack_entry {
+  const void* w;
+  void* wp;
+  void* wp_lo;              /* nullable */
+  int32_t pdt, Cout, Cin_g, taps_total, groups, mode, num_classes, class_n, ntaps, kpad;
+  int16_t srctap[MS_IGEMM_MAX_TAPS];
+} ms_pack_entry;
+int ms_pack_igemm_weight_multi(const ms_pack_entry* table_dev, int n_entries, int blocks_per_entry, void* stream);
 
 /* Weight gradient on tcgen05 (aten::convolution_backward, weight grad): with d the FORWARD descriptor,
  *   dwp[q*class_n + n][t][c] = sum_{b,h,w} dz[b,h,w, off[q] + n] * A5[base[q] + taps[t].chan + c, w + dw, par, h + dh, b]
@@ -174,6 +204,8 @@ int ms_bn_act_fwd_f32(const float* x, const float* scale, const float* shift, fl
  * y may be NULL when only the planes are wanted. */
 /* x (rows, C) fp32 -> planes with row stride row_stride >= C (pad columns zero). */
 int ms_to_planes(const float* x, int64_t rows, int C, int row_stride, void* planes, int pfmt, int64_t pstride, void* stream);
+/* inverse: planes (row stride row_stride) -> x (rows, C) fp32 = hi (+ lo). */
+int ms_planes_to_f32(const void* planes, int pfmt, int64_t pstride, int64_t rows, int C, int row_stride, float* x, void* stream);
 /* backward reductions of act(bn(x)):  dz = dy * (z>0 ? 1 : slope) with z = x*scale+shift,
  * dbeta[c] += sum dz, dgamma_hat[c] += sum dz * xhat  (xhat = (x-mean)*rstd), doubles,
  * caller zeroes.  up2: dy has 2*L rows per sequence and the two rows of a pair are summed. */

@@ -37,6 +37,13 @@ class IgemmDesc(ctypes.Structure):
     ]
 
 
+class PackEntry(ctypes.Structure):
+    """ms_pack_entry (include/mixstage_b200.h)."""
+    _fields_ = [("w", ctypes.c_void_p), ("wp", ctypes.c_void_p), ("wp_lo", ctypes.c_void_p)] + [
+        (n, ctypes.c_int32) for n in ("pdt", "Cout", "Cin_g", "taps_total", "groups", "mode", "num_classes", "class_n",
+                                      "ntaps", "kpad")] + [("srctap", ctypes.c_int16 * MAX_TAPS)]
+
+
 _P, _I, _L, _F, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
 _CD = ctypes.POINTER(ConvDesc)
 _GD = ctypes.POINTER(IgemmDesc)
@@ -52,14 +59,18 @@ PROTOTYPES = {
     "ms_conv_fwd_f32": [_P, _P, _P, _P, _CD, _I, _F, _P],
     "ms_conv_dgrad_f32": [_P, _P, _P, _CD, _P],
     "ms_conv_wgrad_f32": [_P, _P, _P, _CD, _P],
+    "ms_conv_cin1_bnact": [_P, _P, _P, _P, _F, _CD, _P, _P, _I, _L, _P],
     "ms_igemm_bf16": [_GD, _P, _P, _P, _P, _P, _P, _P],
+    "ms_igemm_bf16_fused": [_GD, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P],
     "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P, _P],
+    "ms_pack_igemm_weight_multi": [_P, _I, _I, _P],
     "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],
     "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "ms_col_stats_f32": [_P, _L, _I, _P, _P, _P],
     "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],
     "ms_bn_act_fwd_f32": [_P, _P, _P, _F, _L, _I, _P, _P, _I, _I, _P, _I, _L, _P],
     "ms_to_planes": [_P, _L, _I, _I, _P, _I, _L, _P],
+    "ms_planes_to_f32": [_P, _I, _L, _L, _I, _I, _P, _P],
     "ms_bn_act_bwd_reduce_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _P],
     "ms_bn_act_bwd_apply_f32": [_P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P, _P, _I, _P, _P, _I, _L, _P, _P, _I, _P],
     "ms_bn_stats_finalize": [_P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P],

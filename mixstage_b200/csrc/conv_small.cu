@@ -143,6 +143,73 @@ __global__ void __launch_bounds__(256) fwd_cin1(P p, const float* __restrict__ x
   }
 }
 
+// ---- C_in = 1 forward, 8 output channels per thread (Cout % 8 == 0): the tap addresses are computed once per 8 outputs
+// and every thread stores 32 (fp32) / 16 (bf16 plane) contiguous bytes, consecutive threads consecutive channels.
+// FUSED = 0: y = conv + bias [LeakyReLU]  (training forward, z of the block)
+// FUSED = 1: v = LeakyReLU(conv * scale[n] + shift[n]) (eval-mode BatchNorm folded, conv bias inside shift), written as fp32
+//            (y nullable) and/or bf16 operand planes (hi, lo = bf16(v - hi) at + pstride; nullable) for the next layer.
+template <int FUSED>
+__global__ void __launch_bounds__(256) fwd_cin1_v8(P p, const float* __restrict__ x, const float* __restrict__ wf,
+                                                   const float* __restrict__ bias, const float* __restrict__ scale,
+                                                   const float* __restrict__ shift, float* __restrict__ y,
+                                                   __nv_bfloat16* __restrict__ planes, int pfmt, long long pstride, int act,
+                                                   float slope, long long total8) {
+  const int c8 = p.Cout >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int n0 = (int)(i % c8) * 8;
+    const int pos = (int)(i / c8);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    for (int tap = 0; tap < p.taps; tap++) {
+      long long off;
+      if (!in_pixel(p, pos, tap, off)) continue;
+      const float xv = __ldg(x + off);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)tap * p.Cout + n0));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)tap * p.Cout + n0) + 1);
+      acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+      acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float v = acc[j];
+      if (FUSED) {
+        v = fmaf(v, __ldg(scale + n0 + j), __ldg(shift + n0 + j));
+        v = v > 0.f ? v : v * slope;
+      } else {
+        if (bias) v += __ldg(bias + n0 + j);
+        if (act) v = v > 0.f ? v : v * slope;
+      }
+      acc[j] = v;
+    }
+    const long long o = (long long)pos * p.Cout + n0;
+    if (y) {
+      float4* d4 = reinterpret_cast<float4*>(y + o);
+      d4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      d4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (FUSED && planes) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h2);
+        acc[2 * j] -= __bfloat162float(h2.x);
+        acc[2 * j + 1] -= __bfloat162float(h2.y);
+      }
+      *reinterpret_cast<uint4*>(planes + o) = make_uint4(w[0], w[1], w[2], w[3]);
+      if (pfmt == MS_BF16X2) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+          w[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(planes + pstride + o) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+}
+
 // ---- C_in = 1 wgrad.  dwf: [tap][0][n], zeroed by the caller.  block = taps*Cout threads (<= 1024), grid = pixel chunks
 __global__ void wgrad_cin1(P p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dwf, int M) {
   const int n = threadIdx.x % p.Cout, tap = threadIdx.x / p.Cout;
@@ -152,6 +219,29 @@ __global__ void wgrad_cin1(P p, const float* __restrict__ x, const float* __rest
   for (int pos = p0; pos < p1; pos++) {
     long long off;
     if (in_pixel(p, pos, tap, off)) acc = fmaf(__ldg(x + off), __ldg(dy + (size_t)pos * p.Cout + n), acc);
+  }
+  atomicAdd(dwf + (size_t)tap * p.Cout + n, acc);
+}
+
+// ---- C_in = 1 wgrad, row-wise: a block owns whole output rows (b, ho), so the tap's input row and its validity are
+// resolved once per row and the inner loop over wo is load-load-fma.  Same thread mapping (tap, n) and atomics as above.
+__global__ void wgrad_cin1_rows(P p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dwf,
+                                int rows_total) {
+  const int n = threadIdx.x % p.Cout, tap = threadIdx.x / p.Cout;
+  const int th = tap / p.kw, tw = tap - th * p.kw;
+  const int per = (rows_total + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(rows_total, r0 + per);
+  float acc = 0.f;
+  for (int row = r0; row < r1; row++) {
+    const int b = row / p.Ho, ho = row - b * p.Ho;
+    const int hi = ho * p.sh + th - p.ph;
+    if ((unsigned)hi >= (unsigned)p.H) continue;
+    const float* xr = x + ((size_t)b * p.H + hi) * p.W;
+    const float* dr = dy + (size_t)row * p.Wo * p.Cout + n;
+    for (int wo = 0; wo < p.Wo; wo++) {
+      const int wi = wo * p.sw + tw - p.pw;
+      if ((unsigned)wi < (unsigned)p.W) acc = fmaf(__ldg(xr + wi), __ldg(dr + (size_t)wo * p.Cout), acc);
+    }
   }
   atomicAdd(dwf + (size_t)tap * p.Cout + n, acc);
 }
@@ -181,6 +271,11 @@ int ms_small_conv_fwd(const float* x, const float* wf, const float* bias, float*
   if (d->groups != 1) return 0;
   P p = make(d);
   const int M = d->B * d->Ho * d->Wo;
+  if (d->Cin == 1 && d->Cout % 8 == 0 && (((uintptr_t)wf | (uintptr_t)y) & 15) == 0) {
+    long long total8 = (long long)M * (d->Cout / 8);
+    fwd_cin1_v8<0><<<blocks_for(total8, 256), 256, 0, st>>>(p, x, wf, bias, nullptr, nullptr, y, nullptr, 0, 0, act, slope, total8);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   if (d->Cin == 1 && d->Cout <= 1024) {
     long long total = (long long)M * d->Cout;
     fwd_cin1<<<blocks_for(total, 256), 256, 0, st>>>(p, x, wf, bias, y, act, slope, total);
@@ -192,6 +287,23 @@ int ms_small_conv_fwd(const float* x, const float* wf, const float* bias, float*
     else fwd_small_n<NMAX><<<blocks, 256, 0, st>>>(p, x, wf, bias, y, act, slope, M);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
+  return 0;
+}
+
+extern "C" int ms_conv_cin1_bnact(const float* x, const float* wf, const float* scale, const float* shift, float slope,
+                                  const ms_conv_desc* d, float* y, void* planes, int pfmt, int64_t pstride, void* stream) {
+  using namespace small;
+  if (!x || !wf || !scale || !shift || !d || (!y && !planes)) return MS_EINVAL;
+  if (d->Cin != 1 || d->groups != 1 || d->Cout % 8) return MS_EINVAL;
+  if ((((uintptr_t)wf | (uintptr_t)y | (uintptr_t)planes) & 15) != 0) return MS_EINVAL;
+  if (planes && pfmt != MS_BF16 && pfmt != MS_BF16X2) return MS_EINVAL;
+  if (planes && pfmt == MS_BF16X2 && (pstride <= 0 || pstride % 8)) return MS_EINVAL;
+  P p = make(d);
+  const long long total8 = (long long)d->B * d->Ho * d->Wo * (d->Cout / 8);
+  fwd_cin1_v8<1><<<blocks_for(total8, 256), 256, 0, ms_stream(stream)>>>(p, x, wf, nullptr, scale, shift, y,
+                                                                        reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride, 1,
+                                                                        slope, total8);
+  MS_LAUNCH_CHECK();
   return 0;
 }
 
@@ -211,9 +323,10 @@ int ms_small_conv_wgrad(const float* x, const float* dy, float* dwf, const ms_co
   const int M = d->B * d->Ho * d->Wo;
   if (d->Cin == 1 && p.taps * d->Cout <= 1024) {
     if (cudaMemsetAsync(dwf, 0, sizeof(float) * (size_t)p.taps * d->Cout, st) != cudaSuccess) return -1;
-    int chunks = (M + 511) / 512;
-    if (chunks > ms_num_sms() * 2) chunks = ms_num_sms() * 2;
-    wgrad_cin1<<<chunks, p.taps * d->Cout, 0, st>>>(p, x, dy, dwf, M);
+    const int rows_total = d->B * d->Ho;
+    int chunks = rows_total;
+    if (chunks > ms_num_sms() * 4) chunks = ms_num_sms() * 4;
+    wgrad_cin1_rows<<<chunks, p.taps * d->Cout, 0, st>>>(p, x, dy, dwf, rows_total);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   if (d->Cout <= NMAX && d->Cin > 1) {

@@ -49,6 +49,12 @@ struct IgemmParams {
   long long out_plane_stride;           // MS_BF16X2 output: elements between the hi and lo planes
   int stages;                           // smem ring depth (2..MAX_STAGES)
   int split_k;                          // > 1: gridDim.z CTAs share the k-steps of a tile, fp32 vector reductions into out
+  // fused inference epilogue (ms_igemm_bf16_fused): extra fp32 copy of the result, UNet upsample(x2) + residual
+  float* out_f32;                       // nullable: the result also as fp32 (same element offsets as `out`)
+  const __nv_bfloat16* res;             // up2: residual as bf16 planes laid out like the (2x longer) output
+  long long res_pstride;                // elements between the residual's hi and lo planes
+  int res_planes;                       // 1 or 2
+  int up2;                              // every GEMM row (b, w) produces output rows (b, 2w) and (b, 2w+1)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -264,33 +270,56 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
           f[j] = x;
         }
-        if (p.out_dtype == MS_F32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row_off + c0);
+        const int nrep = p.up2 ? 2 : 1;
+        for (int j2 = 0; j2 < nrep; j2++) {
+          long long off = row_off + c0;
+          float g[16];
 #pragma unroll
-          for (int j = 0; j < 4; j++) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + row_off + c0);
-          uint32_t w[8];
+          for (int j = 0; j < 16; j++) g[j] = f[j];
+          if (p.up2) {
+            // UNet1D decoder step (layers.py:151): y[b, 2w + j2, :] = act(bn(z))[b, w, :] + residual[b, 2w + j2, :]
+            off = (long long)ob * p.os_b * 2 + (long long)(2 * ow + j2) * p.os_w + p.out_off[cls] + n0 + c0;
+            for (int pl = 0; pl < p.res_planes; pl++) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)pl * p.res_pstride + off);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&h2);
-            if (p.out_dtype == MS_BF16X2) {          // residuals for the lo plane
-              f[2 * j] -= __bfloat162float(h2.x);
-              f[2 * j + 1] -= __bfloat162float(h2.y);
+              for (int j = 0; j < 8; j++) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                g[2 * j] += __bfloat162float(h2.x);
+                g[2 * j + 1] += __bfloat162float(h2.y);
+              }
             }
           }
-          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-          if (p.out_dtype == MS_BF16X2) {
-            dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + p.out_plane_stride + row_off + c0);
+          if (p.out_f32 || p.out_dtype == MS_F32) {
+            float4* dst = reinterpret_cast<float4*>((p.out_dtype == MS_F32 ? reinterpret_cast<float*>(out) : p.out_f32) + off);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+          }
+          if (p.out_dtype != MS_F32) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + off);
+            uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(g[2 * j], g[2 * j + 1]);
               w[j] = *reinterpret_cast<uint32_t*>(&h2);
+              if (p.out_dtype == MS_BF16X2) {          // residuals for the lo plane
+                g[2 * j] -= __bfloat162float(h2.x);
+                g[2 * j + 1] -= __bfloat162float(h2.y);
+              }
             }
             dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
             dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            if (p.out_dtype == MS_BF16X2) {
+              dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + p.out_plane_stride + off);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(g[2 * j], g[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
           }
         }
       }
@@ -520,7 +549,44 @@ __global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, Pa
   }
 }
 
+// Table-driven form: blockIdx.y selects the entry, so ONE launch re-tiles every weight of a sub-network (the train step
+// refreshes all packed copies right after the optimiser update instead of ~80 separate launches).
+__global__ void pack_igemm_weight_multi_kernel(const ms_pack_entry* __restrict__ table) {
+  const ms_pack_entry& e = table[blockIdx.y];
+  const long long total = (long long)e.num_classes * e.class_n * e.ntaps * e.kpad;
+  const int Cout_g = e.Cout / e.groups;
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(e.wp);
+  __nv_bfloat16* wp_lo = reinterpret_cast<__nv_bfloat16*>(e.wp_lo);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int kc = (int)(i % e.kpad);
+    long long t2 = i / e.kpad;
+    int t = (int)(t2 % e.ntaps);
+    long long row = t2 / e.ntaps;
+    int cls = (int)(row / e.class_n), r = (int)(row - (long long)cls * e.class_n);
+    float v = 0.f;
+    if (e.mode == 0) {
+      if (row < e.Cout && kc < e.Cin_g) v = ms_ldp(e.w, e.pdt, (row * e.Cin_g + kc) * e.taps_total + e.srctap[t]);
+    } else {
+      int g = e.groups > 1 ? cls : 0;
+      if (kc < Cout_g && r < e.Cin_g)
+        v = ms_ldp(e.w, e.pdt, ((long long)(g * Cout_g + kc) * e.Cin_g + r) * e.taps_total + e.srctap[cls * e.ntaps + t]);
+    }
+    __nv_bfloat16 h = __float2bfloat16(v);
+    wp[i] = h;
+    if (wp_lo) wp_lo[i] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+
 }  // namespace
+
+extern "C" int ms_pack_igemm_weight_multi(const ms_pack_entry* table_dev, int n_entries, int blocks_per_entry, void* stream) {
+  if (!table_dev || n_entries < 1 || n_entries > 65535) return MS_EINVAL;
+  if (blocks_per_entry < 1) blocks_per_entry = 64;
+  dim3 grid((unsigned)blocks_per_entry, (unsigned)n_entries);
+  pack_igemm_weight_multi_kernel<<<grid, 256, 0, ms_stream(stream)>>>(table_dev);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int Cin_g, int taps_total, int groups, int mode,
                                          int num_classes, int class_n, int ntaps, int kpad, const int16_t* srctap_host,
@@ -541,8 +607,16 @@ extern "C" int ms_pack_igemm_weight_bf16(const void* w, int pdt, int Cout, int C
   return 0;
 }
 
-extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
-                             const float* shift, void* out, void* stream) {
+struct IgemmFused {
+  float* out_f32;
+  const void* res;
+  int res_planes;
+  long long res_pstride;
+  int up2;
+};
+
+static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                        const float* shift, void* out, const IgemmFused* fx, void* stream) {
   if (!d || !a || !w || !out) return MS_EINVAL;
   if (d->num_classes < 1 || d->num_classes > MS_IGEMM_MAX_CLASSES) return MS_EINVAL;
   if (d->ntaps < 1 || d->cchunks < 1) return MS_EINVAL;
@@ -608,6 +682,18 @@ extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* 
   for (int i = 0; i < MS_IGEMM_MAX_TAPS; i++)
     for (int j = 0; j < 4; j++) p.taps[i][j] = d->taps[i][j];
   p.out_dtype = d->out_dtype; p.epilogue = d->epilogue; p.slope = d->slope;
+  p.out_f32 = nullptr; p.res = nullptr; p.res_pstride = 0; p.res_planes = 0; p.up2 = 0;
+  if (fx) {
+    if (d->split_k > 1) return MS_EINVAL;
+    if (fx->out_f32 && ((uintptr_t)fx->out_f32 & 15)) return MS_EINVAL;
+    p.out_f32 = d->out_dtype == MS_F32 ? nullptr : fx->out_f32;
+    if (fx->up2) {
+      // 1-D only: out_strides describe ONE GEMM row per (b, w); the written tensor has 2*out_w rows per sequence
+      if (d->out_dims[1] != 1 || !fx->res || (fx->res_planes != 1 && fx->res_planes != 2) || ((uintptr_t)fx->res & 15)) return MS_EINVAL;
+      if (fx->res_planes == 2 && (fx->res_pstride <= 0 || (fx->res_pstride * 2) % 16)) return MS_EINVAL;
+      p.up2 = 1; p.res = reinterpret_cast<const __nv_bfloat16*>(fx->res); p.res_planes = fx->res_planes; p.res_pstride = fx->res_pstride;
+    }
+  }
   // vector stores need 16-byte aligned rows
   const int esz = d->out_dtype == MS_F32 ? 4 : 2;
   if ((p.os_w * esz) % 16 || (p.os_h * esz) % 16 || (p.os_b * esz) % 16) return MS_EINVAL;
@@ -648,6 +734,19 @@ extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* 
   igemm_tc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
   MS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                             const float* shift, void* out, void* stream) {
+  return igemm_launch(d, a, w, bias, scale, shift, out, nullptr, stream);
+}
+
+extern "C" int ms_igemm_bf16_fused(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                                   const float* shift, void* out, float* out_f32, const void* res, int res_planes,
+                                   int64_t res_pstride, int up2, void* stream) {
+  IgemmFused fx;
+  fx.out_f32 = out_f32; fx.res = res; fx.res_planes = res_planes; fx.res_pstride = res_pstride; fx.up2 = up2;
+  return igemm_launch(d, a, w, bias, scale, shift, out, &fx, stream);
 }
 
 static int encode_5d(EncodeTiledFn enc, CUtensorMap* m, const void* base, const int32_t* dims, const int64_t* strides_el,

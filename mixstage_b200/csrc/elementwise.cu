@@ -341,6 +341,19 @@ __global__ void to_planes4_kernel(const float* __restrict__ x, int64_t n4, __nv_
     store_planes4(planes, pfmt, pstride, 4 * i, __ldg(reinterpret_cast<const float4*>(x) + i));
 }
 
+// bf16 planes (row stride rs) -> x (rows, C) fp32: hi (+ lo)
+__global__ void planes_to_f32_kernel(const __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride, int64_t rows, int C,
+                                     int rs, float* __restrict__ x) {
+  int64_t total = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / C;
+    int64_t j = r * rs + (i - r * C);
+    float v = __bfloat162float(planes[j]);
+    if (pfmt == MS_BF16X2) v += __bfloat162float(planes[pstride + j]);
+    x[i] = v;
+  }
+}
+
 __global__ void lrelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope, int64_t n,
                                  float* __restrict__ dz, __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -768,6 +781,16 @@ extern "C" int ms_to_planes(const float* x, int64_t rows, int C, int row_stride,
     to_planes4_kernel<<<ew_blocks(n / 4), EW_THREADS, 0, ST>>>(x, n / 4, pl, pfmt, pstride);
   else
     to_planes_kernel<<<ew_blocks(rows * row_stride), EW_THREADS, 0, ST>>>(x, rows, C, row_stride, pl, pfmt, pstride);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_planes_to_f32(const void* planes, int pfmt, int64_t pstride, int64_t rows, int C, int row_stride, float* x,
+                                void* stream) {
+  if (!x || !planes || rows < 1 || C < 1 || row_stride < C) return MS_EINVAL;
+  if (!planes_ok(planes, pfmt, pstride)) return MS_EINVAL;
+  planes_to_f32_kernel<<<ew_blocks(rows * C), EW_THREADS, 0, ST>>>(reinterpret_cast<const __nv_bfloat16*>(planes), pfmt, pstride,
+                                                                  rows, C, row_stride, x);
   MS_LAUNCH_CHECK();
   return 0;
 }

@@ -8,13 +8,14 @@ reached through the C-ABI in include/mixstage_b200.h; there is no CPU/PyTorch fa
 from __future__ import annotations
 
 import contextlib
+import weakref
 
 import torch
 import torch.nn as nn
 
 from . import ops
 from ._lib import MixStageError
-from .layers import (AudioEncoder, ClusterClassify, ConvNormRelu, Curriculum, EmbLin, Group, PlainConv,
+from .layers import (_run, AudioEncoder, ClusterClassify, ConvNormRelu, Curriculum, EmbLin, Group, PlainConv,
                      PoseEncoder, PoseStyleEncoder, TextEncoder1D, UNet1D)
 from .speech2gesture import Speech2Gesture_D
 
@@ -100,6 +101,13 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         self.cluster = cluster
         self.thresh = Curriculum(0, 1, 1000)
         self.labels_cap_soft = None
+        # Style-sweep cache (reference sampling loop, trainer.py:791-794 with update_kwargs :1367-1386: the SAME batch
+        # is pushed through forward once per target style).  audio_encoder + unet do not depend on the style (52 % of the
+        # forward FLOPs), so in eval mode under no_grad their output is kept and reused while the caller passes the same
+        # audio tensor object, unmodified, and no parameter / running statistic changed.  Set to False to disable.
+        self.cache_encoder = True
+        self._enc_cache = None
+        self.encoder_cache_hits = 0
         self.style_index = None       # last integer style index used for the embedding ('emb' mode)
         # arithmetic of the convolutions: None = process default (ops.set_precision), else "fp32" | "bf16x3" | "bf16"
         self.precision = kwargs.get('precision', None)
@@ -109,6 +117,14 @@ class JointLateClusterSoftStyle4_G(nn.Module):
     def _as_f32_cl(t, B, T):
         """(B,T,F) caller tensor -> contiguous fp32 (B,T,F)."""
         return ops.cast(t, torch.float32).contiguous()
+
+    def _encoder_cache_key(self, a, time_steps):
+        vers = 0
+        for m in (self.audio_encoder, self.unet):
+            for t in list(m.parameters()) + list(m.buffers()):
+                vers += t._version
+        return (a.data_ptr(), a._version, tuple(a.shape), a.dtype, time_steps, vers, ops._weight_epoch, ops._stats_epoch,
+                ops.get_precision())
 
     def forward(self, x, y, time_steps=None, **kwargs):
         with ops.precision_scope(self.precision):
@@ -129,9 +145,19 @@ class JointLateClusterSoftStyle4_G(nn.Module):
             use_pose = fb == 'pose'
         else:
             use_pose = torch.rand(1).item() > self.thresh.step(self.training) and self.training
-        if use_pose:
+        cache_key = None
+        capturing = ops.FORCE_REPACK or (y.is_cuda and torch.cuda.is_current_stream_capturing())
+        if (self.cache_encoder and not use_pose and not self.training and not torch.is_grad_enabled() and not capturing
+                and len(kwargs['input_modalities']) == 1 and kwargs['input_modalities'][0].split('/')[0] == 'audio'):
+            cache_key = self._encoder_cache_key(x[0], time_steps)
+        hit = self._enc_cache if cache_key is not None else None
+        if hit is not None and hit[0]() is x[0] and hit[1] == cache_key:
+            h = hit[2]
+            self.encoder_cache_hits += 1
+        elif use_pose:
             T = y.shape[1]
             h = self.pose_encoder(self._as_f32_cl(y, B, T).view(B, 1, T, y.shape[2]), time_steps)
+            h = self.unet(h)
         else:
             feats = []
             for i, modality in enumerate(kwargs['input_modalities']):
@@ -147,8 +173,9 @@ class JointLateClusterSoftStyle4_G(nn.Module):
                     feats.append(self.audio_encoder(a, time_steps if time_steps is not None else T))
             if len(feats) != 1:
                 raise NotImplementedError("mixstage_b200: exactly one (audio) input modality is accelerated")
-            h = feats[0]                      # (B,1,T,256)
-        h = self.unet(h)                      # (B,1,T,256)
+            h = self.unet(feats[0])           # (B,1,T,256)
+            if cache_key is not None:
+                self._enc_cache = (weakref.ref(x[0]), cache_key, h)
         Bx, _, T, C = h.shape
 
         style = kwargs['style']
@@ -192,7 +219,7 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         self.labels_cap_soft = ops.cast(soft_c.view(Bx, T, K), out_dtype)
 
         # K sub-decoders (grouped) + grouped 1x1 logits + soft mixture (jlcss.py:190-194)
-        d = self.decoder(hc)
+        d = _run(self.decoder, hc, last="planes")
         z = self._logits(self.logits, d)                                      # (B,1,T,K*P)
         pose = ops.mixture(z.view(Bx * T, K * self.out_feats), soft_c).view(Bx, T, self.out_feats)
 

@@ -59,13 +59,15 @@ class ConvNormRelu(nn.Module):
         self.cfg = ops.ConvCfg(kh, kw, sh, sw, ph, pw, groups, 0.2 if leaky else 0.0, has_bn=True, act=True)
         self._packed = ops.PackedWeight()
 
-    def forward(self, x, residual=None, up2=False):
+    def forward(self, x, residual=None, up2=False, want="both"):
         """x: channels-last (B, H, W, C) fp32.  With ``up2`` the output is
-        ``upsample2(act(bn(conv(x)))) + residual`` (UNet1D decoder step, layers.py:151)."""
+        ``upsample2(act(bn(conv(x)))) + residual`` (UNet1D decoder step, layers.py:151).
+        ``want`` ("planes" | "f32" | "both"): which forms of the output the consumers read; only the inference fast
+        path (ops.conv_block) acts on it."""
         n = self.norm
         return ops.conv_block(x, self.conv.weight, self.conv.bias, n.weight, n.bias, self.cfg, self._packed,
                               (n.running_mean, n.running_var, n.num_batches_tracked), self.training,
-                              residual=residual, up2=up2)
+                              residual=residual, up2=up2, want=want)
 
 
 class PlainConv(object):
@@ -78,12 +80,15 @@ class PlainConv(object):
         self.packed = ops.PackedWeight()
 
     def __call__(self, conv, x):
-        return ops.conv_block(x, conv.weight, conv.bias, None, None, self.cfg, self.packed, None, False)
+        return ops.conv_block(x, conv.weight, conv.bias, None, None, self.cfg, self.packed, None, False, want="f32")
 
 
-def _run(blocks, x):
-    for b in blocks:
-        x = b(x)
+def _run(blocks, x, last="f32"):
+    """A chain of blocks: every intermediate activation is only read by the next convolution (operand planes suffice
+    on the inference fast path); the last one is wanted as `last`."""
+    n = len(blocks)
+    for i, b in enumerate(blocks):
+        x = b(x, want="planes" if i < n - 1 else last)
     return x
 
 
@@ -111,21 +116,21 @@ class UNet1D(nn.Module):
             'Input size is {}. It must be >= {}'.format(T, 2 ** (self.max_depth - 1))
         assert num_powers_of_two(T) >= self.max_depth, \
             'Input size is {}. It must be a multiple of 2^(max_depth) = 2^{} = {}'.format(T, self.max_depth, 2 ** self.max_depth)
-        x = _run(self.pre_downsampling_conv, x)
+        x = _run(self.pre_downsampling_conv, x, last="planes")
         residuals = [x]
         d = self.max_depth
         # the last down block feeds `upconv(x) + residual` directly (layers.py:150-151): fuse it
         for i, conv1 in enumerate(self.conv1):
             if i < d - 1:
-                x = conv1(x)
+                x = conv1(x, want="planes")
                 residuals.append(x)
             else:
-                x = conv1(x, residual=residuals[d - 1], up2=True)
+                x = conv1(x, residual=residuals[d - 1], up2=True, want="planes")
         for i, conv2 in enumerate(self.conv2):
             if i < d - 1:
-                x = conv2(x, residual=residuals[d - i - 2], up2=True)     # output already holds next step's input
+                x = conv2(x, residual=residuals[d - i - 2], up2=True, want="planes")   # output already holds next step's input
             else:
-                x = conv2(x)
+                x = conv2(x, want="f32")
         return x
 
 

@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib, igemm
-from ._lib import MS_BF16, MS_BF16X2, ConvDesc, MixStageError, call, dt_code, ptr, stream
+from ._lib import MS_BF16, MS_BF16X2, MS_F32, ConvDesc, MixStageError, call, dt_code, ptr, stream
 
 LEAKY_SLOPE = 0.2
 
@@ -22,6 +22,7 @@ PRECISIONS = ("fp32", "bf16x3", "bf16")
 _precision = "fp32"
 FORCE_REPACK = False        # set while a CUDA graph is being captured: weights change without a version bump
 _weight_epoch = 0            # bumped when parameters change without a torch version bump (graph replays)
+_stats_epoch = 0             # bumped whenever a training-mode BatchNorm updates running statistics in place
 last_gemm_flops = 0.0       # algorithmic FLOPs (2*MAC, unpadded) of the GEMM launch that follows; read by bench.py
 
 
@@ -102,6 +103,33 @@ arena = _Arena()
 DIRECT_GRADS = False
 
 
+class SideWork:
+    """A second stream for the weight-gradient GEMMs of a train step: they depend only on (x planes, dz planes) and feed
+    nothing but the flat gradient buffer, so they run beside the input-gradient chain instead of inside it (also when the
+    step is captured into a CUDA graph: the fork/join becomes graph edges).  Tensors handed to the side stream are kept
+    referenced until join() so the allocator cannot recycle them early."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.keep = []
+        self.forked = False
+
+    def fork(self, *tensors):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self.keep.extend(tensors)
+        self.forked = True
+        return torch.cuda.stream(self.stream)
+
+    def join(self):
+        if self.forked:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep.clear()
+        self.forked = False
+
+
+SIDE = None                  # SideWork of the running train step (set by TrainStep), else None
+
+
 def _sink(p):
     """The .grad buffer of parameter p when direct accumulation applies, else None."""
     if not DIRECT_GRADS or p is None or not p.requires_grad:
@@ -140,6 +168,8 @@ def planes_of(x, fmt, rs):
     pl = getattr(x, "_ms_planes", None)
     if pl is not None and pl.fmt == fmt and pl.rs == rs:
         return pl
+    if x.dtype == torch.bfloat16:
+        x = as_f32(x)           # a planes-only activation in another operand format: go through fp32
     x = _f32c(x)
     C = x.shape[-1]
     rows = x.numel() // C
@@ -155,6 +185,34 @@ def planes_of(x, fmt, rs):
 def attach_planes(y, pl):
     y._ms_planes = pl
     return y
+
+
+def planes_view(pl, shape):
+    """A planes-only activation (inference fast path): the hi plane seen as a bf16 tensor of the activation's shape,
+    carrying the Planes object.  Consumers that need fp32 go through as_f32()."""
+    n = 1
+    for d_ in shape:
+        n *= d_
+    if pl.rs != shape[-1]:
+        raise MixStageError("internal: planes_view needs an unpadded row stride")
+    t = pl.t[:n].view(shape)
+    t._ms_planes = pl
+    return t
+
+
+def as_f32(x):
+    """fp32 contents of an activation: itself, or hi (+ lo) of a planes-only activation."""
+    if x.dtype == torch.float32:
+        return x
+    pl = getattr(x, "_ms_planes", None)
+    if x.dtype != torch.bfloat16 or pl is None:
+        raise MixStageError("internal: expected an fp32 activation or a planes-only one, got %s" % x.dtype)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    call("ms_planes_to_f32", ptr(pl.t), pl.fmt, pl.ps, rows, C, pl.rs, ptr(out), stream())
+    out._ms_planes = pl
+    return out
 
 
 def _need_cuda(t):
@@ -214,9 +272,31 @@ class PackedWeight:
         self.wt = None
         self.bias = None
         self.bias_key = None
+        self.stats_epoch = 0    # bumped when this block's BatchNorm updates its running statistics in place
+        self._src = {}          # slot -> arguments of the getter that filled it (refresh() replays them)
+
+    def refresh(self, entries=None):
+        """Re-derive every cached copy from the current parameters, in place (same buffers: captured CUDA graphs keep
+        pointing at them).  Tensor-core re-tilings are appended to `entries` (for ONE ms_pack_igemm_weight_multi launch)
+        when a list is given."""
+        global FORCE_REPACK
+        old, FORCE_REPACK = FORCE_REPACK, True
+        try:
+            for slot, args in list(self._src.items()):
+                if slot == "f32":
+                    self.get(*args)
+                elif slot == "bias":
+                    self.get_bias(*args)
+                elif slot == "ss":
+                    self.get_eval_ss(*args)
+                else:
+                    self.get_tc(*args, collect=entries)
+        finally:
+            FORCE_REPACK = old
 
     def get(self, weight, desc):
         key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype, weight.device)
+        self._src["f32"] = (weight, desc)
         if key != self.key or FORCE_REPACK:
             w = weight.detach()
             if not w.is_contiguous():
@@ -247,11 +327,12 @@ class PackedWeight:
             pl[key] = (pf, pd)
         return pl[key]
 
-    def get_tc(self, weight, plan, fmt, groups):
+    def get_tc(self, weight, plan, fmt, groups, collect=None):
         """Packed weight planes for `plan` (forward or dgrad tiling).  Returns (tensor, plane stride)."""
         slot = "_tcw%d" % plan.mode
         key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype, weight.device, fmt, plan.wp_numel,
                tuple(plan.srctap))
+        self._src[slot] = (weight, plan, fmt, groups)
         cur = getattr(self, slot, None)
         if cur is not None and cur[0] == key and not FORCE_REPACK:
             return cur[1], cur[2]
@@ -267,17 +348,46 @@ class PackedWeight:
         Cout, Cin_g = w.shape[0], w.shape[1]
         taps_total = w.shape[2] * w.shape[3]
         lo = buf.data_ptr() + 2 * ps if fmt == MS_BF16X2 else None
-        call("ms_pack_igemm_weight_bf16", ptr(w), dt_code(w.dtype), Cout, Cin_g, taps_total, groups, plan.mode,
-             d.num_classes, d.class_n, d.ntaps, plan.kpad, plan.srctap_c, ptr(buf), lo, stream())
+        if collect is not None:
+            e = _lib.PackEntry()
+            e.w, e.wp, e.wp_lo = w.data_ptr(), buf.data_ptr(), lo
+            e.pdt, e.Cout, e.Cin_g, e.taps_total, e.groups, e.mode = dt_code(w.dtype), Cout, Cin_g, taps_total, groups, plan.mode
+            e.num_classes, e.class_n, e.ntaps, e.kpad = d.num_classes, d.class_n, d.ntaps, plan.kpad
+            for i_, t_ in enumerate(plan.srctap):
+                e.srctap[i_] = t_
+            collect.append(e)
+        else:
+            call("ms_pack_igemm_weight_bf16", ptr(w), dt_code(w.dtype), Cout, Cin_g, taps_total, groups, plan.mode,
+                 d.num_classes, d.class_n, d.ntaps, plan.kpad, plan.srctap_c, ptr(buf), lo, stream())
         setattr(self, slot, (key, buf, ps))
         return buf, ps
+
+    def get_eval_ss(self, gamma, beta, cbias, bn_buffers, cfg):
+        """Eval-mode BatchNorm folded to per-channel (scale, shift) with the conv bias inside the shift
+        (GEMM outputs exclude it); recomputed when a parameter, the running statistics or the epochs change."""
+        rm, rv, _ = bn_buffers
+        key = tuple((t.data_ptr(), t._version) for t in (gamma, beta, rm, rv) + ((cbias,) if cbias is not None else ())) + (
+            _weight_epoch, self.stats_epoch, gamma.dtype)
+        self._src["ss"] = (gamma, beta, cbias, bn_buffers, cfg)
+        cur = getattr(self, "_eval_ss", None)
+        if cur is None or cur[0] != key or FORCE_REPACK:
+            C = gamma.numel()
+            ss = cur[1] if cur is not None else torch.empty(4, C, dtype=torch.float32, device=gamma.device)
+            call("ms_bn_finalize", None, None, 1, C, ptr(gamma), ptr(beta), ptr(cbias), ptr(rm), ptr(rv), dt_code(gamma.dtype),
+                 0, cfg.momentum, cfg.eps, ptr(ss[0]), ptr(ss[1]), ptr(ss[2]), ptr(ss[3]), stream())
+            cur = self._eval_ss = (key, ss)
+        return cur[1]
 
     def get_bias(self, bias):
         if bias is None:
             return None
         key = (bias.data_ptr(), bias._version, _weight_epoch, bias.dtype, bias.device)
+        self._src["bias"] = (bias,)
         if key != self.bias_key or FORCE_REPACK:
-            self.bias = cast_raw(bias.detach(), torch.float32)
+            b = bias.detach().contiguous()
+            if self.bias is None or self.bias.numel() != b.numel() or self.bias.device != b.device:
+                self.bias = torch.empty(b.shape, dtype=torch.float32, device=b.device)
+            call("ms_cast", ptr(b), dt_code(b.dtype), ptr(self.bias), MS_F32, b.numel(), stream())     # in place: graphs keep the pointer
             self.bias_key = key
         return self.bias
 
@@ -296,7 +406,7 @@ class ConvCfg:
 
 
 # ---- pieces shared by the CUDA-core and tensor-core variants of the block
-def _bn_scale_shift(z, rows, Cout, gamma, beta, cbias, bn_buffers, training, cfg):
+def _bn_scale_shift(z, rows, Cout, gamma, beta, cbias, bn_buffers, training, cfg, packed=None):
     """Batch statistics + finalize (training: one fused launch that also advances num_batches_tracked) or the
     running-statistics fold (eval).  Returns ss = [scale, shift, mean, rstd] (4, Cout) fp32."""
     rm, rv, nbt = bn_buffers
@@ -306,6 +416,10 @@ def _bn_scale_shift(z, rows, Cout, gamma, beta, cbias, bn_buffers, training, cfg
     if cbias is not None and cbias.dtype != gamma.dtype:
         raise MixStageError("conv bias and BatchNorm parameters must share a dtype")
     if training:
+        global _stats_epoch
+        _stats_epoch += 1                                      # running statistics change in place (no torch version bump)
+        if packed is not None:
+            packed.stats_epoch += 1
         acc = arena.take((2 * Cout + 2,), dev)                 # sum, sumsq, ticket
         base = acc.data_ptr()
         call("ms_bn_stats_finalize", ptr(z), rows, Cout, base, base + 8 * Cout, base + 16 * Cout, ptr(gamma), ptr(beta),
@@ -396,7 +510,8 @@ class _ConvBlock(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2, precision="fp32",
                 carrier=None):
         _need_cuda(x)
-        x = _f32c(x)
+        if x.dtype != torch.bfloat16:          # bf16 = planes-only activation from the inference fast path (tc consumers only)
+            x = _f32c(x)
         B, H, W, Cin = x.shape
         Cout = weight.shape[0]
         desc = make_desc(x.shape, Cout, cfg.kh, cfg.kw, cfg.sh, cfg.sw, cfg.ph, cfg.pw, cfg.groups)
@@ -408,6 +523,7 @@ class _ConvBlock(torch.autograd.Function):
         if precision != "fp32" and tc_eligible(cfg, B, H, W, Cin, Cout, ctx.needs_input_grad[0]):
             return _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, training, up2,
                                desc, _fmt(precision), carrier)
+        x = _f32c(x)
         wf, wt = packed.get(weight, desc)
         b32 = packed.get_bias(bias)
         st = stream()
@@ -423,7 +539,7 @@ class _ConvBlock(torch.autograd.Function):
         if not cfg.has_bn:
             ctx.save_for_backward(x, z)
             return z
-        ss = _bn_scale_shift(z, rows, Cout, gamma, beta, None, bn_buffers, training, cfg)
+        ss = _bn_scale_shift(z, rows, Cout, gamma, beta, None, bn_buffers, training, cfg, packed)
         tc_next = precision != "fp32" and carrier is not None         # the consumer may be a tensor-core layer
         y, yp = _bn_act(z, ss, cfg, rows, Cout, desc, residual, up2, _fmt(precision), tc_next)
         if yp is not None:
@@ -529,7 +645,7 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     if not cfg.has_bn:
         ctx.save_for_backward(xp.t, z)
         return z
-    ss = _bn_scale_shift(z, rows, Cout, gamma, beta, bias, bn_buffers, training, cfg)
+    ss = _bn_scale_shift(z, rows, Cout, gamma, beta, bias, bn_buffers, training, cfg, packed)
     y, yp = _bn_act(z, ss, cfg, rows, Cout, desc, residual, up2, fmt, True)
     ctx.gamma_dtype = gamma.dtype
     ctx.save_for_backward(xp.t, z, ss)
@@ -573,10 +689,21 @@ def _tc_backward(ctx, dy):
         igemm.set_planes(pf, split, xps, 0, dzp.ps)
         nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc)
         pf.desc.split_k = nsplit
-        dwp = torch.empty(nsplit * pf.wp_numel, dtype=torch.float32, device=dev)     # one partial per row slice
-        call("ms_wgrad_bf16", pf.desc, ptr(xpt), ptr(dzp.t), ptr(dwp), st)
         sink = ctx.sinks[0]
-        if sink is not None:
+        if sink is not None and SIDE is not None:
+            with SIDE.fork(xpt, dzp.t):
+                dwp = torch.empty(nsplit * pf.wp_numel, dtype=torch.float32, device=dev)
+                call("ms_wgrad_bf16", pf.desc, ptr(xpt), ptr(dzp.t), ptr(dwp), stream())
+                call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin_g, cfg.kh * cfg.kw, pf.desc.ntaps, pf.kpad, ptr(sink),
+                     dt_code(wdt), nsplit, 1, stream())
+                SIDE.keep.append(dwp)
+            dwp = None
+        else:
+            dwp = torch.empty(nsplit * pf.wp_numel, dtype=torch.float32, device=dev)     # one partial per row slice
+            call("ms_wgrad_bf16", pf.desc, ptr(xpt), ptr(dzp.t), ptr(dwp), st)
+        if dwp is None:
+            pass
+        elif sink is not None:
             call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin_g, cfg.kh * cfg.kw, pf.desc.ntaps, pf.kpad, ptr(sink),
                  dt_code(wdt), nsplit, 1, st)
         else:
@@ -594,8 +721,97 @@ def _tc_backward(ctx, dy):
     return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None, None
 
 
-def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, residual=None, up2=False, precision=None):
-    """weight is the caller's parameter in its own layout/dtype: (Cout, Cin/g, k) or (Cout, Cin/g, kh, kw)."""
+def _tc_eval(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, up2, fmt, want):
+    """Inference fast path of the block (eval mode, no autograd): ONE tcgen05 launch whose epilogue applies the folded
+    BatchNorm + LeakyReLU (+ UNet upsample-and-skip) and writes the next layer's bf16 operand planes directly
+    (want "planes"), fp32 (want "f32") or both -- no fp32 activation round trip through HBM."""
+    B, H, W, Cin = x.shape
+    Cout = weight.shape[0]
+    st, dev = stream(), x.device
+    rs = pad8(Cin)
+    split = fmt == MS_BF16X2
+    xp = planes_of(x, fmt, rs)
+    pf, _ = packed.tc_plans(x.shape, Cout, cfg, rs, False, 3 if split else 1)
+    wp, wps = packed.get_tc(weight, pf, fmt, cfg.groups)
+    Ho, Wo = conv_out(H, cfg.kh, cfg.sh, cfg.ph), conv_out(W, cfg.kw, cfg.sw, cfg.pw)
+    rows = B * Ho * Wo
+    d = pf.desc
+    if cfg.has_bn:
+        ss = packed.get_eval_ss(gamma, beta, bias, bn_buffers, cfg)
+        d.epilogue, d.slope = 1, (cfg.slope if cfg.act else 1.0)
+        b32, scale, shift = None, ptr(ss[0]), ptr(ss[1])
+    else:
+        d.epilogue, d.slope = (2 if cfg.act else 0), cfg.slope
+        b32, scale, shift = packed.get_bias(bias), None, None
+    d.split_k, d.out_numel = 1, 0
+    oshape = (B, 1, 2 * Wo, Cout) if up2 else (B, Ho, Wo, Cout)
+    rows_out = 2 * rows if up2 else rows
+    res = None
+    if up2:
+        if Ho != 1:
+            raise MixStageError("upsample+skip fusion is 1-D only")
+        if tuple(residual.shape) != oshape:
+            raise MixStageError("skip tensor shape %s != %s" % (tuple(residual.shape), oshape))
+        res = planes_of(residual, fmt, Cout)
+    y32 = torch.empty(oshape, dtype=torch.float32, device=dev) if want != "planes" else None
+    yp = alloc_planes(rows_out, Cout, fmt, dev) if want != "f32" else None
+    igemm.set_planes(pf, split, xp.ps, wps, yp.ps if yp is not None else 0)
+    d.out_dtype = fmt if yp is not None else _lib.MS_F32
+    global last_gemm_flops
+    last_gemm_flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
+    call("ms_igemm_bf16_fused", d, ptr(xp.t), ptr(wp), ptr(b32), scale, shift, ptr(yp.t) if yp is not None else ptr(y32),
+         ptr(y32) if yp is not None else None, ptr(res.t) if res is not None else None,
+         (2 if split else 1) if res is not None else 0, res.ps if res is not None else 0, 1 if up2 else 0, st)
+    if y32 is not None:
+        if yp is not None:
+            y32._ms_planes = yp
+        return y32
+    return planes_view(yp, oshape)
+
+
+def _cin1_eval(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, fmt, want):
+    """Inference fast path of the C_in = 1 block (audio_encoder.conv.0): conv + folded BatchNorm + LeakyReLU in one
+    streaming kernel that writes the next layer's operand planes (and fp32 only when asked)."""
+    x = _f32c(x)
+    B, H, W, _ = x.shape
+    w4 = weight.unsqueeze(2) if weight.dim() == 3 else weight
+    Cout = w4.shape[0]
+    desc = make_desc(x.shape, Cout, cfg.kh, cfg.kw, cfg.sh, cfg.sw, cfg.ph, cfg.pw, 1)
+    wf, _ = packed.get(w4, desc)
+    ss = packed.get_eval_ss(gamma, beta, bias, bn_buffers, cfg)
+    oshape = (B, desc.Ho, desc.Wo, Cout)
+    rows = B * desc.Ho * desc.Wo
+    y32 = torch.empty(oshape, dtype=torch.float32, device=x.device) if want != "planes" else None
+    yp = alloc_planes(rows, Cout, fmt, x.device) if want != "f32" else None
+    call("ms_conv_cin1_bnact", ptr(x), ptr(wf), ptr(ss[0]), ptr(ss[1]), cfg.slope if cfg.act else 1.0, desc, ptr(y32),
+         ptr(yp.t) if yp is not None else None, fmt, yp.ps if yp is not None else 0, stream())
+    if y32 is not None:
+        if yp is not None:
+            y32._ms_planes = yp
+        return y32
+    return planes_view(yp, oshape)
+
+
+def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, residual=None, up2=False, precision=None,
+               want="both"):
+    """weight is the caller's parameter in its own layout/dtype: (Cout, Cin/g, k) or (Cout, Cin/g, kh, kw).
+    want ("planes" | "f32" | "both") only matters on the inference fast path (eval mode under torch.no_grad() with a
+    tensor-core precision): which forms of the activation the consumers need."""
+    prec = precision or _precision
+    _need_cuda(x)
+    tc_ok = (prec != "fp32" and x.dim() == 4 and weight.shape[1] * cfg.groups == x.shape[3] and
+             tc_eligible(cfg, x.shape[0], x.shape[1], x.shape[2], x.shape[3], weight.shape[0], False))
+    if tc_ok and not training and not torch.is_grad_enabled():
+        w4 = weight.detach()
+        return _tc_eval(x, w4.unsqueeze(2) if w4.dim() == 3 else w4, bias, gamma, beta, residual, cfg, packed, bn_buffers,
+                        up2, _fmt(prec), want)
+    if (prec != "fp32" and not training and not torch.is_grad_enabled() and cfg.has_bn and x.dim() == 4 and x.shape[3] == 1
+            and cfg.groups == 1 and weight.shape[0] % 8 == 0 and x.dtype == torch.float32):
+        return _cin1_eval(x, weight.detach(), bias, gamma, beta, cfg, packed, bn_buffers, _fmt(prec), want)
+    if x.dtype == torch.bfloat16 and not tc_ok:
+        x = as_f32(x)                       # planes-only activation feeding a CUDA-core layer
+    if residual is not None and residual.dtype == torch.bfloat16:
+        residual = as_f32(residual)
     carrier = _Carrier()
     carrier.sinks = (_sink(weight), _sink(bias), _sink(gamma), _sink(beta))
     if weight.dim() == 3:

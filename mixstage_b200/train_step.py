@@ -102,6 +102,9 @@ class TrainStep:
         self.last_kind = None
         self.replays = 0
         self.warmup_iters = 2
+        self.side = ops.SideWork(dev) if dev.type == "cuda" else None      # weight-gradient GEMMs beside the dgrad chain
+        self._tables = {}            # kind -> (signature, device table, n): entries of the batched weight re-tiling
+        self._pver = None            # flat-parameter versions seen by the last refresh
 
     # ------------------------------------------------------------------ host-side decisions
     def set_lr(self, lr):
@@ -135,6 +138,7 @@ class TrainStep:
         # one arena cleared by a single memset (ops.py)
         ops.arena.begin(self.fG.device)
         ops.DIRECT_GRADS = True
+        ops.SIDE = self.side
         try:
             fake, losses, _ = gan([audio, labels], pose, input_modalities=self.mod, style=style, sample_flag=0,
                                   description=self.description, desc=self.description)
@@ -143,11 +147,56 @@ class TrainStep:
         finally:
             G.force_branch = None
             ops.DIRECT_GRADS = False
+            ops.SIDE = None
             ops.arena.end()
+            if self.side is not None:
+                self.side.join()
         f = self.fG if kind == "G" else self.fD
         f.allreduce_mean(self.group)
         f.clip_adam(self.lr, self.lr_dev, self.betas, self.eps, self.max_norm)
+        if self.use_graphs:
+            # keep every packed copy (bf16 re-tilings, fp32 biases, folded eval BatchNorm) of the sub-network that just
+            # stepped in sync with its parameters, so that no forward has to re-pack anything
+            self._refresh(kind)
         return fake.detach(), torch.stack([l.detach().to(fake.dtype) for l in losses])
+
+    # ------------------------------------------------------------------ packed copies follow the parameters
+    @staticmethod
+    def _packed_of(module):
+        from .layers import ConvNormRelu, PlainConv
+        out = []
+        for m in module.modules():
+            if isinstance(m, ConvNormRelu):
+                out.append(m._packed)
+            for v in vars(m).values():
+                if isinstance(v, PlainConv):
+                    out.append(v.packed)
+        return out
+
+    def _refresh(self, kind):
+        mod = self.G if kind == "G" else self.D
+        entries = []
+        for pw in self._packed_of(mod):
+            pw.refresh(entries)
+        if not entries:
+            return
+        sig = tuple((e.w, e.wp, e.wp_lo, e.mode, e.num_classes, e.class_n, e.ntaps, e.kpad) for e in entries)
+        cur = self._tables.get(kind)
+        if cur is None or cur[0] != sig:
+            if torch.cuda.is_current_stream_capturing():
+                raise MixStageError("internal: packed-weight table changed during graph capture")
+            import ctypes
+            arr = (_lib.PackEntry * len(entries))(*entries)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            cur = (sig, host.to(self.fG.device), len(entries))
+            self._tables[kind] = cur
+        call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 48, stream())
+
+    def refresh(self):
+        """Call after changing parameters or BatchNorm buffers from outside (load_state_dict, manual edits)."""
+        self._refresh("G")
+        self._refresh("D")
+        self._pver = (self.fG.p._version, self.fD.p._version)
 
     def _capture(self, key, batch):
         kind, use_pose = key
@@ -167,16 +216,15 @@ class TrainStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
-        ops.FORCE_REPACK = True
+        # the warm-up bodies ended with _refresh(): every packed copy is valid and stays at its address, so the captured
+        # forward launches no re-packing; the captured step ends with the same refresh for the sub-network it updates
         l0 = _lib.LAUNCHES
-        try:
-            with torch.cuda.graph(g):
-                fake, losses = self._body(kind, use_pose, *self.static)
-        finally:
-            ops.FORCE_REPACK = False
+        with torch.cuda.graph(g):
+            fake, losses = self._body(kind, use_pose, *self.static)
         self.kernels_per_graph[key] = _lib.LAUNCHES - l0      # C-ABI launches recorded in this graph
         torch.cuda.synchronize(dev)
         self._restore(snap)
+        self.refresh()               # the restored parameters' packed copies
         self.graphs[key] = (g, fake, losses)
 
     def _snapshot(self):
@@ -216,6 +264,8 @@ class TrainStep:
             if s.shape != t.shape or s.dtype != t.dtype:
                 raise MixStageError("TrainStep: batch shape/dtype changed (%s vs %s); build a new TrainStep" % (tuple(t.shape), tuple(s.shape)))
             s.copy_(t, non_blocking=True)
+        if self._pver != (self.fG.p._version, self.fD.p._version):
+            self.refresh()           # someone wrote the parameters between steps (load_state_dict, ...)
         g, self.fake, self.losses = self.graphs[key]
         g.replay()
         self.replays += 1

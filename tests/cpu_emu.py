@@ -98,6 +98,17 @@ def ms_conv_fwd_f32(x, wf, bias, y, desc, act, slope, st):
     f32(y, Y.numel()).copy_(Y.permute(0, 2, 3, 1).reshape(-1))
 
 
+def ms_conv_cin1_bnact(x, wf, scale, shift, slope, desc, y, planes, pfmt, pstride, st):
+    d = _d(desc)
+    assert d.Cin == 1 and d.groups == 1
+    X = f32(x, d.B * d.H * d.W).view(d.B, d.H, d.W, 1).permute(0, 3, 1, 2)
+    Z = F.conv2d(X, _weight_from_wf(wf, d), None, (d.sh, d.sw), (d.ph, d.pw)).permute(0, 2, 3, 1)
+    A = _act(Z * f32(scale, d.Cout) + f32(shift, d.Cout), slope).reshape(-1)
+    if y:
+        f32(y, A.numel()).copy_(A)
+    _store_planes(planes, pfmt, pstride, A)
+
+
 def ms_conv_dgrad_f32(dy, wt, dx, desc, st):
     d = _d(desc)
     DY = f32(dy, d.B * d.Ho * d.Wo * d.Cout).view(d.B, d.Ho, d.Wo, d.Cout).permute(0, 3, 1, 2)
@@ -404,6 +415,22 @@ def _tap_slice(Ap, d, q, t, kpad, Bo, Ho, Wo, PADH=16, PADW=16):
 
 
 def ms_igemm_bf16(desc, a, w, bias, scale, shift, out, st):
+    _igemm(desc, a, w, bias, scale, shift, out, None, None, 0, 0, 0)
+
+
+def ms_igemm_bf16_fused(desc, a, w, bias, scale, shift, out, out_f32, res, res_planes, res_pstride, up2, st):
+    assert _d(desc).split_k <= 1
+    _igemm(desc, a, w, bias, scale, shift, out, out_f32, res, res_planes, res_pstride, up2)
+
+
+def ms_planes_to_f32(planes, pfmt, pstride, rows, C, rs, x, st):
+    v = bf16(planes, rows * rs).float()
+    if pfmt == 3:
+        v = v + bf16(planes + 2 * pstride, rows * rs).float()
+    f32(x, rows * C).copy_(v.view(rows, rs)[:, :C].reshape(-1))
+
+
+def _igemm(desc, a, w, bias, scale, shift, out, out_f32, res, res_planes, res_pstride, up2):
     d = _d(desc)
     Wo, Ho, Bo = d.out_dims
     kpad = d.cchunks * 64
@@ -414,8 +441,17 @@ def ms_igemm_bf16(desc, a, w, bias, scale, shift, out, st):
     passes = [(0, 0), (0, 1), (1, 0)] if planes == 2 else [(0, 0)]
     osw, osh, osb = d.out_strides
     out_extent = 1 + (Wo - 1) * osw + (Ho - 1) * osh + (Bo - 1) * osb + max(d.out_off[q] for q in range(d.num_classes)) + d.class_n - 1
+    if up2:
+        assert Ho == 1
+        out_extent = 1 + (2 * Wo - 1) * osw + (Bo - 1) * 2 * osb + max(d.out_off[q] for q in range(d.num_classes)) + d.class_n - 1
     O = f32(out, out_extent) if d.out_dtype == 0 else bf16(out, out_extent)
     Olo = bf16(out + 2 * d.out_plane_stride, out_extent) if d.out_dtype == 3 else None
+    O32 = f32(out_f32, out_extent) if (out_f32 and d.out_dtype != 0) else None
+    R = None
+    if up2:
+        R = bf16(res, out_extent).float()
+        if res_planes == 2:
+            R = R + bf16(res + 2 * res_pstride, out_extent).float()
     for q in range(d.num_classes):
         acc = torch.zeros(Bo, Ho, Wo, d.class_n)
         for t in range(d.ntaps):
@@ -431,12 +467,21 @@ def ms_igemm_bf16(desc, a, w, bias, scale, shift, out, st):
                 acc = acc + f32(bias, d.num_classes * d.class_n)[cols]
             if d.epilogue == 2:
                 acc = torch.where(acc > 0, acc, acc * d.slope)
-        idx = (torch.arange(Bo).view(-1, 1, 1, 1) * osb + torch.arange(Ho).view(1, -1, 1, 1) * osh
-               + torch.arange(Wo).view(1, 1, -1, 1) * osw + d.out_off[q] + torch.arange(d.class_n).view(1, 1, 1, -1))
-        v = acc.reshape(-1)
-        O[idx.reshape(-1)] = v.to(O.dtype)
-        if Olo is not None:
-            Olo[idx.reshape(-1)] = (v - v.to(torch.bfloat16).float()).to(torch.bfloat16)
+        for j2 in range(2 if up2 else 1):
+            if up2:
+                idx = (torch.arange(Bo).view(-1, 1, 1, 1) * 2 * osb + (2 * torch.arange(Wo) + j2).view(1, 1, -1, 1) * osw
+                       + d.out_off[q] + torch.arange(d.class_n).view(1, 1, 1, -1)).reshape(-1)
+                v = acc.reshape(-1) + R[idx]
+            else:
+                idx = (torch.arange(Bo).view(-1, 1, 1, 1) * osb + torch.arange(Ho).view(1, -1, 1, 1) * osh
+                       + torch.arange(Wo).view(1, 1, -1, 1) * osw + d.out_off[q]
+                       + torch.arange(d.class_n).view(1, 1, 1, -1)).reshape(-1)
+                v = acc.reshape(-1)
+            O[idx] = v.to(O.dtype)
+            if Olo is not None:
+                Olo[idx] = (v - v.to(torch.bfloat16).float()).to(torch.bfloat16)
+            if O32 is not None:
+                O32[idx] = v
 
 
 def ms_wgrad_bf16(desc, x, dz, dwp, st):

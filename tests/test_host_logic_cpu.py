@@ -102,3 +102,66 @@ def test_tensor_core_modes_match_oracle(name, precision, tol):
             assert float((gsd[k].double() - v).abs().max()) < 1e-4, k
         for blk, cnt in ref["log_g"].counts.items():
             assert int(gsd[blk + ".norm.num_batches_tracked"]) == cnt, blk
+
+
+@pytest.mark.parametrize("name,precision,tol", [("sample_long", "bf16x3", 1e-3), ("cfg2_eval", "bf16x3", 1e-3),
+                                                ("cfg2_eval", "bf16", 2e-2)])
+def test_inference_fast_path(name, precision, tol, monkeypatch):
+    """Eval mode under no_grad with a tensor-core precision: every tensor-core block is ONE fused launch
+    (ms_igemm_bf16_fused: folded BatchNorm + LeakyReLU (+ UNet upsample/skip) in the GEMM epilogue, operand planes out);
+    the C_in = 1 layer (audio_encoder.conv.0) is one fused streaming launch; no separate normalise kernel runs for the
+    generator trunk."""
+    from mixstage_b200 import _lib, ops
+    names = []
+    inner = ops.call
+
+    def spy(n, *a):
+        names.append(n)
+        inner(n, *a)
+
+    monkeypatch.setattr(ops, "call", spy)
+    got = run_case(name, "cpu", torch.float64, precision=precision)
+    ref = run_oracle(name)
+    assert _rel(got["pose"].double(), ref["pose"]) < tol
+    soft = ref["aux"]["labels_cap_soft"].detach().reshape(got["labels_cap_soft"].shape)
+    assert _rel(got["labels_cap_soft"].double(), soft) < tol
+    assert names.count("ms_igemm_bf16_fused") >= 29          # 7 audio + 12 unet + 6 classify + 4 decoder + logits
+    assert names.count("ms_igemm_bf16") == 0
+    assert names.count("ms_conv_cin1_bnact") == 1
+    assert names.count("ms_bn_act_fwd_f32") <= 1              # only the N=S scorer of the pose-style encoder, when it runs
+
+
+def test_style_sweep_reuses_the_encoder():
+    """Reference sampling loop (trainer.py:791-794, update_kwargs :1367-1386): the same batch goes through forward once
+    per target style.  audio_encoder + unet are style independent, so the second..S-th calls must reuse them and still
+    equal a from-scratch forward; touching the audio tensor or a parameter invalidates the cache."""
+    import mixstage_oracle as O
+    from model_cases import MOD, build
+    from oracle_cases import CFG2
+    G, D, gan = build(CFG2, 64, "cpu", torch.float64)
+    G.eval()
+    G.thresh.value, G.thresh.iters = 1.0, 1000
+    audio, pose, labels, style = O.synth_inputs(4, 64, CFG2)
+    outs = []
+    with torch.no_grad():
+        for shift in range(CFG2.num_speakers):
+            st = (style + shift) % CFG2.num_speakers
+            outs.append(G([audio, labels], pose, input_modalities=MOD, style=st, sample_flag=1, description="test")[0])
+        assert G.encoder_cache_hits == CFG2.num_speakers - 1
+        G.cache_encoder = False
+        for shift in range(CFG2.num_speakers):
+            st = (style + shift) % CFG2.num_speakers
+            ref = G([audio, labels], pose, input_modalities=MOD, style=st, sample_flag=1, description="test")[0]
+            assert torch.equal(ref, outs[shift])
+        assert float((outs[0] - outs[1]).abs().max()) > 1e-3          # the style does change the output
+        G.cache_encoder = True
+        G([audio, labels], pose, input_modalities=MOD, style=style, sample_flag=1, description="test")
+        hits = G.encoder_cache_hits
+        audio.mul_(1.0)                                               # in-place edit: version bump -> miss
+        G([audio, labels], pose, input_modalities=MOD, style=style, sample_flag=1, description="test")
+        assert G.encoder_cache_hits == hits
+        G([audio, labels], pose, input_modalities=MOD, style=style, sample_flag=1, description="test")
+        assert G.encoder_cache_hits == hits + 1
+        G.unet.conv2[0].conv.weight.mul_(1.0)                         # parameter edit -> miss
+        G([audio, labels], pose, input_modalities=MOD, style=style, sample_flag=1, description="test")
+        assert G.encoder_cache_hits == hits + 1

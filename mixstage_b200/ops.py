@@ -296,7 +296,9 @@ class PackedWeight:
 
     def get(self, weight, desc):
         key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype, weight.device)
-        self._src["f32"] = (weight, desc)
+        # detached: a stored view with a grad_fn would keep the parameter's AccumulateGrad node (and the stream it was
+        # created on) alive across iterations, which breaks CUDA-graph capture of the next backward
+        self._src["f32"] = (weight.detach(), desc)
         if key != self.key or FORCE_REPACK:
             w = weight.detach()
             if not w.is_contiguous():
@@ -332,7 +334,7 @@ class PackedWeight:
         slot = "_tcw%d" % plan.mode
         key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype, weight.device, fmt, plan.wp_numel,
                tuple(plan.srctap))
-        self._src[slot] = (weight, plan, fmt, groups)
+        self._src[slot] = (weight.detach(), plan, fmt, groups)
         cur = getattr(self, slot, None)
         if cur is not None and cur[0] == key and not FORCE_REPACK:
             return cur[1], cur[2]
@@ -368,7 +370,8 @@ class PackedWeight:
         rm, rv, _ = bn_buffers
         key = tuple((t.data_ptr(), t._version) for t in (gamma, beta, rm, rv) + ((cbias,) if cbias is not None else ())) + (
             _weight_epoch, self.stats_epoch, gamma.dtype)
-        self._src["ss"] = (gamma, beta, cbias, bn_buffers, cfg)
+        self._src["ss"] = (gamma.detach(), beta.detach(), None if cbias is None else cbias.detach(),
+                           tuple(None if b is None else b.detach() for b in bn_buffers), cfg)
         cur = getattr(self, "_eval_ss", None)
         if cur is None or cur[0] != key or FORCE_REPACK:
             C = gamma.numel()
@@ -382,7 +385,7 @@ class PackedWeight:
         if bias is None:
             return None
         key = (bias.data_ptr(), bias._version, _weight_epoch, bias.dtype, bias.device)
-        self._src["bias"] = (bias,)
+        self._src["bias"] = (bias.detach(),)
         if key != self.bias_key or FORCE_REPACK:
             b = bias.detach().contiguous()
             if self.bias is None or self.bias.numel() != b.numel() or self.bias.device != b.device:

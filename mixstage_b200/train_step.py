@@ -104,6 +104,8 @@ class TrainStep:
         self.warmup_iters = 2
         self.side = ops.SideWork(dev) if dev.type == "cuda" else None      # weight-gradient GEMMs beside the dgrad chain
         self._tables = {}            # kind -> (signature, device table, n): entries of the batched weight re-tiling
+        for pw in self._packed_of(self.G) + self._packed_of(self.D):
+            pw._src.clear()          # recipes recorded before the parameters moved into the flat buffers are stale
         self._pver = None            # flat-parameter versions seen by the last refresh
 
     # ------------------------------------------------------------------ host-side decisions

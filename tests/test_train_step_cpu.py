@@ -103,3 +103,33 @@ def test_steps_match_oracle_loop(precision):
         assert dict(G.named_parameters())["logits.weight"].data_ptr() >= ts.fG.p.data_ptr()
     finally:
         M.set_precision("fp32")
+
+
+def test_packed_weight_recipes_hold_no_autograd_graph():
+    """PackedWeight._src replays the packing of every cached copy after an optimiser step.  Its tensors must be detached:
+    a stored view with a grad_fn keeps the parameter's AccumulateGrad node -- and the stream it was created on -- alive
+    across iterations, and the next backward captured into a CUDA graph then fails with
+    cudaErrorStreamCaptureIsolation (seen on B200 in round 1)."""
+    spec = O.Spec(num_speakers=4)
+    torch.manual_seed(0)
+    M.set_precision("bf16x3")
+    try:
+        G, D, gan = build(spec, 64, "cpu", torch.float64)
+        G.thresh.value, G.thresh.iters = 1.0, 1000
+        ts = M.TrainStep(gan, use_graphs=False)
+        audio, pose, labels, style = O.synth_inputs(2, 64, spec)
+        for kind in ("G", "D"):
+            ts.step(audio, labels, pose, style, kind=kind)
+        seen = 0
+        for pw in ts._packed_of(G) + ts._packed_of(D):
+            for args in pw._src.values():
+                flat = []
+                for a in args:
+                    flat.extend(a if isinstance(a, (tuple, list)) else [a])
+                for a in flat:
+                    if torch.is_tensor(a):
+                        seen += 1
+                        assert a.grad_fn is None and not a.requires_grad
+        assert seen > 50
+    finally:
+        M.set_precision("fp32")

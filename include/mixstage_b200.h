@@ -140,6 +140,17 @@ int ms_igemm_bf16(const ms_igemm_desc* d, const void* a, const void* w, const fl
 int ms_igemm_bf16_fused(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
                         const float* shift, void* out, float* out_f32, const void* res, int res_planes,
                         int64_t res_pstride, int up2, void* stream);
+/* The soft cluster mixture (index_select_outputs, joint_late_cluster_soft_style.py:106-115, called at :194) folded into
+ * the sub-decoder GEMMs so that the per-cluster outputs (B,T,K*P) never reach HBM:
+ *   row_w_mode 1 (last grouped decoder block, classes = clusters): result[row, class q columns] *= row_w[row*row_w_stride + q]
+ *                 applied after scale/shift + LeakyReLU, before the bf16 conversion;
+ *   row_w_mode 2 (the grouped 1x1 `logits` conv run as ONE dense GEMM over the K*256 weighted channels, whose accumulator
+ *                 is then sum_k w_k * logits_k): result[row, n] += sum_{k<mix_k} row_w[row*row_w_stride + k] * bias[k*N + n],
+ *                 N = num_classes*class_n <= 128, epilogue 0, mix_k <= 16.
+ * row = (b*out_dims[1] + h)*out_dims[0] + w.  Same outputs as ms_igemm_bf16_fused (planes and/or fp32); split_k <= 1. */
+int ms_igemm_bf16_mix(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                      const float* shift, void* out, float* out_f32, const float* row_w, int row_w_stride, int row_w_mode,
+                      int mix_k, void* stream);
 /* Re-tile a conv weight (Cout, Cin/g, kh*kw) of dtype pdt into Wp (bf16).
  * mode 0 (forward):  Wp[q*class_n + r][t][c] = w[q*class_n + r][c][srctap[t]]            (c < Cin/g, else 0)
  * mode 1 (dgrad):    Wp[q*class_n + r][t][n] = w[g*Cout/g + n][r][srctap[q*ntaps + t]]   (n < Cout/g, r < Cin/g, else 0)

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "ms_conv_cin1_bnact": [_P, _P, _P, _P, _F, _CD, _P, _P, _I, _L, _P],
     "ms_igemm_bf16": [_GD, _P, _P, _P, _P, _P, _P, _P],
     "ms_igemm_bf16_fused": [_GD, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P],
+    "ms_igemm_bf16_mix": [_GD, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P, _P],
     "ms_pack_igemm_weight_multi": [_P, _I, _I, _P],
     "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],

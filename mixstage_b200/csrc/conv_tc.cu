@@ -21,6 +21,7 @@
 //
 // The same kernel serves forward and input-gradient (descriptors differ); see ms_igemm_desc.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -55,6 +56,11 @@ struct IgemmParams {
   long long res_pstride;                // elements between the residual's hi and lo planes
   int res_planes;                       // 1 or 2
   int up2;                              // every GEMM row (b, w) produces output rows (b, 2w) and (b, 2w+1)
+  // cluster mixture folded into the sub-decoder GEMMs (ms_igemm_bf16_mix; persistent kernel only)
+  const float* row_w;                   // nullable: soft cluster weights [rows][row_w_stride]
+  int row_w_stride;
+  int row_w_mode;                       // 1: result *= row_w[row][class]; 2: result += sum_k row_w[row][k] * bias[k*N + n]
+  int mix_k;                            // mode 2: number of clusters K (<= 16)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +130,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+
+// wait for the outstanding tcgen05.ld; the loaded registers pass THROUGH the statement so that no use can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -326,6 +341,306 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Persistent form of the same GEMM (every launch that is not split-K).
+//
+// The one-tile-per-CTA kernel above serialises  mainloop -> epilogue  inside a CTA; ncu (profiles/r01_igemm_infer_*)
+// showed the epilogue (TMEM -> registers -> scale/shift -> global stores, with the per-column constants fetched from
+// global memory on the critical path) taking ~2x the mainloop, i.e. the tensor pipe idle two thirds of the time.
+// Here one CTA per SM walks a static round-robin list of tiles with
+//   * TWO accumulator buffers in TMEM (2 x block_n columns): the MMA warp fills buffer (i+1)&1 while the epilogue
+//     warps drain buffer i&1 (tmem_full / tmem_empty mbarriers),
+//   * the smem operand ring running straight across tile boundaries (the TMA producer never drains),
+//   * 8 epilogue warps (two per TMEM lane quadrant, each taking half of the tile's columns),
+//   * the tile's per-column constants (BN scale/shift or bias) staged in shared memory BEFORE the accumulator is ready.
+// Epilogue extras (ms_igemm_bf16_mix): multiply every row by its soft cluster weight (row_w_mode 1) so that the grouped
+// 1x1 `logits` convolution that follows becomes ONE dense GEMM over K*256 channels whose accumulator IS the mixture
+// sum_k w_k * logits_k (jlcss.py:106-115,190-194) -- the per-cluster outputs (B,T,K*P) are never written to HBM;
+// row_w_mode 2 adds the mixed bias sum_k w_k * b_k in that GEMM's epilogue.
+// ---------------------------------------------------------------------------------------------
+constexpr int PERSIST_THREADS = 320;     // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr int EPI_THREADS = 256;
+constexpr int MIX_MAX_K = 16, MIX_MAX_N = 128;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int w0, h0, b0, cls, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile, int ny) {
+  TileCoord t;
+  const int y = tile % ny;
+  int mt = tile / ny;
+  const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+  const int th = mt % p.tiles_h; mt /= p.tiles_h;
+  t.w0 = tw * p.box_w; t.h0 = th * p.box_h; t.b0 = mt * p.box_b;
+  t.cls = y / p.n_tiles_per_class;
+  t.n0 = (y - t.cls * p.n_tiles_per_class) * p.block_n;
+  return t;
+}
+
+// 16 consecutive output columns of one row: activation / row weight / residual / stores
+__device__ __forceinline__ void epilogue_store16(const IgemmParams& p, void* __restrict__ out, const float (&f)[16],
+                                                 long long off, long long off_up, int nrep) {
+  for (int j2 = 0; j2 < nrep; j2++) {
+    float g[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) g[j] = f[j];
+    long long o = off;
+    if (p.up2) {
+      // UNet1D decoder step (layers.py:151): y[b, 2w + j2, :] = act(bn(z))[b, w, :] + residual[b, 2w + j2, :]
+      o = off_up + (long long)j2 * p.os_w;
+      for (int pl = 0; pl < p.res_planes; pl++) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + (long long)pl * p.res_pstride + o);
+        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+          g[2 * j] += __bfloat162float(h2.x);
+          g[2 * j + 1] += __bfloat162float(h2.y);
+        }
+      }
+    }
+    if (p.out_f32 || p.out_dtype == MS_F32) {
+      float4* dst = reinterpret_cast<float4*>((p.out_dtype == MS_F32 ? reinterpret_cast<float*>(out) : p.out_f32) + o);
+#pragma unroll
+      for (int j = 0; j < 4; j++) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+    }
+    if (p.out_dtype != MS_F32) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o);
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(g[2 * j], g[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h2);
+        if (p.out_dtype == MS_BF16X2) {          // residuals for the lo plane
+          g[2 * j] -= __bfloat162float(h2.x);
+          g[2 * j + 1] -= __bfloat162float(h2.y);
+        }
+      }
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      if (p.out_dtype == MS_BF16X2) {
+        dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + p.out_plane_stride + o);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(g[2 * j], g[2 * j + 1]);
+          w[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                        const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
+                        const __grid_constant__ IgemmParams p, const float* __restrict__ bias, const float* __restrict__ scale,
+                        const float* __restrict__ shift, void* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  const int STAGES = p.stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_scale[2][256], s_shift[2][256];
+  __shared__ float s_mixb[MIX_MAX_K * MIX_MAX_N];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.ntaps * p.cchunks * p.npass;
+  const int ny = p.n_tiles_per_class * p.num_classes;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * ny;
+  uint32_t cols_per_buf = 32;
+  while (cols_per_buf < (uint32_t)p.block_n) cols_per_buf <<= 1;
+  const uint32_t tmem_cols = 2 * cols_per_buf;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    if (p.npass > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
+    }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], EPI_THREADS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer: the ring never drains between tiles =================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, ny);
+        const int tap_base = p.shared_taps ? 0 : t.cls * p.ntaps;
+        const int chan_base = p.a_chan_base[t.cls];
+        const int wrow = t.cls * p.class_n + t.n0;
+        for (int kg = 0; kg < num_k; kg++) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int kk = kg / p.npass, pass = kg - kk * p.npass;          // split-bf16: hi*hi, hi*lo, lo*hi
+          const int tap = kk / p.cchunks, cc = kk - tap * p.cchunks;
+          const short* tp = p.taps[tap_base + tap];
+          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + b_stage_bytes);
+          tma_load_5d(pass == 2 ? &map_a_lo : &map_a, &full_bar[s], smem_a + (size_t)s * A_STAGE_BYTES,
+                      chan_base + tp[0] + cc * BLOCK_K, t.w0 + tp[1], tp[2], t.h0 + tp[3], t.b0);
+          tma_load_2d(pass == 1 ? &map_w_lo : &map_w, &full_bar[s], smem_b + (size_t)s * b_stage_bytes, kk * BLOCK_K, wrow);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: accumulator buffer lt & 1 =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);     // epilogue drained this buffer (tile lt - 2)
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)buf * cols_per_buf;
+        for (int ks = 0; ks < num_k; ks++) {
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + (size_t)s * A_STAGE_BYTES));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + (size_t)s * b_stage_bytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+            umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue: 8 warps; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =================
+    const int et = (int)threadIdx.x - 64;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;                       // tile row == TMEM lane
+    const int wi = r % p.box_w;
+    const int hi = (r / p.box_w) % p.box_h;
+    const int bi = r / (p.box_w * p.box_h);
+    const int chunks = p.block_n >> 4;
+    const int chunks_h = (chunks + 1) >> 1;
+    const int c_beg = half * chunks_h, c_end = min(chunks, c_beg + chunks_h);
+    const bool act = p.epilogue != 0 && p.slope != 1.f;
+    const int nrep = p.up2 ? 2 : 1;
+    const int ncols_total = p.num_classes * p.class_n;
+    if (p.row_w_mode == 2) {
+      for (int i = et; i < p.mix_k * MIX_MAX_N; i += EPI_THREADS) {
+        const int k = i / MIX_MAX_N, n = i - k * MIX_MAX_N;
+        s_mixb[i] = (bias && n < ncols_total) ? __ldg(bias + (long long)k * ncols_total + n) : 0.f;
+      }
+    }
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
+      const int buf = lt & 1;
+      const TileCoord t = decode_tile(p, tile, ny);
+      const int ncol = t.cls * p.class_n + t.n0;             // global column (bias / scale index)
+      // per-column constants of this tile -> shared memory, while the MMAs are still running
+      for (int i = et; i < p.block_n; i += EPI_THREADS) {
+        float sc = 1.f, sh = 0.f;
+        if (t.n0 + i < p.class_n) {
+          if (p.epilogue == 1) { sc = __ldg(scale + ncol + i); sh = __ldg(shift + ncol + i); }
+          else if (bias && p.row_w_mode != 2) sh = __ldg(bias + ncol + i);
+        }
+        s_scale[buf][i] = sc;
+        s_shift[buf][i] = sh;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      const int ow = t.w0 + wi, oh = t.h0 + hi, ob = t.b0 + bi;
+      const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
+      const long long row_off = (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + p.out_off[t.cls] + t.n0;
+      const long long row_off_up = (long long)ob * p.os_b * 2 + (long long)(2 * ow) * p.os_w + p.out_off[t.cls] + t.n0;
+      float rw = 1.f;
+      float mw[MIX_MAX_K];
+      if (p.row_w_mode != 0 && valid) {
+        const float* wr = p.row_w + ((long long)(ob * p.out_h + oh) * p.out_w + ow) * p.row_w_stride;
+        if (p.row_w_mode == 1) rw = __ldg(wr + t.cls);
+        else {
+#pragma unroll
+          for (int k = 0; k < MIX_MAX_K; k++) mw[k] = k < p.mix_k ? __ldg(wr + k) : 0.f;
+        }
+      }
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * cols_per_buf;
+      uint32_t va[16], vb[16];
+      if (c_beg < c_end) tmem_ld16(taddr + (uint32_t)(c_beg * 16), va);
+      for (int c = c_beg; c < c_end; c += 2) {
+        // chunk c (in va), prefetching chunk c + 1 into vb; then chunk c + 1, prefetching c + 2 into va
+#pragma unroll
+        for (int sub = 0; sub < 2; sub++) {
+          const int cc = c + sub;
+          if (cc >= c_end) break;
+          uint32_t (&cur)[16] = sub == 0 ? va : vb;
+          uint32_t (&nxt)[16] = sub == 0 ? vb : va;
+          tmem_wait_ld16(cur);
+          if (cc + 1 < c_end) tmem_ld16(taddr + (uint32_t)((cc + 1) * 16), nxt);
+          const int c0 = cc * 16;
+          if (valid && (t.n0 + c0) < p.class_n) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) f[j] = fmaf(__uint_as_float(cur[j]), s_scale[buf][c0 + j], s_shift[buf][c0 + j]);
+            if (p.row_w_mode == 2) {
+#pragma unroll
+              for (int k = 0; k < MIX_MAX_K; k++) {
+                if (k < p.mix_k) {
+#pragma unroll
+                  for (int j = 0; j < 16; j++) f[j] = fmaf(mw[k], s_mixb[k * MIX_MAX_N + t.n0 + c0 + j], f[j]);
+                }
+              }
+            }
+            if (act) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
+            }
+            if (p.row_w_mode == 1) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) f[j] *= rw;
+            }
+            epilogue_store16(p, out, f, row_off + c0, row_off_up + c0, nrep);
+          }
+        }
+      }
+      // all tcgen05.ld of this buffer have completed (wait::ld above): hand it back to the MMA warp
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -613,7 +928,19 @@ struct IgemmFused {
   int res_planes;
   long long res_pstride;
   int up2;
+  const float* row_w;
+  int row_w_stride, row_w_mode, mix_k;
 };
+
+// MS_IGEMM_LEGACY=1 routes every launch to the one-tile-per-CTA kernel (A/B timing, debugging)
+static bool igemm_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MS_IGEMM_LEGACY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
                         const float* shift, void* out, const IgemmFused* fx, void* stream) {
@@ -683,8 +1010,22 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
     for (int j = 0; j < 4; j++) p.taps[i][j] = d->taps[i][j];
   p.out_dtype = d->out_dtype; p.epilogue = d->epilogue; p.slope = d->slope;
   p.out_f32 = nullptr; p.res = nullptr; p.res_pstride = 0; p.res_planes = 0; p.up2 = 0;
+  p.row_w = nullptr; p.row_w_stride = 0; p.row_w_mode = 0; p.mix_k = 0;
   if (fx) {
     if (d->split_k > 1) return MS_EINVAL;
+    if (fx->row_w_mode) {
+      if (!fx->row_w || fx->up2 || fx->row_w_stride < 1) return MS_EINVAL;
+      if (fx->row_w_mode == 1) {
+        if (fx->row_w_stride < d->num_classes) return MS_EINVAL;
+      } else if (fx->row_w_mode == 2) {
+        // mixed bias: bias is [mix_k][num_classes*class_n]; one tile covers every column
+        if (fx->mix_k < 1 || fx->mix_k > MIX_MAX_K || fx->row_w_stride < fx->mix_k) return MS_EINVAL;
+        if (d->num_classes * d->class_n > MIX_MAX_N || d->epilogue != 0) return MS_EINVAL;
+      } else {
+        return MS_EINVAL;
+      }
+      p.row_w = fx->row_w; p.row_w_stride = fx->row_w_stride; p.row_w_mode = fx->row_w_mode; p.mix_k = fx->mix_k;
+    }
     if (fx->out_f32 && ((uintptr_t)fx->out_f32 & 15)) return MS_EINVAL;
     p.out_f32 = d->out_dtype == MS_F32 ? nullptr : fx->out_f32;
     if (fx->up2) {
@@ -711,13 +1052,33 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
     split = (num_k_total + per - 1) / per;            // every slice owns at least one k-step
   }
   p.split_k = split;
+  const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * d->num_classes;
+  if (tiles < 1 || tiles > 0x7fffffffLL) return MS_EINVAL;
+  if (split == 1 && !(igemm_legacy() && p.row_w_mode == 0)) {
+    // ---- persistent kernel: one CTA per SM, double-buffered TMEM accumulators, ring across tiles
+    int stages = (int)((227 * 1024 - 15 * 1024) / stage_bytes);      // static smem: constants + mixed bias + barriers
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return MS_EINVAL;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    static bool attr_set_p = false;
+    if (!attr_set_p) {
+      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 15 * 1024 + 1024));
+      attr_set_p = true;
+    }
+    const unsigned grid = (unsigned)(tiles < ms_num_sms() ? tiles : ms_num_sms());
+    igemm_tc_persist_kernel<<<grid, PERSIST_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+    MS_LAUNCH_CHECK();
+    return 0;
+  }
+  if (p.row_w_mode != 0) return MS_EINVAL;
   const int k_per_cta = (num_k_total + split - 1) / split;
   int stages = (int)((227 * 1024 - 4096) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > k_per_cta) stages = k_per_cta < 2 ? 2 : k_per_cta;
   {
     // more CTAs than SMs: keep the ring under half of the shared memory so that two CTAs are co-resident
-    const long long ctas = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * d->num_classes * split;
+    const long long ctas = tiles * split;
     const int half = (int)((113 * 1024 - 2048) / stage_bytes);
     if (ctas > ms_num_sms() && half >= 3 && stages > half) stages = half;
   }
@@ -746,6 +1107,16 @@ extern "C" int ms_igemm_bf16_fused(const ms_igemm_desc* d, const void* a, const 
                                    int64_t res_pstride, int up2, void* stream) {
   IgemmFused fx;
   fx.out_f32 = out_f32; fx.res = res; fx.res_planes = res_planes; fx.res_pstride = res_pstride; fx.up2 = up2;
+  fx.row_w = nullptr; fx.row_w_stride = 0; fx.row_w_mode = 0; fx.mix_k = 0;
+  return igemm_launch(d, a, w, bias, scale, shift, out, &fx, stream);
+}
+
+extern "C" int ms_igemm_bf16_mix(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
+                                 const float* shift, void* out, float* out_f32, const float* row_w, int row_w_stride,
+                                 int row_w_mode, int mix_k, void* stream) {
+  IgemmFused fx;
+  fx.out_f32 = out_f32; fx.res = nullptr; fx.res_planes = 0; fx.res_pstride = 0; fx.up2 = 0;
+  fx.row_w = row_w; fx.row_w_stride = row_w_stride; fx.row_w_mode = row_w_mode; fx.mix_k = mix_k;
   return igemm_launch(d, a, w, bias, scale, shift, out, &fx, stream);
 }
 

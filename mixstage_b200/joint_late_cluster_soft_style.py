@@ -94,6 +94,7 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         self.logits = nn.Conv1d(in_channels * self.num_clusters, out_feats * self.num_clusters, kernel_size=1, stride=1,
                                 groups=self.num_clusters)
         self._logits = PlainConv(self.logits)
+        self._mixed_logits = ops.MixedLogits()
         self.classify_cluster = ClusterClassify(num_clusters=self.num_clusters, groups=1,
                                                 input_channels=self.style_dim + in_channels)
         self.eye = nn.Parameter(torch.eye(self.num_clusters, self.num_clusters), requires_grad=False)
@@ -219,9 +220,17 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         self.labels_cap_soft = ops.cast(soft_c.view(Bx, T, K), out_dtype)
 
         # K sub-decoders (grouped) + grouped 1x1 logits + soft mixture (jlcss.py:190-194)
-        d = _run(self.decoder, hc, last="planes")
-        z = self._logits(self.logits, d)                                      # (B,1,T,K*P)
-        pose = ops.mixture(z.view(Bx * T, K * self.out_feats), soft_c).view(Bx, T, self.out_feats)
+        if (not self.training and ops.fast_eval() and ops.MixedLogits.eligible(self.out_feats, K, self.in_channels)
+                and self.decoder[-1].cfg.groups == K):
+            # inference: the mixture rides inside the GEMMs -- cluster weights in the last sub-decoder epilogue, the grouped
+            # logits as one dense GEMM accumulating sum_k w_k * logits_k; (B,T,K*P) is never materialised
+            d = _run(self.decoder[:-1], hc, last="planes")
+            d = self.decoder[-1](d, want="planes", row_w=soft_c)
+            pose = self._mixed_logits(d, self.logits.weight, self.logits.bias, soft_c).view(Bx, T, self.out_feats)
+        else:
+            d = _run(self.decoder, hc, last="planes")
+            z = self._logits(self.logits, d)                                      # (B,1,T,K*P)
+            pose = ops.mixture(z.view(Bx * T, K * self.out_feats), soft_c).view(Bx, T, self.out_feats)
 
         if flag:
             ctxm = some_grad(self.pose_style_encoder) if self.some_grad_flag else contextlib.nullcontext()

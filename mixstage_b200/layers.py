@@ -59,7 +59,7 @@ class ConvNormRelu(nn.Module):
         self.cfg = ops.ConvCfg(kh, kw, sh, sw, ph, pw, groups, 0.2 if leaky else 0.0, has_bn=True, act=True)
         self._packed = ops.PackedWeight()
 
-    def forward(self, x, residual=None, up2=False, want="both"):
+    def forward(self, x, residual=None, up2=False, want="both", row_w=None):
         """x: channels-last (B, H, W, C) fp32.  With ``up2`` the output is
         ``upsample2(act(bn(conv(x)))) + residual`` (UNet1D decoder step, layers.py:151).
         ``want`` ("planes" | "f32" | "both"): which forms of the output the consumers read; only the inference fast
@@ -67,7 +67,7 @@ class ConvNormRelu(nn.Module):
         n = self.norm
         return ops.conv_block(x, self.conv.weight, self.conv.bias, n.weight, n.bias, self.cfg, self._packed,
                               (n.running_mean, n.running_var, n.num_batches_tracked), self.training,
-                              residual=residual, up2=up2, want=want)
+                              residual=residual, up2=up2, want=want, row_w=row_w)
 
 
 class PlainConv(object):

@@ -690,7 +690,7 @@ def _tc_backward(ctx, dy):
     last_gemm_flops = ctx.flops
     if need_w:
         igemm.set_planes(pf, split, xps, 0, dzp.ps)
-        nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc)
+        nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc, npass=3 if split else 1)
         pf.desc.split_k = nsplit
         sink = ctx.sinks[0]
         if sink is not None and SIDE is not None:
@@ -724,7 +724,7 @@ def _tc_backward(ctx, dy):
     return dx, dw, dbias, dgamma, dbeta, dres, None, None, None, None, None, None, None
 
 
-def _tc_eval(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, up2, fmt, want):
+def _tc_eval(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, up2, fmt, want, row_w=None):
     """Inference fast path of the block (eval mode, no autograd): ONE tcgen05 launch whose epilogue applies the folded
     BatchNorm + LeakyReLU (+ UNet upsample-and-skip) and writes the next layer's bf16 operand planes directly
     (want "planes"), fp32 (want "f32") or both -- no fp32 activation round trip through HBM."""
@@ -762,14 +762,78 @@ def _tc_eval(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, up
     d.out_dtype = fmt if yp is not None else _lib.MS_F32
     global last_gemm_flops
     last_gemm_flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
-    call("ms_igemm_bf16_fused", d, ptr(xp.t), ptr(wp), ptr(b32), scale, shift, ptr(yp.t) if yp is not None else ptr(y32),
-         ptr(y32) if yp is not None else None, ptr(res.t) if res is not None else None,
-         (2 if split else 1) if res is not None else 0, res.ps if res is not None else 0, 1 if up2 else 0, st)
+    if row_w is not None:
+        # soft cluster weight of every row applied in the epilogue (classes = clusters): the mixture moves into the GEMMs
+        if up2 or row_w.dtype != torch.float32 or not row_w.is_contiguous() or row_w.numel() != rows * d.num_classes:
+            raise MixStageError("row weights must be contiguous fp32 (rows, groups)")
+        call("ms_igemm_bf16_mix", d, ptr(xp.t), ptr(wp), ptr(b32), scale, shift, ptr(yp.t) if yp is not None else ptr(y32),
+             ptr(y32) if yp is not None else None, ptr(row_w), d.num_classes, 1, 0, st)
+    else:
+        call("ms_igemm_bf16_fused", d, ptr(xp.t), ptr(wp), ptr(b32), scale, shift, ptr(yp.t) if yp is not None else ptr(y32),
+             ptr(y32) if yp is not None else None, ptr(res.t) if res is not None else None,
+             (2 if split else 1) if res is not None else 0, res.ps if res is not None else 0, 1 if up2 else 0, st)
     if y32 is not None:
         if yp is not None:
             y32._ms_planes = yp
         return y32
     return planes_view(yp, oshape)
+
+
+def fast_eval(precision=None):
+    """True when blocks run on the inference fast path: tensor-core arithmetic, no autograd."""
+    return (precision or _precision) != "fp32" and not torch.is_grad_enabled()
+
+
+class MixedLogits:
+    """The grouped 1x1 `logits` convolution + index_select_outputs (jlcss.py:83,106-115,194) as ONE dense GEMM on the
+    inference fast path.  With the last sub-decoder block's epilogue having multiplied every row of cluster k's 256
+    channels by its soft weight w_k (conv_block(row_w=...)),
+        pose[row, p] = sum_k sum_c W[k*P + p, c] * (w_k * a_k[row, c]) + sum_k w_k * b[k*P + p]
+    is a (rows, K*256) x (K*256, P) product accumulated in TMEM; the (B,T,K*P) per-cluster outputs are never written."""
+
+    def __init__(self):
+        self.packed = PackedWeight()
+        self.key = None
+        self.dense = None
+
+    @staticmethod
+    def eligible(P, K, Cg):
+        return P % 16 == 0 and 16 <= P <= 128 and K <= 16 and (K * Cg) % 64 == 0
+
+    def __call__(self, x, weight, bias, soft):
+        """x: planes-only (B,1,T,K*Cg) already row-weighted; weight (K*P, Cg, 1); bias (K*P,); soft (rows, K) fp32."""
+        B, H, W, Ct = x.shape
+        KP, Cg = weight.shape[0], weight.shape[1]
+        K = Ct // Cg
+        P = KP // K
+        key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype)
+        if key != self.key or FORCE_REPACK:
+            dense = weight.detach().view(K, P, Cg).permute(1, 0, 2).reshape(P, K * Cg, 1, 1)
+            if self.dense is not None and self.dense.shape == dense.shape and self.dense.dtype == dense.dtype:
+                self.dense.copy_(dense)        # same buffer: captured graphs / cached re-tilings keep pointing at it
+            else:
+                self.dense = dense.contiguous()
+            self.key = key             # (the copy bumps self.dense's version: get_tc re-tiles it)
+        fmt = x._ms_planes.fmt
+        split = fmt == MS_BF16X2
+        cfg = ConvCfg(1, 1, 1, 1, 0, 0, 1, 0.0, has_bn=False, act=False)
+        xp = planes_of(x, fmt, Ct)
+        pf, _ = self.packed.tc_plans((B, H, W, Ct), P, cfg, Ct, False, 3 if split else 1)
+        pf.desc.block_n = P
+        wp, wps = self.packed.get_tc(self.dense, pf, fmt, 1)
+        b32 = self.packed.get_bias(bias)
+        d = pf.desc
+        d.epilogue, d.slope, d.split_k, d.out_numel = 0, 1.0, 1, 0
+        igemm.set_planes(pf, split, xp.ps, wps, 0)
+        d.out_dtype = _lib.MS_F32
+        rows = B * H * W
+        if soft.dtype != torch.float32 or not soft.is_contiguous() or soft.numel() != rows * K:
+            raise MixStageError("mixture weights must be contiguous fp32 (rows, K)")
+        y = torch.empty((B, H, W, P), dtype=torch.float32, device=x.device)
+        global last_gemm_flops
+        last_gemm_flops = 2.0 * rows * KP * Cg
+        call("ms_igemm_bf16_mix", d, ptr(xp.t), ptr(wp), ptr(b32), None, None, ptr(y), None, ptr(soft), K, 2, K, stream())
+        return y
 
 
 def _cin1_eval(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, fmt, want):
@@ -796,7 +860,7 @@ def _cin1_eval(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, fmt, want)
 
 
 def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, residual=None, up2=False, precision=None,
-               want="both"):
+               want="both", row_w=None):
     """weight is the caller's parameter in its own layout/dtype: (Cout, Cin/g, k) or (Cout, Cin/g, kh, kw).
     want ("planes" | "f32" | "both") only matters on the inference fast path (eval mode under torch.no_grad() with a
     tensor-core precision): which forms of the activation the consumers need."""
@@ -807,7 +871,9 @@ def conv_block(x, weight, bias, gamma, beta, cfg, packed, bn_buffers, training, 
     if tc_ok and not training and not torch.is_grad_enabled():
         w4 = weight.detach()
         return _tc_eval(x, w4.unsqueeze(2) if w4.dim() == 3 else w4, bias, gamma, beta, residual, cfg, packed, bn_buffers,
-                        up2, _fmt(prec), want)
+                        up2, _fmt(prec), want, row_w)
+    if row_w is not None:
+        raise MixStageError("row weights are an inference-fast-path epilogue (eval mode, no autograd, tensor-core precision)")
     if (prec != "fp32" and not training and not torch.is_grad_enabled() and cfg.has_bn and x.dim() == 4 and x.shape[3] == 1
             and cfg.groups == 1 and weight.shape[0] % 8 == 0 and x.dtype == torch.float32):
         return _cin1_eval(x, weight.detach(), bias, gamma, beta, cfg, packed, bn_buffers, _fmt(prec), want)

@@ -423,6 +423,15 @@ def ms_igemm_bf16_fused(desc, a, w, bias, scale, shift, out, out_f32, res, res_p
     _igemm(desc, a, w, bias, scale, shift, out, out_f32, res, res_planes, res_pstride, up2)
 
 
+def ms_igemm_bf16_mix(desc, a, w, bias, scale, shift, out, out_f32, row_w, row_w_stride, row_w_mode, mix_k, st):
+    """row_w_mode 1: result * row_w[row, class]; 2: result + sum_k row_w[row, k] * bias[k, n] (epilogue 0, one class)."""
+    d = _d(desc)
+    assert d.split_k <= 1 and row_w_mode in (1, 2) and row_w
+    if row_w_mode == 2:
+        assert d.epilogue == 0 and 1 <= mix_k <= 16 and d.num_classes * d.class_n <= 128
+    _igemm(desc, a, w, bias, scale, shift, out, out_f32, None, 0, 0, 0, (row_w, row_w_stride, row_w_mode, mix_k))
+
+
 def ms_planes_to_f32(planes, pfmt, pstride, rows, C, rs, x, st):
     v = bf16(planes, rows * rs).float()
     if pfmt == 3:
@@ -430,7 +439,7 @@ def ms_planes_to_f32(planes, pfmt, pstride, rows, C, rs, x, st):
     f32(x, rows * C).copy_(v.view(rows, rs)[:, :C].reshape(-1))
 
 
-def _igemm(desc, a, w, bias, scale, shift, out, out_f32, res, res_planes, res_pstride, up2):
+def _igemm(desc, a, w, bias, scale, shift, out, out_f32, res, res_planes, res_pstride, up2, mix=None):
     d = _d(desc)
     Wo, Ho, Bo = d.out_dims
     kpad = d.cchunks * 64
@@ -462,11 +471,17 @@ def _igemm(desc, a, w, bias, scale, shift, out, out_f32, res, res_planes, res_ps
         if d.epilogue == 1:
             acc = acc * f32(scale, d.num_classes * d.class_n)[cols] + f32(shift, d.num_classes * d.class_n)[cols]
             acc = torch.where(acc > 0, acc, acc * d.slope)
+        elif mix is not None and mix[2] == 2:
+            N = d.num_classes * d.class_n
+            RW = f32(mix[0], Bo * Ho * Wo * mix[1]).view(Bo, Ho, Wo, mix[1])[..., :mix[3]]
+            acc = acc + RW @ f32(bias, mix[3] * N).view(mix[3], N)[:, cols]
         else:
             if bias:
                 acc = acc + f32(bias, d.num_classes * d.class_n)[cols]
             if d.epilogue == 2:
                 acc = torch.where(acc > 0, acc, acc * d.slope)
+        if mix is not None and mix[2] == 1:
+            acc = acc * f32(mix[0], Bo * Ho * Wo * mix[1]).view(Bo, Ho, Wo, mix[1])[..., q:q + 1]
         for j2 in range(2 if up2 else 1):
             if up2:
                 idx = (torch.arange(Bo).view(-1, 1, 1, 1) * 2 * osb + (2 * torch.arange(Wo) + j2).view(1, 1, -1, 1) * osw

@@ -108,7 +108,8 @@ def test_tensor_core_modes_match_oracle(name, precision, tol):
                                                 ("cfg2_eval", "bf16", 2e-2)])
 def test_inference_fast_path(name, precision, tol, monkeypatch):
     """Eval mode under no_grad with a tensor-core precision: every tensor-core block is ONE fused launch
-    (ms_igemm_bf16_fused: folded BatchNorm + LeakyReLU (+ UNet upsample/skip) in the GEMM epilogue, operand planes out);
+    (ms_igemm_bf16_fused / ms_igemm_bf16_mix: folded BatchNorm + LeakyReLU (+ UNet upsample/skip, + cluster mixture) in the
+    GEMM epilogue, operand planes out);
     the C_in = 1 layer (audio_encoder.conv.0) is one fused streaming launch; no separate normalise kernel runs for the
     generator trunk."""
     from mixstage_b200 import _lib, ops
@@ -125,7 +126,11 @@ def test_inference_fast_path(name, precision, tol, monkeypatch):
     assert _rel(got["pose"].double(), ref["pose"]) < tol
     soft = ref["aux"]["labels_cap_soft"].detach().reshape(got["labels_cap_soft"].shape)
     assert _rel(got["labels_cap_soft"].double(), soft) < tol
-    assert names.count("ms_igemm_bf16_fused") >= 29          # 7 audio + 12 unet + 6 classify + 4 decoder + logits
+    assert names.count("ms_igemm_bf16_fused") >= 28          # 7 audio + 12 unet + 6 classify + 3 decoder
+    # the soft mixture rides inside the GEMMs: cluster weights in the last sub-decoder block's epilogue, the grouped logits
+    # as one dense GEMM with the mixed bias -- no per-cluster (B,T,K*P) tensor, no mixture kernel
+    assert names.count("ms_igemm_bf16_mix") == 2
+    assert names.count("ms_mixture_fwd_f32") == 0
     assert names.count("ms_igemm_bf16") == 0
     assert names.count("ms_conv_cin1_bnact") == 1
     assert names.count("ms_bn_act_fwd_f32") <= 1              # only the N=S scorer of the pose-style encoder, when it runs

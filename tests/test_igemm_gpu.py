@@ -160,7 +160,7 @@ def test_split_bf16_fwd_dgrad_wgrad(g):
     assert err < 3e-5 * float(dref.abs().max()), (err, float(dref.abs().max()))
 
     igemm.set_planes(pf, True, xps, 0, dzps)
-    nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc)
+    nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc, npass=3)
     pf.desc.split_k = nsplit
     dwp = torch.full((nsplit * pf.wp_numel,), float("nan"), device="cuda")
     _lib.call("ms_wgrad_bf16", pf.desc, ptr(xp), ptr(dzp), ptr(dwp), st)
@@ -169,3 +169,110 @@ def test_split_bf16_fwd_dgrad_wgrad(g):
     torch.cuda.synchronize()
     err = float((dw.cpu() - wref).abs().max())
     assert err < 3e-5 * float(wref.abs().max()), (err, float(wref.abs().max()))
+
+
+# ---- persistent kernel: CTAs that walk several tiles (accumulator double buffering, ring across tile boundaries)
+MANY = [
+    (640, 1, 64, 256, 512, 1, 3, 1, 1, 0, 1, 1),     # 320 row tiles x 2 column tiles = 640 tiles on 148 CTAs
+    (96, 1, 64, 1024, 1024, 1, 3, 1, 1, 0, 1, 4),    # grouped: 48 row tiles x 4 classes
+    (40, 32, 32, 64, 64, 4, 4, 2, 2, 1, 1, 1),       # 2-D stride 2, N = 64
+]
+
+
+@pytest.mark.parametrize("g", MANY)
+@pytest.mark.parametrize("planes", [1, 2])
+def test_persistent_many_tiles(g, planes):
+    torch.manual_seed(11)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups = g
+    Ho, Wo = _conv_out(H, kh, sh, ph), _conv_out(W, kw, sw, pw)
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(B, H, W, Cin, device="cuda")
+    w = torch.randn(Cout, Cin // groups, kh, kw, dtype=torch.float64, device="cuda") / (Cin // groups * kh * kw) ** 0.5
+    if planes == 1:
+        x = x.to(torch.bfloat16).float()
+        w = w.to(torch.bfloat16).double()
+    scale, shift = torch.rand(Cout, device="cuda") + 0.5, torch.randn(Cout, device="cuda") * 0.1
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w, None, stride=(sh, sw), padding=(ph, pw), groups=groups).permute(0, 2, 3, 1)
+    ref = F.leaky_relu(ref * scale.double() + shift.double(), 0.2)
+    plan = igemm.make_fwd(B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, groups, Ho, Wo, out_dtype=_lib.MS_F32, epilogue=1, slope=0.2)
+    d = plan.desc
+    ps = (plan.wp_numel + 7) // 8 * 8
+    wp = torch.zeros(2 * ps, dtype=torch.bfloat16, device="cuda")
+    _lib.call("ms_pack_igemm_weight_bf16", ptr(w), 1, Cout, Cin // groups, kh * kw, groups, 0, d.num_classes, d.class_n,
+              d.ntaps, plan.kpad, plan.srctap_c, ptr(wp), wp.data_ptr() + 2 * ps, st)
+    xp, xps = _planes(x)
+    igemm.set_planes(plan, planes == 2, xps, ps, 0)
+    out = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda")
+    _lib.call("ms_igemm_bf16", d, ptr(xp), ptr(wp), None, ptr(scale), ptr(shift), ptr(out), st)
+    torch.cuda.synchronize()
+    err = float((out.double() - ref).abs().max())
+    assert err < (1e-3 if planes == 1 else 3e-5) * float(ref.abs().max()), (err, float(ref.abs().max()))
+    # planes + fp32 outputs of the fused form agree with each other and with the plain launch
+    d.out_dtype = _lib.MS_BF16X2 if planes == 2 else _lib.MS_BF16
+    ops_ = (out.numel() + 7) // 8 * 8
+    d.out_plane_stride = ops_
+    yp = torch.zeros(2 * ops_, dtype=torch.bfloat16, device="cuda")
+    y32 = torch.full_like(out, float("nan"))
+    _lib.call("ms_igemm_bf16_fused", d, ptr(xp), ptr(wp), None, ptr(scale), ptr(shift), ptr(yp), ptr(y32), None, 0, 0, 0, st)
+    torch.cuda.synchronize()
+    assert torch.equal(y32, out)
+    got = yp[:out.numel()].float() + (yp[ops_:ops_ + out.numel()].float() if planes == 2 else 0)
+    tol = 2 ** -8 if planes == 1 else 2 ** -15
+    assert float((got - out.reshape(-1)).abs().max()) <= tol * float(out.abs().max())
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_mixture_inside_the_gemms(planes):
+    """row_w_mode 1 (cluster weight per row and class in the grouped block's epilogue) and row_w_mode 2 (dense logits GEMM over
+    the K weighted channel groups + mixed bias) against index_select_outputs' definition (jlcss.py:106-115)."""
+    torch.manual_seed(13)
+    K, Cg, P, B, T = 8, 256, 96, 40, 64
+    st = torch.cuda.current_stream().cuda_stream
+    rows = B * T
+    x = torch.randn(B, 1, T, K * Cg, device="cuda")
+    w1 = torch.randn(K * Cg, Cg, 1, 3, dtype=torch.float64, device="cuda") / (Cg * 3) ** 0.5
+    wl = torch.randn(K * P, Cg, 1, 1, dtype=torch.float64, device="cuda") / Cg ** 0.5
+    bl = torch.randn(K * P, device="cuda")
+    soft = torch.softmax(torch.randn(rows, K, device="cuda"), -1).contiguous()
+    if planes == 1:
+        x, w1, wl = x.to(torch.bfloat16).float(), w1.to(torch.bfloat16).double(), wl.to(torch.bfloat16).double()
+    scale, shift = torch.rand(K * Cg, device="cuda") + 0.5, torch.randn(K * Cg, device="cuda") * 0.1
+    h = F.conv2d(x.double().permute(0, 3, 1, 2), w1, None, padding=(0, 1), groups=K).permute(0, 2, 3, 1)
+    h = F.leaky_relu(h * scale.double() + shift.double(), 0.2)                                   # (B,1,T,K*Cg)
+    hw = (h.view(rows, K, Cg) * soft.double().unsqueeze(-1)).view(B, 1, T, K * Cg)
+    # ---- mode 1
+    plan = igemm.make_fwd(B, 1, T, K * Cg, K * Cg, 1, 3, 1, 1, 0, 1, K, 1, T, epilogue=1, slope=0.2)
+    d = plan.desc
+    fmt = _lib.MS_BF16X2 if planes == 2 else _lib.MS_BF16
+    ps = (plan.wp_numel + 7) // 8 * 8
+    wp = torch.zeros(2 * ps, dtype=torch.bfloat16, device="cuda")
+    _lib.call("ms_pack_igemm_weight_bf16", ptr(w1), 1, K * Cg, Cg, 3, K, 0, d.num_classes, d.class_n, d.ntaps, plan.kpad,
+              plan.srctap_c, ptr(wp), wp.data_ptr() + 2 * ps, st)
+    xp, xps = _planes(x)
+    n = rows * K * Cg
+    ops_ = (n + 7) // 8 * 8
+    igemm.set_planes(plan, planes == 2, xps, ps, ops_)
+    d.out_dtype = fmt
+    yp = torch.zeros(2 * ops_, dtype=torch.bfloat16, device="cuda")
+    y32 = torch.full((B, 1, T, K * Cg), float("nan"), device="cuda")
+    _lib.call("ms_igemm_bf16_mix", d, ptr(xp), ptr(wp), None, ptr(scale), ptr(shift), ptr(yp), ptr(y32), ptr(soft), K, 1, 0, st)
+    torch.cuda.synchronize()
+    tol = 1e-3 if planes == 1 else 3e-5
+    assert float((y32.double() - hw).abs().max()) < tol * float(hw.abs().max())
+    # ---- mode 2 on the kernel's own planes
+    A = yp[:n].double() + (yp[ops_:ops_ + n].double() if planes == 2 else 0)                     # the weighted planes, exactly
+    ref = torch.einsum("rkc,kpc->rp", A.view(rows, K, Cg), wl.view(K, P, Cg)) + soft.double() @ bl.double().view(K, P)
+    dense = wl.view(K, P, Cg).permute(1, 0, 2).reshape(P, K * Cg, 1, 1).contiguous()
+    p2 = igemm.make_fwd(B, 1, T, K * Cg, P, 1, 1, 1, 1, 0, 0, 1, 1, T)
+    d2 = p2.desc
+    d2.block_n = P
+    ps2 = (p2.wp_numel + 7) // 8 * 8
+    wp2 = torch.zeros(2 * ps2, dtype=torch.bfloat16, device="cuda")
+    _lib.call("ms_pack_igemm_weight_bf16", ptr(dense), 1, P, K * Cg, 1, 1, 0, d2.num_classes, d2.class_n, d2.ntaps, p2.kpad,
+              p2.srctap_c, ptr(wp2), wp2.data_ptr() + 2 * ps2, st)
+    igemm.set_planes(p2, planes == 2, ops_, ps2, 0)
+    pose = torch.full((B, 1, T, P), float("nan"), device="cuda")
+    _lib.call("ms_igemm_bf16_mix", d2, ptr(yp), ptr(wp2), ptr(bl), None, None, ptr(pose), None, ptr(soft), K, 2, K, st)
+    torch.cuda.synchronize()
+    err = float((pose.double().view(rows, P) - ref).abs().max())
+    assert err < (1e-3 if planes == 1 else 3e-5) * float(ref.abs().max()), (err, float(ref.abs().max()))

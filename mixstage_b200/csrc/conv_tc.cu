@@ -445,6 +445,52 @@ __device__ __forceinline__ void epilogue_store16(const IgemmParams& p, void* __r
   }
 }
 
+// Lean epilogue bodies for the layouts that carry almost all of the traffic (VARIANT != 0): no residual / upsample, no
+// extra fp32 copy; per-column constants read as float4 from shared memory, LeakyReLU as max(x, slope * x) (0 <= slope <= 1).
+//   1: bf16 planes out     2: fp32 out     3: bf16 planes out, every row scaled by its cluster weight (row_w_mode 1)
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+               "r"(g), "r"(h)
+               : "memory");
+}
+
+template <int VARIANT>
+__device__ __forceinline__ void epilogue_chunk_fast(const uint32_t (&cur)[16], const float* __restrict__ sc,
+                                                    const float* __restrict__ sh, float slope, float rw, void* __restrict__ dst) {
+  float f[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; j4++) {
+    const float4 a = *reinterpret_cast<const float4*>(sc + 4 * j4);
+    const float4 b = *reinterpret_cast<const float4*>(sh + 4 * j4);
+    f[4 * j4 + 0] = fmaf(__uint_as_float(cur[4 * j4 + 0]), a.x, b.x);
+    f[4 * j4 + 1] = fmaf(__uint_as_float(cur[4 * j4 + 1]), a.y, b.y);
+    f[4 * j4 + 2] = fmaf(__uint_as_float(cur[4 * j4 + 2]), a.z, b.z);
+    f[4 * j4 + 3] = fmaf(__uint_as_float(cur[4 * j4 + 3]), a.w, b.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    f[j] = fmaxf(f[j], f[j] * slope);
+    if (VARIANT == 3) f[j] *= rw;
+  }
+  // 256-bit stores (sm_100 STG.256): every lane fills whole 32-byte sectors of its own output row
+  if (VARIANT == 2) {
+    st_global_v8(dst, __float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]),
+                 __float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+    st_global_v8(reinterpret_cast<uint8_t*>(dst) + 32, __float_as_uint(f[8]), __float_as_uint(f[9]), __float_as_uint(f[10]),
+                 __float_as_uint(f[11]), __float_as_uint(f[12]), __float_as_uint(f[13]), __float_as_uint(f[14]), __float_as_uint(f[15]));
+  } else {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    st_global_v8(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+  }
+}
+
+template <int VARIANT>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                         const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
@@ -461,8 +507,9 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_scale[2][256], s_shift[2][256];
-  __shared__ float s_mixb[MIX_MAX_K * MIX_MAX_N];
+  __shared__ __align__(16) float s_scale[2][256];
+  __shared__ __align__(16) float s_shift[2][256];
+  __shared__ float s_mixb[VARIANT == 0 ? MIX_MAX_K * MIX_MAX_N : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.ntaps * p.cchunks * p.npass;
@@ -556,12 +603,13 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const bool act = p.epilogue != 0 && p.slope != 1.f;
     const int nrep = p.up2 ? 2 : 1;
     const int ncols_total = p.num_classes * p.class_n;
-    if (p.row_w_mode == 2) {
+    if (VARIANT == 0 && p.row_w_mode == 2) {
       for (int i = et; i < p.mix_k * MIX_MAX_N; i += EPI_THREADS) {
         const int k = i / MIX_MAX_N, n = i - k * MIX_MAX_N;
         s_mixb[i] = (bias && n < ncols_total) ? __ldg(bias + (long long)k * ncols_total + n) : 0.f;
       }
     }
+    const float slope_eff = act ? p.slope : 1.f;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
       const int buf = lt & 1;
@@ -581,8 +629,31 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       const int ow = t.w0 + wi, oh = t.h0 + hi, ob = t.b0 + bi;
       const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
       const long long row_off = (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + p.out_off[t.cls] + t.n0;
-      const long long row_off_up = (long long)ob * p.os_b * 2 + (long long)(2 * ow) * p.os_w + p.out_off[t.cls] + t.n0;
       float rw = 1.f;
+      if constexpr (VARIANT != 0) {
+        if (VARIANT == 3 && valid) rw = __ldg(p.row_w + ((long long)(ob * p.out_h + oh) * p.out_w + ow) * p.row_w_stride + t.cls);
+        // columns of this tile that exist (class_n is a multiple of 16): chunks past them are skipped
+        const int c_lim = min(c_end, (p.class_n - t.n0) >> 4);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(out) + (row_off + c_beg * 16) * (VARIANT == 2 ? 4 : 2);
+        mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * cols_per_buf;
+        uint32_t va[16], vb[16];
+        if (c_beg < c_lim) tmem_ld16(taddr + (uint32_t)(c_beg * 16), va);
+        for (int c = c_beg; c < c_lim; c += 2) {
+          tmem_wait_ld16(va);
+          if (c + 1 < c_lim) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), vb);
+          if (valid) epilogue_chunk_fast<VARIANT>(va, &s_scale[buf][c * 16], &s_shift[buf][c * 16], slope_eff, rw, dst);
+          dst += 16 * (VARIANT == 2 ? 4 : 2);
+          if (c + 1 < c_lim) {
+            tmem_wait_ld16(vb);
+            if (c + 2 < c_lim) tmem_ld16(taddr + (uint32_t)((c + 2) * 16), va);
+            if (valid) epilogue_chunk_fast<VARIANT>(vb, &s_scale[buf][c * 16 + 16], &s_shift[buf][c * 16 + 16], slope_eff, rw, dst);
+            dst += 16 * (VARIANT == 2 ? 4 : 2);
+          }
+        }
+      } else {
+      const long long row_off_up = (long long)ob * p.os_b * 2 + (long long)(2 * ow) * p.os_w + p.out_off[t.cls] + t.n0;
       float mw[MIX_MAX_K];
       if (p.row_w_mode != 0 && valid) {
         const float* wr = p.row_w + ((long long)(ob * p.out_h + oh) * p.out_w + ow) * p.row_w_stride;
@@ -632,6 +703,7 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             epilogue_store16(p, out, f, row_off + c0, row_off_up + c0, nrep);
           }
         }
+      }
       }
       // all tcgen05.ld of this buffer have completed (wait::ld above): hand it back to the MMA warp
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -942,6 +1014,16 @@ static bool igemm_legacy() {
   return v == 1;
 }
 
+// MS_IGEMM_GENERIC_EPILOGUE=1 keeps the persistent kernel on its generic epilogue body (A/B timing, debugging)
+static bool igemm_generic_epilogue() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MS_IGEMM_GENERIC_EPILOGUE");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
                         const float* shift, void* out, const IgemmFused* fx, void* stream) {
   if (!d || !a || !w || !out) return MS_EINVAL;
@@ -1061,13 +1143,34 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
     if (stages < 2) return MS_EINVAL;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024;
+    // lean epilogue variants (see epilogue_chunk_fast); everything else takes the generic body
+    int variant = 0;
+    const float slope_eff = (d->epilogue != 0 && d->slope != 1.f) ? d->slope : 1.f;
+    bool al32 = ((uintptr_t)out & 31) == 0 && (p.os_w * esz) % 32 == 0 && (p.os_h * esz) % 32 == 0 && (p.os_b * esz) % 32 == 0;
+    for (int i = 0; i < d->num_classes; i++) al32 = al32 && (p.out_off[i] * esz) % 32 == 0;
+    if (al32 && !p.up2 && !p.out_f32 && slope_eff >= 0.f && slope_eff <= 1.f) {
+      if (p.out_dtype == MS_BF16 && p.row_w_mode == 0) variant = 1;
+      else if (p.out_dtype == MS_F32 && p.row_w_mode == 0) variant = 2;
+      else if (p.out_dtype == MS_BF16 && p.row_w_mode == 1) variant = 3;
+    }
+    if (igemm_generic_epilogue()) variant = 0;
     static bool attr_set_p = false;
     if (!attr_set_p) {
-      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 15 * 1024 + 1024));
+      const int dyn = 227 * 1024 - 15 * 1024 + 1024;
+      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
       attr_set_p = true;
     }
     const unsigned grid = (unsigned)(tiles < ms_num_sms() ? tiles : ms_num_sms());
-    igemm_tc_persist_kernel<<<grid, PERSIST_THREADS, smem, ms_stream(stream)>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+    cudaStream_t cs = ms_stream(stream);
+    switch (variant) {
+      case 1: igemm_tc_persist_kernel<1><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
+      case 2: igemm_tc_persist_kernel<2><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
+      case 3: igemm_tc_persist_kernel<3><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
+      default: igemm_tc_persist_kernel<0><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
+    }
     MS_LAUNCH_CHECK();
     return 0;
   }

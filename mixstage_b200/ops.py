@@ -795,6 +795,18 @@ class MixedLogits:
         self.packed = PackedWeight()
         self.key = None
         self.dense = None
+        self._w = None              # detached view of the grouped weight the dense copy was derived from
+
+    def refresh_dense(self):
+        """Re-derive the dense (P, K*Cg) copy from the grouped weight, in place (TrainStep: the parameters were updated by
+        a kernel that does not bump torch versions; captured graphs keep pointing at the same buffer)."""
+        if self._w is None or self.dense is None:
+            return
+        KP, Cg = self._w.shape[0], self._w.shape[1]
+        P = self.dense.shape[0]
+        K = KP // P
+        self.dense.copy_(self._w.view(K, P, Cg).permute(1, 0, 2).reshape(P, K * Cg, 1, 1))
+        self.key = None
 
     @staticmethod
     def eligible(P, K, Cg):
@@ -807,8 +819,9 @@ class MixedLogits:
         K = Ct // Cg
         P = KP // K
         key = (weight.data_ptr(), weight._version, _weight_epoch, weight.dtype)
+        self._w = weight.detach()
         if key != self.key or FORCE_REPACK:
-            dense = weight.detach().view(K, P, Cg).permute(1, 0, 2).reshape(P, K * Cg, 1, 1)
+            dense = self._w.view(K, P, Cg).permute(1, 0, 2).reshape(P, K * Cg, 1, 1)
             if self.dense is not None and self.dense.shape == dense.shape and self.dense.dtype == dense.dtype:
                 self.dense.copy_(dense)        # same buffer: captured graphs / cached re-tilings keep pointing at it
             else:

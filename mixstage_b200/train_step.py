@@ -173,11 +173,17 @@ class TrainStep:
             for v in vars(m).values():
                 if isinstance(v, PlainConv):
                     out.append(v.packed)
+                elif isinstance(v, ops.MixedLogits):
+                    out.append(v.packed)
         return out
 
     def _refresh(self, kind):
         mod = self.G if kind == "G" else self.D
         entries = []
+        for m in mod.modules():
+            for v in vars(m).values():
+                if isinstance(v, ops.MixedLogits):
+                    v.refresh_dense()            # dense (P, K*256) copy of the grouped logits weight, before its re-tiling
         for pw in self._packed_of(mod):
             pw.refresh(entries)
         if not entries:
@@ -213,6 +219,14 @@ class TrainStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            if not self.graphs:
+                # before the FIRST capture run every (kind, branch) body once: each one registers the packed copies it
+                # reads (train-mode tilings, the eval-mode generator's folded BatchNorm / dense logits of a D-step, the
+                # pose encoder of the curriculum branch), so that the refresh captured at the end of every graph covers
+                # ALL copies of the sub-network it updates -- not only those its own body happened to touch
+                for k2, p2 in (("G", False), ("D", False), ("G", True)):
+                    if (k2, p2) != (kind, use_pose):
+                        self._body(k2, p2, *self.static)
             for _ in range(self.warmup_iters):
                 self._body(kind, use_pose, *self.static)
         torch.cuda.current_stream(dev).wait_stream(side)

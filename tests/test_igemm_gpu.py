@@ -239,7 +239,7 @@ def test_mixture_inside_the_gemms(planes):
     scale, shift = torch.rand(K * Cg, device="cuda") + 0.5, torch.randn(K * Cg, device="cuda") * 0.1
     h = F.conv2d(x.double().permute(0, 3, 1, 2), w1, None, padding=(0, 1), groups=K).permute(0, 2, 3, 1)
     h = F.leaky_relu(h * scale.double() + shift.double(), 0.2)                                   # (B,1,T,K*Cg)
-    hw = (h.view(rows, K, Cg) * soft.double().unsqueeze(-1)).view(B, 1, T, K * Cg)
+    hw = (h.reshape(rows, K, Cg) * soft.double().unsqueeze(-1)).reshape(B, 1, T, K * Cg)
     # ---- mode 1
     plan = igemm.make_fwd(B, 1, T, K * Cg, K * Cg, 1, 3, 1, 1, 0, 1, K, 1, T, epilogue=1, slope=0.2)
     d = plan.desc

@@ -374,13 +374,37 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load delivered to the same shared-memory offset (and the same mbarrier offset) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 struct TileCoord {
   int w0, h0, b0, cls, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile, int ny) {
+// tile group g of a cluster of CSZ CTAs = CSZ consecutive 128-row tiles of the same (class, column tile); rank picks the row tile
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int g, int ny, int csz, int rank) {
   TileCoord t;
-  const int y = tile % ny;
-  int mt = tile / ny;
+  const int y = g % ny;
+  int mt = (g / ny) * csz + rank;
   const int tw = mt % p.tiles_w; mt /= p.tiles_w;
   const int th = mt % p.tiles_h; mt /= p.tiles_h;
   t.w0 = tw * p.box_w; t.h0 = th * p.box_h; t.b0 = mt * p.box_b;
@@ -490,7 +514,11 @@ __device__ __forceinline__ void epilogue_chunk_fast(const uint32_t (&cur)[16], c
   }
 }
 
-template <int VARIANT>
+// CSZ > 1: thread-block clusters of CSZ CTAs along M.  Every CTA loads its own 128 activation rows and 1/CSZ of the weight
+// tile, multicasting that slice into all CSZ shared memories: the L2 read traffic per k-step drops from 16 + 32 KB to
+// 16 + 32/CSZ KB per CTA.  (Opt-in, MS_IGEMM_CLUSTER: it turned out not to be the bound, see igemm_cluster_size.)
+// A stage is reusable once the MMAs of ALL CSZ CTAs have read it: the empty barriers count CSZ multicast commits.
+template <int VARIANT, int CSZ>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                         const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
@@ -514,7 +542,10 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.ntaps * p.cchunks * p.npass;
   const int ny = p.n_tiles_per_class * p.num_classes;
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * ny;
+  const int crank = CSZ > 1 ? (int)cluster_ctarank() : 0;
+  const int cid = (int)blockIdx.x / CSZ, ncl = (int)gridDim.x / CSZ;
+  const int total_tiles = ((p.tiles_w * p.tiles_h * p.tiles_b + CSZ - 1) / CSZ) * ny;      // tile groups
+  constexpr uint16_t cmask = (uint16_t)((1u << CSZ) - 1u);
   uint32_t cols_per_buf = 32;
   while (cols_per_buf < (uint32_t)p.block_n) cols_per_buf <<= 1;
   const uint32_t tmem_cols = 2 * cols_per_buf;
@@ -526,7 +557,7 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
     }
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CSZ); }
     for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], EPI_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -536,6 +567,7 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CSZ > 1) cluster_sync_all();         // peers' barriers are initialised before anything is multicast to them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -544,8 +576,10 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, ny);
+      const uint32_t b_slice_bytes = b_stage_bytes / CSZ;
+      const int b_slice_rows = p.block_n / CSZ;
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
+        const TileCoord t = decode_tile(p, tile, ny, CSZ, crank);
         const int tap_base = p.shared_taps ? 0 : t.cls * p.ntaps;
         const int chan_base = p.a_chan_base[t.cls];
         const int wrow = t.cls * p.class_n + t.n0;
@@ -557,7 +591,11 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + b_stage_bytes);
           tma_load_5d(pass == 2 ? &map_a_lo : &map_a, &full_bar[s], smem_a + (size_t)s * A_STAGE_BYTES,
                       chan_base + tp[0] + cc * BLOCK_K, t.w0 + tp[1], tp[2], t.h0 + tp[3], t.b0);
-          tma_load_2d(pass == 1 ? &map_w_lo : &map_w, &full_bar[s], smem_b + (size_t)s * b_stage_bytes, kk * BLOCK_K, wrow);
+          if (CSZ == 1)
+            tma_load_2d(pass == 1 ? &map_w_lo : &map_w, &full_bar[s], smem_b + (size_t)s * b_stage_bytes, kk * BLOCK_K, wrow);
+          else     // this CTA's slice of the weight tile, delivered to every CTA of the cluster
+            tma_load_2d_mc(pass == 1 ? &map_w_lo : &map_w, &full_bar[s], smem_b + (size_t)s * b_stage_bytes + (size_t)crank * b_slice_bytes,
+                           kk * BLOCK_K, wrow + crank * b_slice_rows, cmask);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -569,7 +607,7 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       int s = 0;
       uint32_t ph = 0;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
+      for (int tile = cid; tile < total_tiles; tile += ncl, lt++) {
         const int buf = lt & 1;
         mbar_wait(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);     // epilogue drained this buffer (tile lt - 2)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -582,7 +620,8 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; k++)
             umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          if (CSZ == 1) umma_commit(&empty_bar[s]);
+          else umma_commit_mc(&empty_bar[s], cmask);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         umma_commit(&tmem_full_bar[buf]);
@@ -611,9 +650,9 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
     const float slope_eff = act ? p.slope : 1.f;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, lt++) {
+    for (int tile = cid; tile < total_tiles; tile += ncl, lt++) {
       const int buf = lt & 1;
-      const TileCoord t = decode_tile(p, tile, ny);
+      const TileCoord t = decode_tile(p, tile, ny, CSZ, crank);
       const int ncol = t.cls * p.class_n + t.n0;             // global column (bias / scale index)
       // per-column constants of this tile -> shared memory, while the MMAs are still running
       for (int i = et; i < p.block_n; i += EPI_THREADS) {
@@ -714,6 +753,7 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CSZ > 1) cluster_sync_all();         // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -1024,6 +1064,54 @@ static bool igemm_generic_epilogue() {
   return v == 1;
 }
 
+// MS_IGEMM_CLUSTER=1|2|4 forces the cluster size where the geometry allows it (A/B timing)
+static int igemm_cluster_size(long long m_tiles, long long ny, int block_n) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MS_IGEMM_CLUSTER");
+    forced = e ? atoi(e) : 0;
+  }
+  // Default 1: measured on B200 (profiles/r01_cluster_multicast_ab.txt) the multicast does not pay -- the bound is the
+  // ~43 B/clk each SM can ingest, which a multicast delivery does not lower; only a larger tile per SM does.
+  (void)ny;
+  int c = 1;
+  if (forced == 1 || forced == 2 || forced == 4) c = forced;
+  while (c > 1 && (block_n % (8 * c) || m_tiles < c)) c >>= 1;     // weight slices are whole 8-row swizzle atoms
+  return c;
+}
+
+template <int V, int C>
+static int launch_persist(long long groups, size_t smem, cudaStream_t cs, const CUtensorMap& map_a, const CUtensorMap& map_w,
+                          const CUtensorMap& map_a_lo, const CUtensorMap& map_w_lo, const IgemmParams& p, const float* bias,
+                          const float* scale, const float* shift, void* out) {
+  static int max_clusters = -1;
+  const int dyn = 227 * 1024 - 15 * 1024 + 1024;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(PERSIST_THREADS); cfg.stream = cs;
+  cfg.attrs = at; cfg.numAttrs = C > 1 ? 1 : 0;
+  if (max_clusters < 0) {
+    MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<V, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    int n = ms_num_sms() / C;
+    if (C > 1) {
+      cfg.gridDim = dim3((unsigned)(ms_num_sms() / C * C)); cfg.dynamicSmemBytes = dyn;
+      if (cudaOccupancyMaxActiveClusters(&n, igemm_tc_persist_kernel<V, C>, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+      }
+      if (n > ms_num_sms() / C) n = ms_num_sms() / C;
+    }
+    max_clusters = n;
+  }
+  const long long ncl = groups < max_clusters ? groups : max_clusters;
+  cfg.gridDim = dim3((unsigned)(ncl * C));
+  cfg.dynamicSmemBytes = smem;
+  MS_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_persist_kernel<V, C>, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out));
+  return 0;
+}
+
 static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, const float* bias, const float* scale,
                         const float* shift, void* out, const IgemmFused* fx, void* stream) {
   if (!d || !a || !w || !out) return MS_EINVAL;
@@ -1041,6 +1129,15 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
   if (((uintptr_t)a & 15) || ((uintptr_t)w & 15) || ((uintptr_t)out & 15)) return MS_EINVAL;
   EncodeTiledFn enc = get_encode();
   if (!enc) return MS_ENOTSUP;
+
+  // thread-block cluster size of the persistent kernel (weight-tile multicast): only where there are enough row tiles
+  int csz = 1;
+  if (d->split_k <= 1 && !igemm_legacy()) {
+    const long long mt = (long long)((d->out_dims[0] + d->box[1] - 1) / d->box[1]) * ((d->out_dims[1] + d->box[3] - 1) / d->box[3]) *
+                         ((d->out_dims[2] + d->box[4] - 1) / d->box[4]);
+    const long long ny = (long long)((d->class_n + d->block_n - 1) / d->block_n) * d->num_classes;
+    csz = igemm_cluster_size(mt, ny, d->block_n);
+  }
 
   const int planes = d->planes == 2 ? 2 : 1;
   if (d->planes != 1 && d->planes != 2) return MS_EINVAL;
@@ -1067,7 +1164,7 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
       const long long ktot = (long long)d->ntaps * d->cchunks * BLOCK_K;
       cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)((long long)d->num_classes * d->class_n)};
       cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-      cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)d->block_n}, es[2] = {1, 1};
+      cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(d->block_n / csz)}, es[2] = {1, 1};
       CUresult r = enc(pl ? &map_w_lo : &map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(wq), dims, strides,
                        box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1154,25 +1251,20 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
       else if (p.out_dtype == MS_BF16 && p.row_w_mode == 1) variant = 3;
     }
     if (igemm_generic_epilogue()) variant = 0;
-    static bool attr_set_p = false;
-    if (!attr_set_p) {
-      const int dyn = 227 * 1024 - 15 * 1024 + 1024;
-      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-      MS_CUDA(cudaFuncSetAttribute(igemm_tc_persist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-      attr_set_p = true;
-    }
-    const unsigned grid = (unsigned)(tiles < ms_num_sms() ? tiles : ms_num_sms());
     cudaStream_t cs = ms_stream(stream);
-    switch (variant) {
-      case 1: igemm_tc_persist_kernel<1><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
-      case 2: igemm_tc_persist_kernel<2><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
-      case 3: igemm_tc_persist_kernel<3><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
-      default: igemm_tc_persist_kernel<0><<<grid, PERSIST_THREADS, smem, cs>>>(map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
+    const long long groups = (((long long)p.tiles_w * p.tiles_h * p.tiles_b + csz - 1) / csz) * p.n_tiles_per_class * d->num_classes;
+    int rc = MS_EINVAL;
+#define MS_PERSIST_CASE(V, C) \
+  case (V) * 8 + (C): rc = launch_persist<V, C>(groups, smem, cs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out); break;
+    switch (variant * 8 + csz) {
+      MS_PERSIST_CASE(0, 1) MS_PERSIST_CASE(0, 2) MS_PERSIST_CASE(0, 4)
+      MS_PERSIST_CASE(1, 1) MS_PERSIST_CASE(1, 2) MS_PERSIST_CASE(1, 4)
+      MS_PERSIST_CASE(2, 1) MS_PERSIST_CASE(2, 2) MS_PERSIST_CASE(2, 4)
+      MS_PERSIST_CASE(3, 1) MS_PERSIST_CASE(3, 2) MS_PERSIST_CASE(3, 4)
+      default: break;
     }
-    MS_LAUNCH_CHECK();
-    return 0;
+#undef MS_PERSIST_CASE
+    return rc;
   }
   if (p.row_w_mode != 0) return MS_EINVAL;
   const int k_per_cta = (num_k_total + split - 1) / split;

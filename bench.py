@@ -313,7 +313,20 @@ def run_cuda(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        _leave(dist)
+
+
+def _leave(dist):
+    """End of a multi-rank run.  Tearing NCCL down while captured CUDA graphs still hold all-reduce nodes of that
+    communicator hung on the 2-GPU box (both ranks inside destroy_process_group), so: everything measured is already
+    printed, meet once more, then leave without running the communicator's destructor."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        os._exit(0)
 
 
 # --------------------------------------------------------------------------------------------
@@ -463,7 +476,7 @@ def run_infer(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        _leave(dist)
 
 
 def cpu_infer_sweep(B, S, steps, warmup, dtype=torch.float64):

@@ -254,6 +254,152 @@ P make(const ms_conv_desc* d) {
   return p;
 }
 
+
+// ---- C_in = 1, 3x3, stride 1, pad 1 (audio_encoder.conv.0), row-wise: a thread owns 8 output channels of TWO adjacent
+// output pixels; its 72 weights and 16 epilogue constants live in registers for the whole launch, the 3x4 input window is
+// read once per pixel pair (L1 hits), and consecutive threads store consecutive 16/32-byte pieces of a pixel's channel
+// vector.  ~14 instructions per output instead of ~33 for fwd_cin1_v8 (tap addressing + weight reloads per pixel).
+// Requires 128 % (Cout/8) == 0 so that a thread's channel group never changes (128-thread blocks: ~136 registers per thread).
+template <int FUSED>
+__global__ void __launch_bounds__(128) fwd_cin1_k3(int B, int H, int W, int Cout, const float* __restrict__ x,
+                                                   const float* __restrict__ wf, const float* __restrict__ bias,
+                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                   float* __restrict__ y, __nv_bfloat16* __restrict__ planes, int pfmt,
+                                                   long long pstride, int act, float slope) {
+  const int cgs = Cout >> 3;
+  const int cg = threadIdx.x % cgs, n0 = cg * 8;
+  const int wp0 = threadIdx.x / cgs, wp_step = blockDim.x / cgs;
+  const int wpairs = (W + 1) >> 1;
+  float wreg[9][8], sc[8], sh[8];
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wf + (size_t)t * Cout + n0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(wf + (size_t)t * Cout + n0) + 1);
+    wreg[t][0] = a.x; wreg[t][1] = a.y; wreg[t][2] = a.z; wreg[t][3] = a.w;
+    wreg[t][4] = b.x; wreg[t][5] = b.y; wreg[t][6] = b.z; wreg[t][7] = b.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (FUSED) { sc[j] = __ldg(scale + n0 + j); sh[j] = __ldg(shift + n0 + j); }
+    else { sc[j] = 1.f; sh[j] = bias ? __ldg(bias + n0 + j) : 0.f; }
+  }
+  const float sl = (FUSED || act) ? slope : 1.f;
+  const bool lrelu_max = sl >= 0.f && sl <= 1.f;          // LeakyReLU as max(v, slope * v)
+  const int rows = B * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int h = row % H;
+    const float* xr = x + (size_t)row * W;
+    const bool up = h > 0, dn = h + 1 < H;
+    for (int wp = wp0; wp < wpairs; wp += wp_step) {
+      const int w = 2 * wp;
+      float xv[3][4];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const bool rok = r == 0 ? up : (r == 2 ? dn : true);
+        const float* xp = xr + (r - 1) * W + w;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int ww = w + c - 1;
+          xv[r][c] = (rok && ww >= 0 && ww < W) ? __ldg(xp + c - 1) : 0.f;
+        }
+      }
+      float a0[8], a1[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { a0[j] = 0.f; a1[j] = 0.f; }
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            a0[j] = fmaf(xv[r][c], wreg[r * 3 + c][j], a0[j]);
+            a1[j] = fmaf(xv[r][c + 1], wreg[r * 3 + c][j], a1[j]);
+          }
+#pragma unroll
+      for (int px = 0; px < 2; px++) {
+        if (w + px >= W) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float t = fmaf(px == 0 ? a0[j] : a1[j], sc[j], sh[j]);
+          v[j] = lrelu_max ? fmaxf(t, t * sl) : (t > 0.f ? t : t * sl);
+        }
+        const long long o = ((long long)row * W + w + px) * Cout + n0;
+        if (y) {
+          float4* d4 = reinterpret_cast<float4*>(y + o);
+          d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+          d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (FUSED && planes) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            v[2 * j] -= __bfloat162float(h2.x);
+            v[2 * j + 1] -= __bfloat162float(h2.y);
+          }
+          *reinterpret_cast<uint4*>(planes + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (pfmt == MS_BF16X2) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(planes + pstride + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+  }
+}
+
+inline bool cin1_k3_ok(const ms_conv_desc* d) {
+  const int cgs = d->Cout / 8;
+  return d->Cin == 1 && d->groups == 1 && d->kh == 3 && d->kw == 3 && d->sh == 1 && d->sw == 1 && d->ph == 1 && d->pw == 1 &&
+         d->Cout % 8 == 0 && cgs >= 1 && cgs <= 128 && 128 % cgs == 0 && d->Ho == d->H && d->Wo == d->W;
+}
+
+// ---- small-N forward for 1x1 convolutions over 256 channels (ClusterClassify.logits, layers.py:459): a lane owns 8
+// consecutive channels, whose N x 8 weights stay in registers; per pixel it reads 32 contiguous bytes (the warp one 1 KB
+// row), does 8N FMAs and joins the butterfly reduction.  wf: [0][c][n].
+template <int N>
+__global__ void __launch_bounds__(256) fwd_small_n_k1c256(int M, int Cout, const float* __restrict__ x,
+                                                          const float* __restrict__ wf, const float* __restrict__ bias,
+                                                          float* __restrict__ y, int act, float slope) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float wreg[8][N];
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+#pragma unroll
+    for (int n = 0; n < N; n++) wreg[c][n] = n < Cout ? __ldg(wf + (size_t)(lane * 8 + c) * Cout + n) : 0.f;
+  for (int pos = warp; pos < M; pos += nwarps) {
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)pos * 256 + lane * 8);
+    const float4 u = __ldg(xp), v = __ldg(xp + 1);
+    const float xv[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+    float acc[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) acc[n] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+#pragma unroll
+      for (int n = 0; n < N; n++) acc[n] = fmaf(xv[c], wreg[c][n], acc[n]);
+#pragma unroll
+    for (int n = 0; n < N; n++) acc[n] = ms_warp_sum(acc[n]);
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < N; n++)
+        if (n < Cout) {
+          float t = acc[n] + (bias ? bias[n] : 0.f);
+          if (act) t = t > 0.f ? t : t * slope;
+          y[(size_t)pos * Cout + n] = t;
+        }
+    }
+  }
+}
+
 inline int blocks_for(long long work, int per_block) {
   long long b = (work + per_block - 1) / per_block;
   long long cap = (long long)ms_num_sms() * 8;
@@ -271,6 +417,12 @@ int ms_small_conv_fwd(const float* x, const float* wf, const float* bias, float*
   if (d->groups != 1) return 0;
   P p = make(d);
   const int M = d->B * d->Ho * d->Wo;
+  if (cin1_k3_ok(d) && (((uintptr_t)wf | (uintptr_t)y) & 15) == 0) {
+    int blocks = d->B * d->H;
+    if (blocks > ms_num_sms() * 24) blocks = ms_num_sms() * 24;
+    fwd_cin1_k3<0><<<blocks, 128, 0, st>>>(d->B, d->H, d->W, d->Cout, x, wf, bias, nullptr, nullptr, y, nullptr, 0, 0, act, slope);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   if (d->Cin == 1 && d->Cout % 8 == 0 && (((uintptr_t)wf | (uintptr_t)y) & 15) == 0) {
     long long total8 = (long long)M * (d->Cout / 8);
     fwd_cin1_v8<0><<<blocks_for(total8, 256), 256, 0, st>>>(p, x, wf, bias, nullptr, nullptr, y, nullptr, 0, 0, act, slope, total8);
@@ -279,6 +431,11 @@ int ms_small_conv_fwd(const float* x, const float* wf, const float* bias, float*
   if (d->Cin == 1 && d->Cout <= 1024) {
     long long total = (long long)M * d->Cout;
     fwd_cin1<<<blocks_for(total, 256), 256, 0, st>>>(p, x, wf, bias, y, act, slope, total);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
+  if (d->Cout <= 8 && d->Cin == 256 && p.taps == 1 && d->sh == 1 && d->sw == 1 && d->ph == 0 && d->pw == 0 &&
+      ((uintptr_t)x & 15) == 0) {
+    fwd_small_n_k1c256<8><<<blocks_for((long long)M * 32, 256), 256, 0, st>>>(M, d->Cout, x, wf, bias, y, act, slope);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   if (d->Cout <= NMAX) {
@@ -298,6 +455,14 @@ extern "C" int ms_conv_cin1_bnact(const float* x, const float* wf, const float* 
   if ((((uintptr_t)wf | (uintptr_t)y | (uintptr_t)planes) & 15) != 0) return MS_EINVAL;
   if (planes && pfmt != MS_BF16 && pfmt != MS_BF16X2) return MS_EINVAL;
   if (planes && pfmt == MS_BF16X2 && (pstride <= 0 || pstride % 8)) return MS_EINVAL;
+  if (cin1_k3_ok(d) && slope >= 0.f) {
+    int blocks = d->B * d->H;
+    if (blocks > ms_num_sms() * 24) blocks = ms_num_sms() * 24;
+    fwd_cin1_k3<1><<<blocks, 128, 0, ms_stream(stream)>>>(d->B, d->H, d->W, d->Cout, x, wf, nullptr, scale, shift, y,
+                                                          reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride, 1, slope);
+    MS_LAUNCH_CHECK();
+    return 0;
+  }
   P p = make(d);
   const long long total8 = (long long)d->B * d->Ho * d->Wo * (d->Cout / 8);
   fwd_cin1_v8<1><<<blocks_for(total8, 256), 256, 0, ms_stream(stream)>>>(p, x, wf, nullptr, scale, shift, y,

@@ -67,6 +67,8 @@ CONVS += [
     (2, 1, 15, 256, 1, 1, 4, 1, 1, 0, 0, 1),        # D.logits N=1, p=0
     (2, 1, 16, 128, 256, 1, 4, 1, 1, 0, 1, 1),      # D.conv3 k4 s1 p1 (16 -> 15)
     (2, 1, 64, 96, 64, 1, 4, 1, 2, 0, 1, 1),        # D.conv1
+    (3, 5, 7, 1, 16, 3, 3, 1, 1, 1, 1, 1),          # C_in=1 3x3 row kernel: odd width, short height, 2 channel groups
+    (1, 1, 300, 256, 5, 1, 1, 1, 1, 0, 0, 1),       # 1x1 over 256 channels, N=5 (< 8), rows not a multiple of the grid
 ]
 
 
@@ -100,6 +102,33 @@ def test_conv_fwd_dgrad_wgrad(c):
     close(g64a, c64a, 1e-9)
     close(g64a - 1.0, c64, 1e-6)
     assert torch.equal(g64, c64)
+
+
+@pytest.mark.parametrize("c,fmt", [((2, 16, 64, 1, 64, 3, 3, 1, 1, 1, 1, 1), 2), ((3, 5, 7, 1, 16, 3, 3, 1, 1, 1, 1, 1), 3),
+                                   ((2, 6, 10, 1, 24, 3, 3, 1, 1, 1, 1, 1), 3)])
+def test_conv_cin1_bnact(c, fmt):
+    """audio_encoder.conv.0 in eval mode: conv + folded BatchNorm + LeakyReLU in one kernel, fp32 and bf16 planes out
+    (fmt 2 = MS_BF16, 3 = MS_BF16X2); the third case (24 channels = 3 groups) takes the generic C_in=1 kernel."""
+    torch.manual_seed(4)
+    d = _desc(c)
+    B, H, W, Cin, Cout, kh, kw, sh, sw, ph, pw, g = c
+    assert fmt in (_lib.MS_BF16, _lib.MS_BF16X2)
+    x = torch.randn(B, H, W, 1)
+    w = torch.randn(Cout, 1, kh, kw, dtype=torch.float64) / 3.0
+    n = w.numel()
+    (wf, wt), _ = run_both("ms_pack_conv_weight_f32", [(w, "in"), 1, d, (torch.zeros(n), "out"), (torch.zeros(n), "out")])
+    scale, shift = torch.rand(Cout) + 0.5, torch.randn(Cout) * 0.2
+    numel = B * H * W * Cout
+    ps = (numel + 7) // 8 * 8
+    planes = torch.zeros(2 * ps, dtype=torch.bfloat16)
+    (yg, pg), (yc, pc) = run_both("ms_conv_cin1_bnact", [(x, "in"), (wf, "in"), (scale, "in"), (shift, "in"), 0.2, d,
+                                                         (torch.zeros(numel), "out"), (planes, "out"), fmt, ps])
+    close(yg, yc)
+    # planes: hi within one bf16 ulp of the CPU spec (the fp32 values differ in the last bits), hi + lo ~ fp32 value
+    assert float((pg[:numel].float() - pc[:numel].float()).abs().max()) <= 2 ** -7 * float(yc.abs().max())
+    if fmt == _lib.MS_BF16X2:
+        rec = pg[:numel].float() + pg[ps:ps + numel].float()
+        assert float((rec - yg).abs().max()) <= 2 ** -15 * float(yc.abs().max()) + 1e-7
 
 
 @pytest.mark.parametrize("rows,C,L,up2", [(1024, 256, 64, 0), (64, 256, 2, 1), (32, 25, 1, 0), (2048, 2048, 64, 0), (8192, 64, 64, 0)])

@@ -61,6 +61,7 @@ struct IgemmParams {
   int row_w_stride;
   int row_w_mode;                       // 1: result *= row_w[row][class]; 2: result += sum_k row_w[row][k] * bias[k*N + n]
   int mix_k;                            // mode 2: number of clusters K (<= 16)
+  int dbg;                              // MS_IGEMM_DBG (timing experiments only): bit 0 = lean epilogue computes but does not store
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,6 +142,16 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
@@ -480,7 +491,7 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, ui
 }
 
 template <int VARIANT>
-__device__ __forceinline__ void epilogue_chunk_fast(const uint32_t (&cur)[16], const float* __restrict__ sc,
+__device__ __forceinline__ void epilogue_chunk_fast(const uint32_t* cur, const float* __restrict__ sc,
                                                     const float* __restrict__ sh, float slope, float rw, void* __restrict__ dst) {
   float f[16];
 #pragma unroll
@@ -511,6 +522,65 @@ __device__ __forceinline__ void epilogue_chunk_fast(const uint32_t (&cur)[16], c
       w[j] = *reinterpret_cast<uint32_t*>(&h2);
     }
     st_global_v8(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+  }
+}
+
+// One warp's share of a tile on the lean path: chunks [c_beg, c_lim) of 16 columns of its 32 rows.  TMEM is read 32 columns
+// at a time (tcgen05.ld ... .x32), the next load in flight while the current 32 columns are scaled, activated, packed and
+// stored; an odd trailing chunk takes a 16-column load.  `release` hands the accumulator buffer back to the MMA warp once the
+// last load has landed.  (Measured alternative, profiles/r01_igemm_epilogue_experiments.txt: pulling all 128 columns out
+// first and releasing before the math was 3 % SLOWER -- 168 registers, spills, stores bunched at the end of the tile.)
+#define MS_TIE16(a, o)                                                                                                          \
+  asm volatile("" : "+r"(a[o + 0]), "+r"(a[o + 1]), "+r"(a[o + 2]), "+r"(a[o + 3]), "+r"(a[o + 4]), "+r"(a[o + 5]), "+r"(a[o + 6]), \
+               "+r"(a[o + 7]), "+r"(a[o + 8]), "+r"(a[o + 9]), "+r"(a[o + 10]), "+r"(a[o + 11]), "+r"(a[o + 12]), "+r"(a[o + 13]), \
+               "+r"(a[o + 14]), "+r"(a[o + 15])::"memory")
+// wait for the outstanding tcgen05.ld; the loaded registers pass THROUGH statements placed after it, so no use can move above
+#define MS_WAIT_LD32(a)                                              \
+  do {                                                               \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");     \
+    MS_TIE16(a, 0);                                                  \
+    MS_TIE16(a, 16);                                                 \
+  } while (0)
+template <int VARIANT, typename Release>
+__device__ __forceinline__ void lean_epilogue_tile(uint32_t taddr, int c_beg, int c_lim, bool valid, const float* __restrict__ sc,
+                                                   const float* __restrict__ sh, float slope, float rw, uint8_t* __restrict__ dst,
+                                                   int dbg, Release release) {
+  constexpr int CB = 16 * (VARIANT == 2 ? 4 : 2);          // output bytes per 16-column chunk
+  const bool st = valid && !(dbg & 1);
+  const int nch = c_lim - c_beg;
+  const int n2 = nch >> 1;                                  // 32-column units
+  uint32_t va[32], vb[32];
+  if (n2 > 0) tmem_ld32(taddr + (uint32_t)(c_beg * 16), va);
+  for (int u = 0; u < n2; u += 2) {
+    const int c = c_beg + 2 * u;
+    MS_WAIT_LD32(va);
+    if (u + 1 < n2) tmem_ld32(taddr + (uint32_t)((c + 2) * 16), vb);
+    else if (!(nch & 1)) release();
+    if (st) {
+      epilogue_chunk_fast<VARIANT>(va, sc + c * 16, sh + c * 16, slope, rw, dst);
+      epilogue_chunk_fast<VARIANT>(va + 16, sc + c * 16 + 16, sh + c * 16 + 16, slope, rw, dst + CB);
+    }
+    dst += 2 * CB;
+    if (u + 1 < n2) {
+      MS_WAIT_LD32(vb);
+      if (u + 2 < n2) tmem_ld32(taddr + (uint32_t)((c + 4) * 16), va);
+      else if (!(nch & 1)) release();
+      if (st) {
+        epilogue_chunk_fast<VARIANT>(vb, sc + c * 16 + 32, sh + c * 16 + 32, slope, rw, dst);
+        epilogue_chunk_fast<VARIANT>(vb + 16, sc + c * 16 + 48, sh + c * 16 + 48, slope, rw, dst + CB);
+      }
+      dst += 2 * CB;
+    }
+  }
+  if (nch & 1) {
+    const int c = c_lim - 1;
+    uint32_t vt[16];
+    tmem_ld16(taddr + (uint32_t)(c * 16), vt);
+    tmem_wait_ld16(vt);
+    release();
+    if (st) epilogue_chunk_fast<VARIANT>(vt, sc + c * 16, sh + c * 16, slope, rw, dst);
+  } else if (n2 == 0) {
+    release();
   }
 }
 
@@ -588,6 +658,11 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           const int kk = kg / p.npass, pass = kg - kk * p.npass;          // split-bf16: hi*hi, hi*lo, lo*hi
           const int tap = kk / p.cchunks, cc = kk - tap * p.cchunks;
           const short* tp = p.taps[tap_base + tap];
+          if (p.dbg & 2) {               // timing experiment: no operand loads, the MMAs run on whatever is in smem
+            mbar_arrive(&full_bar[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + b_stage_bytes);
           tma_load_5d(pass == 2 ? &map_a_lo : &map_a, &full_bar[s], smem_a + (size_t)s * A_STAGE_BYTES,
                       chan_base + tp[0] + cc * BLOCK_K, t.w0 + tp[1], tp[2], t.h0 + tp[3], t.b0);
@@ -617,9 +692,11 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + (size_t)s * A_STAGE_BYTES));
           const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + (size_t)s * b_stage_bytes));
+          if (!(p.dbg & 4)) {            // timing experiment (bit 2): loads only, no MMAs
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; k++)
-            umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+              umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+          }
           if (CSZ == 1) umma_commit(&empty_bar[s]);
           else umma_commit_mc(&empty_bar[s], cmask);
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -677,20 +754,12 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * cols_per_buf;
-        uint32_t va[16], vb[16];
-        if (c_beg < c_lim) tmem_ld16(taddr + (uint32_t)(c_beg * 16), va);
-        for (int c = c_beg; c < c_lim; c += 2) {
-          tmem_wait_ld16(va);
-          if (c + 1 < c_lim) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), vb);
-          if (valid) epilogue_chunk_fast<VARIANT>(va, &s_scale[buf][c * 16], &s_shift[buf][c * 16], slope_eff, rw, dst);
-          dst += 16 * (VARIANT == 2 ? 4 : 2);
-          if (c + 1 < c_lim) {
-            tmem_wait_ld16(vb);
-            if (c + 2 < c_lim) tmem_ld16(taddr + (uint32_t)((c + 2) * 16), va);
-            if (valid) epilogue_chunk_fast<VARIANT>(vb, &s_scale[buf][c * 16 + 16], &s_shift[buf][c * 16 + 16], slope_eff, rw, dst);
-            dst += 16 * (VARIANT == 2 ? 4 : 2);
-          }
-        }
+        uint64_t* ebar = &tmem_empty_bar[buf];
+        lean_epilogue_tile<VARIANT>(taddr, c_beg, max(c_beg, c_lim), valid, s_scale[buf], s_shift[buf], slope_eff, rw, dst, p.dbg, [&]() {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ebar);
+        });
       } else {
       const long long row_off_up = (long long)ob * p.os_b * 2 + (long long)(2 * ow) * p.os_w + p.out_off[t.cls] + t.n0;
       float mw[MIX_MAX_K];
@@ -744,11 +813,13 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         }
       }
       }
-      // all tcgen05.ld of this buffer have completed (wait::ld above): hand it back to the MMA warp
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if constexpr (VARIANT == 0) {
+        // all tcgen05.ld of this buffer have completed (wait::ld above): hand it back to the MMA warp
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -757,6 +828,224 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair form (tcgen05 cta_group::2): two CTAs on the SMs of one TPC compute a 256 x block_n tile together.
+//
+// Why: every SM can take in ~43 B/clk of operands (profiles/r01_cluster_multicast_ab.txt); a 128 x 256 tile needs
+// 16 KB (A) + 32 KB (W) per 64-deep k-step = 96 B/clk at full tensor rate, so the single-CTA kernel tops out near 45-50 %
+// tensor-active.  In a pair each CTA loads its own 128 activation rows and HALF of the weight tile (block_n/2 rows); the
+// tensor cores read the other half from the peer's shared memory.  32 KB per k-step per SM = 64 B/clk.
+//
+//   * one UMMA = 256 x block_n x 16, issued by the leader CTA (cluster rank 0) only; accumulator rows 0..127 live in the
+//     leader's TMEM, rows 128..255 in the peer's, at the same column offset (tcgen05.alloc.cta_group::2 in both CTAs)
+//   * both producers signal the LEADER's full barrier (peer: TMA with .cta_group::2 + a remote arrive); the leader's
+//     tcgen05.commit.cta_group::2 multicasts to both CTAs' empty / accumulator-full barriers
+//   * each CTA's 8 epilogue warps drain that CTA's 128 rows (lean epilogue bodies only: VARIANT 1..3) and arrive on the
+//     leader's accumulator-empty barrier (peer: remote arrive)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default (cta-scope) semantics as CUTLASS's ClusterBarrier::arrive(cta_id): ".release.cluster" compiles to a GPU-scope
+  // MEMBAR per arrive, which throttled the peer's producer to half speed; TMA data is tracked by complete_tx, the TMEM
+  // hand-over by tcgen05.fence::before_thread_sync
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+igemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
+                     const __grid_constant__ IgemmParams p, const float* __restrict__ bias, const float* __restrict__ scale,
+                     const float* __restrict__ shift, void* __restrict__ out) {
+  static_assert(VARIANT >= 1 && VARIANT <= 3, "pair kernel: lean epilogues only");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_half_bytes = (uint32_t)(p.block_n / 2) * BLOCK_K * 2;     // this CTA's half of the weight tile
+  const int STAGES = p.stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];      // used in the leader only
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];         // used in the leader only
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_scale[2][256];
+  __shared__ __align__(16) float s_shift[2][256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.ntaps * p.cchunks * p.npass;
+  const int ny = p.n_tiles_per_class * p.num_classes;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  const int cid = (int)blockIdx.x / 2, ncl = (int)gridDim.x / 2;
+  const int total_tiles = ((p.tiles_w * p.tiles_h * p.tiles_b + 1) / 2) * ny;      // pair tiles
+  uint32_t cols_per_buf = 32;
+  while (cols_per_buf < (uint32_t)p.block_n) cols_per_buf <<= 1;
+  const uint32_t tmem_cols = 2 * cols_per_buf;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    if (p.npass > 1) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
+    }
+    // full: the leader's arrive.expect_tx + the peer's remote arrive; empty / accumulator-full: one multicast commit;
+    // accumulator-empty: the epilogue warps of both CTAs
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * (EPI_THREADS / 32)); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs): own A rows + own half of W; completion lands on the leader's barrier
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int b_half_rows = p.block_n / 2;
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
+        const TileCoord t = decode_tile(p, tile, ny, 2, crank);
+        const int tap_base = p.shared_taps ? 0 : t.cls * p.ntaps;
+        const int chan_base = p.a_chan_base[t.cls];
+        const int wrow = t.cls * p.class_n + t.n0 + crank * b_half_rows;
+        for (int kg = 0; kg < num_k; kg++) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int kk = kg / p.npass, pass = kg - kk * p.npass;          // split-bf16: hi*hi, hi*lo, lo*hi
+          const int tap = kk / p.cchunks, cc = kk - tap * p.cchunks;
+          const short* tp = p.taps[tap_base + tap];
+          const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * (A_STAGE_BYTES + b_half_bytes));
+          tma_load_5d_pair(pass == 2 ? &map_a_lo : &map_a, lbar, smem_a + (size_t)s * A_STAGE_BYTES,
+                           chan_base + tp[0] + cc * BLOCK_K, t.w0 + tp[1], tp[2], t.h0 + tp[3], t.b0);
+          tma_load_2d_pair(pass == 1 ? &map_w_lo : &map_w, lbar, smem_b + (size_t)s * b_half_bytes, kk * BLOCK_K, wrow);
+          if (!leader) mbar_arrive_cluster(lbar);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: leader only =================
+    if (lane == 0 && leader) {
+      // D=f32, A=B=bf16, K-major, N = block_n, M = 256 (pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
+      int lt = 0;
+      for (int tile = cid; tile < total_tiles; tile += ncl, lt++) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)buf * cols_per_buf;
+        for (int ks = 0; ks < num_k; ks++) {
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + (size_t)s * A_STAGE_BYTES));
+          const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + (size_t)s * b_half_bytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+            umma_bf16_pair(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit_pair(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs): this CTA's 128 rows =================
+    const int et = (int)threadIdx.x - 64;
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int wi = r % p.box_w;
+    const int hi = (r / p.box_w) % p.box_h;
+    const int bi = r / (p.box_w * p.box_h);
+    const int chunks = p.block_n >> 4;
+    const int chunks_h = (chunks + 1) >> 1;
+    const int c_beg = half * chunks_h, c_end = min(chunks, c_beg + chunks_h);
+    const bool act = p.epilogue != 0 && p.slope != 1.f;
+    const float slope_eff = act ? p.slope : 1.f;
+    int lt = 0;
+    for (int tile = cid; tile < total_tiles; tile += ncl, lt++) {
+      const int buf = lt & 1;
+      const TileCoord t = decode_tile(p, tile, ny, 2, crank);
+      const int ncol = t.cls * p.class_n + t.n0;
+      for (int i = et; i < p.block_n; i += EPI_THREADS) {
+        float sc = 1.f, sh = 0.f;
+        if (t.n0 + i < p.class_n) {
+          if (p.epilogue == 1) { sc = __ldg(scale + ncol + i); sh = __ldg(shift + ncol + i); }
+          else if (bias) sh = __ldg(bias + ncol + i);
+        }
+        s_scale[buf][i] = sc;
+        s_shift[buf][i] = sh;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      const int ow = t.w0 + wi, oh = t.h0 + hi, ob = t.b0 + bi;
+      const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
+      const long long row_off = (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + p.out_off[t.cls] + t.n0;
+      float rw = 1.f;
+      if (VARIANT == 3 && valid) rw = __ldg(p.row_w + ((long long)(ob * p.out_h + oh) * p.out_w + ow) * p.row_w_stride + t.cls);
+      const int c_lim = min(c_end, (p.class_n - t.n0) >> 4);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(out) + (row_off + c_beg * 16) * (VARIANT == 2 ? 4 : 2);
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)lt >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * cols_per_buf;
+      const uint32_t ebar = mapa_u32(smem_u32(&tmem_empty_bar[buf]), 0);     // the leader's MMA warp waits on it
+      lean_epilogue_tile<VARIANT>(taddr, c_beg, max(c_beg, c_lim), valid, s_scale[buf], s_shift[buf], slope_eff, rw, dst, p.dbg, [&]() {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ebar);
+      });
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -1080,6 +1369,49 @@ static int igemm_cluster_size(long long m_tiles, long long ny, int block_n) {
   return c;
 }
 
+// CTA pairs (igemm_tc_pair_kernel) for GEMMs with enough 128-row tiles to keep every SM pair busy; MS_IGEMM_PAIR=0 disables,
+// MS_IGEMM_PAIR=2 forces them wherever the geometry allows (tests)
+static bool igemm_use_pair(long long m_tiles, long long ny, int block_n) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("MS_IGEMM_PAIR");
+    mode = e ? atoi(e) : 1;
+  }
+  if (mode == 0 || block_n % 32 || block_n < 32 || m_tiles < 2) return false;
+  if (mode == 2) return true;
+  return m_tiles * ny >= 2LL * ms_num_sms();
+}
+
+template <int V>
+static int launch_pair(long long groups, size_t smem, cudaStream_t cs, const CUtensorMap& map_a, const CUtensorMap& map_w,
+                       const CUtensorMap& map_a_lo, const CUtensorMap& map_w_lo, const IgemmParams& p, const float* bias,
+                       const float* scale, const float* shift, void* out) {
+  static int max_pairs = -1;
+  const int dyn = 227 * 1024 - 7 * 1024 + 1024;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(PERSIST_THREADS); cfg.stream = cs;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (max_pairs < 0) {
+    MS_CUDA(cudaFuncSetAttribute(igemm_tc_pair_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    int n = ms_num_sms() / 2;
+    cfg.gridDim = dim3((unsigned)(ms_num_sms() / 2 * 2)); cfg.dynamicSmemBytes = dyn;
+    if (cudaOccupancyMaxActiveClusters(&n, igemm_tc_pair_kernel<V>, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 1;
+    }
+    if (n > ms_num_sms() / 2) n = ms_num_sms() / 2;
+    max_pairs = n;
+  }
+  const long long ncl = groups < max_pairs ? groups : max_pairs;
+  cfg.gridDim = dim3((unsigned)(ncl * 2));
+  cfg.dynamicSmemBytes = smem;
+  MS_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pair_kernel<V>, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out));
+  return 0;
+}
+
 template <int V, int C>
 static int launch_persist(long long groups, size_t smem, cudaStream_t cs, const CUtensorMap& map_a, const CUtensorMap& map_w,
                           const CUtensorMap& map_a_lo, const CUtensorMap& map_w_lo, const IgemmParams& p, const float* bias,
@@ -1130,13 +1462,33 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
   EncodeTiledFn enc = get_encode();
   if (!enc) return MS_ENOTSUP;
 
-  // thread-block cluster size of the persistent kernel (weight-tile multicast): only where there are enough row tiles
+  // epilogue body of the persistent kernels: lean variants (see epilogue_chunk_fast) where the layout allows, else generic
+  int variant = 0;
+  {
+    const int esz0 = d->out_dtype == MS_F32 ? 4 : 2;
+    const float slope_eff = (d->epilogue != 0 && d->slope != 1.f) ? d->slope : 1.f;
+    bool al32 = ((uintptr_t)out & 31) == 0 && (d->out_strides[0] * esz0) % 32 == 0 && (d->out_strides[1] * esz0) % 32 == 0 &&
+                (d->out_strides[2] * esz0) % 32 == 0;
+    for (int i = 0; i < d->num_classes; i++) al32 = al32 && (d->out_off[i] * esz0) % 32 == 0;
+    const bool up2 = fx && fx->up2;
+    const bool extra_f32 = fx && fx->out_f32 && d->out_dtype != MS_F32;
+    const int rwm = fx ? fx->row_w_mode : 0;
+    if (al32 && !up2 && !extra_f32 && slope_eff >= 0.f && slope_eff <= 1.f) {
+      if (d->out_dtype == MS_BF16 && rwm == 0) variant = 1;
+      else if (d->out_dtype == MS_F32 && rwm == 0) variant = 2;
+      else if (d->out_dtype == MS_BF16 && rwm == 1) variant = 3;
+    }
+    if (igemm_generic_epilogue()) variant = 0;
+  }
+  // thread-block cluster size of the persistent kernel (weight-tile multicast, opt-in) / CTA pairs (cta_group::2)
   int csz = 1;
+  bool pair = false;
   if (d->split_k <= 1 && !igemm_legacy()) {
     const long long mt = (long long)((d->out_dims[0] + d->box[1] - 1) / d->box[1]) * ((d->out_dims[1] + d->box[3] - 1) / d->box[3]) *
                          ((d->out_dims[2] + d->box[4] - 1) / d->box[4]);
     const long long ny = (long long)((d->class_n + d->block_n - 1) / d->block_n) * d->num_classes;
-    csz = igemm_cluster_size(mt, ny, d->block_n);
+    pair = variant != 0 && igemm_use_pair(mt, ny, d->block_n);
+    csz = pair ? 2 : igemm_cluster_size(mt, ny, d->block_n);
   }
 
   const int planes = d->planes == 2 ? 2 : 1;
@@ -1190,6 +1542,14 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
   p.out_dtype = d->out_dtype; p.epilogue = d->epilogue; p.slope = d->slope;
   p.out_f32 = nullptr; p.res = nullptr; p.res_pstride = 0; p.res_planes = 0; p.up2 = 0;
   p.row_w = nullptr; p.row_w_stride = 0; p.row_w_mode = 0; p.mix_k = 0;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("MS_IGEMM_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
   if (fx) {
     if (d->split_k > 1) return MS_EINVAL;
     if (fx->row_w_mode) {
@@ -1240,17 +1600,22 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
     if (stages < 2) return MS_EINVAL;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024;
-    // lean epilogue variants (see epilogue_chunk_fast); everything else takes the generic body
-    int variant = 0;
-    const float slope_eff = (d->epilogue != 0 && d->slope != 1.f) ? d->slope : 1.f;
-    bool al32 = ((uintptr_t)out & 31) == 0 && (p.os_w * esz) % 32 == 0 && (p.os_h * esz) % 32 == 0 && (p.os_b * esz) % 32 == 0;
-    for (int i = 0; i < d->num_classes; i++) al32 = al32 && (p.out_off[i] * esz) % 32 == 0;
-    if (al32 && !p.up2 && !p.out_f32 && slope_eff >= 0.f && slope_eff <= 1.f) {
-      if (p.out_dtype == MS_BF16 && p.row_w_mode == 0) variant = 1;
-      else if (p.out_dtype == MS_F32 && p.row_w_mode == 0) variant = 2;
-      else if (p.out_dtype == MS_BF16 && p.row_w_mode == 1) variant = 3;
+    if (pair) {
+      // CTA pairs: each CTA stages 16 KB of A + its half of the weight tile per k-step
+      const size_t pstage = A_STAGE_BYTES + (size_t)(d->block_n / 2) * BLOCK_K * 2;
+      int pst = (int)((227 * 1024 - 7 * 1024) / pstage);
+      if (pst > MAX_STAGES) pst = MAX_STAGES;
+      p.stages = pst;
+      const long long pgroups = (((long long)p.tiles_w * p.tiles_h * p.tiles_b + 1) / 2) * p.n_tiles_per_class * d->num_classes;
+      const size_t psmem = (size_t)pst * pstage + 1024;
+      cudaStream_t pcs = ms_stream(stream);
+      switch (variant) {
+        case 1: return launch_pair<1>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+        case 2: return launch_pair<2>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+        case 3: return launch_pair<3>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+        default: return MS_EINVAL;
+      }
     }
-    if (igemm_generic_epilogue()) variant = 0;
     cudaStream_t cs = ms_stream(stream);
     const long long groups = (((long long)p.tiles_w * p.tiles_h * p.tiles_b + csz - 1) / csz) * p.n_tiles_per_class * d->num_classes;
     int rc = MS_EINVAL;

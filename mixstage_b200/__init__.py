@@ -8,11 +8,11 @@ from ._lib import MixStageError, load as load_library            # noqa: F401
 from .gan import GAN                                              # noqa: F401
 from .joint_late_cluster_soft_style import (JointLateClusterSoftStyle4_D,      # noqa: F401
                                             JointLateClusterSoftStyle4_G)
-from .speech2gesture import Speech2Gesture_D                      # noqa: F401
+from .speech2gesture import Speech2Gesture_D, Speech2Gesture_G    # noqa: F401
 from .ops import get_precision, precision_scope, set_precision    # noqa: F401
 from .train_step import FlatState, TrainStep                      # noqa: F401
 
-__all__ = ["JointLateClusterSoftStyle4_G", "JointLateClusterSoftStyle4_D", "Speech2Gesture_D", "GAN",
+__all__ = ["JointLateClusterSoftStyle4_G", "JointLateClusterSoftStyle4_D", "Speech2Gesture_D", "Speech2Gesture_G", "GAN",
            "install", "MixStageError", "TrainStep", "FlatState", "set_precision", "get_precision", "precision_scope"]
 
 
@@ -36,5 +36,6 @@ def install(namespace=None):
         d["JointLateClusterSoftStyle4_G"] = JointLateClusterSoftStyle4_G
         d["JointLateClusterSoftStyle4_D"] = JointLateClusterSoftStyle4_D
         d["Speech2Gesture_D"] = Speech2Gesture_D
+        d["Speech2Gesture_G"] = Speech2Gesture_G
         d["GAN"] = GAN
     return targets

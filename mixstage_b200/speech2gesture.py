@@ -1,10 +1,49 @@
-"""Pose discriminator, mirror of reference src/model/speech2gesture.py:67-100."""
+"""Speech2Gesture baseline generator and pose discriminator, mirrors of reference src/model/speech2gesture.py:13-100."""
 import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import ConvNormRelu, PlainConv
+from .layers import AudioEncoder, ConvNormRelu, PlainConv, UNet1D, _run
 from ._lib import MixStageError
+
+
+class Speech2Gesture_G(nn.Module):
+    '''
+    Baseline: http://people.eecs.berkeley.edu/~shiry/projects/speech2gesture/ (reference speech2gesture.py:13-40;
+    SURVEY.md §8f row 4).  Same constructor, state_dict keys and forward(x, y, time_steps=None, **kwargs) as the reference;
+    runs on the kernels of the Mix-StAGE generator (audio encoder, UNet, four ConvNormRelu blocks, 1x1 logits).
+
+    input_shape:  (N, time, frequency)
+    output_shape: (N, time, pose_feats)
+    '''
+
+    def __init__(self, time_steps=64, in_channels=256, out_feats=104, p=0, **kwargs):
+        super().__init__()
+        self.audio_encoder = AudioEncoder(output_feats=time_steps, p=p)
+        self.unet = UNet1D(input_channels=in_channels, output_channels=in_channels, p=p)
+        self.decoder = nn.Sequential(*[ConvNormRelu(in_channels, in_channels, type='1d', leaky=True, downsample=False, p=p)
+                                       for _ in range(4)])
+        self.logits = nn.Conv1d(in_channels, out_feats, kernel_size=1, stride=1)
+        self._logits = PlainConv(self.logits)
+        self.precision = kwargs.get('precision', None)
+
+    def forward(self, x, y=None, time_steps=None, **kwargs):
+        """x: audio (B,T,F) or (B,1,T,F) (a list [audio, ...] as the trainer passes it is accepted too) ->
+        (pose (B,T,P) in the dtype of the input, [])."""
+        with ops.precision_scope(self.precision):
+            if isinstance(x, (list, tuple)):
+                x = x[0]
+            ops._need_cuda(x)
+            dtype = x.dtype
+            if x.dim() == 4:
+                x = x.squeeze(1)
+            B, T, Fm = x.shape
+            a = ops.cast(x, torch.float32).contiguous().view(B, T, Fm, 1)          # NHWC with C = 1
+            h = self.audio_encoder(a, time_steps if time_steps is not None else T)
+            h = self.unet(h)
+            h = _run(self.decoder, h, last="f32")
+            z = self._logits(self.logits, h)                                        # (B,1,T,P)
+            return ops.cast(z.view(B, z.shape[2], z.shape[3]), dtype), []
 
 
 class Speech2Gesture_D(nn.Module):

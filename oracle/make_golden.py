@@ -16,6 +16,10 @@ norms as fp64.  Cases (BASELINE.json configs):
   cfg2_pose_branch   curriculum branch (pose encoder instead of audio encoder), G-step
   cfg5_stress_small  config 5 shape at B=2: T256 S25 K16 argmax=0 (soft style), G-step
   sample_long        sampling layout: batch 1 x (2*64) frames, style (2,64) (trainer.py:778-786)
+  stage_k1_gstep     StAGE variant (num_clusters=1, src/jobs/stage.py): B8 S4, G-step          
+  s2g_eval / s2g_train   Speech2Gesture_G baseline (speech2gesture.py:13-40): eval forward; train forward + L1 backward
+
+    python oracle/make_golden.py [case ...]     # default: all cases
 """
 import os
 import sys
@@ -153,6 +157,44 @@ def run_g_only(ns, spec, B, T, training, sample_flag, description, long_layout=F
             "cluster_argmax": G.labels_cap_soft.argmax(-1).numpy().astype(np.int16)}
 
 
+S2G_SEED = 9
+S2G_GRADS = ["logits.weight", "decoder.3.norm.weight", "unet.conv1.4.norm.weight", "audio_encoder.conv.0.conv.weight"]
+
+
+def run_s2g(ns, P, B, T, training):
+    """Speech2Gesture_G on the synthetic audio batch; train mode also back-propagates mean|pose - y| (the trainer's
+    L1 criterion, trainer.py:1268-1285 with args.loss = L1Loss) and records gradients / BatchNorm side effects."""
+    spec = O.Spec(num_speakers=4, out_feats=P)
+    G = ns.S2G(time_steps=T, out_feats=P).double()
+    G.load_state_dict(O.synth_state(O.s2g_state_shapes(P), S2G_SEED))
+    audio, pose, _, _ = O.synth_inputs(B, T, spec)
+    G.train(training)
+    sd0 = {k: v.clone() for k, v in G.state_dict().items()}
+    if training:
+        out, il = G(audio.clone(), pose)
+        loss = (out - pose).abs().mean()
+        loss.backward()
+    else:
+        with torch.no_grad():
+            out, il = G(audio.clone(), pose)
+        loss = (out - pose).abs().mean()
+    res = {"pose": f32(out), "losses": np.array([float(loss)], dtype=np.float64)}
+    if training:
+        gp = dict(G.named_parameters())
+        names = [n for n, p in gp.items() if p.grad is not None]
+        res["grad_names"] = np.array(names)
+        res["grad_norms"] = np.array([float(gp[n].grad.norm()) for n in names], dtype=np.float64)
+        for n in S2G_GRADS:
+            res["grad/" + n] = f32(gp[n].grad)
+        sd1 = G.state_dict()
+        nbt = {k: int(sd1[k] - sd0[k]) for k in sd1 if k.endswith("num_batches_tracked")}
+        res["nbt_names"] = np.array(list(nbt.keys()))
+        res["nbt_incr"] = np.array(list(nbt.values()), dtype=np.int64)
+        for k in ("unet.conv1.4.norm.running_mean", "decoder.0.norm.running_var"):
+            res["gstat/" + k] = f32(sd1[k])
+    return res
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ns = ref_loader.load()
@@ -169,11 +211,19 @@ def main():
         "cfg2_pose_branch": lambda: run_gan(ns, cfg2, 16, 64, "G", pose_branch=True),
         "cfg5_stress_small": lambda: run_gan(ns, cfg5, 2, 256, "G"),
         "sample_long": lambda: run_g_only(ns, cfg2, 2, 64, False, 1, "test", long_layout=True),
+        "stage_k1_gstep": lambda: run_gan(ns, O.Spec(num_speakers=4, num_clusters=1), 8, 64, "G"),
+        "s2g_eval": lambda: run_s2g(ns, 96, 8, 64, False),
+        "s2g_train": lambda: run_s2g(ns, 96, 8, 64, True),
     }
+    only = sys.argv[1:]
     for name, fn in cases.items():
+        if only and name not in only:
+            continue
         res = fn()
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
         print(name, "losses", res["losses"], "pose", res["pose"].shape)
+    if only:
+        return
     # state_dict key/shape contract of the reference classes
     G, D, _ = build(ns, cfg2, 64)
     with open(os.path.join(OUT, "state_dict_keys.txt"), "w") as f:

@@ -474,6 +474,48 @@ def clip_and_adam(params: List[torch.Tensor], grads: List[torch.Tensor], m, v, s
     return total
 
 
+
+# --------------------------------------------------------------------------
+# Speech2Gesture_G baseline
+# --------------------------------------------------------------------------
+def s2g_decoder_table(c=256):
+    """speech2gesture.py:23-27: four k3 s1 ConvNormRelu blocks, no groups."""
+    return [("decoder.%d" % i, c, c, 3, 1, 1, 1) for i in range(4)]
+
+
+def s2g_state_shapes(out_feats: int, c: int = 256) -> Dict[str, Tuple[Tuple[int, ...], str]]:
+    """state_dict of the reference Speech2Gesture_G (speech2gesture.py:20-28): audio_encoder, unet, decoder.{0-3},
+    logits (out_feats, 256, 1)."""
+    out: Dict[str, Tuple[Tuple[int, ...], str]] = {}
+
+    def block(name, ci, co, k):
+        ks = tuple(k) if isinstance(k, tuple) else (k,)
+        out[name + ".conv.weight"] = ((co, ci) + ks, "conv_w")
+        out[name + ".conv.bias"] = ((co,), "conv_b:" + str(ci * _prod(ks)))
+        out[name + ".norm.weight"] = ((co,), "bn_w")
+        out[name + ".norm.bias"] = ((co,), "bn_b")
+        out[name + ".norm.running_mean"] = ((co,), "bn_rm")
+        out[name + ".norm.running_var"] = ((co,), "bn_rv")
+        out[name + ".norm.num_batches_tracked"] = ((), "nbt")
+
+    for (n, ci, co, k, s, p, g) in audio_encoder_table() + unet_table(c) + s2g_decoder_table(c):
+        block(n, ci, co, k)
+    out["logits.weight"] = ((out_feats, c, 1), "conv_w")
+    out["logits.bias"] = ((out_feats,), "conv_b:%d" % c)
+    return out
+
+
+def s2g_forward(sd, audio, time_steps, training, log: Optional[BNLog] = None):
+    """Speech2Gesture_G.forward, speech2gesture.py:30-40: audio (B,T,F) -> unsqueeze(1) -> audio_encoder -> unet ->
+    decoder -> 1x1 logits -> transpose.  Returns (pose (B,T,P), [])."""
+    x = audio.unsqueeze(1) if audio.dim() == 3 else audio
+    x = audio_encoder(x, sd, time_steps, training, log)
+    x = unet1d(x, sd, training, log)
+    x = run_table(x, sd, s2g_decoder_table(), training, log)
+    x = F.conv1d(x, sd["logits.weight"], sd["logits.bias"])
+    return x.transpose(-1, -2), []
+
+
 def flops_per_sequence(spec: Spec, T: int, train_description: bool) -> float:
     """Algorithmic conv FLOPs (2*MAC) of one forward per sequence, SURVEY.md §8d /
     Appendix A closed forms: MAC = L_out * C_out_total * (C_in/groups) * k."""

@@ -90,4 +90,5 @@ def load():
     ns.G = mods["joint_late_cluster_soft_style"].JointLateClusterSoftStyle4_G
     ns.D = mods["joint_late_cluster_soft_style"].JointLateClusterSoftStyle4_D
     ns.GAN = mods["gan"].GAN
+    ns.S2G = mods["speech2gesture"].Speech2Gesture_G
     return ns

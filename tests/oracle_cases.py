@@ -7,6 +7,7 @@ import mixstage_oracle as O
 CFG1 = O.Spec(num_speakers=2)
 CFG2 = O.Spec(num_speakers=4)
 CFG5 = O.Spec(num_speakers=25, num_clusters=16, argmax=0, time_steps=256)
+STAGE = O.Spec(num_speakers=4, num_clusters=1)      # StAGE variant: one sub-decoder (src/jobs/stage.py)
 
 # name -> (spec, B, T, kind, kwargs)
 CASES = {
@@ -18,6 +19,7 @@ CASES = {
     "cfg2_pose_branch": (CFG2, 16, 64, "gan", dict(step="G", use_pose_encoder=True)),
     "cfg5_stress_small": (CFG5, 2, 256, "gan", dict(step="G")),
     "sample_long": (CFG2, 2, 64, "g_long", dict(training=False, sample_flag=1, description="test")),
+    "stage_k1_gstep": (STAGE, 8, 64, "gan", dict(step="G")),
 }
 G_SEED, D_SEED = 7, 8
 

@@ -16,7 +16,8 @@ def _emu(monkeypatch):
 
 
 GRAD_TOL = 1e-2
-GRAD_TOL_CASE = {"cfg5_stress_small": 5e-2}     # B=2: one flipped mask is 1/sqrt(512 rows) of a tensor
+GRAD_TOL_CASE = {"cfg5_stress_small": 5e-2,     # B=2: one flipped mask is 1/sqrt(512 rows) of a tensor
+                 "stage_k1_gstep": 3e-2}        # B=8 (half the rows of the B=16 cases)
 
 
 def _rel(a, b):
@@ -24,7 +25,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("name", ["cfg1_eval_sample", "cfg1_train_fwd", "cfg2_gstep", "cfg2_dstep", "cfg2_eval",
-                                  "cfg2_pose_branch", "cfg5_stress_small", "sample_long"])
+                                  "cfg2_pose_branch", "cfg5_stress_small", "sample_long", "stage_k1_gstep"])
 def test_module_graph_matches_oracle(name):
     got = run_case(name, "cpu", torch.float64)
     ref = run_oracle(name)

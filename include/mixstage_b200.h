@@ -293,6 +293,18 @@ int ms_clip_adam(void* p, const void* g, void* m, void* v, int dt, int64_t n, co
                  double lr, double beta1, double beta2, double eps, double max_norm, const double* lr_dev, void* stream);
 /* lr_dev (nullable, device double): overrides lr, so a captured CUDA graph follows a learning-rate schedule. */
 
+/* ---- the step before the hot path: pose preprocessing on the device, fp64 like the reference.
+ * Replaces, per batch, trainer.py:1290-1308 = KMeans.predict(RemoveJoints(pose)) (src/data/transform.py:352-410, 463-510)
+ * and RemoveJoints(ZNorm(pose)) (src/data/transform.py:221-226) with one pass over the raw pose batch.
+ *   x (B,T,Pr) raw pose; cols[P] kept columns (RemoveJoints as a gather); mean/var (Pr) ZNorm statistics;
+ *   centers (K,D) k-means centres; feats_host[nfeats] in {1 pose, 2 velocity, 3 speed, 4 acceleration}, D = sum of widths;
+ *   y (B,T,P) normalised pose (nullable); labels (B,T) int64 argmin (nullable); soft (B,T,K) soft labels (nullable). */
+int ms_pose_prepare(const double* x, const double* mean, const double* var, const int32_t* cols, const double* centers,
+                    int B, int T, int Pr, int P, int K, const int32_t* feats_host, int nfeats, double eps, double* y,
+                    int64_t* labels, double* soft, void* stream);
+/* ZNorm.inv_znorm (src/data/transform.py:228-229): out = x * sqrt(var) + mean over the last dimension C. */
+int ms_inv_znorm(const double* x, const double* mean, const double* var, int64_t rows, int C, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,7 @@ _P, _I, _L, _F, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_flo
 _CD = ctypes.POINTER(ConvDesc)
 _GD = ctypes.POINTER(IgemmDesc)
 _S16 = ctypes.POINTER(ctypes.c_int16)
+_S32 = ctypes.POINTER(ctypes.c_int32)
 
 # name -> argtypes (mirrors include/mixstage_b200.h; tests/test_capi_symbols.py checks both ways)
 PROTOTYPES = {
@@ -94,6 +95,8 @@ PROTOTYPES = {
     "ms_scalar_finish": [_P, _D, _P, _P],
     "ms_grad_sqnorm": [_P, _I, _L, _P, _P, _P],
     "ms_clip_adam": [_P, _P, _P, _P, _I, _L, _P, _P, _D, _D, _D, _D, _D, _P, _P],
+    "ms_pose_prepare": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _S32, _I, _D, _P, _P, _P, _P],
+    "ms_inv_znorm": [_P, _P, _P, _L, _I, _P, _P],
 }
 
 _LIB = None

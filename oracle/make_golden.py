@@ -17,6 +17,7 @@ norms as fp64.  Cases (BASELINE.json configs):
   cfg5_stress_small  config 5 shape at B=2: T256 S25 K16 argmax=0 (soft style), G-step
   sample_long        sampling layout: batch 1 x (2*64) frames, style (2,64) (trainer.py:778-786)
   stage_k1_gstep     StAGE variant (num_clusters=1, src/jobs/stage.py): B8 S4, G-step          
+  prep_pvs_k8 / prep_pva_k16   KMeans.predict + ZNorm on a raw pose batch (src/data/transform.py)     
   s2g_eval / s2g_train   Speech2Gesture_G baseline (speech2gesture.py:13-40): eval forward; train forward + L1 backward
 
     python oracle/make_golden.py [case ...]     # default: all cases
@@ -195,6 +196,28 @@ def run_s2g(ns, P, B, T, training):
     return res
 
 
+PREP_FEATS = ["pose", "velocity", "speed"]
+PREP_MASK = [0, 7, 8, 9]
+
+
+def run_prep(feats, K):
+    """KMeans.predict / ZNorm.znorm of the reference (its own function bodies, ref_loader.load_transform_functions) on a
+    synthetic raw pose batch.  RemoveJoints' slicing lives in un-vendored pycasper: the oracle's remove_joints stands in."""
+    import types
+    fns = ref_loader.load_transform_functions()
+    x, mean, var, centers = O.synth_prep(4, 64, K, feats)
+    xr = O.remove_joints(x, PREP_MASK)
+    km = types.SimpleNamespace(feats=feats, centers=centers)
+    km.get_feats = lambda t: fns["KMeans.get_feats"](km, t)
+    labels = fns["KMeans.predict"](km, xr.clone())
+    soft = fns["KMeans.predict"](km, xr.clone(), soft_labels=True)
+    zn = fns["ZNorm.znorm"](None, x, [mean.view(1, 1, -1), var.view(1, 1, -1)])
+    y = O.remove_joints(zn, PREP_MASK)
+    inv = fns["ZNorm.inv_znorm"](None, zn[..., 4:5].expand(-1, -1, x.shape[-1]).contiguous(), [mean.view(1, 1, -1), var.abs().view(1, 1, -1)])
+    return {"labels": labels.numpy().astype(np.int16), "soft": soft.numpy(), "y": y.numpy(), "inv": inv[:1].numpy(),
+            "pose": np.zeros((1,), dtype=np.float32), "losses": np.zeros((0,))}
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ns = ref_loader.load()
@@ -214,6 +237,8 @@ def main():
         "stage_k1_gstep": lambda: run_gan(ns, O.Spec(num_speakers=4, num_clusters=1), 8, 64, "G"),
         "s2g_eval": lambda: run_s2g(ns, 96, 8, 64, False),
         "s2g_train": lambda: run_s2g(ns, 96, 8, 64, True),
+        "prep_pvs_k8": lambda: run_prep(PREP_FEATS, 8),
+        "prep_pva_k16": lambda: run_prep(["pose", "velocity", "acceleration"], 16),
     }
     only = sys.argv[1:]
     for name, fn in cases.items():

@@ -516,6 +516,90 @@ def s2g_forward(sd, audio, time_steps, training, log: Optional[BNLog] = None):
     return x.transpose(-1, -2), []
 
 
+
+# --------------------------------------------------------------------------
+# Pose preprocessing in front of the hot path, src/data/transform.py
+# --------------------------------------------------------------------------
+def remove_joints(x, mask, num_joints=52):
+    """RemoveJoints.__call__ (transform.py:499-508): view (B,T,2,J), drop the joints in `mask` along the last dimension,
+    flatten back.  The slicing itself is pycasper.torchUtils.remove_slices (un-vendored, parity unpinned): taken to remove
+    exactly the listed indices and keep the order of the rest."""
+    B, T, _ = x.shape
+    keep = [j for j in range(num_joints) if j not in set(mask)]
+    return x.reshape(B, T, 2, num_joints)[..., keep].reshape(B, T, -1)
+
+
+def znorm(x, mean, var, eps=1e-8):
+    """ZNorm.znorm (transform.py:221-226)."""
+    mask_std = (var >= 0).to(torch.double)
+    std = (var * mask_std) ** 0.5
+    mask = (std == 0).to(torch.double)
+    std = (mask * eps) + (1 - mask) * std
+    return (x - mean) / std
+
+
+def inv_znorm(x, mean, var):
+    """ZNorm.inv_znorm (transform.py:228-229)."""
+    return x * (var ** 0.5) + mean
+
+
+def kmeans_feats(x, feats):
+    """KMeans.get_feats (transform.py:352-380), 'spatial' excluded."""
+    out = []
+    for feat in feats:
+        if feat == "pose":
+            out.append(x)
+        elif feat == "velocity":
+            v = torch.zeros_like(x)
+            v[:, 1:, :] = x[:, 1:] - x[:, :-1]
+            out.append(v)
+        elif feat == "speed":
+            v = torch.zeros_like(x)
+            v[:, 1:, :] = x[:, 1:] - x[:, :-1]
+            v = v.reshape(v.shape[0], v.shape[1], 2, -1)
+            out.append((v ** 2).sum(dim=-2) ** 0.5)
+        elif feat == "acceleration":
+            v = torch.zeros_like(x)
+            v[:, 1:, :] = x[:, 1:] - x[:, :-1]
+            a = torch.zeros_like(x)
+            a[:, 1:, :] = v[:, 1:] - v[:, :-1]
+            out.append(a)
+        else:
+            raise KeyError(feat)
+    return torch.cat(out, dim=-1)
+
+
+def kmeans_predict(x, centers, feats, soft_labels=False):
+    """KMeans.predict (transform.py:392-407): squared distances of the frame features to the centres; hard labels = index
+    of the minimum, soft labels = softmax(-mse / mean(mse))."""
+    f = kmeans_feats(x.double(), feats)
+    shp = list(f.shape)
+    f = f.view(-1, 1, shp[-1])
+    mse = ((centers.view(1, *centers.shape) - f) ** 2).sum(dim=-1)
+    if soft_labels:
+        return F.softmax(-mse / mse.mean(-1).unsqueeze(-1), dim=-1).view(shp[:-1] + [centers.shape[0]])
+    return mse.min(dim=-1)[1].view(shp[:-1])
+
+
+def synth_prep(B, T, K, feats, seed=31, num_joints=52, mask=(0, 7, 8, 9)):
+    """Synthetic raw pose batch, ZNorm statistics (one zero and one negative variance exercise the eps rules) and k-means
+    centres (features of random frames of a second batch, so that nearest-centre margins are realistic)."""
+    g = torch.Generator().manual_seed(seed)
+    Pr = 2 * num_joints
+    scale = 20.0 + 100.0 * torch.rand(Pr, generator=g, dtype=torch.float64)
+    off = 50.0 * torch.randn(Pr, generator=g, dtype=torch.float64)
+    walk = torch.cumsum(torch.randn(B, T, Pr, generator=g, dtype=torch.float64) * 0.05, dim=1)
+    x = (torch.randn(B, 1, Pr, generator=g, dtype=torch.float64) + walk) * scale + off
+    mean = off + torch.randn(Pr, generator=g, dtype=torch.float64)
+    var = scale ** 2 * (0.5 + torch.rand(Pr, generator=g, dtype=torch.float64))
+    var[3] = 0.0
+    var[60] = -1.0
+    walk2 = torch.cumsum(torch.randn(K, 4, Pr, generator=g, dtype=torch.float64) * 0.05, dim=1)
+    x2 = (torch.randn(K, 1, Pr, generator=g, dtype=torch.float64) + walk2) * scale + off
+    centers = kmeans_feats(remove_joints(x2, mask, num_joints), feats)[:, -1, :].contiguous()
+    return x, mean, var, centers
+
+
 def flops_per_sequence(spec: Spec, T: int, train_description: bool) -> float:
     """Algorithmic conv FLOPs (2*MAC) of one forward per sequence, SURVEY.md §8d /
     Appendix A closed forms: MAC = L_out * C_out_total * (C_in/groups) * k."""

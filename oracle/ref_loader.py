@@ -92,3 +92,28 @@ def load():
     ns.GAN = mods["gan"].GAN
     ns.S2G = mods["speech2gesture"].Speech2Gesture_G
     return ns
+
+
+def load_transform_functions():
+    """The reference's own KMeans.get_feats / KMeans.predict / ZNorm.znorm / ZNorm.inv_znorm (src/data/transform.py), compiled
+    from their source WITHOUT importing the module (its imports need h5py/librosa, absent here): the function definitions
+    are cut out of the file with `ast` and executed unchanged; `self` is whatever object the caller passes."""
+    import ast
+    import torch
+    path = os.path.join(REF_SRC, "data", "transform.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    want = {("KMeans", "get_feats"), ("KMeans", "predict"), ("ZNorm", "znorm"), ("ZNorm", "inv_znorm")}
+    out = {}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef):
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and (node.name, fn.name) in want:
+                    mod = ast.Module(body=[fn], type_ignores=[])
+                    env = {"torch": torch}
+                    exec(compile(mod, path, "exec"), env)
+                    out[node.name + "." + fn.name] = env[fn.name]
+    missing = [k for k in want if k[0] + "." + k[1] not in out]
+    if missing:
+        raise RuntimeError("reference functions not found: %s" % missing)
+    return out

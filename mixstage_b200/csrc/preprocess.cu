@@ -117,7 +117,7 @@ __global__ void inv_znorm_kernel(const double* __restrict__ x, const double* __r
   const long long total = rows * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
-    out[i] = x[i] * sqrt(var[c]) + mean[c];
+    out[i] = __dadd_rn(__dmul_rn(x[i], sqrt(var[c])), mean[c]);      // separate multiply and add, as torch evaluates it (no FMA)
   }
 }
 

@@ -305,6 +305,13 @@ int ms_pose_prepare(const double* x, const double* mean, const double* var, cons
 /* ZNorm.inv_znorm (src/data/transform.py:228-229): out = x * sqrt(var) + mean over the last dimension C. */
 int ms_inv_znorm(const double* x, const double* mean, const double* var, int64_t rows, int C, double* out, void* stream);
 
+/* Evaluation metrics of TrainerBase.calculate_metrics (src/model/trainer.py:865-907) in one pass on the device:
+ * L1 / VelL1 (src/evaluation/metrics.py:94-131) on the normalised full-width poses y, gt (B,T,2J) and PCK
+ * (metrics.py:247-303) on the un-normalised (mean/var, 2J), root-centred frames.  keep[J]: 1 for joints outside the mask.
+ * acc[2] = {sum |y-gt|, sum |vel(y)-vel(gt)|} over kept joints; cnt[nalpha*J] = frames with dist_j < alpha * max(h, w). */
+int ms_pose_metrics(const double* y, const double* gt, const double* mean, const double* var, const uint8_t* keep,
+                    int B, int T, int J, const double* alphas_host, int nalpha, double* acc, uint64_t* cnt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

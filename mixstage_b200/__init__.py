@@ -11,10 +11,10 @@ from .joint_late_cluster_soft_style import (JointLateClusterSoftStyle4_D,      #
 from .speech2gesture import Speech2Gesture_D, Speech2Gesture_G    # noqa: F401
 from .ops import get_precision, precision_scope, set_precision    # noqa: F401
 from .train_step import FlatState, TrainStep                      # noqa: F401
-from .preprocess import PosePreprocessor                          # noqa: F401
+from .preprocess import PoseMetrics, PosePreprocessor             # noqa: F401
 
 __all__ = ["JointLateClusterSoftStyle4_G", "JointLateClusterSoftStyle4_D", "Speech2Gesture_D", "Speech2Gesture_G", "GAN",
-           "install", "MixStageError", "TrainStep", "FlatState", "PosePreprocessor", "set_precision", "get_precision", "precision_scope"]
+           "install", "MixStageError", "TrainStep", "FlatState", "PosePreprocessor", "PoseMetrics", "set_precision", "get_precision", "precision_scope"]
 
 
 def install(namespace=None):

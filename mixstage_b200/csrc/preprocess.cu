@@ -164,3 +164,93 @@ extern "C" int ms_inv_znorm(const double* x, const double* mean, const double* v
   MS_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Evaluation metrics on the device: what TrainerBase.calculate_metrics (src/model/trainer.py:865-907)
+// computes per batch on the host after a D2H copy -- L1 and VelL1 on the normalised full-width poses
+// (src/evaluation/metrics.py:94-131), PCK on the un-normalised, root-centred frames (metrics.py:247-303) -- in ONE pass
+// over (y_cap, y_gt); only 2 doubles + 2*J counters leave the GPU.  One warp per frame, lanes over joints.
+//   acc[0] = sum |y - gt| over kept joints, acc[1] = sum |vel(y) - vel(gt)| over kept joints (t >= 1)
+//   cnt[a * J + j] = number of frames with dist_j < alpha_a * max(h, w)   (exact integer counts)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct MetricParams {
+  int B, T, J, nalpha;
+  double alpha[4];
+};
+
+__global__ void __launch_bounds__(128)
+pose_metrics_kernel(const double* __restrict__ y, const double* __restrict__ gt, const double* __restrict__ mean,
+                    const double* __restrict__ var, const unsigned char* __restrict__ keep, double* __restrict__ acc,
+                    unsigned long long* __restrict__ cnt, MetricParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int W = 2 * p.J;
+  const long long frames = (long long)p.B * p.T;
+  double l1 = 0.0, vl = 0.0;
+  for (long long fr = (long long)blockIdx.x * 4 + warp; fr < frames; fr += (long long)gridDim.x * 4) {
+    const int t = (int)(fr % p.T);
+    const double* yr = y + fr * W;
+    const double* gr = gt + fr * W;
+    double gx_min = 1e300, gx_max = -1e300, gy_min = 1e300, gy_max = -1e300;
+    for (int j = lane; j < p.J; j += 32) {
+      const double yx = yr[j], yy = yr[p.J + j], gx = gr[j], gy = gr[p.J + j];
+      if (keep[j]) {
+        l1 += fabs(yx - gx) + fabs(yy - gy);
+        if (t > 0) {
+          vl += fabs((yx - yr[j - W]) - (gx - gr[j - W])) + fabs((yy - yr[p.J + j - W]) - (gy - gr[p.J + j - W]));
+        }
+      }
+      // PCK threshold box of the ground truth: un-normalised (inv_znorm), root joint at (0,0)
+      const double ugx = j == 0 ? 0.0 : __dadd_rn(__dmul_rn(gx, sqrt(var[j])), mean[j]);
+      const double ugy = j == 0 ? 0.0 : __dadd_rn(__dmul_rn(gy, sqrt(var[p.J + j])), mean[p.J + j]);
+      gx_min = fmin(gx_min, ugx); gx_max = fmax(gx_max, ugx);
+      gy_min = fmin(gy_min, ugy); gy_max = fmax(gy_max, ugy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      gx_min = fmin(gx_min, __shfl_xor_sync(0xffffffffu, gx_min, o));
+      gx_max = fmax(gx_max, __shfl_xor_sync(0xffffffffu, gx_max, o));
+      gy_min = fmin(gy_min, __shfl_xor_sync(0xffffffffu, gy_min, o));
+      gy_max = fmax(gy_max, __shfl_xor_sync(0xffffffffu, gy_max, o));
+    }
+    const double box = fmax(gx_max - gx_min, gy_max - gy_min);      // max(h, w) (metrics.py:276-279)
+    for (int j = lane; j < p.J; j += 32) {
+      double dx = 0.0, dy = 0.0;
+      if (j != 0) {
+        const double sx = sqrt(var[j]), sy = sqrt(var[p.J + j]);
+        dx = __dadd_rn(__dmul_rn(yr[j], sx), mean[j]) - __dadd_rn(__dmul_rn(gr[j], sx), mean[j]);
+        dy = __dadd_rn(__dmul_rn(yr[p.J + j], sy), mean[p.J + j]) - __dadd_rn(__dmul_rn(gr[p.J + j], sy), mean[p.J + j]);
+      }
+      const double dist = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      for (int a = 0; a < p.nalpha; a++)
+        if (dist < p.alpha[a] * box) atomicAdd(cnt + (size_t)a * p.J + j, 1ull);
+    }
+  }
+  l1 = ms_warp_sum_d(l1);
+  vl = ms_warp_sum_d(vl);
+  if (lane == 0) {
+    atomicAdd(acc, l1);
+    atomicAdd(acc + 1, vl);
+  }
+}
+
+}  // namespace
+
+extern "C" int ms_pose_metrics(const double* y, const double* gt, const double* mean, const double* var, const uint8_t* keep,
+                               int B, int T, int J, const double* alphas_host, int nalpha, double* acc, uint64_t* cnt, void* stream) {
+  if (!y || !gt || !mean || !var || !keep || !acc || !cnt || !alphas_host) return MS_EINVAL;
+  if (B < 1 || T < 1 || J < 1 || nalpha < 1 || nalpha > 4) return MS_EINVAL;
+  MetricParams p;
+  p.B = B; p.T = T; p.J = J; p.nalpha = nalpha;
+  for (int i = 0; i < 4; i++) p.alpha[i] = i < nalpha ? alphas_host[i] : 0.0;
+  MS_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), ms_stream(stream)));
+  MS_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint64_t) * (size_t)nalpha * J, ms_stream(stream)));
+  long long blocks = ((long long)B * T + 3) / 4;
+  const long long cap = (long long)ms_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  pose_metrics_kernel<<<(unsigned)blocks, 128, 0, ms_stream(stream)>>>(y, gt, mean, var, keep, acc,
+                                                                       reinterpret_cast<unsigned long long*>(cnt), p);
+  MS_LAUNCH_CHECK();
+  return 0;
+}

@@ -112,3 +112,70 @@ class PosePreprocessor:
         out = torch.empty_like(x)
         call("ms_inv_znorm", ptr(x), ptr(self.mean), ptr(self.var), x.numel() // self.Pr, self.Pr, ptr(out), stream())
         return out
+
+
+class PoseMetrics:
+    """L1, VelL1 and PCK of the reference's evaluation loop (src/evaluation/metrics.py:94-131, 247-303, driven by
+    TrainerBase.calculate_metrics, src/model/trainer.py:865-907) accumulated from ONE kernel per batch on the device
+    (`ms_pose_metrics`); the running averages follow AverageMeter's weighting (metrics.py:36-62) so `get_averages(desc)`
+    returns the reference's keys and values.  Inputs are the full-width normalised poses (masked joints re-inserted)."""
+
+    def __init__(self, muvar, num_joints=52, mask=(0, 7, 8, 9), alphas=(0.1, 0.2), device="cuda"):
+        self.device = torch.device(device)
+        self.J = int(num_joints)
+        self.mask = sorted(int(m) for m in mask)
+        self.alphas = [float(a) for a in alphas]
+        keep = torch.ones(self.J, dtype=torch.uint8)
+        keep[self.mask] = 0
+        self.keep = keep.to(self.device)
+        self.nkeep = int(keep.sum())
+        self.mean = torch.as_tensor(muvar[0], dtype=torch.float64).reshape(-1).contiguous().to(self.device)
+        self.var = torch.as_tensor(muvar[1], dtype=torch.float64).reshape(-1).contiguous().to(self.device)
+        self._alphas_c = (ctypes.c_double * len(self.alphas))(*self.alphas)
+        self.reset()
+
+    def reset(self):
+        z = lambda: torch.zeros((), dtype=torch.float64)                                # noqa: E731
+        self.l1_sum, self.vel_sum, self.n = z(), z(), 0
+        self.pck_joint_sum = torch.zeros(len(self.alphas), self.J, dtype=torch.float64)   # sum of (per-call mean) * n
+        self.pck_alpha_sum = torch.zeros(len(self.alphas), dtype=torch.float64)
+        self.pck_n, self.pck_alpha_n = 0, 0
+        self.pck_sum, self.pck_cnt = z(), 0
+
+    def __call__(self, y_cap, y_gt):
+        """y_cap, y_gt: (B, T, 2J) CUDA tensors (normalised).  One kernel, one 8*(2 + nalpha*J)-byte read-back."""
+        if not (y_cap.is_cuda and y_gt.is_cuda) or y_cap.shape != y_gt.shape or y_cap.shape[-1] != 2 * self.J:
+            raise MixStageError("PoseMetrics: CUDA tensors of shape (B, T, %d) required" % (2 * self.J))
+        y = y_cap.to(torch.float64).contiguous()
+        g = y_gt.to(torch.float64).contiguous()
+        B, T, _ = y.shape
+        acc = torch.empty(2, dtype=torch.float64, device=y.device)
+        cnt = torch.empty(len(self.alphas) * self.J, dtype=torch.int64, device=y.device)
+        call("ms_pose_metrics", ptr(y), ptr(g), ptr(self.mean), ptr(self.var), ptr(self.keep), B, T, self.J, self._alphas_c,
+             len(self.alphas), ptr(acc), ptr(cnt), stream())
+        acc, cnt = acc.cpu(), cnt.cpu().view(len(self.alphas), self.J).double()
+        # L1 / VelL1: l1_loss means, AverageMeter.update(val, n=B)
+        self.l1_sum += acc[0] / (B * T * 2 * self.nkeep) * B
+        if T > 1:
+            self.vel_sum += acc[1] / (B * (T - 1) * 2 * self.nkeep) * B
+        self.n += B
+        # PCK on (B*T) frames: per joint update(pck.mean(0)[j], n=frames); per alpha update(pck[:, kept].mean(), n=frames*|kept|)
+        F_ = B * T
+        self.pck_joint_sum += cnt / F_ * F_
+        self.pck_n += F_
+        kept = self.keep.cpu().bool()
+        for a in range(len(self.alphas)):
+            self.pck_alpha_sum[a] += cnt[a][kept].sum() / (F_ * self.nkeep) * (F_ * self.nkeep)
+        self.pck_alpha_n += F_ * self.nkeep
+        for a in range(len(self.alphas)):                   # metrics.py:271-272: running average of the running averages
+            self.pck_sum += (self.pck_alpha_sum[a] / self.pck_alpha_n) * (F_ * self.nkeep)
+            self.pck_cnt += F_ * self.nkeep
+
+    def get_averages(self, desc):
+        out = {"%s_L1" % desc: float(self.l1_sum / max(self.n, 1)), "%s_VelL1" % desc: float(self.vel_sum / max(self.n, 1))}
+        for a, al in enumerate(self.alphas):
+            for j in range(self.J):
+                out["%s_pck_%s_%d" % (desc, al, j)] = float(self.pck_joint_sum[a, j] / max(self.pck_n, 1))
+            out["%s_pck_%s" % (desc, al)] = float(self.pck_alpha_sum[a] / max(self.pck_alpha_n, 1))
+        out["%s_pck" % desc] = float(self.pck_sum / max(self.pck_cnt, 1))
+        return out

@@ -18,6 +18,7 @@ norms as fp64.  Cases (BASELINE.json configs):
   sample_long        sampling layout: batch 1 x (2*64) frames, style (2,64) (trainer.py:778-786)
   stage_k1_gstep     StAGE variant (num_clusters=1, src/jobs/stage.py): B8 S4, G-step          
   prep_pvs_k8 / prep_pva_k16   KMeans.predict + ZNorm on a raw pose batch (src/data/transform.py)     
+  metrics_l1_vel_pck     L1 / VelL1 / PCK running averages over two batches (src/evaluation/metrics.py)  (§8f row 4)
   s2g_eval / s2g_train   Speech2Gesture_G baseline (speech2gesture.py:13-40): eval forward; train forward + L1 backward
 
     python oracle/make_golden.py [case ...]     # default: all cases
@@ -218,6 +219,30 @@ def run_prep(feats, K):
             "pose": np.zeros((1,), dtype=np.float32), "losses": np.zeros((0,))}
 
 
+def run_metrics():
+    """The reference's own L1 / VelL1 / PCK classes (ref_loader.load_metric_classes) driven as calculate_metrics drives them
+    (trainer.py:886-907) on two synthetic batches; stores get_averages('test')."""
+    env = ref_loader.load_metric_classes()
+    mean, var, batches = O.synth_metric_batches()
+    l1, vel, pck = env["L1"](), env["VelL1"](), env["PCK"](num_joints=52)
+    for y_cap, y_ in batches:
+        l1(y_cap, y_, PREP_MASK)
+        vel(y_cap, y_, PREP_MASK)
+        yu = (y_cap * (var.view(1, 1, -1) ** 0.5) + mean.view(1, 1, -1))          # ZNorm.inv_znorm, transform.py:228
+        gu = (y_ * (var.view(1, 1, -1) ** 0.5) + mean.view(1, 1, -1))
+        yu = yu.view(yu.shape[0], yu.shape[1], 2, -1).view(-1, 2, 52).clone()
+        gu = gu.view(gu.shape[0], gu.shape[1], 2, -1).view(-1, 2, 52).clone()
+        yu[..., 0] = 0
+        gu[..., 0] = 0
+        pck(yu, gu, PREP_MASK)
+    av = {}
+    for m in (l1, vel, pck):
+        av.update(m.get_averages("test"))
+    keys = sorted(av)
+    return {"keys": np.array(keys), "values": np.array([av[k] for k in keys], dtype=np.float64),
+            "pose": np.zeros((1,), dtype=np.float32), "losses": np.zeros((0,))}
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ns = ref_loader.load()
@@ -239,6 +264,7 @@ def main():
         "s2g_train": lambda: run_s2g(ns, 96, 8, 64, True),
         "prep_pvs_k8": lambda: run_prep(PREP_FEATS, 8),
         "prep_pva_k16": lambda: run_prep(["pose", "velocity", "acceleration"], 16),
+        "metrics_l1_vel_pck": run_metrics,
     }
     only = sys.argv[1:]
     for name, fn in cases.items():

@@ -600,6 +600,66 @@ def synth_prep(B, T, K, feats, seed=31, num_joints=52, mask=(0, 7, 8, 9)):
     return x, mean, var, centers
 
 
+
+def synth_metric_batches(seed=41, num_joints=52):
+    """Two batches (B=3 and B=2, T=16) of normalised full-width poses: ground truth and a noisy prediction."""
+    g = torch.Generator().manual_seed(seed)
+    Pr = 2 * num_joints
+    mean = 30.0 * torch.randn(Pr, generator=g, dtype=torch.float64)
+    var = (20.0 + 60.0 * torch.rand(Pr, generator=g, dtype=torch.float64)) ** 2
+    out = []
+    for B in (3, 2):
+        gt = torch.randn(B, 1, Pr, generator=g, dtype=torch.float64) + torch.cumsum(
+            torch.randn(B, 16, Pr, generator=g, dtype=torch.float64) * 0.1, dim=1)
+        noise = torch.randn(B, 16, Pr, generator=g, dtype=torch.float64) * torch.rand(1, 1, Pr, generator=g, dtype=torch.float64) * 0.6
+        out.append((gt + noise, gt))
+    return mean, var, out
+
+
+def pose_metrics(batches, mean, var, mask, alphas=(0.1, 0.2), num_joints=52, desc="test"):
+    """L1 / VelL1 / PCK as TrainerBase.calculate_metrics drives them (trainer.py:865-907; metrics.py:94-131, 247-303),
+    with AverageMeter's weighting (metrics.py:36-62)."""
+    J = num_joints
+    keep = [j for j in range(J) if j not in set(mask)]
+    l1_s = vel_s = 0.0
+    n = 0
+    pj = torch.zeros(len(alphas), J, dtype=torch.float64)
+    pa = torch.zeros(len(alphas), dtype=torch.float64)
+    pn = pan = 0
+    ps, pc = 0.0, 0
+    for y, gt in batches:
+        B, T, _ = y.shape
+        y4, g4 = y.view(B, T, 2, J), gt.view(B, T, 2, J)
+        l1_s += float(F.l1_loss(y4[..., keep], g4[..., keep])) * B
+        vel_s += float(F.l1_loss((y4[:, 1:] - y4[:, :-1])[..., keep], (g4[:, 1:] - g4[:, :-1])[..., keep])) * B
+        n += B
+        yu = inv_znorm(y, mean.view(1, 1, -1), var.view(1, 1, -1)).reshape(-1, 2, J).clone()
+        gu = inv_znorm(gt, mean.view(1, 1, -1), var.view(1, 1, -1)).reshape(-1, 2, J).clone()
+        yu[..., 0] = 0
+        gu[..., 0] = 0
+        dist = ((yu - gu) ** 2).sum(dim=1) ** 0.5
+        h = gu[:, 0, :].max(dim=-1).values - gu[:, 0, :].min(dim=-1).values
+        w = gu[:, 1, :].max(dim=-1).values - gu[:, 1, :].min(dim=-1).values
+        Fr = B * T
+        for a, al in enumerate(alphas):
+            thresh = al * torch.max(torch.stack([h, w], dim=-1), dim=-1, keepdim=True).values
+            pck = (dist < thresh).to(torch.float)
+            pj[a] += pck.mean(dim=0).double() * Fr
+            pa[a] += float(pck[:, keep].mean()) * Fr * len(keep)
+        pn += Fr
+        pan += Fr * len(keep)
+        for a in range(len(alphas)):
+            ps += float(pa[a] / pan) * Fr * len(keep)
+            pc += Fr * len(keep)
+    out = {"%s_L1" % desc: l1_s / n, "%s_VelL1" % desc: vel_s / n}
+    for a, al in enumerate(alphas):
+        for j in range(J):
+            out["%s_pck_%s_%d" % (desc, al, j)] = float(pj[a, j] / pn)
+        out["%s_pck_%s" % (desc, al)] = float(pa[a] / pan)
+    out["%s_pck" % desc] = ps / pc
+    return out
+
+
 def flops_per_sequence(spec: Spec, T: int, train_description: bool) -> float:
     """Algorithmic conv FLOPs (2*MAC) of one forward per sequence, SURVEY.md §8d /
     Appendix A closed forms: MAC = L_out * C_out_total * (C_in/groups) * k."""

@@ -117,3 +117,17 @@ def load_transform_functions():
     if missing:
         raise RuntimeError("reference functions not found: %s" % missing)
     return out
+
+
+def load_metric_classes():
+    """The reference's AverageMeter, L1, VelL1 and PCK classes (src/evaluation/metrics.py), compiled from their source
+    without importing the module (its imports need the data pipeline)."""
+    import ast
+    import torch
+    path = os.path.join(REF_SRC, "evaluation", "metrics.py")
+    tree = ast.parse(open(path).read())
+    env = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in ("AverageMeter", "L1", "VelL1", "PCK"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), env)
+    return env

@@ -96,3 +96,44 @@ def test_cpu_tensor_is_rejected():
     pp = M.PosePreprocessor(muvar=(torch.zeros(104), torch.ones(104)), centers=torch.zeros(2, 240))
     with pytest.raises(M.MixStageError):
         pp(torch.zeros(1, 4, 104, dtype=torch.float64))
+
+
+# ---------------------------------------------------------------------------- evaluation metrics
+def _metric_dicts(golden_dir):
+    gold = load_golden(golden_dir, "metrics_l1_vel_pck")
+    gd = dict(zip([str(k) for k in gold["keys"]], gold["values"]))
+    mean, var, batches = O.synth_metric_batches()
+    return gd, mean, var, batches
+
+
+def _compare_metrics(av, gd):
+    assert set(av) == set(gd) and len(gd) == 2 + 2 * 52 + 2 + 1
+    for k, v in gd.items():
+        if k.endswith("_L1") or k.endswith("_VelL1"):
+            assert abs(av[k] - v) <= 1e-12 * abs(v), (k, av[k], v)
+        else:                       # the reference keeps PCK in fp32 (metrics.py:274): its running sums round at 6e-8
+            assert abs(av[k] - v) <= 2e-7, (k, av[k], v)
+
+
+def test_metrics_oracle_matches_reference_golden(golden_dir):
+    gd, mean, var, batches = _metric_dicts(golden_dir)
+    _compare_metrics(O.pose_metrics(batches, mean, var, MASK), gd)
+    assert 0.5 < gd["test_pck"] < 0.99 and gd["test_pck_0.1"] < gd["test_pck_0.2"]      # thresholds discriminate
+
+
+@pytest.mark.gpu
+def test_cuda_pose_metrics_match_oracle_and_golden(golden_dir):
+    import mixstage_b200 as M
+    gd, mean, var, batches = _metric_dicts(golden_dir)
+    pm = M.PoseMetrics((mean, var), num_joints=52, mask=MASK, alphas=(0.1, 0.2))
+    for y, g in batches:
+        pm(y.cuda(), g.cuda())
+    av = pm.get_averages("test")
+    _compare_metrics(av, gd)
+    ref = O.pose_metrics(batches, mean, var, MASK)
+    for k in ref:
+        assert abs(av[k] - ref[k]) <= 2e-7, k
+    pm.reset()
+    pm(batches[1][0].cuda(), batches[1][1].cuda())
+    one = O.pose_metrics(batches[1:], mean, var, MASK)
+    assert abs(pm.get_averages("test")["test_L1"] - one["test_L1"]) < 1e-12

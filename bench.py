@@ -34,6 +34,16 @@ MOD = ["audio/log_mel_400"]
 T = 64
 
 
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel family from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(path))[workload]
+        return d["traffic_bytes_per_launch"], d["source"]
+    except Exception:
+        return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -302,8 +312,9 @@ def run_cuda(args):
             "gpu_launches": launches,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
-                         "kernel": ("igemm_tc_kernel + wgrad_tc_kernel (tcgen05 implicit GEMM: fwd+dgrad+wgrad, %d launches "
+                         "frac": achieved_tf / peak_tf, "traffic": ncu_traffic("train")[0],
+                         "traffic_source": ncu_traffic("train")[1],
+                         "kernel": ("igemm_tc_kernel + igemm_tc_persist_kernel + wgrad_tc_kernel (tcgen05 implicit GEMM: fwd+dgrad+wgrad, %d launches "
                                     "per G+D step pair; algorithmic FLOPs, split-bf16 issues 3x the MMAs)" % len(dom)) if tc else
                                    "conv_gemm_simt (fwd+dgrad+wgrad, %d launches per G+D step pair, fp32 CUDA cores)" % len(dom),
                          "gemm_ms_per_step_pair": conv_ms, "all_conv_ms_per_step_pair": all_ms,
@@ -466,8 +477,9 @@ def run_infer(args):
             "gpu_launches": launches, "encoder_cache_hits": hits,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
-                         "kernel": "igemm_tc_kernel, fused inference epilogue (%d launches per step; algorithmic FLOPs%s)" % (
+                         "frac": achieved_tf / peak_tf, "traffic": ncu_traffic("infer")[0],
+                         "traffic_source": ncu_traffic("infer")[1],
+                         "kernel": "igemm_tc_persist_kernel / igemm_tc_pair_kernel, fused inference epilogue (%d launches per step; algorithmic FLOPs%s)" % (
                              len(records), ", split-bf16 issues 3x the MMAs" if prec == "bf16x3" else ""),
                          "gemm_ms_per_step": gemm_ms, "peak_source": "%s bf16 sustained" % pk_kind},
             "cpu_baseline": {"value": 2 * cpu_b * S / cpu_dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",

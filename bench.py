@@ -212,12 +212,28 @@ def run_cuda(args):
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = 5 * 8
 
+    # e2e leg: every step's five losses are read on the host, through pinned buffers and one step behind the launch, so the
+    # host enqueues step i+1 (H2D of its batch into the static buffers, graph replay) while the GPU still runs step i
+    loss_pin = [torch.empty(5, dtype=torch.float64).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    loss_log = []
+
     def step(i, batch, read_loss):
         kind = "G" if i % 2 == 0 else "D"
         fake, losses = ts.step(*batch, kind=kind)           # batch: host (pinned) or device tensors -> static buffers
         if read_loss:
-            return losses.cpu()             # D2H read of the step's five losses (synchronises)
+            b = i & 1
+            loss_pin[b].copy_(losses, non_blocking=True)    # D2H read of the step's five losses
+            loss_ev[b].record()
+            if i > 0:
+                loss_ev[b ^ 1].synchronize()
+                loss_log.append(float(loss_pin[b ^ 1][0]))  # the previous step's losses are on the host now
         return None
+
+    def drain(nsteps):
+        b = (nsteps - 1) & 1
+        loss_ev[b].synchronize()
+        loss_log.append(float(loss_pin[b][0]))
 
     def barrier():
         if world > 1:
@@ -231,6 +247,8 @@ def run_cuda(args):
         e0.record()
         for i in range(nsteps):
             step(i, host if e2e else resident, e2e)
+        if e2e:
+            drain(nsteps)                   # the last step's losses
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -308,7 +326,8 @@ def run_cuda(args):
                        "l2": "no explicit flush: per-step working set (fp64 params + packed fp32 weights + grads + "
                              "Adam state ~0.9 GB) exceeds the 126 MB L2"},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "mixstage_b200.TrainStep.step(pinned host batch) + losses.cpu()"},
+                    "api": "mixstage_b200.TrainStep.step(pinned host batch); every step's losses copied to pinned host memory and "
+                           "read one step behind the launch (%d reads)" % len(loss_log)},
             "gpu_launches": launches,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",

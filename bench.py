@@ -146,7 +146,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B, S = args.batch, 4
+    B, S = args.batch, args.speakers
     steps, warmup = args.steps, args.warmup
     dt = cpu_train_steps(B, S, steps, warmup)
     val = steps * B / dt
@@ -154,7 +154,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: GAN train step (alternating G/D), B=%d, T=64, S=4, K=8, fp64" % B},
+        "config": {"workload": "configs[1]: GAN train step (alternating G/D), B=%d, T=64, S=%d, K=8, fp64" % (B, S)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": "%d train steps (G/D alternating) after %d warm-up, oracle port of the reference "
                                    "algorithm (torch CPU fp64, %d threads); the reference is Python and "
@@ -195,7 +195,7 @@ def run_cuda(args):
     _lib.load()
     ops.set_precision(args.precision)
 
-    B, S = args.batch, 4
+    B, S = args.batch, args.speakers
     spec = O.Spec(num_speakers=S)
     G, D, gan = build_model(spec, T, dev, torch.float64)
     gan.train()
@@ -319,9 +319,10 @@ def run_cuda(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (split-bf16 operands, f32 accumulate)",
                                            "bf16": "bf16 (f32 accumulate)"}[args.precision], "data": "synthetic",
-            "config": {"workload": "configs[1]: GAN train step (G on even, D on odd iterations), B=%d per GPU, T=64, "
-                                   "S=4, K=8, gan=1, L1Loss, fp64 master params/inputs, precision=%s, %s" % (
-                                       B, args.precision, "CUDA-graph replay" if ts.use_graphs else "eager launches"),
+            "config": {"workload": "%s: GAN train step (G on even, D on odd iterations), B=%d per GPU, T=64, "
+                                   "S=%d, K=8, gan=1, L1Loss, fp64 master params/inputs, precision=%s, %s" % (
+                                       "configs[1]" if (B, S) == (16, 4) else "configs[3] per-GPU slice" if (B, S) == (128, 8) else "variant",
+                                       B, S, args.precision, "CUDA-graph replay" if ts.use_graphs else "eager launches"),
                        "global_batch": B * world, "parallelism": "dp%d" % world,
                        "l2": "no explicit flush: per-step working set (fp64 params + packed fp32 weights + grads + "
                              "Adam state ~0.9 GB) exceeds the 126 MB L2"},
@@ -538,6 +539,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--batch", type=int, default=None, help="sequences per GPU (default 16 train, 1024 infer)")
+    ap.add_argument("--speakers", type=int, default=4, help="train workload: number of speakers S (configs[1]: 4, configs[3]: 8)")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train: BASELINE configs[1] GAN train step (default); infer: configs[2] style-sweep inference")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])

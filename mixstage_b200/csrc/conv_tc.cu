@@ -541,13 +541,35 @@ __device__ __forceinline__ void epilogue_chunk_fast(const uint32_t* cur, const f
     MS_TIE16(a, 0);                                                  \
     MS_TIE16(a, 16);                                                 \
   } while (0)
-template <int VARIANT, typename Release>
+template <int VARIANT, bool X32 = true, typename Release>
 __device__ __forceinline__ void lean_epilogue_tile(uint32_t taddr, int c_beg, int c_lim, bool valid, const float* __restrict__ sc,
                                                    const float* __restrict__ sh, float slope, float rw, uint8_t* __restrict__ dst,
                                                    int dbg, Release release) {
   constexpr int CB = 16 * (VARIANT == 2 ? 4 : 2);          // output bytes per 16-column chunk
   const bool st = valid && !(dbg & 1);
   const int nch = c_lim - c_beg;
+  if constexpr (!X32) {
+    // 16 columns per load, two buffers (the 16-epilogue-warp configuration has 112 registers per thread)
+    uint32_t va[16], vb[16];
+    if (nch > 0) tmem_ld16(taddr + (uint32_t)(c_beg * 16), va);
+    else release();
+    for (int i = 0; i < nch; i += 2) {
+      const int c = c_beg + i;
+      tmem_wait_ld16(va);
+      if (i + 1 < nch) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), vb);
+      else release();
+      if (st) epilogue_chunk_fast<VARIANT>(va, sc + c * 16, sh + c * 16, slope, rw, dst);
+      dst += CB;
+      if (i + 1 < nch) {
+        tmem_wait_ld16(vb);
+        if (i + 2 < nch) tmem_ld16(taddr + (uint32_t)((c + 2) * 16), va);
+        else release();
+        if (st) epilogue_chunk_fast<VARIANT>(vb, sc + c * 16 + 16, sh + c * 16 + 16, slope, rw, dst);
+        dst += CB;
+      }
+    }
+    return;
+  }
   const int n2 = nch >> 1;                                  // 32-column units
   uint32_t va[32], vb[32];
   if (n2 > 0) tmem_ld32(taddr + (uint32_t)(c_beg * 16), va);
@@ -885,13 +907,15 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                : "memory");
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+// EW = epilogue warps per TMEM lane quadrant: 2 (8 warps, 320 threads) or 4 (16 warps, 576 threads, 112 registers each).
+template <int VARIANT, int EW>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
 igemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                      const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ IgemmParams p, const float* __restrict__ bias, const float* __restrict__ scale,
                      const float* __restrict__ shift, void* __restrict__ out) {
   static_assert(VARIANT >= 1 && VARIANT <= 3, "pair kernel: lean epilogues only");
+  constexpr int EPI_T = 128 * EW;                 // epilogue threads
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t b_half_bytes = (uint32_t)(p.block_n / 2) * BLOCK_K * 2;     // this CTA's half of the weight tile
@@ -927,7 +951,7 @@ igemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // full: the leader's arrive.expect_tx + the peer's remote arrive; empty / accumulator-full: one multicast commit;
     // accumulator-empty: the epilogue warps of both CTAs
     for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * (EPI_THREADS / 32)); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 2 * (EPI_T / 32)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -997,14 +1021,14 @@ igemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ================= epilogue (both CTAs): this CTA's 128 rows =================
     const int et = (int)threadIdx.x - 64;
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;                 // which share of the tile's columns
     const int r = q * 32 + lane;
     const int wi = r % p.box_w;
     const int hi = (r / p.box_w) % p.box_h;
     const int bi = r / (p.box_w * p.box_h);
     const int chunks = p.block_n >> 4;
-    const int chunks_h = (chunks + 1) >> 1;
-    const int c_beg = half * chunks_h, c_end = min(chunks, c_beg + chunks_h);
+    const int chunks_h = (chunks + EW - 1) / EW;
+    const int c_beg = min(chunks, part * chunks_h), c_end = min(chunks, c_beg + chunks_h);
     const bool act = p.epilogue != 0 && p.slope != 1.f;
     const float slope_eff = act ? p.slope : 1.f;
     int lt = 0;
@@ -1012,7 +1036,7 @@ igemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       const int buf = lt & 1;
       const TileCoord t = decode_tile(p, tile, ny, 2, crank);
       const int ncol = t.cls * p.class_n + t.n0;
-      for (int i = et; i < p.block_n; i += EPI_THREADS) {
+      for (int i = et; i < p.block_n; i += EPI_T) {
         float sc = 1.f, sh = 0.f;
         if (t.n0 + i < p.class_n) {
           if (p.epilogue == 1) { sc = __ldg(scale + ncol + i); sh = __ldg(shift + ncol + i); }
@@ -1021,7 +1045,7 @@ igemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         s_scale[buf][i] = sc;
         s_shift[buf][i] = sh;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_T) : "memory");
       const int ow = t.w0 + wi, oh = t.h0 + hi, ob = t.b0 + bi;
       const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
       const long long row_off = (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + p.out_off[t.cls] + t.n0;
@@ -1033,7 +1057,7 @@ igemm_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * cols_per_buf;
       const uint32_t ebar = mapa_u32(smem_u32(&tmem_empty_bar[buf]), 0);     // the leader's MMA warp waits on it
-      lean_epilogue_tile<VARIANT>(taddr, c_beg, max(c_beg, c_lim), valid, s_scale[buf], s_shift[buf], slope_eff, rw, dst, p.dbg, [&]() {
+      lean_epilogue_tile<VARIANT, EW == 2>(taddr, c_beg, max(c_beg, c_lim), valid, s_scale[buf], s_shift[buf], slope_eff, rw, dst, p.dbg, [&]() {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ebar);
@@ -1382,7 +1406,17 @@ static bool igemm_use_pair(long long m_tiles, long long ny, int block_n) {
   return m_tiles * ny >= 2LL * ms_num_sms();
 }
 
-template <int V>
+// MS_IGEMM_EPI16=1: 16 epilogue warps in the pair kernel (experiment; default 8)
+static bool igemm_epi16() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MS_IGEMM_EPI16");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int V, int EW>
 static int launch_pair(long long groups, size_t smem, cudaStream_t cs, const CUtensorMap& map_a, const CUtensorMap& map_w,
                        const CUtensorMap& map_a_lo, const CUtensorMap& map_w_lo, const IgemmParams& p, const float* bias,
                        const float* scale, const float* shift, void* out) {
@@ -1392,13 +1426,13 @@ static int launch_pair(long long groups, size_t smem, cudaStream_t cs, const CUt
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(PERSIST_THREADS); cfg.stream = cs;
+  cfg.blockDim = dim3(64 + 128 * EW); cfg.stream = cs;
   cfg.attrs = at; cfg.numAttrs = 1;
   if (max_pairs < 0) {
-    MS_CUDA(cudaFuncSetAttribute(igemm_tc_pair_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    MS_CUDA(cudaFuncSetAttribute(igemm_tc_pair_kernel<V, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     int n = ms_num_sms() / 2;
     cfg.gridDim = dim3((unsigned)(ms_num_sms() / 2 * 2)); cfg.dynamicSmemBytes = dyn;
-    if (cudaOccupancyMaxActiveClusters(&n, igemm_tc_pair_kernel<V>, &cfg) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n, igemm_tc_pair_kernel<V, EW>, &cfg) != cudaSuccess || n < 1) {
       cudaGetLastError();
       n = 1;
     }
@@ -1408,7 +1442,7 @@ static int launch_pair(long long groups, size_t smem, cudaStream_t cs, const CUt
   const long long ncl = groups < max_pairs ? groups : max_pairs;
   cfg.gridDim = dim3((unsigned)(ncl * 2));
   cfg.dynamicSmemBytes = smem;
-  MS_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pair_kernel<V>, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out));
+  MS_CUDA(cudaLaunchKernelEx(&cfg, igemm_tc_pair_kernel<V, EW>, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out));
   return 0;
 }
 
@@ -1609,10 +1643,18 @@ static int igemm_launch(const ms_igemm_desc* d, const void* a, const void* w, co
       const long long pgroups = (((long long)p.tiles_w * p.tiles_h * p.tiles_b + 1) / 2) * p.n_tiles_per_class * d->num_classes;
       const size_t psmem = (size_t)pst * pstage + 1024;
       cudaStream_t pcs = ms_stream(stream);
+      if (igemm_epi16()) {
+        switch (variant) {
+          case 1: return launch_pair<1, 4>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+          case 2: return launch_pair<2, 4>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+          case 3: return launch_pair<3, 4>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+          default: return MS_EINVAL;
+        }
+      }
       switch (variant) {
-        case 1: return launch_pair<1>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
-        case 2: return launch_pair<2>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
-        case 3: return launch_pair<3>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+        case 1: return launch_pair<1, 2>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+        case 2: return launch_pair<2, 2>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
+        case 3: return launch_pair<3, 2>(pgroups, psmem, pcs, map_a, map_w, map_a_lo, map_w_lo, p, bias, scale, shift, out);
         default: return MS_EINVAL;
       }
     }

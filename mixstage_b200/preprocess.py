@@ -23,6 +23,11 @@ from ._lib import MixStageError, call, ptr, stream
 FEATS = {"pose": 1, "velocity": 2, "speed": 3, "acceleration": 4}
 
 
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise MixStageError("%s: CUDA tensor required (mixstage_b200 has no CPU fallback)" % what)
+
+
 class PosePreprocessor:
     """mask: joints removed by RemoveJoints (default [0, 7, 8, 9], src/argsUtils.py:21); muvar: (mean, var) of the raw pose
     as ZNorm stores them (shape (..., Pr)); centers: (K, D) k-means centres (KMeans.centers); feats: the feature list the
@@ -60,8 +65,7 @@ class PosePreprocessor:
 
     # ------------------------------------------------------------------
     def _check(self, x):
-        if not x.is_cuda:
-            raise MixStageError("PosePreprocessor: raw pose must be a CUDA tensor (no CPU fallback)")
+        _need_cuda(x, "PosePreprocessor")
         if x.dim() != 3 or x.shape[-1] != self.Pr:
             raise MixStageError("raw pose must be (B, T, %d)" % self.Pr)
         return x.to(torch.float64).contiguous()          # KMeans.predict: x.double() (transform.py:393)
@@ -106,8 +110,9 @@ class PosePreprocessor:
 
     def inv_znorm(self, x):
         """ZNorm.inv_znorm (transform.py:228-229) on a full-width (.., 2J) pose."""
-        if not x.is_cuda or x.shape[-1] != self.Pr or self.mean is None:
-            raise MixStageError("inv_znorm: CUDA tensor (..., %d) and muvar required" % self.Pr)
+        _need_cuda(x, "inv_znorm")
+        if x.shape[-1] != self.Pr or self.mean is None:
+            raise MixStageError("inv_znorm: tensor (..., %d) and muvar required" % self.Pr)
         x = x.to(torch.float64).contiguous()
         out = torch.empty_like(x)
         call("ms_inv_znorm", ptr(x), ptr(self.mean), ptr(self.var), x.numel() // self.Pr, self.Pr, ptr(out), stream())
@@ -144,8 +149,10 @@ class PoseMetrics:
 
     def __call__(self, y_cap, y_gt):
         """y_cap, y_gt: (B, T, 2J) CUDA tensors (normalised).  One kernel, one 8*(2 + nalpha*J)-byte read-back."""
-        if not (y_cap.is_cuda and y_gt.is_cuda) or y_cap.shape != y_gt.shape or y_cap.shape[-1] != 2 * self.J:
-            raise MixStageError("PoseMetrics: CUDA tensors of shape (B, T, %d) required" % (2 * self.J))
+        _need_cuda(y_cap, "PoseMetrics")
+        _need_cuda(y_gt, "PoseMetrics")
+        if y_cap.shape != y_gt.shape or y_cap.dim() != 3 or y_cap.shape[-1] != 2 * self.J:
+            raise MixStageError("PoseMetrics: tensors of shape (B, T, %d) required" % (2 * self.J))
         y = y_cap.to(torch.float64).contiguous()
         g = y_gt.to(torch.float64).contiguous()
         B, T, _ = y.shape

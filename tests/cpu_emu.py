@@ -551,6 +551,66 @@ def ms_clip_adam(p, g, m, v, dt, n, sqnorm, step, lr, b1, b2, eps, max_norm, lr_
     P.copy_((P.double() - lr / (1 - b1 ** t) * md / denom).to(P.dtype))
 
 
+
+# ---- the rows either side of the hot path (csrc/preprocess.cu)
+def _i32(p, n):
+    return _arr(p, n, np.int32)
+
+
+def ms_pose_prepare(x, mean, var, cols, centers, B, T, Pr, P, K, feats_host, nfeats, eps, y, labels, soft, st):
+    X = f64(x, B * T * Pr).view(B, T, Pr)
+    idx = _i32(cols, P).long()
+    Xr = X[..., idx]
+    if y:
+        m, v = f64(mean, Pr)[idx], f64(var, Pr)[idx]
+        sd = torch.sqrt(torch.where(v >= 0, v, torch.zeros_like(v)))
+        sd = torch.where(sd == 0, torch.full_like(sd, eps), sd)
+        f64(y, B * T * P).copy_(((Xr - m) / sd).reshape(-1))
+    if not labels and not soft:
+        return
+    V = torch.zeros_like(Xr)
+    V[:, 1:] = Xr[:, 1:] - Xr[:, :-1]
+    A = torch.zeros_like(Xr)
+    A[:, 1:] = V[:, 1:] - V[:, :-1]
+    parts = []
+    for i in range(nfeats):
+        f = int(feats_host[i])
+        if f == 3:
+            parts.append(torch.sqrt(V[..., : P // 2] ** 2 + V[..., P // 2:] ** 2))
+        else:
+            parts.append({1: Xr, 2: V, 4: A}[f])
+    Fm = torch.cat(parts, -1)
+    D = Fm.shape[-1]
+    C = f64(centers, K * D).view(K, D)
+    mse = ((C.view(1, 1, K, D) - Fm.unsqueeze(2)) ** 2).sum(-1)
+    if labels:
+        i64(labels, B * T).copy_(mse.argmin(-1).reshape(-1))
+    if soft:
+        f64(soft, B * T * K).copy_(torch.softmax(-mse / mse.mean(-1, keepdim=True), -1).reshape(-1))
+
+
+def ms_inv_znorm(x, mean, var, rows, C, out, st):
+    f64(out, rows * C).copy_((f64(x, rows * C).view(rows, C) * torch.sqrt(f64(var, C)) + f64(mean, C)).reshape(-1))
+
+
+def ms_pose_metrics(y, gt, mean, var, keep, B, T, J, alphas_host, nalpha, acc, cnt, st):
+    W = 2 * J
+    Y, G = f64(y, B * T * W).view(B, T, 2, J), f64(gt, B * T * W).view(B, T, 2, J)
+    kp = _arr(keep, J, np.uint8).bool()
+    a = f64(acc, 2)
+    a[0] = (Y - G).abs()[..., kp].sum()
+    a[1] = ((Y[:, 1:] - Y[:, :-1]) - (G[:, 1:] - G[:, :-1])).abs()[..., kp].sum()
+    sd, m = torch.sqrt(f64(var, W)).view(2, J), f64(mean, W).view(2, J)
+    Yu, Gu = (Y * sd + m).reshape(-1, 2, J).clone(), (G * sd + m).reshape(-1, 2, J).clone()
+    Yu[..., 0] = 0
+    Gu[..., 0] = 0
+    dist = ((Yu - Gu) ** 2).sum(1).sqrt()
+    box = torch.maximum(Gu[:, 0].max(-1).values - Gu[:, 0].min(-1).values, Gu[:, 1].max(-1).values - Gu[:, 1].min(-1).values)
+    c = i64(cnt, nalpha * J).view(nalpha, J)
+    for i in range(nalpha):
+        c[i] = (dist < float(alphas_host[i]) * box[:, None]).sum(0)
+
+
 def install(monkeypatch):
     """Route mixstage_b200's kernel calls to the CPU specification (tests only)."""
     from mixstage_b200 import _lib, ops, speech2gesture, joint_late_cluster_soft_style as j
@@ -564,3 +624,7 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "call", call)
     monkeypatch.setattr(ops, "stream", lambda: None)
     monkeypatch.setattr(ops, "_need_cuda", lambda t: None)
+    from mixstage_b200 import preprocess
+    monkeypatch.setattr(preprocess, "call", call)
+    monkeypatch.setattr(preprocess, "stream", lambda: None)
+    monkeypatch.setattr(preprocess, "_need_cuda", lambda t, what: None)

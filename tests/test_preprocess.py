@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 
+import cpu_emu
 import mixstage_oracle as O
 from oracle_cases import load_golden
 
@@ -140,3 +141,42 @@ def test_cuda_pose_metrics_match_oracle_and_golden(golden_dir):
     pm(batches[1][0].cuda(), batches[1][1].cuda())
     one = O.pose_metrics(batches[1:], mean, var, MASK)
     assert abs(pm.get_averages("test")["test_L1"] - one["test_L1"]) < 1e-12
+
+
+# ---------------------------------------------------------------------------- host logic on the CPU kernel specification
+@pytest.mark.parametrize("name", list(CASES))
+def test_preprocessor_host_logic_on_cpu_spec(monkeypatch, golden_dir, name):
+    """Column gather built from the joint mask, feature coding, output shapes/dtypes and the separate entry points of
+    PosePreprocessor, with ms_pose_prepare routed to tests/cpu_emu.py."""
+    import mixstage_b200 as M
+    cpu_emu.install(monkeypatch)
+    feats, K = CASES[name]
+    gold = load_golden(golden_dir, name)
+    x, mean, var, centers, labels, soft, y, zn, inv = _oracle(name)
+    pp = M.PosePreprocessor(num_joints=52, mask=MASK, muvar=(mean, var), centers=centers, feats=feats, device="cpu")
+    assert pp.P == 96 and pp.D == centers.shape[1] and pp.cols.tolist()[:3] == [1, 2, 3] and pp.cols.tolist()[48] == 53
+    yg, lg = pp(x)
+    assert (lg.numpy() == gold["labels"]).all()
+    np.testing.assert_allclose(yg.numpy(), gold["y"], rtol=1e-14, atol=0)
+    _, sg = pp(x, soft_labels=True)
+    np.testing.assert_allclose(sg.numpy(), gold["soft"], rtol=1e-12, atol=1e-15)
+    assert torch.equal(pp.predict(x), lg) and torch.equal(pp.normalize(x), yg)
+    with pytest.raises(M.MixStageError):
+        pp(x[..., :100])
+    with pytest.raises(M.MixStageError):
+        M.PosePreprocessor(feats=["pose", "spatial"], device="cpu")
+    with pytest.raises(M.MixStageError):
+        M.PosePreprocessor(centers=torch.zeros(8, 7), device="cpu")
+
+
+def test_metrics_host_logic_on_cpu_spec(monkeypatch, golden_dir):
+    """AverageMeter-style weighting of PoseMetrics over two batches of different size, kernel routed to tests/cpu_emu.py."""
+    import mixstage_b200 as M
+    cpu_emu.install(monkeypatch)
+    gd, mean, var, batches = _metric_dicts(golden_dir)
+    pm = M.PoseMetrics((mean, var), num_joints=52, mask=MASK, alphas=(0.1, 0.2), device="cpu")
+    for y, g in batches:
+        pm(y, g)
+    _compare_metrics(pm.get_averages("test"), gd)
+    with pytest.raises(M.MixStageError):
+        pm(batches[0][0], batches[1][1])

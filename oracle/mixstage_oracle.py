@@ -19,6 +19,13 @@ run, and ``tests/test_oracle_vs_reference.py`` re-checks it live whenever
 ``LambdaScheduler``) are un-vendored: their semantics are defined in
 ``oracle/ref_loader.py`` and are "parity unpinned" (SURVEY.md §8c).
 
+Rows either side of the path, same rules: ``s2g_forward`` (Speech2Gesture_G) and the K=1 StAGE case are
+pinned to golden vectors of the executed reference classes; ``kmeans_feats`` / ``kmeans_predict`` / ``znorm`` /
+``inv_znorm`` and ``pose_metrics`` are pinned to the reference's OWN function / class bodies (src/data/transform.py,
+src/evaluation/metrics.py), cut out of the source with ``ast`` and executed unchanged because the modules around them
+import h5py/librosa (``ref_loader.load_transform_functions`` / ``load_metric_classes``).  ``remove_joints`` stands in for
+pycasper's un-vendored ``remove_slices``: parity unpinned.
+
 Reference citations are relative to /root/reference/src/model/.
 """
 from __future__ import annotations

@@ -857,10 +857,12 @@ igemm_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 // ---------------------------------------------------------------------------------------------
 // CTA-pair form (tcgen05 cta_group::2): two CTAs on the SMs of one TPC compute a 256 x block_n tile together.
 //
-// Why: every SM can take in ~43 B/clk of operands (profiles/r01_cluster_multicast_ab.txt); a 128 x 256 tile needs
-// 16 KB (A) + 32 KB (W) per 64-deep k-step = 96 B/clk at full tensor rate, so the single-CTA kernel tops out near 45-50 %
-// tensor-active.  In a pair each CTA loads its own 128 activation rows and HALF of the weight tile (block_n/2 rows); the
-// tensor cores read the other half from the peer's shared memory.  32 KB per k-step per SM = 64 B/clk.
+// A 128 x 256 tile stages 16 KB (A) + 32 KB (W) per 64-deep k-step = 96 B/clk per SM at full tensor rate, and the
+// single-CTA kernel was observed taking in ~43 B/clk.  In a pair each CTA loads its own 128 activation rows and HALF of the
+// weight tile (block_n/2 rows); the tensor cores read the other half from the peer's shared memory: 32 KB per k-step per
+// SM = 64 B/clk, and a 6-deep instead of a 4-deep ring in the same shared memory.  Measured (profiles/
+// r01_igemm_epilogue_experiments.txt): 36.8 -> 33.4 us on the M=65536 N=256 K=768 layers, 67 % tensor-active on the long-K
+// audio layer; the K=768 layers stay near 47 % (wave quantisation + per-launch prologue, see the log's addendum).
 //
 //   * one UMMA = 256 x block_n x 16, issued by the leader CTA (cluster rank 0) only; accumulator rows 0..127 live in the
 //     leader's TMEM, rows 128..255 in the peer's, at the same column offset (tcgen05.alloc.cta_group::2 in both CTAs)
@@ -1384,8 +1386,8 @@ static int igemm_cluster_size(long long m_tiles, long long ny, int block_n) {
     const char* e = getenv("MS_IGEMM_CLUSTER");
     forced = e ? atoi(e) : 0;
   }
-  // Default 1: measured on B200 (profiles/r01_cluster_multicast_ab.txt) the multicast does not pay -- the bound is the
-  // ~43 B/clk each SM can ingest, which a multicast delivery does not lower; only a larger tile per SM does.
+  // Default 1: measured on B200 (profiles/r01_cluster_multicast_ab.txt) the multicast does not pay: L2 slice reads are not
+  // the bound of these launches (nor, as the CTA-pair kernel later showed, is the per-SM operand ingest).
   (void)ny;
   int c = 1;
   if (forced == 1 || forced == 2 || forced == 4) c = forced;

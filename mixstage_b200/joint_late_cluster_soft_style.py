@@ -46,6 +46,11 @@ class JointLateClusterSoftStyle4_G(nn.Module):
     output_shape: (N, time, pose_feats)
     '''
 
+    # Sub-modules the reference constructs (and checkpoints) but whose parameters no accelerated forward touches: the text
+    # encoder (text modalities raise here), style_dec / style_dec_gr (never called in the reference's forward either,
+    # jlcss.py:117-209), concat_encoder (text only) and smoothen (unused).  TrainStep leaves them out of its flat buffers.
+    UNUSED_PARAMETER_PREFIXES = ("text_encoder.", "style_dec.", "style_dec_gr.", "concat_encoder.", "smoothen.")
+
     def __init__(self, time_steps=64, in_channels=256, out_feats=104, p=0, num_clusters=8, cluster=None,
                  style_dict={}, style_dim=10, lambda_id=1, train_only=0, softmax=1, argmax=0,
                  some_grad_flag=False, **kwargs):

@@ -30,8 +30,13 @@ ALIGN = 4       # parameter offsets in elements: 16-byte aligned for fp32, 32-by
 class FlatState:
     """Flat parameter / gradient / Adam-moment buffers of one sub-network."""
 
-    def __init__(self, module):
-        self.params = [p for p in module.parameters() if p.requires_grad]
+    def __init__(self, module, skip=()):
+        """skip: name prefixes of parameters that no forward of `module` ever touches (parameter holders kept for
+        state_dict compatibility).  Their gradient is identically zero, so Adam never moves them (m = v = 0 gives a zero
+        update): leaving them out of the flat buffers changes nothing but the bytes zeroed, normed, all-reduced and
+        stepped over."""
+        skip = tuple(skip)
+        self.params = [p for n, p in module.named_parameters() if p.requires_grad and not (skip and n.startswith(skip))]
         if not self.params:
             raise ValueError("module has no trainable parameters")
         p0 = self.params[0]
@@ -85,7 +90,8 @@ class TrainStep:
     def __init__(self, gan, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, use_graphs=True, group=None,
                  input_modalities=("audio/log_mel_400",), description="train"):
         self.gan, self.G, self.D = gan, gan.G, gan.D
-        self.fG, self.fD = FlatState(self.G), FlatState(self.D)
+        self.fG = FlatState(self.G, skip=getattr(self.G, "UNUSED_PARAMETER_PREFIXES", ()))
+        self.fD = FlatState(self.D)
         self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
         dev = self.fG.device
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float64, device=dev)

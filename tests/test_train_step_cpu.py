@@ -44,7 +44,8 @@ def test_steps_match_oracle_loop(precision):
         audio, pose, labels, style = O.synth_inputs(B, T, spec)
         sd = leafify(O.synth_state(O.g_state_shapes(spec), G_SEED))
         sdd = leafify(O.synth_state(O.d_state_shapes(spec.out_feats), D_SEED))
-        gnp = [(n, p) for n, p in G.named_parameters() if p.requires_grad]
+        gnp = [(n, p) for n, p in G.named_parameters() if p.requires_grad and not n.startswith(G.UNUSED_PARAMETER_PREFIXES)]
+        assert sum(p.numel() for _, p in gnp) < 0.8 * sum(p.numel() for p in G.parameters())      # ~26 % are mere holders
         dnp = [(n, p) for n, p in D.named_parameters() if p.requires_grad]
         assert [id(p) for _, p in gnp] == [id(p) for p in ts.fG.params]
         nstep = {"G": 0, "D": 0}

@@ -136,6 +136,17 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         with ops.precision_scope(self.precision):
             return self._forward(x, y, time_steps, **kwargs)
 
+    def _mark(self, t, stage):
+        """Data-parallel training with overlapped gradient exchange (TrainStep(overlap_allreduce=True)): when the gradient
+        of activation `t` arrives in backward, every layer downstream of it has finished its backward, so the parameter
+        gradients of those layers are final and their all-reduce can start while the upstream layers still run."""
+        cb = getattr(self, 'grad_ready_hook', None)
+        if cb is not None and torch.is_tensor(t) and t.requires_grad:
+            def hook(g, _stage=stage, _cb=cb):
+                _cb(_stage)
+            t.register_hook(hook)
+        return t
+
     def _forward(self, x, y, time_steps=None, **kwargs):
         internal_losses = []
         labels = x[-1]                      # cluster labels ride along with the inputs (jlcss.py:119)
@@ -163,7 +174,7 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         elif use_pose:
             T = y.shape[1]
             h = self.pose_encoder(self._as_f32_cl(y, B, T).view(B, 1, T, y.shape[2]), time_steps)
-            h = self.unet(h)
+            h = self.unet(self._mark(h, 'encoder_out'))
         else:
             feats = []
             for i, modality in enumerate(kwargs['input_modalities']):
@@ -179,7 +190,7 @@ class JointLateClusterSoftStyle4_G(nn.Module):
                     feats.append(self.audio_encoder(a, time_steps if time_steps is not None else T))
             if len(feats) != 1:
                 raise NotImplementedError("mixstage_b200: exactly one (audio) input modality is accelerated")
-            h = self.unet(feats[0])           # (B,1,T,256)
+            h = self.unet(self._mark(feats[0], 'encoder_out'))           # (B,1,T,256)
             if cache_key is not None:
                 self._enc_cache = (weakref.ref(x[0]), cache_key, h)
         Bx, _, T, C = h.shape
@@ -214,7 +225,8 @@ class JointLateClusterSoftStyle4_G(nn.Module):
                 raise MixStageError("style must be (B,T) int64 or (B,T,S) float")
             id_in_loss = torch.zeros((), dtype=torch.float32, device=h.device)
         self.style_index = idx
-        hc = ops.style_concat(h, self.style_emb.emb.weight, idx=idx, soft=soft_style, rep=rep)   # (B,1,T,266)
+        hc = ops.style_concat(self._mark(h, 'unet_out'), self.style_emb.emb.weight, idx=idx, soft=soft_style, rep=rep)   # (B,1,T,266)
+        hc = self._mark(hc, 'hc')
 
         # cluster classifier: softmax weights + CE vs k-means labels (jlcss.py:183-187)
         score_c = self.classify_cluster(hc)                                   # (B,1,T,K)

@@ -36,7 +36,9 @@ class FlatState:
         update): leaving them out of the flat buffers changes nothing but the bytes zeroed, normed, all-reduced and
         stepped over."""
         skip = tuple(skip)
-        self.params = [p for n, p in module.named_parameters() if p.requires_grad and not (skip and n.startswith(skip))]
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad and not (skip and n.startswith(skip))]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
         if not self.params:
             raise ValueError("module has no trainable parameters")
         p0 = self.params[0]
@@ -50,6 +52,16 @@ class FlatState:
             self.offsets.append(off)
             off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         self.numel = off
+        # contiguous range of every top-level sub-module (parameters are registered module by module)
+        self.segments = {}
+        for i, n in enumerate(self.names):
+            top = n.split(".")[0]
+            beg = self.offsets[i]
+            end = self.offsets[i + 1] if i + 1 < len(self.offsets) else self.numel
+            b0, e0 = self.segments.get(top, (beg, beg))
+            if e0 != beg and top in self.segments:
+                raise ValueError("parameters of %s are not contiguous in registration order" % top)
+            self.segments[top] = (b0, end)
         mk = lambda: torch.zeros(self.numel, dtype=self.dtype, device=self.device)       # noqa: E731
         self.p, self.g, self.m, self.v = mk(), mk(), mk(), mk()
         for p, o in zip(self.params, self.offsets):
@@ -87,8 +99,11 @@ class TrainStep:
     """gan: mixstage_b200.GAN already on its device/dtype (`.to(device).double()` as the reference's trainer does,
     trainer.py:138).  Do not call `.to()/.double()` on the model afterwards: parameters are views of flat buffers."""
 
+    # activation whose gradient has arrived -> generator sub-modules whose parameter gradients are final (see G._mark)
+    READY = {"hc": ("logits", "decoder", "classify_cluster"), "unet_out": ("style_emb",), "encoder_out": ("unet",)}
+
     def __init__(self, gan, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, use_graphs=True, group=None,
-                 input_modalities=("audio/log_mel_400",), description="train"):
+                 input_modalities=("audio/log_mel_400",), description="train", overlap_allreduce=False):
         self.gan, self.G, self.D = gan, gan.G, gan.D
         self.fG = FlatState(self.G, skip=getattr(self.G, "UNUSED_PARAMETER_PREFIXES", ()))
         self.fD = FlatState(self.D)
@@ -113,6 +128,11 @@ class TrainStep:
         for pw in self._packed_of(self.G) + self._packed_of(self.D):
             pw._src.clear()          # recipes recorded before the parameters moved into the flat buffers are stale
         self._pver = None            # flat-parameter versions seen by the last refresh
+        # opt-in: all-reduce the generator's gradients segment by segment while backward is still running (NOT yet
+        # validated on multi-GPU hardware; numerics covered by tests/test_parallel_cpu.py with gloo)
+        self.overlap = bool(overlap_allreduce)
+        self.comm = torch.cuda.Stream(device=dev) if (self.overlap and dev.type == "cuda") else None
+        self._reduced, self._works = [], []
 
     # ------------------------------------------------------------------ host-side decisions
     def set_lr(self, lr):
@@ -147,6 +167,9 @@ class TrainStep:
         ops.arena.begin(self.fG.device)
         ops.DIRECT_GRADS = True
         ops.SIDE = self.side
+        overlap = self.overlap and kind == "G" and self._world() > 1
+        self._reduced, self._works = [], []
+        G.grad_ready_hook = self._on_ready if overlap else None
         try:
             fake, losses, _ = gan([audio, labels], pose, input_modalities=self.mod, style=style, sample_flag=0,
                                   description=self.description, desc=self.description)
@@ -154,19 +177,66 @@ class TrainStep:
             loss.backward()
         finally:
             G.force_branch = None
+            G.grad_ready_hook = None
             ops.DIRECT_GRADS = False
             ops.SIDE = None
             ops.arena.end()
             if self.side is not None:
                 self.side.join()
         f = self.fG if kind == "G" else self.fD
-        f.allreduce_mean(self.group)
+        if overlap:
+            self._finish_overlapped()
+        else:
+            f.allreduce_mean(self.group)
         f.clip_adam(self.lr, self.lr_dev, self.betas, self.eps, self.max_norm)
         if self.use_graphs:
             # keep every packed copy (bf16 re-tilings, fp32 biases, folded eval BatchNorm) of the sub-network that just
             # stepped in sync with its parameters, so that no forward has to re-pack anything
             self._refresh(kind)
         return fake.detach(), torch.stack([l.detach().to(fake.dtype) for l in losses])
+
+    # ------------------------------------------------------------------ overlapped gradient exchange (opt-in)
+    def _world(self):
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
+    def _reduce_range(self, beg, end):
+        if end <= beg:
+            return
+        chunk = self.fG.g[beg:end]
+        ws = self._world()
+        if self.comm is None:                       # CPU (gloo): no streams
+            chunk.div_(ws)
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        cur = torch.cuda.current_stream()
+        self.comm.wait_stream(cur)                  # BatchNorm / bias gradients are written on the compute stream
+        if self.side is not None:
+            self.comm.wait_stream(self.side.stream) # weight gradients on the side stream
+        with torch.cuda.stream(self.comm):
+            chunk.div_(ws)
+            self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _on_ready(self, stage):
+        for top in self.READY.get(stage, ()):
+            seg = self.fG.segments.get(top)
+            if seg is not None and seg not in self._reduced:
+                self._reduced.append(seg)
+                self._reduce_range(*seg)
+
+    def _finish_overlapped(self):
+        """Everything not exchanged from a hook (audio / pose encoder, pose-style encoder, gaps), then join."""
+        done = sorted(self._reduced)
+        pos = 0
+        for beg, end in done + [(self.fG.numel, self.fG.numel)]:
+            self._reduce_range(pos, beg)
+            pos = max(pos, end)
+        for w in self._works:
+            w.wait()
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
+        self._reduced, self._works = [], []
 
     # ------------------------------------------------------------------ packed copies follow the parameters
     @staticmethod

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap=None):
     for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -33,12 +33,13 @@ def _worker(rank, world, port, out):
     G, D, gan = build(spec, T, "cpu", torch.float64)
     G.thresh.value, G.thresh.iters = 1.0, 1000
     parallel.sync_host_rng(11212)
-    ts = M.TrainStep(gan, use_graphs=False)
+    ts = M.TrainStep(gan, use_graphs=False, overlap_allreduce=bool(overlap))
     full = O.synth_inputs(world * B, T, spec)
     audio, pose, labels, style = parallel.shard_batch(full, rank, world)
     kinds = []
-    for _ in range(2):
-        ts.step(audio, labels, pose, style)              # coin flips from the shared host RNG
+    for i in range(2):
+        # coin flips from the shared host RNG; the overlap comparison forces one step of each kind
+        ts.step(audio, labels, pose, style, kind=("G", "D")[i] if overlap is not None else None)
         kinds.append(ts.last_kind)
     res = {"kinds": kinds, "pG": ts.fG.p.clone(), "pD": ts.fD.p.clone(), "gG": ts.fG.g.clone(), "gD": ts.fD.g.clone(),
            "steps": (int(ts.fG.step_count), int(ts.fD.step_count))}
@@ -58,6 +59,25 @@ def test_two_rank_train_step(tmp_path):
     for k in ("pG", "pD", "gG", "gD"):
         assert torch.equal(r0[k], r1[k]), k                 # replicas stay bit-identical
     assert float(r0["gG"].abs().max()) > 0 or float(r0["gD"].abs().max()) > 0
+
+
+@pytest.mark.timeout(900)
+def test_overlapped_allreduce_equals_single_allreduce(tmp_path):
+    """TrainStep(overlap_allreduce=True): the generator's gradients are exchanged segment by segment from backward hooks
+    (decoder / logits / classifier first, then style embedding, UNet, and the rest at the end).  Same element-wise
+    operations as the single all-reduce, so parameters and gradients must be bit-identical."""
+    world = 2
+    res = {}
+    for overlap in (False, True):
+        d = tmp_path / ("overlap%d" % overlap)
+        d.mkdir()
+        mp.spawn(_worker, args=(world, 31500 + os.getpid() % 2000 + int(overlap), str(d), overlap), nprocs=world, join=True)
+        res[overlap] = [torch.load(os.path.join(d, "rank%d.pt" % r)) for r in range(world)]
+    for r in range(world):
+        assert res[False][r]["kinds"] == res[True][r]["kinds"] == ["G", "D"]
+        for k in ("pG", "pD", "gG", "gD"):
+            assert torch.equal(res[False][r][k], res[True][r][k]), (r, k)
+    assert torch.equal(res[True][0]["pG"], res[True][1]["pG"])
 
 
 def test_shard_batch_and_flatgrads():

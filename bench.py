@@ -203,7 +203,7 @@ def run_cuda(args):
     parallel.sync_host_rng(11212)
     # the repo's public train-step API: zero_grad + GAN.forward + backward + (all-reduce) + clip + Adam,
     # replayed from CUDA graphs (mixstage_b200/train_step.py)
-    ts = M.TrainStep(gan, lr=1e-4, max_norm=1.0, use_graphs=not args.no_graphs)
+    ts = M.TrainStep(gan, lr=1e-4, max_norm=1.0, use_graphs=not args.no_graphs, overlap_allreduce=args.overlap_allreduce)
 
     # per-rank synthetic shard (weak scaling: B sequences per GPU), pinned host copies for the e2e leg
     audio, pose, labels, style = O.synth_inputs(B, T, spec, seed=11212 + rank)
@@ -544,6 +544,8 @@ def main():
                     help="train: BASELINE configs[1] GAN train step (default); infer: configs[2] style-sweep inference")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16x3", "bf16"], help="default bf16x3 train, bf16 infer")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="train, N > 1: exchange the generator's gradients segment by segment during backward (experimental)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.workload == "infer" and args.impl == "cuda":

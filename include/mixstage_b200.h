@@ -64,6 +64,10 @@ int ms_unpack_conv_wgrad(const float* dwf, const ms_conv_desc* d, void* dw, int 
  * straight into its flat, pre-zeroed gradient buffer (no per-tensor accumulation kernels afterwards). */
 /* dst[i] = (T_dst) src[i]; dtypes MS_F32/MS_F64/MS_BF16. */
 int ms_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream);
+/* dst[i] = (T_dst)(src[i] * scale), MS_F32/MS_F64, src == dst allowed for equal dtypes.  The staging casts of the
+ * data-parallel gradient exchange (fp64 flat gradients <-> fp32 all-reduce buffer, scaled by 1/world): replaces the
+ * `grad / world_size` + NCCL bucket copies a DistributedDataParallel wrapper around trainer.py:1138-1146 would do. */
+int ms_scale_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, double scale, void* stream);
 
 /* ---- convolution as implicit GEMM, fp32 SIMT (conv1d/conv2d call sites:
  * layers.py:60-70 via :78; speech2gesture.py:76,90; jlcss.py:83; layers.py:459) ------ */

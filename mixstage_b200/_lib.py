@@ -57,6 +57,7 @@ PROTOTYPES = {
     "ms_pack_conv_weight_f32": [_P, _I, _CD, _P, _P, _P],
     "ms_unpack_conv_wgrad": [_P, _CD, _P, _I, _I, _P],
     "ms_cast": [_P, _I, _P, _I, _L, _P],
+    "ms_scale_cast": [_P, _I, _P, _I, _L, _D, _P],
     "ms_conv_fwd_f32": [_P, _P, _P, _P, _CD, _I, _F, _P],
     "ms_conv_dgrad_f32": [_P, _P, _P, _CD, _P],
     "ms_conv_wgrad_f32": [_P, _P, _P, _CD, _P],

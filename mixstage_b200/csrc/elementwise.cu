@@ -35,6 +35,29 @@ __global__ void cast_kernel<float, double>(const float* __restrict__ s, double* 
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = (double)s[i];
 }
 
+// d[i] = (D)(s[i] * scale), vectorised where both pointers allow: the staging casts of the fp32 gradient exchange
+// (train_step.py: fp64 flat gradients -> fp32 staging, scaled by 1/world; and back)
+template <typename S, typename D>
+__global__ void scale_cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n, double scale) {
+  const int64_t n2 = n >> 1;
+  const bool vec = ((reinterpret_cast<uintptr_t>(s) % (2 * sizeof(S))) | (reinterpret_cast<uintptr_t>(d) % (2 * sizeof(D)))) == 0;
+  if (vec) {
+    struct alignas(2 * sizeof(S)) S2 { S a, b; };
+    struct alignas(2 * sizeof(D)) D2 { D a, b; };
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+      const S2 v = reinterpret_cast<const S2*>(s)[i];
+      D2 o;
+      o.a = (D)((double)v.a * scale);
+      o.b = (D)((double)v.b * scale);
+      reinterpret_cast<D2*>(d)[i] = o;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = (D)((double)s[n - 1] * scale);
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      d[i] = (D)((double)s[i] * scale);
+  }
+}
+
 // w (Cout, Cin_g, kh, kw) -> wf[g][tap][c][n], wt[g][tap][n][c]
 __global__ void pack_weight_kernel(const void* __restrict__ w, int pdt, int Cout, int Cin_g, int taps, int groups,
                                    float* __restrict__ wf, float* __restrict__ wt) {
@@ -689,6 +712,19 @@ extern "C" int ms_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, 
   CASE(double, MS_F64, __nv_bfloat16, MS_BF16)
   CASE(__nv_bfloat16, MS_BF16, float, MS_F32)
   CASE(__nv_bfloat16, MS_BF16, double, MS_F64)
+#undef CASE
+  return MS_EINVAL;
+}
+
+extern "C" int ms_scale_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, double scale, void* stream) {
+  if (!src || !dst || n < 0) return MS_EINVAL;
+  if (n == 0) return 0;
+  int blocks = ew_blocks((n + 1) / 2);
+#define CASE(S, SD, D, DD) if (sdt == SD && ddt == DD) { scale_cast_kernel<S, D><<<blocks, EW_THREADS, 0, ST>>>((const S*)src, (D*)dst, n, scale); MS_LAUNCH_CHECK(); return 0; }
+  CASE(float, MS_F32, float, MS_F32)
+  CASE(float, MS_F32, double, MS_F64)
+  CASE(double, MS_F64, float, MS_F32)
+  CASE(double, MS_F64, double, MS_F64)
 #undef CASE
   return MS_EINVAL;
 }

@@ -9,27 +9,52 @@ from . import ops
 
 
 class LambdaScheduler:
-    """Stand-in for pycasper.torchUtils.LambdaScheduler (un-vendored; semantics defined in
-    oracle/ref_loader.py: constant lambdas)."""
+    """Stand-in for pycasper.torchUtils.LambdaScheduler (un-vendored and un-pinned upstream, so parity is unpinned here;
+    semantics defined in oracle/ref_loader.py: constant lambdas).  The schedule is an INJECTABLE object: pass
+    ``GAN(..., lambda_scheduler=obj)`` (or assign ``gan.lambda_scheduler``) with any object whose ``step()`` returns
+    ``[lambda_D, lambda_gan]`` for the coming training forward (reference call site gan.py:30-33,103) -- e.g. pycasper's
+    own class when it is installed next to the reference."""
 
     def __init__(self, lambdas, **kwargs):
         self.lambdas = list(lambdas)
+        self.kwargs = dict(kwargs)
 
     def step(self):
         return list(self.lambdas)
 
 
+class RampLambdaScheduler(LambdaScheduler):
+    """A schedule in the shape the reference's arguments describe (``kind='incremental', max_interval=300,
+    max_lambda=2``): every ``max_interval`` training forwards each lambda grows by its initial value until it reaches
+    ``max_lambda``.  NOT pinned against pycasper (source absent); provided so that a varying schedule can be exercised
+    through the device-resident lambdas of TrainStep."""
+
+    def __init__(self, lambdas, max_interval=300, max_lambda=2, **kwargs):
+        super().__init__(lambdas, max_interval=max_interval, max_lambda=max_lambda, **kwargs)
+        self.base = list(lambdas)
+        self.max_interval, self.max_lambda = int(max_interval), float(max_lambda)
+        self.calls = 0
+
+    def step(self):
+        k = self.calls // max(1, self.max_interval)
+        self.calls += 1
+        return [min(self.max_lambda, b * (1 + k)) for b in self.base]
+
+
 class GAN(nn.Module):
     def __init__(self, G, D, dg_iter_ratio=1, lambda_D=1, lambda_gan=1, lr=0.0001, criterion='MSELoss', optim='Adam',
-                 joint=False, update_D_prob_flag=True, no_grad=True, **kwargs):
+                 joint=False, update_D_prob_flag=True, no_grad=True, lambda_scheduler=None, **kwargs):
         super().__init__()
         self.G = G
         self.D = D
         self.D_prob = dg_iter_ratio / (dg_iter_ratio + 1)
         self.lambda_D = lambda_D
         self.lambda_gan = lambda_gan
-        self.lambda_scheduler = LambdaScheduler([self.lambda_D, self.lambda_gan], kind='incremental', max_interval=300,
-                                                max_lambda=2)
+        self.lambda_scheduler = lambda_scheduler if lambda_scheduler is not None else LambdaScheduler(
+            [self.lambda_D, self.lambda_gan], kind='incremental', max_interval=300, max_lambda=2)
+        # TrainStep keeps [lambda_D, lambda_gan] in device memory (captured CUDA graphs read them there) and steps the
+        # scheduler itself, once per real iteration; None = this forward steps the scheduler and multiplies host floats
+        self.lambda_dev = None
         self.G_flag = True
         self.lr = lr
         if criterion != 'L1Loss':
@@ -67,7 +92,12 @@ class GAN(nn.Module):
         if 'input_modalities' not in kwargs:
             kwargs['input_modalities'] = self.input_modalities
         if self.training:
-            self.lambda_D, self.lambda_gan = self.lambda_scheduler.step()
+            if self.lambda_dev is None:
+                self.lambda_D, self.lambda_gan = self.lambda_scheduler.step()
+                lam_D, lam_gan = self.lambda_D, self.lambda_gan
+            else:
+                ld = self.lambda_dev if self.lambda_dev.dtype == dt else self.lambda_dev.to(dt)
+                lam_D, lam_gan = ld[0], ld[1]          # views: the graph reads the current values at replay
             if self.force_step is None:
                 d_step = torch.rand(1).item() < self.D_prob          # gan.py:105
             else:
@@ -80,7 +110,7 @@ class GAN(nn.Module):
                 self.G.train(self.training)
                 self.fake_flag = True
                 fake_score = self._score(fake_pose.detach())
-                fake_D_loss = self.lambda_D * self._l1(fake_score, None, 0.0, dt)
+                fake_D_loss = lam_D * self._l1(fake_score, None, 0.0, dt)
                 real_score = self._score(y_pose)
                 real_D_loss = self._l1(real_score, None, 1.0, dt)
                 internal_losses.append(real_D_loss)
@@ -95,7 +125,7 @@ class GAN(nn.Module):
                         fake_score = self._score(fake_pose)
                 else:
                     fake_score = self._score(fake_pose)
-                G_gan_loss = self.lambda_gan * self._l1(fake_score, None, 1.0, dt)
+                G_gan_loss = lam_gan * self._l1(fake_score, None, 1.0, dt)
                 pose_loss = self._l1(fake_pose, y_pose, 0.0, dt)
                 internal_losses.append(pose_loss)
                 internal_losses.append(G_gan_loss)

@@ -132,6 +132,20 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         return (a.data_ptr(), a._version, tuple(a.shape), a.dtype, time_steps, vers, ops._weight_epoch, ops._stats_epoch,
                 ops.get_precision())
 
+    @contextlib.contextmanager
+    def style_sweep(self):
+        """The reference's sample_all_styles loop (trainer.py:791-794, 1367-1386) as an explicit scope: inside it the
+        encoder + UNet output of an audio tensor is reused across the target styles even while a CUDA graph is being
+        captured (the cached activation and its consumers then live in the same graph); the cache is dropped on exit."""
+        old = getattr(self, '_sweep_active', False)
+        self._sweep_active = True
+        self._enc_cache = None
+        try:
+            yield self
+        finally:
+            self._sweep_active = old
+            self._enc_cache = None
+
     def forward(self, x, y, time_steps=None, **kwargs):
         with ops.precision_scope(self.precision):
             return self._forward(x, y, time_steps, **kwargs)
@@ -163,7 +177,8 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         else:
             use_pose = torch.rand(1).item() > self.thresh.step(self.training) and self.training
         cache_key = None
-        capturing = ops.FORCE_REPACK or (y.is_cuda and torch.cuda.is_current_stream_capturing())
+        capturing = (ops.FORCE_REPACK or (y.is_cuda and torch.cuda.is_current_stream_capturing())) and not getattr(
+            self, '_sweep_active', False)
         if (self.cache_encoder and not use_pose and not self.training and not torch.is_grad_enabled() and not capturing
                 and len(kwargs['input_modalities']) == 1 and kwargs['input_modalities'][0].split('/')[0] == 'audio'):
             cache_key = self._encoder_cache_key(x[0], time_steps)

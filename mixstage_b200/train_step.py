@@ -71,6 +71,7 @@ class FlatState:
             p.grad = self.g[o:o + n].view(p.shape)
         self.step_count = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.sqnorm = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.x32 = None             # fp32 staging of the gradient exchange (allocated on the first multi-rank step)
 
     def zero_grad(self):
         self.g.zero_()
@@ -78,14 +79,37 @@ class FlatState:
             if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + o * self.g.element_size():
                 p.grad = self.g[o:o + p.numel()].view(p.shape)
 
-    def allreduce_mean(self, group=None):
+    def reduce_range(self, beg, end, group=None, fp32=True, async_op=False):
+        """Mean of g[beg:end] over the ranks, in place.  With fp64 master gradients and fp32=True the exchange itself is
+        fp32 (half the NVLink bytes): one kernel scales by 1/world and narrows into a persistent staging buffer, the
+        all-reduce (SUM) runs on the staging range, one kernel widens back.  Every rank performs the same element-wise
+        operations, so replicas stay bit-identical.  Returns the async work handle (or None)."""
+        if end <= beg:
+            return None
+        ws = dist.get_world_size(group)
+        chunk = self.g[beg:end]
+        n = end - beg
+        st = stream()
+        if fp32 and self.dtype == torch.float64:
+            if self.x32 is None:
+                self.x32 = torch.empty(self.numel, dtype=torch.float32, device=self.device)
+            stage = self.x32[beg:end]
+            call("ms_scale_cast", ptr(chunk), _lib.MS_F64, ptr(stage), _lib.MS_F32, n, 1.0 / ws, st)
+            w = dist.all_reduce(stage, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            if w is not None and self.device.type != "cuda":
+                w.wait()            # gloo: the widening below runs on the host right away
+                w = None
+            call("ms_scale_cast", ptr(stage), _lib.MS_F32, ptr(chunk), _lib.MS_F64, n, 1.0, st)
+            return w
+        call("ms_scale_cast", ptr(chunk), dt_code(self.dtype), ptr(chunk), dt_code(self.dtype), n, 1.0 / ws, st)
+        return dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    def allreduce_mean(self, group=None, fp32=True):
         if not (dist.is_available() and dist.is_initialized()):
             return
-        ws = dist.get_world_size(group)
-        if ws == 1:
+        if dist.get_world_size(group) == 1:
             return
-        self.g.div_(ws)
-        dist.all_reduce(self.g, op=dist.ReduceOp.SUM, group=group)
+        self.reduce_range(0, self.numel, group, fp32)
 
     def clip_adam(self, lr, lr_dev, betas, eps, max_norm):
         st = stream()
@@ -103,7 +127,21 @@ class TrainStep:
     READY = {"hc": ("logits", "decoder", "classify_cluster"), "unet_out": ("style_emb",), "encoder_out": ("unet",)}
 
     def __init__(self, gan, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, use_graphs=True, group=None,
-                 input_modalities=("audio/log_mel_400",), description="train", overlap_allreduce=False):
+                 input_modalities=("audio/log_mel_400",), description="train", overlap_allreduce=True,
+                 exchange_dtype="fp32", rng_seed=None, check_agreement=False):
+        """One TrainStep (and one CUDA device) per process: the scratch arena, the direct-gradient switch and the
+        side stream are module-level state of mixstage_b200.ops, and the kernels' lazily set function attributes are
+        per process.
+
+        overlap_allreduce / exchange_dtype: data-parallel runs exchange the generator's gradients in four buckets
+        launched from backward hooks on a communication stream (decoder + logits + classifier first, ... audio encoder
+        last) while backward is still running, as fp32 ("fp32", default: half the bytes of the fp64 master gradients)
+        or in the master dtype ("native").
+        rng_seed: seed of the generator the D/G coin and the curriculum draw come from.  None = the process-global CPU
+        generator in a single-process run (the reference's own RNG consumption, gan.py:105 / jlcss.py:127) and a
+        dedicated generator seeded with the reference's seed 11212 on every rank of a data-parallel run: ranks then
+        choose the same (kind, branch) graphs whatever else consumes the global generator.
+        check_agreement: debug aid, all-gathers (kind, branch) every step and raises on disagreement (host sync)."""
         self.gan, self.G, self.D = gan, gan.G, gan.D
         self.fG = FlatState(self.G, skip=getattr(self.G, "UNUSED_PARAMETER_PREFIXES", ()))
         self.fD = FlatState(self.D)
@@ -122,6 +160,7 @@ class TrainStep:
         self.fake = None
         self.last_kind = None
         self.replays = 0
+        self.eager_steps = 0         # steps whose batch shape differed from the captured one (run eagerly)
         self.warmup_iters = 2
         self.side = ops.SideWork(dev) if dev.type == "cuda" else None      # weight-gradient GEMMs beside the dgrad chain
         self._tables = {}            # kind -> (signature, device table, n): entries of the batched weight re-tiling
@@ -131,8 +170,20 @@ class TrainStep:
         # opt-in: all-reduce the generator's gradients segment by segment while backward is still running (NOT yet
         # validated on multi-GPU hardware; numerics covered by tests/test_parallel_cpu.py with gloo)
         self.overlap = bool(overlap_allreduce)
+        if exchange_dtype not in ("fp32", "native"):
+            raise MixStageError("exchange_dtype must be 'fp32' or 'native'")
+        self.exchange_fp32 = exchange_dtype == "fp32"
         self.comm = torch.cuda.Stream(device=dev) if (self.overlap and dev.type == "cuda") else None
         self._reduced, self._works = [], []
+        if rng_seed is None and self._world() > 1:
+            rng_seed = 11212
+        self.rng = None if rng_seed is None else torch.Generator().manual_seed(int(rng_seed))
+        self.check_agreement = bool(check_agreement)
+        # [lambda_D, lambda_gan] in device memory: the GAN forward multiplies by these (captured graphs read the current
+        # values at replay); the injectable scheduler (gan.lambda_scheduler) is stepped once per real iteration below
+        self.lambda_dev = torch.tensor([float(gan.lambda_D), float(gan.lambda_gan)], dtype=self.fG.dtype, device=dev)
+        self._lam_host = [float(gan.lambda_D), float(gan.lambda_gan)]
+        self._old_tables = []        # superseded packed-weight tables stay alive as long as this object does
 
     # ------------------------------------------------------------------ host-side decisions
     def set_lr(self, lr):
@@ -144,15 +195,27 @@ class TrainStep:
         """Same draws, in the same order, as the reference: D/G coin (gan.py:105), then the curriculum draw inside
         G.forward (jlcss.py:127; consumed in eval mode too)."""
         gan, G = self.gan, self.G
-        coin = torch.rand(1).item()
+        coin = torch.rand(1, generator=self.rng).item()
         if kind is None:
             kind = "D" if coin < gan.D_prob else "G"
-        u = torch.rand(1).item()
+        u = torch.rand(1, generator=self.rng).item()
         if kind == "G":
             use_pose = u > G.thresh.step(True)
         else:
             G.thresh.step(False)
             use_pose = False
+        if self.check_agreement and self._world() > 1:
+            mine = (kind, bool(use_pose))
+            seen = [None] * self._world()
+            dist.all_gather_object(seen, mine, group=self.group)
+            if any(o != mine for o in seen):
+                raise MixStageError("TrainStep: ranks disagree on (step kind, curriculum branch): %s" % (seen,))
+        # the injectable lambda schedule advances once per real training iteration (reference: gan.py:103)
+        lam = [float(v) for v in gan.lambda_scheduler.step()]
+        gan.lambda_D, gan.lambda_gan = lam
+        if lam != self._lam_host:
+            self._lam_host = lam
+            self.lambda_dev.copy_(torch.tensor(lam, dtype=self.lambda_dev.dtype))
         return kind, bool(use_pose)
 
     # ------------------------------------------------------------------ the step body (eager, and what gets captured)
@@ -160,7 +223,9 @@ class TrainStep:
         gan, G = self.gan, self.G
         self.fG.zero_grad()
         self.fD.zero_grad()
+        old_force, old_lam = gan.force_step, gan.lambda_dev
         gan.force_step = kind
+        gan.lambda_dev = self.lambda_dev
         G.force_branch = "pose" if use_pose else "audio"
         # kernels accumulate parameter gradients straight into the flat buffers and draw their fp64 accumulators from
         # one arena cleared by a single memset (ops.py)
@@ -178,6 +243,7 @@ class TrainStep:
         finally:
             G.force_branch = None
             G.grad_ready_hook = None
+            gan.force_step, gan.lambda_dev = old_force, old_lam       # a direct gan(...) call draws its own coin again
             ops.DIRECT_GRADS = False
             ops.SIDE = None
             ops.arena.end()
@@ -187,7 +253,7 @@ class TrainStep:
         if overlap:
             self._finish_overlapped()
         else:
-            f.allreduce_mean(self.group)
+            f.allreduce_mean(self.group, self.exchange_fp32)
         f.clip_adam(self.lr, self.lr_dev, self.betas, self.eps, self.max_norm)
         if self.use_graphs:
             # keep every packed copy (bf16 re-tilings, fp32 biases, folded eval BatchNorm) of the sub-network that just
@@ -204,19 +270,17 @@ class TrainStep:
     def _reduce_range(self, beg, end):
         if end <= beg:
             return
-        chunk = self.fG.g[beg:end]
-        ws = self._world()
         if self.comm is None:                       # CPU (gloo): no streams
-            chunk.div_(ws)
-            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            self.fG.reduce_range(beg, end, self.group, self.exchange_fp32)
             return
         cur = torch.cuda.current_stream()
         self.comm.wait_stream(cur)                  # BatchNorm / bias gradients are written on the compute stream
         if self.side is not None:
             self.comm.wait_stream(self.side.stream) # weight gradients on the side stream
         with torch.cuda.stream(self.comm):
-            chunk.div_(ws)
-            self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            w = self.fG.reduce_range(beg, end, self.group, self.exchange_fp32, async_op=True)
+            if w is not None:
+                self._works.append(w)
 
     def _on_ready(self, stage):
         for top in self.READY.get(stage, ()):
@@ -269,6 +333,12 @@ class TrainStep:
         if cur is None or cur[0] != sig:
             if torch.cuda.is_current_stream_capturing():
                 raise MixStageError("internal: packed-weight table changed during graph capture")
+            if cur is not None:
+                # graphs captured so far launch the batched re-tiling with the OLD table (pointer and entry count): keep
+                # that table alive, and drop the graphs -- they would skip the new entries; the next step re-captures
+                self._old_tables.append(cur)
+                self.graphs.clear()
+                self.kernels_per_graph.clear()
             import ctypes
             arr = (_lib.PackEntry * len(entries))(*entries)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -350,11 +420,17 @@ class TrainStep:
             ops.bump_weight_epoch()
             return self.fake, self.losses
         key = (kind, use_pose)
+        if self.static is not None and any(s.shape != t.shape or s.dtype != t.dtype for s, t in zip(self.static, batch)):
+            # e.g. the trailing partial batch of a DataLoader without drop_last: the same body, launched eagerly
+            dev = self.fG.device
+            self.fake, self.losses = self._body(kind, use_pose, *[t.to(dev, non_blocking=True) for t in batch])
+            ops.bump_weight_epoch()
+            self._pver = (self.fG.p._version, self.fD.p._version)
+            self.eager_steps += 1
+            return self.fake, self.losses
         if key not in self.graphs:
             self._capture(key, batch)
         for s, t in zip(self.static, batch):
-            if s.shape != t.shape or s.dtype != t.dtype:
-                raise MixStageError("TrainStep: batch shape/dtype changed (%s vs %s); build a new TrainStep" % (tuple(t.shape), tuple(s.shape)))
             s.copy_(t, non_blocking=True)
         if self._pver != (self.fG.p._version, self.fD.p._version):
             self.refresh()           # someone wrote the parameters between steps (load_state_dict, ...)

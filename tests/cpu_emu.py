@@ -51,6 +51,11 @@ def ms_cast(src, sdt, dst, ddt, n, st):
     param(dst, n, ddt).copy_(param(src, n, sdt))
 
 
+def ms_scale_cast(src, sdt, dst, ddt, n, scale, st):
+    v = param(src, n, sdt).double() * scale
+    param(dst, n, ddt).copy_(v.to(param(dst, n, ddt).dtype))
+
+
 def ms_pack_conv_weight_f32(w, pdt, desc, wf, wt, st):
     d = _d(desc)
     g, taps = d.groups, d.kh * d.kw

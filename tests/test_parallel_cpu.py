@@ -33,6 +33,8 @@ def _worker(rank, world, port, out, overlap=None):
     G, D, gan = build(spec, T, "cpu", torch.float64)
     G.thresh.value, G.thresh.iters = 1.0, 1000
     parallel.sync_host_rng(11212)
+    if rank == 1:
+        torch.rand(3)              # ranks may consume the global generator differently: TrainStep draws from its own
     ts = M.TrainStep(gan, use_graphs=False, overlap_allreduce=bool(overlap))
     full = O.synth_inputs(world * B, T, spec)
     audio, pose, labels, style = parallel.shard_batch(full, rank, world)
@@ -80,7 +82,7 @@ def test_overlapped_allreduce_equals_single_allreduce(tmp_path):
     assert torch.equal(res[True][0]["pG"], res[True][1]["pG"])
 
 
-def test_shard_batch_and_flatgrads():
+def test_shard_batch():
     from mixstage_b200 import parallel
     t = torch.arange(24).view(8, 3)
     a, = parallel.shard_batch([t], 1, 4)

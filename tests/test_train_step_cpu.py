@@ -134,3 +134,56 @@ def test_packed_weight_recipes_hold_no_autograd_graph():
         assert seen > 50
     finally:
         M.set_precision("fp32")
+
+
+def test_lambda_schedule_is_injectable_and_force_step_is_restored():
+    """VERDICT a17 / ADVICE: the [lambda_D, lambda_gan] schedule is an injectable object stepped once per iteration, its
+    values reach the losses through device-resident scalars (what a captured graph reads), and TrainStep leaves
+    `gan.force_step` as it found it, so a later direct `gan(...)` call draws its own coin again (gan.py:105)."""
+    from mixstage_b200.gan import RampLambdaScheduler
+    spec = O.Spec(num_speakers=4)
+    torch.manual_seed(0)
+    G, D, gan = build(spec, 64, "cpu", torch.float64)
+    gan.lambda_scheduler = RampLambdaScheduler([1.0, 1.0], max_interval=1, max_lambda=3)      # 1, 2, 3, 3, ...
+    G.thresh.value, G.thresh.iters = 1.0, 1000
+    ts = M.TrainStep(gan, use_graphs=False)
+    audio, pose, labels, style = O.synth_inputs(2, 64, spec)
+    sd = O.synth_state(O.g_state_shapes(spec), G_SEED)
+    sdd = O.synth_state(O.d_state_shapes(spec.out_feats), D_SEED)
+    assert gan.force_step is None
+    want = [1.0, 2.0, 3.0]
+    for it in range(3):
+        with torch.no_grad():
+            for k, v in G.state_dict().items():
+                sd[k] = v.clone()
+            for k, v in D.state_dict().items():
+                sdd[k] = v.clone()
+        _, losses = ts.step(audio, labels, pose, style, kind="G")
+        assert gan.force_step is None and gan.lambda_dev is None
+        assert ts.lambda_dev.tolist() == [want[it], want[it]]
+        with torch.no_grad():
+            _, l2, _ = O.gan_forward(sd, sdd, spec, audio, labels, pose, style, step="G", lambda_gan=want[it])
+        assert abs(float(losses[1]) - float(l2[1])) < 2e-4 * max(1.0, abs(float(l2[1]))), (it, losses, l2)
+    # a direct training-mode call consumes exactly one global-RNG draw for the coin and one for the curriculum
+    gan.train()
+    torch.manual_seed(123)
+    gan([audio, labels], pose, input_modalities=["audio/log_mel_400"], style=style, sample_flag=0, description="train")
+    after = torch.rand(1).item()
+    torch.manual_seed(123)
+    torch.rand(1), torch.rand(1)
+    assert torch.rand(1).item() == after
+
+
+def test_own_generator_isolates_the_coin_flips_from_the_global_rng():
+    spec = O.Spec(num_speakers=4)
+    G, D, gan = build(spec, 64, "cpu", torch.float64)
+    kinds = []
+    for extra in (0, 5):
+        ts = M.TrainStep.__new__(M.TrainStep)
+        ts.gan, ts.G, ts.group, ts.check_agreement = gan, G, None, False
+        ts.rng = torch.Generator().manual_seed(11212)
+        ts.lambda_dev, ts._lam_host = torch.ones(2, dtype=torch.float64), [1.0, 1.0]
+        torch.manual_seed(7)
+        torch.rand(extra)                      # another consumer of the global generator on "this rank"
+        kinds.append([ts._decide(None) for _ in range(16)])
+    assert kinds[0] == kinds[1] and {k for k, _ in kinds[0]} == {"G", "D"}

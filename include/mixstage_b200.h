@@ -186,6 +186,54 @@ int ms_wgrad_bf16(const ms_igemm_desc* d, const void* x, const void* dz, float* 
 int ms_unpack_igemm_wgrad(const float* dwp, int Cout, int Cin_g, int taps_total, int ntaps, int kpad, void* dw, int pdt,
                           int nsplit, int accumulate, void* stream);
 
+/* ---- Fused TRAINING blocks (csrc/conv_train.cu): ConvNormRelu.forward in train mode (layers.py:78: conv -> BatchNorm with
+ * batch statistics -> LeakyReLU, plus UNet1D's `upconv(x) + residual`, layers.py:151) and its backward, ONE persistent
+ * cooperative launch each (grid <= #SMs, device-wide barriers between the phases) instead of three dependent kernels. */
+typedef struct ms_block_bn {
+  int32_t C;                /* channels = num_classes * class_n of the GEMM */
+  int32_t pdt;              /* dtype of gamma / beta / conv_bias / running statistics: MS_F32 or MS_F64 */
+  int32_t training;         /* forward: must be 1; backward: 1 = batch-statistics formula, 0 = dz = scale * dy * act' */
+  float momentum, eps, slope;
+  const void* gamma;
+  const void* beta;
+  const void* conv_bias;    /* nullable; the GEMM output excludes it (enters the running-mean update only) */
+  void* running_mean;       /* updated in place (forward) */
+  void* running_var;
+  int64_t* num_batches_tracked;   /* nullable, += 1 (forward) */
+  double* sums;             /* [2][C] ZERO-FILLED by the caller: forward sum / sum of squares; backward dgamma / dbeta */
+  float* ss;                /* [4][C] scale, shift, mean, rstd: written by the forward, read by the backward */
+} ms_block_bn;
+/* Forward: z = igemm(d, a, w) (fp32, dense (rows, C); ZERO-FILLED by the caller when d->split_k > 1: k-slices combine with
+ * vector reductions), batch statistics of z, finalize (as ms_bn_finalize, training) and y = act(z*scale + shift)
+ * [up2: y[b,2l+r,:] = act(..)[b,l,:] + res[b,2l+r,:]] as fp32 (y, nullable) and/or operand planes (nullable).
+ * d: forward descriptor with out_dtype MS_F32, epilogue 0.  sync: 4 zero-filled bytes (device barrier counter). */
+int ms_conv_block_train_fwd(const ms_igemm_desc* d, const void* a, const void* w, float* z, const ms_block_bn* bn,
+                            float* y, void* planes, int pfmt, int64_t pstride, const float* res, const void* res_planes,
+                            int res_pfmt, int64_t res_pstride, int up2, void* sync, void* stream);
+/* bn->training == 0 turns the same launch into the small-batch form of the INFERENCE block (eval-mode ConvNormRelu with
+ * the BatchNorm folded into bn->ss = [scale, shift] by ms_bn_finalize; no statistics phase, nothing updated): at batch
+ * 16 a layer has fewer tiles than SMs, and k-slices across the whole machine + one barrier beat ms_igemm_bf16_fused's one
+ * CTA per tile.  The skip tensor of up2 comes as fp32 (res) or as operand planes (res_planes, res_pfmt, res_pstride). */
+/* Backward: dz = d(act(bn(z)))/dz . dy -> operand planes dz_planes (row stride C; the A operand of the input-gradient
+ * GEMM and of ms_wgrad_bf16[_acc]); grad_gamma / grad_beta (nullable, dtype gdt) += dgamma / dbeta; then, when dg is not
+ * NULL, dx = igemm(dg, dz_planes, wt) (fp32; ZERO-FILLED by the caller when dg->split_k > 1).  dy has 2*rows_per_seq rows
+ * per sequence when up2 (both upsampled rows feed the same z row). */
+int ms_conv_block_train_bwd(const ms_igemm_desc* dg, const float* dy, const float* z, const ms_block_bn* bn,
+                            int64_t rows, int up2, int rows_per_seq, void* dz_planes, int pfmt, int64_t pstride,
+                            void* grad_gamma, void* grad_beta, int gdt, const void* wt, float* dx, void* sync,
+                            void* stream);
+/* ms_wgrad_bf16 with every pixel slice ADDING its tile into one fp32 accumulator acc[classes*class_n][ntaps][cchunks*64]
+ * (zero-filled by the caller once per step) -- no per-slice partials, no summing kernel. */
+int ms_wgrad_bf16_acc(const ms_igemm_desc* d, const void* x, const void* dz, float* acc, void* stream);
+/* Every weight-gradient accumulator of a sub-network -> its parameter-gradient tensor (Cout, Cin/g, taps) in ONE launch:
+ * dw[o][c][t] (+)= acc[o][t][c].  table_dev: DEVICE array. */
+typedef struct ms_wgrad_entry {
+  const void* acc;
+  void* dw;
+  int32_t pdt, Cout, Cin_g, taps, kpad, accumulate;
+} ms_wgrad_entry;
+int ms_unpack_wgrad_multi(const ms_wgrad_entry* table_dev, int n_entries, int blocks_per_entry, void* stream);
+
 /* ---- BatchNorm (+LeakyReLU) pieces, nn.BatchNorm1d/2d at layers.py:64,70 and
  * nn.LeakyReLU(0.2) at layers.py:72-73, applied as in ConvNormRelu.forward (:78) ------ */
 /* column sums over rows: sum[c] += x[r,c], sumsq[c] += x[r,c]^2 (double accumulators,

@@ -44,7 +44,23 @@ class PackEntry(ctypes.Structure):
                                       "ntaps", "kpad")] + [("srctap", ctypes.c_int16 * MAX_TAPS)]
 
 
+class BlockBn(ctypes.Structure):
+    """ms_block_bn (include/mixstage_b200.h): the BatchNorm + activation side of a fused block."""
+    _fields_ = [("C", ctypes.c_int32), ("pdt", ctypes.c_int32), ("training", ctypes.c_int32),
+                ("momentum", ctypes.c_float), ("eps", ctypes.c_float), ("slope", ctypes.c_float),
+                ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("conv_bias", ctypes.c_void_p),
+                ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p), ("num_batches_tracked", ctypes.c_void_p),
+                ("sums", ctypes.c_void_p), ("ss", ctypes.c_void_p)]
+
+
+class WgradEntry(ctypes.Structure):
+    """ms_wgrad_entry (include/mixstage_b200.h)."""
+    _fields_ = [("acc", ctypes.c_void_p), ("dw", ctypes.c_void_p)] + [
+        (n, ctypes.c_int32) for n in ("pdt", "Cout", "Cin_g", "taps", "kpad", "accumulate")]
+
+
 _P, _I, _L, _F, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+_BN = ctypes.POINTER(BlockBn)
 _CD = ctypes.POINTER(ConvDesc)
 _GD = ctypes.POINTER(IgemmDesc)
 _S16 = ctypes.POINTER(ctypes.c_int16)
@@ -68,6 +84,10 @@ PROTOTYPES = {
     "ms_pack_igemm_weight_bf16": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _S16, _P, _P, _P],
     "ms_pack_igemm_weight_multi": [_P, _I, _I, _P],
     "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],
+    "ms_conv_block_train_fwd": [_GD, _P, _P, _P, _BN, _P, _P, _I, _L, _P, _P, _I, _L, _I, _P, _P],
+    "ms_conv_block_train_bwd": [_GD, _P, _P, _BN, _L, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P],
+    "ms_wgrad_bf16_acc": [_GD, _P, _P, _P, _P],
+    "ms_unpack_wgrad_multi": [_P, _I, _I, _P],
     "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],
     "ms_col_stats_f32": [_P, _L, _I, _P, _P, _P],
     "ms_bn_finalize": [_P, _P, _L, _I, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P],

@@ -210,30 +210,6 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 }
 
 // ------------------------------------------------------------------ BN apply + LeakyReLU (+ upsample x2 + skip)
-__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-// hi plane always; lo plane (residual of the bf16 rounding) when fmt == MS_BF16X2.  i = element index (multiple of 4)
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* __restrict__ pl, int fmt, int64_t ps, int64_t i, float4 o) {
-  __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&h0);
-  u.y = *reinterpret_cast<uint32_t*>(&h1);
-  *reinterpret_cast<uint2*>(pl + i) = u;
-  if (fmt == MS_BF16X2) {
-    uint2 v;
-    v.x = pack_bf162(o.x - __bfloat162float(h0.x), o.y - __bfloat162float(h0.y));
-    v.y = pack_bf162(o.z - __bfloat162float(h1.x), o.w - __bfloat162float(h1.y));
-    *reinterpret_cast<uint2*>(pl + ps + i) = v;
-  }
-}
-__device__ __forceinline__ void store_planes1(__nv_bfloat16* __restrict__ pl, int fmt, int64_t ps, int64_t i, float o) {
-  __nv_bfloat16 h = __float2bfloat16_rn(o);
-  pl[i] = h;
-  if (fmt == MS_BF16X2) pl[ps + i] = __float2bfloat16_rn(o - __bfloat162float(h));
-}
-
 template <int VEC>
 __global__ void bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                   float slope, int64_t rows_out, int C, float* __restrict__ y,

@@ -68,6 +68,8 @@ class _Arena:
     def __init__(self):
         self.buf, self.keep = None, []
         self.off = self.used = self.need = 0
+        self.buf32 = None           # second pool: zero-filled fp32 (split-K outputs that k-slices reduce into)
+        self.off32 = self.used32 = self.need32 = 0
         self.active = False
 
     def begin(self, device):
@@ -77,12 +79,35 @@ class _Arena:
             self.buf = torch.zeros(max(self.need, 1 << 15), dtype=torch.float64, device=device)
         else:
             self.buf.zero_()
+        if self.need32:
+            if self.buf32 is None or self.buf32.device != device or self.buf32.numel() < self.need32:
+                if self.buf32 is not None:
+                    self.keep.append(self.buf32)
+                self.buf32 = torch.zeros(self.need32, dtype=torch.float32, device=device)
+            else:
+                self.buf32.zero_()
         self.off = self.used = 0
+        self.off32 = self.used32 = 0
         self.active = True
 
     def end(self):
         self.need = max(self.need, self.used)
+        self.need32 = max(self.need32, self.used32)
         self.active = False
+
+    def take_f32(self, shape, device):
+        """Zero-filled fp32 tensor (an output that split-K slices reduce into): from the per-step pool inside a train
+        step (one memset per step for all of them), else torch.zeros."""
+        n = 1
+        for d_ in shape:
+            n *= d_
+        n_al = (n + 63) // 64 * 64             # 256-byte granularity: TMA / vector accesses stay aligned
+        self.used32 += n_al
+        if not self.active or self.buf32 is None or self.buf32.device != device or self.off32 + n_al > self.buf32.numel():
+            return torch.zeros(shape, dtype=torch.float32, device=device)
+        t = self.buf32[self.off32:self.off32 + n].view(shape)
+        self.off32 += n_al
+        return t
 
     def take(self, shape, device):
         n = 1
@@ -128,6 +153,47 @@ class SideWork:
 
 
 SIDE = None                  # SideWork of the running train step (set by TrainStep), else None
+
+import os as _os
+# Fused blocks (csrc/conv_train.cu): training-mode ConvNormRelu forward / backward as ONE cooperative launch each, and the
+# small-batch inference block with split-K.  MS_FUSED_BLOCKS=0 keeps the three-kernel path (A/B timing, debugging).
+FUSED_BLOCKS = _os.environ.get("MS_FUSED_BLOCKS", "1") != "0"
+
+
+class WgradAccum:
+    """Persistent fp32 weight-gradient accumulators of one kind of train step (ms_wgrad_bf16_acc adds every pixel slice's
+    tile in place) and the list of (accumulator -> parameter gradient) conversions that ONE ms_unpack_wgrad_multi launch
+    performs at the end of backward.  Accumulators are carved from 32 MB chunks and never move (captured graphs hold
+    their addresses); the step zero-fills the chunks before backward."""
+    CHUNK = 8 << 20            # elements
+
+    def __init__(self):
+        self.chunks, self.off = [], 0
+        self.slots = {}         # id(PackedWeight) -> accumulator
+        self.entries = {}       # (acc ptr, sink ptr) -> WgradEntry fields
+
+    def acc_for(self, packed, n, device):
+        t = self.slots.get(id(packed))
+        if t is not None and t.numel() == n and t.device == device:
+            return t
+        n_al = (n + 63) // 64 * 64
+        if not self.chunks or self.chunks[-1].device != device or self.off + n_al > self.chunks[-1].numel():
+            self.chunks.append(torch.zeros(max(self.CHUNK, n_al), dtype=torch.float32, device=device))
+            self.off = 0
+        t = self.chunks[-1][self.off:self.off + n]
+        self.off += n_al
+        self.slots[id(packed)] = t
+        return t
+
+    def note(self, acc, sink, Cout, Cin_g, taps, kpad, dtype):
+        self.entries[(acc.data_ptr(), sink.data_ptr())] = (acc.data_ptr(), sink.data_ptr(), dt_code(dtype), Cout, Cin_g, taps, kpad, 1)
+
+    def zero(self):
+        for c in self.chunks:
+            c.zero_()
+
+
+WACC = None                  # WgradAccum of the running train step (set by TrainStep), else None: per-slice partials
 
 
 def _sink(p):
@@ -625,7 +691,6 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     pf, pd = packed.tc_plans(x.shape, Cout, cfg, rs, need_dx, 3 if split else 1)
     wp, wps = packed.get_tc(weight, pf, fmt, cfg.groups)
     rows = B * desc.Ho * desc.Wo
-    z = torch.empty((B, desc.Ho, desc.Wo, Cout), dtype=torch.float32, device=dev)
     d = pf.desc
     igemm.set_planes(pf, split, xp.ps, wps, 0)
     d.out_dtype = _lib.MS_F32
@@ -633,10 +698,17 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     d.epilogue, d.slope = (2 if fuse_act else 0), cfg.slope
     b32 = None if cfg.has_bn else packed.get_bias(bias)
     d.split_k = 1 if fuse_act else igemm.igemm_split(d, 3 if split else 1)
-    d.out_numel = z.numel()
     global last_gemm_flops
     last_gemm_flops = ctx.flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
-    call("ms_igemm_bf16", d, ptr(xp.t), ptr(wp), ptr(b32), None, None, ptr(z), st)
+    # training-mode BatchNorm blocks: GEMM + statistics + normalise in ONE cooperative launch (csrc/conv_train.cu)
+    fused = FUSED_BLOCKS and cfg.has_bn and training and Cout % 16 == 0 and Cout <= 8192
+    zshape = (B, desc.Ho, desc.Wo, Cout)
+    if fused:
+        z = arena.take_f32(zshape, dev) if d.split_k > 1 else torch.empty(zshape, dtype=torch.float32, device=dev)
+    else:
+        z = torch.empty(zshape, dtype=torch.float32, device=dev)
+        d.out_numel = z.numel()
+        call("ms_igemm_bf16", d, ptr(xp.t), ptr(wp), ptr(b32), None, None, ptr(z), st)
     ctx.tc, ctx.fmt = True, fmt
     ctx.cfg, ctx.desc, ctx.training, ctx.up2 = cfg, desc, training, up2
     ctx.rows, ctx.Cout, ctx.rs = rows, Cout, rs
@@ -645,16 +717,62 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     ctx.x_shape, ctx.xp_meta = tuple(x.shape), (xp.rs, xp.ps)
     ctx.param_dtypes = (weight.dtype, None if bias is None else bias.dtype)
     ctx.has_res = residual is not None
+    ctx.packed = packed
+    ctx.fused = False
     if not cfg.has_bn:
         ctx.save_for_backward(xp.t, z)
         return z
-    ss = _bn_scale_shift(z, rows, Cout, gamma, beta, bias, bn_buffers, training, cfg, packed)
-    y, yp = _bn_act(z, ss, cfg, rows, Cout, desc, residual, up2, fmt, True)
+    if fused:
+        ss, y, yp = _fused_block_fwd(d, xp, wp, z, rows, Cout, gamma, beta, bias, bn_buffers, cfg, packed, desc, residual,
+                                     up2, fmt)
+        ctx.fused = True
+    else:
+        ss = _bn_scale_shift(z, rows, Cout, gamma, beta, bias, bn_buffers, training, cfg, packed)
+        y, yp = _bn_act(z, ss, cfg, rows, Cout, desc, residual, up2, fmt, True)
     ctx.gamma_dtype = gamma.dtype
     ctx.save_for_backward(xp.t, z, ss)
     if yp is not None and carrier is not None:
         carrier.planes = yp           # attached to the output by conv_block (autograd returns a fresh tensor object)
     return y
+
+
+def _block_bn(C, gamma, beta, cbias, bn_buffers, cfg, training, sums, ss):
+    b = _lib.BlockBn()
+    b.C, b.pdt, b.training = C, dt_code(gamma.dtype), 1 if training else 0
+    b.momentum, b.eps, b.slope = cfg.momentum, cfg.eps, (cfg.slope if cfg.act else 1.0)
+    b.gamma, b.beta, b.conv_bias = ptr(gamma), ptr(beta), ptr(cbias)
+    if bn_buffers is not None:
+        b.running_mean, b.running_var, b.num_batches_tracked = ptr(bn_buffers[0]), ptr(bn_buffers[1]), ptr(bn_buffers[2])
+    b.sums, b.ss = ptr(sums), ptr(ss)
+    return b
+
+
+def _fused_block_fwd(d, xp, wp, z, rows, Cout, gamma, beta, cbias, bn_buffers, cfg, packed, desc, residual, up2, fmt):
+    """z = igemm, batch statistics, finalize, y = act(bn(z)) [upsample x2 + skip] -> fp32 + operand planes: one launch."""
+    global _stats_epoch
+    dev = z.device
+    if cbias is not None and cbias.dtype != gamma.dtype:
+        raise MixStageError("conv bias and BatchNorm parameters must share a dtype")
+    _stats_epoch += 1
+    packed.stats_epoch += 1
+    B = z.shape[0]
+    if up2:
+        if desc.Ho != 1:
+            raise MixStageError("upsample+skip fusion is 1-D only")
+        oshape = (B, 1, 2 * desc.Wo, Cout)
+        res = _f32c(residual)
+        if tuple(res.shape) != oshape:
+            raise MixStageError("skip tensor shape %s != %s" % (tuple(res.shape), oshape))
+    else:
+        oshape, res = tuple(z.shape), None
+    y = torch.empty(oshape, dtype=torch.float32, device=dev)
+    yp = alloc_planes(y.numel() // Cout, Cout, fmt, dev)
+    ss = torch.empty(4, Cout, dtype=torch.float32, device=dev)
+    acc = arena.take((2 * Cout + 2,), dev)             # sum, sumsq, barrier counter
+    bn = _block_bn(Cout, gamma, beta, cbias, bn_buffers, cfg, True, acc, ss)
+    call("ms_conv_block_train_fwd", d, ptr(xp.t), ptr(wp), ptr(z), bn, ptr(y), ptr(yp.t), yp.fmt, yp.ps, ptr(res), None, 0, 0,
+         1 if up2 else 0, acc.data_ptr() + 16 * Cout, stream())
+    return ss, y, yp
 
 
 def _tc_backward(ctx, dy):
@@ -667,7 +785,42 @@ def _tc_backward(ctx, dy):
     split = fmt == MS_BF16X2
     dzp = alloc_planes(rows, Cout, fmt, dev)
     wdt, bdt = ctx.param_dtypes
-    if cfg.has_bn:
+    pf, pd = ctx.plans
+    xrs, xps = ctx.xp_meta
+    B, H, W, Cin = ctx.x_shape
+    fused_dx = None
+    if cfg.has_bn and ctx.fused and ctx.training and need_g and need_be and (ctx.sinks[2] is None) == (ctx.sinks[3] is None):
+        # BatchNorm backward (reductions + apply -> dz planes, affine gradients) and the input-gradient GEMM: one launch
+        xpt, z, ss = ctx.saved_tensors
+        sg, sb = ctx.sinks[2], ctx.sinks[3]
+        if sg is None:
+            dgamma = torch.zeros(Cout, dtype=ctx.gamma_dtype, device=dev)
+            dbeta = torch.zeros(Cout, dtype=ctx.gamma_dtype, device=dev)
+            sg, sb = dgamma, dbeta
+        red = arena.take((2 * Cout + 2,), dev)         # dgamma, dbeta, barrier counter
+        bn = _lib.BlockBn()
+        bn.C, bn.pdt, bn.training = Cout, dt_code(ctx.gamma_dtype), 1
+        bn.momentum, bn.eps, bn.slope = cfg.momentum, cfg.eps, (cfg.slope if cfg.act else 1.0)
+        bn.sums, bn.ss = ptr(red), ptr(ss)
+        bn.gamma = bn.beta = ptr(ss)                    # not read by the backward; non-NULL for the argument check
+        dgd, wtp, dxf = None, None, None
+        global last_gemm_flops
+        last_gemm_flops = ctx.flops if need_x else 0.0
+        if need_x:
+            wt, wtps = ctx.wt
+            igemm.set_planes(pd, split, dzp.ps, wtps, 0)
+            pd.desc.split_k = igemm.igemm_split(pd.desc, 3 if split else 1)
+            dshape = (B, H, W, xrs)
+            dxf = arena.take_f32(dshape, dev) if pd.desc.split_k > 1 else torch.empty(dshape, dtype=torch.float32, device=dev)
+            dgd, wtp = pd.desc, wt
+        call("ms_conv_block_train_bwd", dgd, ptr(dy), ptr(z), bn, rows, 1 if ctx.up2 else 0, desc.Wo, ptr(dzp.t), fmt, dzp.ps,
+             ptr(sg), ptr(sb), dt_code(ctx.gamma_dtype), ptr(wtp), ptr(dxf), red.data_ptr() + 16 * Cout, st)
+        if need_x:
+            fused_dx = dxf if xrs == Cin else dxf[..., :Cin]
+        dz = None
+        if ctx.has_res and need_res:
+            dres = dy
+    elif cfg.has_bn:
         xpt, z, ss = ctx.saved_tensors
         need_f32 = need_b and bdt is not None and not ctx.training
         dz, dgamma, dbeta = _bn_act_backward(ctx, dy, z, ss, need_f32, dzp)
@@ -682,18 +835,24 @@ def _tc_backward(ctx, dy):
             dz = dy
             call("ms_to_planes", ptr(dy), rows, Cout, Cout, ptr(dzp.t), fmt, dzp.ps, st)
     dbias = _bias_grad(ctx, dz)
-    pf, pd = ctx.plans
-    xrs, xps = ctx.xp_meta
-    B, H, W, Cin = ctx.x_shape
     Cin_g = Cin // cfg.groups
-    global last_gemm_flops
     last_gemm_flops = ctx.flops
     if need_w:
         igemm.set_planes(pf, split, xps, 0, dzp.ps)
         nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc, npass=3 if split else 1)
         pf.desc.split_k = nsplit
         sink = ctx.sinks[0]
-        if sink is not None and SIDE is not None:
+        if sink is not None and WACC is not None and FUSED_BLOCKS:
+            # every pixel slice adds into ONE persistent accumulator; the step converts all of them in one launch
+            acc = WACC.acc_for(ctx.packed, pf.wp_numel, dev)
+            WACC.note(acc, sink, Cout, Cin_g, cfg.kh * cfg.kw, pf.kpad, wdt)
+            if SIDE is not None:
+                with SIDE.fork(xpt, dzp.t):
+                    call("ms_wgrad_bf16_acc", pf.desc, ptr(xpt), ptr(dzp.t), ptr(acc), stream())
+            else:
+                call("ms_wgrad_bf16_acc", pf.desc, ptr(xpt), ptr(dzp.t), ptr(acc), st)
+            dwp = None
+        elif sink is not None and SIDE is not None:
             with SIDE.fork(xpt, dzp.t):
                 dwp = torch.empty(nsplit * pf.wp_numel, dtype=torch.float32, device=dev)
                 call("ms_wgrad_bf16", pf.desc, ptr(xpt), ptr(dzp.t), ptr(dwp), stream())
@@ -713,7 +872,9 @@ def _tc_backward(ctx, dy):
             dw = torch.empty((Cout, Cin_g, cfg.kh, cfg.kw), dtype=wdt, device=dev)
             call("ms_unpack_igemm_wgrad", ptr(dwp), Cout, Cin_g, cfg.kh * cfg.kw, pf.desc.ntaps, pf.kpad, ptr(dw),
                  dt_code(wdt), nsplit, 0, st)
-    if need_x:
+    if fused_dx is not None:
+        dx = fused_dx
+    elif need_x:
         wt, wtps = ctx.wt
         igemm.set_planes(pd, split, dzp.ps, wtps, 0)
         dxf = torch.empty((B, H, W, xrs), dtype=torch.float32, device=dev)
@@ -758,9 +919,28 @@ def _tc_eval(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, up
         res = planes_of(residual, fmt, Cout)
     y32 = torch.empty(oshape, dtype=torch.float32, device=dev) if want != "planes" else None
     yp = alloc_planes(rows_out, Cout, fmt, dev) if want != "f32" else None
+    global last_gemm_flops
+    ksplit = igemm.igemm_split(d, 3 if split else 1) if (FUSED_BLOCKS and cfg.has_bn and row_w is None and Cout <= 8192) else 1
+    if ksplit > 1:
+        # small batch: fewer tiles than SMs.  k-slices over the whole machine reduce into an fp32 tile in L2, one device-wide
+        # barrier, then the folded BatchNorm + LeakyReLU (+ upsample/skip) -> planes / fp32: still ONE launch (conv_train.cu)
+        d.epilogue, d.split_k, d.out_dtype = 0, ksplit, _lib.MS_F32
+        igemm.set_planes(pf, split, xp.ps, wps, 0)
+        z = arena.take_f32((B, Ho, Wo, Cout), dev)
+        sync = arena.take((2,), dev)
+        bn = _block_bn(Cout, gamma, beta, None, None, cfg, False, None, ss)
+        bn.sums = ptr(sync)                  # unused in inference form; non-NULL for the argument check
+        last_gemm_flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
+        call("ms_conv_block_train_fwd", d, ptr(xp.t), ptr(wp), ptr(z), bn, ptr(y32), ptr(yp.t) if yp is not None else None,
+             fmt, yp.ps if yp is not None else 0, None, ptr(res.t) if res is not None else None, fmt,
+             res.ps if res is not None else 0, 1 if up2 else 0, ptr(sync), st)
+        if y32 is not None:
+            if yp is not None:
+                y32._ms_planes = yp
+            return y32
+        return planes_view(yp, oshape)
     igemm.set_planes(pf, split, xp.ps, wps, yp.ps if yp is not None else 0)
     d.out_dtype = fmt if yp is not None else _lib.MS_F32
-    global last_gemm_flops
     last_gemm_flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
     if row_w is not None:
         # soft cluster weight of every row applied in the epilogue (classes = clusters): the mixture moves into the GEMMs

@@ -183,6 +183,10 @@ class TrainStep:
         # values at replay); the injectable scheduler (gan.lambda_scheduler) is stepped once per real iteration below
         self.lambda_dev = torch.tensor([float(gan.lambda_D), float(gan.lambda_gan)], dtype=self.fG.dtype, device=dev)
         self._lam_host = [float(gan.lambda_D), float(gan.lambda_gan)]
+        # persistent weight-gradient accumulators, one set per kind of step (a G-step also produces the discriminator's
+        # -- unused -- weight gradients, a D-step only the discriminator's), and the device tables of their conversion
+        self.wacc = {"G": ops.WgradAccum(), "D": ops.WgradAccum()}
+        self._wtables = {}
         self._old_tables = []        # superseded packed-weight tables stay alive as long as this object does
 
     # ------------------------------------------------------------------ host-side decisions
@@ -232,6 +236,9 @@ class TrainStep:
         ops.arena.begin(self.fG.device)
         ops.DIRECT_GRADS = True
         ops.SIDE = self.side
+        wacc = self.wacc[kind]
+        wacc.zero()
+        ops.WACC = wacc
         overlap = self.overlap and kind == "G" and self._world() > 1
         self._reduced, self._works = [], []
         G.grad_ready_hook = self._on_ready if overlap else None
@@ -246,9 +253,11 @@ class TrainStep:
             gan.force_step, gan.lambda_dev = old_force, old_lam       # a direct gan(...) call draws its own coin again
             ops.DIRECT_GRADS = False
             ops.SIDE = None
+            ops.WACC = None
             ops.arena.end()
             if self.side is not None:
                 self.side.join()
+        self._flush_wgrads(kind)
         f = self.fG if kind == "G" else self.fD
         if overlap:
             self._finish_overlapped()
@@ -346,6 +355,28 @@ class TrainStep:
             self._tables[kind] = cur
         call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 48, stream())
 
+    def _flush_wgrads(self, kind):
+        """Every weight-gradient accumulator of this step -> the flat gradient buffers, one launch."""
+        ents = list(self.wacc[kind].entries.values())
+        if not ents:
+            return
+        sig = tuple(ents)
+        cur = self._wtables.get(kind)
+        if cur is None or cur[0] != sig:
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise MixStageError("internal: weight-gradient table changed during graph capture")
+            if cur is not None:
+                self._old_tables.append(cur)
+                self.graphs.clear()
+                self.kernels_per_graph.clear()
+            arr = (_lib.WgradEntry * len(ents))()
+            for i, e in enumerate(ents):
+                (arr[i].acc, arr[i].dw, arr[i].pdt, arr[i].Cout, arr[i].Cin_g, arr[i].taps, arr[i].kpad, arr[i].accumulate) = e
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            cur = (sig, host.to(self.fG.device), len(ents))
+            self._wtables[kind] = cur
+        call("ms_unpack_wgrad_multi", ptr(cur[1]), cur[2], 32, stream())
+
     def refresh(self):
         """Call after changing parameters or BatchNorm buffers from outside (load_state_dict, manual edits)."""
         self._refresh("G")
@@ -383,11 +414,12 @@ class TrainStep:
         l0 = _lib.LAUNCHES
         with torch.cuda.graph(g):
             fake, losses = self._body(kind, use_pose, *self.static)
-        self.kernels_per_graph[key] = _lib.LAUNCHES - l0      # C-ABI launches recorded in this graph
+        n_launch = _lib.LAUNCHES - l0                         # C-ABI launches recorded in this graph
         torch.cuda.synchronize(dev)
         self._restore(snap)
-        self.refresh()               # the restored parameters' packed copies
+        self.refresh()               # the restored parameters' packed copies (may drop OTHER graphs: see _refresh)
         self.graphs[key] = (g, fake, losses)
+        self.kernels_per_graph[key] = n_launch
 
     def _snapshot(self):
         bufs = [b for m in (self.G, self.D) for b in m.buffers()]

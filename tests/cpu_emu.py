@@ -528,6 +528,72 @@ def ms_wgrad_bf16(desc, x, dz, dwp, st):
             out[q * d.class_n:(q + 1) * d.class_n, t] = acc
 
 
+def _ptr(v):
+    if v is None:
+        return 0
+    return int(v) if not hasattr(v, "value") else int(v.value or 0)
+
+
+def ms_conv_block_train_fwd(desc, a, w, z, bn, y, planes, pfmt, pstride, res, res_planes, res_pfmt, res_pstride, up2, sync, st):
+    """Fused block = the composition of the unfused specifications (igemm, statistics + finalize, normalise)."""
+    d, b = _d(desc), _d(bn)
+    C = d.num_classes * d.class_n
+    Wo, Ho, Bo = d.out_dims
+    rows = Wo * Ho * Bo
+    assert b.C == C and d.epilogue == 0 and d.out_dtype == 0
+    f32(z, rows * C).zero_()
+    _igemm(desc, a, w, None, None, None, z, None, None, 0, 0, 0)
+    ss = _ptr(b.ss)
+    if b.training:
+        sums = _ptr(b.sums)
+        ms_bn_stats_finalize(z, rows, C, sums, sums + 8 * C, None, _ptr(b.gamma), _ptr(b.beta), _ptr(b.conv_bias) or None,
+                             _ptr(b.running_mean), _ptr(b.running_var), _ptr(b.num_batches_tracked) or None, b.pdt, b.momentum, b.eps,
+                             ss, ss + 4 * C, ss + 8 * C, ss + 12 * C, st)
+    rows_out = 2 * rows if up2 else rows
+    r32 = res
+    if up2 and not res:
+        R = bf16(res_planes, rows_out * C).float()
+        if res_pfmt == 3:
+            R = R + bf16(res_planes + 2 * res_pstride, rows_out * C).float()
+        keep = R.contiguous()
+        r32 = keep.data_ptr()
+    tmp = torch.empty(rows_out * C, dtype=torch.float32)
+    ms_bn_act_fwd_f32(z, ss, ss + 4 * C, b.slope, rows, C, y if y else tmp.data_ptr(), r32 if up2 else None, up2, Wo,
+                      planes, pfmt, pstride, st)
+
+
+def ms_conv_block_train_bwd(dg, dy, z, bn, rows, up2, L, dzp, pfmt, pstride, ggamma, gbeta, gdt, wt, dx, sync, st):
+    b = _d(bn)
+    C = b.C
+    ss, red = _ptr(b.ss), _ptr(b.sums)
+    ms_bn_act_bwd_reduce_f32(dy, z, ss, ss + 4 * C, ss + 8 * C, ss + 12 * C, b.slope, rows, C, up2, L, red, red + 8 * C, st)
+    ms_bn_act_bwd_apply_f32(dy, z, ss, ss + 4 * C, ss + 8 * C, ss + 12 * C, b.slope, rows, C, up2, L, red, red + 8 * C, b.training,
+                            None, dzp, pfmt, pstride, ggamma, gbeta, gdt, st)
+    if dg is not None:
+        d = _d(dg)
+        Wo, Ho, Bo = d.out_dims
+        _igemm(dg, dzp, wt, None, None, None, dx, None, None, 0, 0, 0)
+
+
+def ms_wgrad_bf16_acc(desc, x, dz, acc, st):
+    d = _d(desc)
+    kpad = d.cchunks * 64
+    n = d.num_classes * d.class_n * d.ntaps * kpad
+    old_split = d.split_k
+    tmp = torch.zeros(max(1, old_split) * n, dtype=torch.float32)
+    ms_wgrad_bf16(desc, x, dz, tmp.data_ptr(), st)
+    f32(acc, n).add_(tmp.view(max(1, old_split), n).sum(0))
+
+
+def ms_unpack_wgrad_multi(table, n_entries, blocks, st):
+    from mixstage_b200 import _lib
+    raw = (ctypes.c_char * (ctypes.sizeof(_lib.WgradEntry) * n_entries)).from_address(int(table))
+    arr = (_lib.WgradEntry * n_entries).from_buffer_copy(raw)
+    for e in arr:
+        G = f32(e.acc, e.Cout * e.taps * e.kpad).view(e.Cout, e.taps, e.kpad)[:, :, :e.Cin_g].permute(0, 2, 1).reshape(-1)
+        _store(e.dw, G.numel(), e.pdt, G, e.accumulate)
+
+
 def ms_unpack_igemm_wgrad(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, nsplit, accumulate, st):
     G = f32(dwp, nsplit * Cout * ntaps * kpad).view(nsplit, Cout, ntaps, kpad).sum(0)[:, :, :Cin_g].permute(0, 2, 1).reshape(-1)
     _store(dw, G.numel(), pdt, G, accumulate)

@@ -1,0 +1,178 @@
+"""The fused training / small-batch inference blocks (csrc/conv_train.cu: one cooperative launch per ConvNormRelu and
+direction, weight gradients accumulated in place) against the three-kernel path they replace (GEMM, statistics + finalize,
+normalise; reduce, apply, input-gradient GEMM; per-slice weight-gradient partials + summing kernel), layer by layer on the
+geometries of the generator, and against the oracle's train-loop body through TrainStep.  The unfused path is itself pinned
+to the oracle by tests/test_parity_gpu.py, so agreement here at 1e-5 (only the order of fp32 split-K reductions differs)
+carries that pin over."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+# (B, H, W, Cin, Cout per group, type, downsample, kernel, stride, groups, up2 residual length factor)
+GEOMS = {
+    "unet_pre_k3": dict(B=16, L=64, cin=256, cout=256, down=False),
+    "unet_down_k4s2": dict(B=16, L=64, cin=256, cout=256, down=True),
+    "unet_bottom_rows32": dict(B=16, L=4, cin=256, cout=256, down=True),
+    "unet_up2_skip": dict(B=16, L=8, cin=256, cout=256, down=False, up2=True),
+    "classify0_cin266": dict(B=16, L=64, cin=266, cout=256, down=False),
+    "decoder_grouped_k8": dict(B=16, L=64, cin=256, cout=256, down=False, groups=8),
+    "pose_style_small": dict(B=16, L=16, cin=64, cout=128, down=True),
+    "audio2d_k3": dict(B=16, H=32, W=32, cin=64, cout=128, down=False, two_d=True),
+    "audio2d_k4s2": dict(B=16, H=64, W=64, cin=64, cout=64, down=True, two_d=True),
+    "audio2d_k3x8": dict(B=16, H=8, W=8, cin=256, cout=256, two_d=True, kernel=(3, 8), stride=1),
+    "b128_k3": dict(B=128, L=64, cin=256, cout=256, down=False),
+    "b128_decoder_grouped": dict(B=128, L=64, cin=256, cout=256, down=False, groups=8),
+    "b3_ragged": dict(B=3, L=32, cin=128, cout=256, down=False),
+}
+
+
+def _make(g, dtype=torch.float64):
+    from mixstage_b200.layers import ConvNormRelu
+    torch.manual_seed(5)
+    kw = {}
+    if "kernel" in g:
+        kw = dict(kernel_size=g["kernel"], stride=g["stride"])
+    m = ConvNormRelu(g["cin"], g["cout"], type="2d" if g.get("two_d") else "1d", leaky=True, downsample=g.get("down", False),
+                     groups=g.get("groups", 1), **kw)
+    with torch.no_grad():
+        m.norm.weight.uniform_(0.5, 1.5)
+        m.norm.bias.uniform_(-0.5, 0.5)
+    return m.to("cuda", dtype)
+
+
+def _run(name, fused, precision):
+    from mixstage_b200 import ops
+    g = GEOMS[name]
+    old_f, old_p = ops.FUSED_BLOCKS, ops.get_precision()
+    ops.FUSED_BLOCKS = fused
+    ops.set_precision(precision)
+    try:
+        m = _make(g)
+        m.train()
+        G = g.get("groups", 1)
+        torch.manual_seed(11)
+        if g.get("two_d"):
+            x = torch.randn(g["B"], g["H"], g["W"], g["cin"] * G, device="cuda")
+        else:
+            x = torch.randn(g["B"], 1, g["L"], g["cin"] * G, device="cuda")
+        x.requires_grad_(True)
+        res = None
+        if g.get("up2"):
+            res = torch.randn(g["B"], 1, 2 * g["L"], g["cout"] * G, device="cuda", requires_grad=True)
+            y = m(x, residual=res, up2=True)
+        else:
+            y = m(x)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        out = dict(y=y.detach(), dx=x.grad, dw=m.conv.weight.grad, dgamma=m.norm.weight.grad, dbeta=m.norm.bias.grad,
+                   rm=m.norm.running_mean.clone(), rv=m.norm.running_var.clone(), nbt=int(m.norm.num_batches_tracked),
+                   planes=ops.as_f32(ops.planes_view(y._ms_planes, y.shape)) if getattr(y, "_ms_planes", None) is not None else None)
+        if res is not None:
+            out["dres"] = res.grad
+        return out
+    finally:
+        ops.FUSED_BLOCKS = old_f
+        ops.set_precision(old_p)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("name", list(GEOMS))
+def test_fused_block_equals_three_kernel_path(name, precision):
+    a = _run(name, True, precision)
+    b = _run(name, False, precision)
+    assert a["nbt"] == b["nbt"] == 1
+    for k in ("y", "rm", "rv", "dgamma", "dbeta", "dx", "dw", "dres", "planes"):
+        if k not in b or b[k] is None:
+            continue
+        assert a[k] is not None, k
+        # identical arithmetic up to the order of fp32 split-K / atomic reductions; dz planes are bf16-rounded from values
+        # that may differ in the last fp32 bit, which moves dx / dw by ~1e-6 in split-bf16 mode and ~1e-3 of an ulp-flip in bf16
+        tol = 2e-5 if precision == "bf16x3" else 2e-3
+        assert _rel(a[k], b[k]) < tol, (name, k, _rel(a[k], b[k]))
+
+
+def test_fused_kernels_are_launched(monkeypatch):
+    from mixstage_b200 import ops
+    seen = []
+    orig = ops.call
+    monkeypatch.setattr(ops, "call", lambda n, *a: (seen.append(n), orig(n, *a))[1])
+    _run("unet_pre_k3", True, "bf16x3")
+    assert "ms_conv_block_train_fwd" in seen and "ms_conv_block_train_bwd" in seen
+    assert "ms_bn_stats_finalize" not in seen and "ms_bn_act_bwd_reduce_f32" not in seen and "ms_igemm_bf16" not in seen
+
+
+@pytest.mark.parametrize("name", ["unet_pre_k3", "unet_up2_skip", "audio2d_k3x8", "decoder_grouped_k8"])
+def test_small_batch_inference_block_equals_persistent_kernel(name):
+    """Eval mode under no_grad: the split-K + barrier form (ms_conv_block_train_fwd, training = 0) against
+    ms_igemm_bf16_fused's one-CTA-per-tile persistent kernel."""
+    from mixstage_b200 import ops
+    g = GEOMS[name]
+    outs = []
+    for fused in (True, False):
+        old_f, old_p = ops.FUSED_BLOCKS, ops.get_precision()
+        ops.FUSED_BLOCKS = fused
+        ops.set_precision("bf16x3")
+        try:
+            m = _make(g)
+            with torch.no_grad():
+                m.norm.running_mean.uniform_(-0.3, 0.3)
+                m.norm.running_var.uniform_(0.5, 2.0)
+            m.eval()
+            G = g.get("groups", 1)
+            torch.manual_seed(11)
+            shape = (g["B"], g["H"], g["W"], g["cin"] * G) if g.get("two_d") else (g["B"], 1, g["L"], g["cin"] * G)
+            x = torch.randn(*shape, device="cuda")
+            with torch.no_grad():
+                if g.get("up2"):
+                    res = torch.randn(g["B"], 1, 2 * g["L"], g["cout"] * G, device="cuda")
+                    y = m(x, residual=res, up2=True, want="both")
+                else:
+                    y = m(x, want="both")
+            torch.cuda.synchronize()
+            outs.append((y.clone(), ops.as_f32(ops.planes_view(y._ms_planes, y.shape))))
+        finally:
+            ops.FUSED_BLOCKS = old_f
+            ops.set_precision(old_p)
+    assert _rel(outs[0][0], outs[1][0]) < 2e-5
+    assert _rel(outs[0][1], outs[1][1]) < 2e-5
+
+
+@pytest.mark.parametrize("kind", ["G", "D"])
+def test_train_step_fused_equals_unfused(kind):
+    """One step of TrainStep (graphs off) from the same state with the fused blocks + in-place weight-gradient accumulation
+    on and off: same losses, same generated poses, same flat gradients."""
+    import mixstage_b200 as M
+    import mixstage_oracle as O
+    from mixstage_b200 import ops
+    from model_cases import build
+    spec = O.Spec(num_speakers=4)
+    res = {}
+    for fused in (True, False):
+        old = ops.FUSED_BLOCKS
+        ops.FUSED_BLOCKS = fused
+        M.set_precision("bf16x3")
+        try:
+            G, D, gan = build(spec, 64, "cuda", torch.float64)
+            G.thresh.value, G.thresh.iters = 1.0, 1000
+            ts = M.TrainStep(gan, use_graphs=False)
+            audio, pose, labels, style = [t.cuda() for t in O.synth_inputs(16, 64, spec)]
+            fake, losses = ts.step(audio, labels, pose, style, kind=kind)
+            torch.cuda.synchronize()
+            res[fused] = (fake.clone(), losses.clone(), ts.fG.g.clone(), ts.fD.g.clone())
+        finally:
+            ops.FUSED_BLOCKS = old
+            M.set_precision("fp32")
+    (fa, la, ga, da), (fb, lb, gb, db) = res[True], res[False]
+    assert _rel(fa, fb) < 1e-4
+    assert torch.allclose(la, lb, rtol=1e-4, atol=1e-6), (la, lb)
+    # gradients: LeakyReLU masks of pre-activations within 1e-7 of zero may flip between the two reduction orders
+    if kind == "G":
+        assert _rel(ga, gb) < 5e-3, _rel(ga, gb)
+    assert _rel(da, db) < 5e-3, _rel(da, db)

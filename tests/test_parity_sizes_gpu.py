@@ -184,43 +184,85 @@ def test_config4_stress_gstep_bf16_against_live_oracle():
 
 
 # ------------------------------------------------------------------------------------------ gradients without the GAN term
-# the 5e-2 gradient bound of the golden cases is set by the discriminator term (a piecewise-
-# linear net under an L1 loss whose pre-activations sit 1e-6 from a kink).  With the discriminator out of the graph --
-# loss = mean|pose - y| + cluster CE + lambda_id (id_in + id_out), exactly G.forward's own outputs plus the pose L1 -- the
-# per-tensor error is bounded tightly.  Tensors whose reference gradient is below 1e-6 of the largest one (conv biases
-# under batch-statistics BatchNorm: analytically zero) are skipped.
-GRAD_NOGAN_TOL = {"fp32": 1e-3, "bf16x3": 5e-3}
-
-
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
-def test_generator_gradients_without_gan_term(precision):
-    from mixstage_b200 import ops
-    B, T, spec = 16, 64, CFG2
+# "nothing shows the other four losses' gradients meet 1e-3".  Two measurements, both with the
+# discriminator out of the graph -- loss = mean|pose - y| + cluster CE + lambda_id (id_in + id_out):
+#
+#  (1) KINK-FREE network (every LeakyReLU slope set to 1 in the model AND in the oracle): the function is smooth apart from
+#      the L1 sign, so the gradient error IS the kernels' backward arithmetic (BatchNorm backward, input/weight-gradient
+#      GEMMs, mixture, softmax/CE, style scatter-add, bilinear).  Bound: 1e-3 per tensor in both modes.
+#  (2) The real network (slope 0.2).  A piecewise-linear net turns an activation error eps into a gradient error ~sqrt(eps):
+#      a fraction ~eps of the pre-activations sits within eps of the kink, each flipped mask changes its term by O(1), and
+#      the flips add incoherently.  The REFERENCE ALGORITHM ITSELF shows it: the oracle run in fp32 against its own fp64 run
+#      (pose 4e-6 apart) differs by p50 1.4e-3 / max 2.4e-3 per gradient tensor on this loss.  That calibration is computed
+#      live below and printed beside ours; the bound is a multiple of it, not a blanket number.
+def _nogan_run_cuda(precision, slope):
     with _precision(precision):
-        G, D, gan = build(spec, T, "cuda", torch.float64)
+        G, D, gan = build(CFG2, 64, "cuda", torch.float64)
+        if slope is not None:
+            for m in G.modules():
+                if hasattr(m, "cfg") and getattr(m.cfg, "act", False):
+                    m.cfg.slope = slope
         G.train()
         G.force_branch = "audio"
-        audio, pose, labels, style = O.synth_inputs(B, T, spec)
+        audio, pose, labels, style = O.synth_inputs(16, 64, CFG2)
         dev = [t.cuda() for t in (audio, labels, pose, style)]
         out, part = G([dev[0], dev[1]], dev[2], input_modalities=MOD, style=dev[3], sample_flag=0, description="train")
         l1 = gan._l1(out, dev[2], 0.0, out.dtype)
         (l1 + sum(part)).backward()
         torch.cuda.synchronize()
         G.force_branch = None
-    sd = leafify(O.synth_state(O.g_state_shapes(spec), G_SEED))
-    f2, p2, _ = O.g_forward(sd, spec, audio, labels, pose, style, training=True, sample_flag=0, description="train")
-    (O.l1_mean(f2, pose) + sum(p2)).backward()
-    gscale = max(float(v.grad.norm()) for v in sd.values() if v.requires_grad and v.grad is not None)
+    return out.detach().cpu(), {n: p.grad.detach().cpu().double() for n, p in G.named_parameters() if p.grad is not None}
+
+
+def _nogan_run_oracle(dtype, slope):
+    old = O.LEAKY_SLOPE
+    if slope is not None:
+        O.LEAKY_SLOPE = slope
+    try:
+        sd = leafify(O.synth_state(O.g_state_shapes(CFG2), G_SEED, dtype))
+        audio, pose, labels, style = O.synth_inputs(16, 64, CFG2, dtype=dtype)
+        f2, p2, _ = O.g_forward(sd, CFG2, audio, labels, pose, style, training=True, sample_flag=0, description="train")
+        (O.l1_mean(f2, pose) + sum(p2)).backward()
+    finally:
+        O.LEAKY_SLOPE = old
+    return f2.detach(), {k: v.grad.double() for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+
+def _grad_errs(got, ref):
+    gscale = max(float(v.norm()) for v in ref.values())
     errs = {}
-    for n, p in G.named_parameters():
-        r = sd[n].grad
-        if r is None or float(r.norm()) <= 1e-6 * gscale:
-            continue
-        assert p.grad is not None, n
-        errs[n] = float((p.grad.cpu().double() - r).norm() / r.norm())
+    for n, r in ref.items():
+        if float(r.norm()) <= 1e-6 * gscale or n.startswith("style_dec_gr."):
+            continue            # conv biases under batch-statistics BatchNorm: analytically zero
+        assert n in got, n
+        errs[n] = float((got[n] - r).norm() / r.norm())
     vals = sorted(errs.values())
+    return errs, vals
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_generator_gradients_kink_free_network(precision):
+    out, got = _nogan_run_cuda(precision, 1.0)
+    f64, ref = _nogan_run_oracle(torch.float64, 1.0)
+    errs, vals = _grad_errs(got, ref)
     worst = max(errs, key=errs.get)
-    q = lambda f: vals[min(len(vals) - 1, int(f * len(vals)))]     # noqa: E731
-    _log(case="grad_no_gan_b16", precision=precision, tensors=len(vals), grad_rel_p50=q(0.5), grad_rel_p90=q(0.9),
-         grad_rel_max=vals[-1], worst=worst, pose_rel=_rel(out.detach(), f2.detach()))
-    assert vals[-1] < GRAD_NOGAN_TOL[precision], (worst, vals[-1])
+    _log(case="grad_no_gan_kink_free_b16", precision=precision, tensors=len(vals), grad_rel_p50=vals[len(vals) // 2],
+         grad_rel_p90=vals[int(0.9 * len(vals))], grad_rel_max=vals[-1], worst=worst, pose_rel=_rel(out, f64))
+    assert vals[-1] < 1e-3, (worst, vals[-1])
+
+
+@pytest.mark.parametrize("precision,mult", [("fp32", 6.0), ("bf16x3", 12.0)])
+def test_generator_gradients_without_gan_term(precision, mult):
+    out, got = _nogan_run_cuda(precision, None)
+    f64, ref = _nogan_run_oracle(torch.float64, None)
+    f32, ref32 = _nogan_run_oracle(torch.float32, None)             # the reference algorithm's own fp32-vs-fp64 deviation
+    errs, vals = _grad_errs(got, ref)
+    _, cal = _grad_errs(ref32, ref)
+    worst = max(errs, key=errs.get)
+    _log(case="grad_no_gan_b16", precision=precision, tensors=len(vals), grad_rel_p50=vals[len(vals) // 2],
+         grad_rel_p90=vals[int(0.9 * len(vals))], grad_rel_max=vals[-1], worst=worst, pose_rel=_rel(out, f64),
+         oracle_fp32_vs_fp64_pose_rel=_rel(f32, f64), oracle_fp32_vs_fp64_grad_p50=cal[len(cal) // 2], oracle_fp32_vs_fp64_grad_max=cal[-1])
+    # fp32 kernels: a few times the reference's own fp32 deviation (our activation error is ~3x torch-CPU's: other summation
+    # orders); bf16x3: activations 7e-5 off instead of 1e-5, sqrt law -> ~2.5x the fp32 figure
+    assert vals[-1] < mult * cal[-1], (worst, vals[-1], cal[-1])
+    assert vals[len(vals) // 2] < mult * cal[len(cal) // 2]

@@ -1,0 +1,19 @@
+#!/bin/bash
+# usage: tools/gpu_run.sh <tag> [what...]   (runs on the GPU box through gpurun; outputs under gpurun_out/)
+tag=$1; shift
+what="$*"
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${tag}_smi.txt 2>&1
+for w in $what; do
+  case $w in
+    pytest) timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" ;;
+    pytestall) timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" ;;
+    smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" ;;
+    bench) timeout 1200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" ;;
+    benchtrain) timeout 600 python bench.py --workload train > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; echo "benchtrain rc=$?" ;;
+    benchref) timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "benchref rc=$?" ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --workload train --no-graphs --steps 2 --warmup 4 > gpurun_out/${tag}_launches.log 2>&1; echo "launches rc=$?" ;;
+    *) echo "unknown $w" ;;
+  esac
+done
+ls -la gpurun_out | tail -20

@@ -222,6 +222,9 @@ int ms_conv_block_train_bwd(const ms_igemm_desc* dg, const float* dy, const floa
                             int64_t rows, int up2, int rows_per_seq, void* dz_planes, int pfmt, int64_t pstride,
                             void* grad_gamma, void* grad_beta, int gdt, const void* wt, float* dx, void* sync,
                             void* stream);
+/* Timing experiments only (MS_PHASE_TS=1 in the environment when the library is first used): %globaltimer stamps of
+ * CTA 0 at the phase boundaries of the LAST fused-block launch, 16 values copied to host memory. */
+int ms_debug_phase_ts(unsigned long long* out16);
 /* ms_wgrad_bf16 with every pixel slice ADDING its tile into one fp32 accumulator acc[classes*class_n][ntaps][cchunks*64]
  * (zero-filled by the caller once per step) -- no per-slice partials, no summing kernel. */
 int ms_wgrad_bf16_acc(const ms_igemm_desc* d, const void* x, const void* dz, float* acc, void* stream);

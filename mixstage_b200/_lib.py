@@ -86,6 +86,7 @@ PROTOTYPES = {
     "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],
     "ms_conv_block_train_fwd": [_GD, _P, _P, _P, _BN, _P, _P, _I, _L, _P, _P, _I, _L, _I, _P, _P],
     "ms_conv_block_train_bwd": [_GD, _P, _P, _BN, _L, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P],
+    "ms_debug_phase_ts": [_P],
     "ms_wgrad_bf16_acc": [_GD, _P, _P, _P, _P],
     "ms_unpack_wgrad_multi": [_P, _I, _I, _P],
     "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],

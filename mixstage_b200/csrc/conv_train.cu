@@ -1,38 +1,38 @@
 // Fused TRAINING blocks of ConvNormRelu (reference src/model/layers.py:32-78): one launch per block and direction.
 //
 // A training-mode block is  z = conv(x)  ->  batch statistics of z  ->  y = LeakyReLU(BN(z)) [upsample x2 + skip]
-// and needs a grid-wide reduction in the middle, so the round-1 path ran it as three dependent kernels forward
-// (GEMM, statistics + finalize, normalise) and three backward (reduce, apply, input-gradient GEMM), each 3-25 us at
-// batch 16: the step was ~300 dependent launches deep.  Here one PERSISTENT launch of at most one CTA per SM walks the
-// phases with device-wide barriers between them (all CTAs are co-resident: cooperative launch, grid <= #SMs):
+// and needs a grid-wide reduction in the middle.  One PERSISTENT launch of at most one CTA per SM walks the phases with
+// device-wide barriers between them (all CTAs co-resident: cooperative launch, grid <= #SMs).
 //
-//   forward   [GEMM tiles: TMA -> tcgen05.mma -> TMEM -> z (split-K slices combine with red.global.add.v4.f32)]
-//             | barrier | per-channel sum / sum-of-squares of z (fp64 atomics) | barrier |
-//             finalize (scale/shift/mean/rstd, running statistics, batch counter) + normalise + LeakyReLU (+ UNet
-//             upsample x2 + skip) -> fp32 activation and the next GEMM's bf16 operand planes (hi [, lo])
-//   backward  per-channel reductions of dy*act' and dy*act'*xhat | barrier | dz = BN-backward(dy) -> bf16 operand planes,
-//             affine-parameter gradients into the flat gradient buffer | barrier |
+//   forward, full-K form (split_k == 1; every layer whose tiles keep the machine busy on their own)
+//             [GEMM tiles: TMA -> tcgen05.mma -> TMEM; the epilogue warps write z AND reduce the per-channel sum / sum of
+//              squares of their 32 rows straight from the accumulator registers (shuffle butterfly, fp64 atomics per warp)]
+//             | ONE barrier | finalize the tile's own channels, normalise + LeakyReLU (+ UNet upsample x2 + skip) reading
+//             the accumulators that are STILL IN TMEM (up to 512 columns of resident tiles per CTA; larger layers re-read z)
+//             -> fp32 activation and the next GEMM's bf16 operand planes (hi [, lo])
+//   forward, split-K form (few tiles, long K: audio encoder tail, UNet bottleneck)
+//             [k-slices over the whole machine, red.global.add.v4.f32 into z] | barrier | statistics over (64-channel x row
+//             block) slabs, one fp64 atomic per channel and slab | barrier | finalize + normalise from z
+//   backward  per-channel reductions of dy*act' and dy*act'*xhat over slabs | barrier | dz = BN-backward(dy) -> bf16 operand
+//             planes, affine-parameter gradients into the flat gradient buffer | barrier |
 //             [input-gradient GEMM tiles reading those planes through TMA -> dx]
 //
-// The GEMM phase is the one-tile-per-work-item tcgen05 pipeline of conv_tc.cu (same descriptors, same tap tables, same
-// split-bf16 passes) run as a loop over (tile, k-slice) work items with one TMEM accumulator; the element-wise phases are
-// the arithmetic of elementwise.cu's BatchNorm kernels, statement for statement, so results agree with the unfused path
-// to the order of the fp32 split-K reductions.  z stays in L2 between the phases at the batch sizes this path serves.
+// Split-bf16 operands (hi + lo planes): ONE k-step stages A_hi, A_lo, W_hi, W_lo once and issues hi*hi + hi*lo + lo*hi from
+// the same shared-memory tiles -- 4 tile loads per 3 MMA passes instead of the 6 of pass-by-pass staging; the L2 -> SM
+// operand traffic (~6300 B/clk chip-wide, B300_MICROARCH.md) is what bounds these small-batch GEMMs.
 //
 // Also here: the weight gradient accumulated in place (red.global.add.v4.f32 into ONE persistent fp32 accumulator per
-// weight, instead of one partial per pixel slice summed by a second kernel) and the table-driven kernel that converts
-// every accumulator of a sub-network into its flat gradient buffer in one launch.
+// weight) and the table-driven kernel that converts every accumulator of a sub-network into its flat gradient buffer.
 #include <cstring>
 #include "tc_common.cuh"
 
 namespace {
 
 constexpr int TB_THREADS = 256;       // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: TMEM epilogue; all 8: element-wise phases
-constexpr int TB_STAGES = 4;
-constexpr uint32_t TB_B_STAGE_BYTES = 256 * BLOCK_K * 2;                 // room for the widest weight tile (32 KB)
-constexpr uint32_t TB_STAGE_BYTES = A_STAGE_BYTES + TB_B_STAGE_BYTES;      // 48 KB
-constexpr uint32_t TB_RING_BYTES = TB_STAGES * TB_STAGE_BYTES;            // 192 KB, reused as scratch by the element-wise phases
-constexpr uint32_t GRID_SPIN_LIMIT = 1u << 24;
+constexpr uint32_t TB_RING_BYTES = 196608;      // operand ring (192 KB); reused as scratch by the element-wise phases
+constexpr int TB_MAX_STAGES = 8;
+constexpr int TB_MAX_SLOTS = 16;      // TMEM accumulator slots per CTA (resident tiles)
+constexpr uint32_t GRID_SPIN_LIMIT = 1u << 26;
 
 // BatchNorm side of a block
 struct BnParams {
@@ -48,8 +48,19 @@ struct BnParams {
   float* ss;                  // [4][C]: scale, shift, mean, rstd (written forward, read backward)
 };
 
+// Execution shape of a GEMM phase (chosen by the host wrapper)
+struct GemmCfg {
+  int stages;                 // ring depth
+  uint32_t stage_bytes;       // one k-step: A planes (16 KB each) + W planes (block_n * 128 B each)
+  uint32_t w_plane_bytes;
+  int nslots;                 // TMEM accumulator slots: 2 (streaming) or the tiles of a CTA (resident)
+  int resident;               // accumulators are kept (never handed back) for the normalise pass
+  int stats;                  // epilogue reduces per-channel sum / sum of squares of the valid rows
+  int split_k;                // k-slices per tile (> 1: vector reductions into a zero-filled output)
+};
+
 struct FwdIO {
-  float* z;                   // (rows, C) fp32 GEMM output; zero-filled by the caller when split_k > 1
+  float* z;                   // (rows, C) fp32 GEMM output (nullable in inference form); zero-filled by the caller when split_k > 1
   float* y;                   // nullable (rows_out, C) fp32 activation
   __nv_bfloat16* planes;      // nullable operand planes of the activation
   int pfmt;
@@ -61,6 +72,7 @@ struct FwdIO {
   int up2, L;                 // L = GEMM rows per sequence (1-D)
   long long rows;             // GEMM rows
   unsigned int* sync;         // zero-filled barrier counter
+  int dbg;
 };
 
 struct BwdIO {
@@ -77,27 +89,36 @@ struct BwdIO {
   float* dx;                  // nullable: input gradient (zero-filled by the caller when split_k > 1)
   int has_gemm;
   unsigned int* sync;
+  int dbg;
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
+// MS_PHASE_TS=1 (timing experiments only): CTA 0 stamps %globaltimer at the phase boundaries of the last fused launch
+__device__ unsigned long long g_phase_ts[16];
+__device__ __forceinline__ void phase_ts(int dbg, int i) {
+  if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_phase_ts[i] = t;
+  }
+}
+
+// Device-wide barrier on a monotonically increasing counter: bar.sync orders the CTA's writes before thread 0's release
+// (cumulativity), thread 0 arrives with a release reduction and polls with acquire loads.
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target, int dbg = 0, int ts = 0) {
   __syncthreads();
+  phase_ts(dbg, ts);
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
     unsigned int spins = 0, v;
     while (true) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
       if (v >= target) break;
       if (++spins > GRID_SPIN_LIMIT) __trap();       // a CTA that never arrives must not hang the GPU
-      __nanosleep(40);
     }
-    __threadfence();
   }
   __syncthreads();
 }
 
-// Pipeline state that survives from one GEMM phase to the next inside a launch (ring slot / parity per role thread,
-// accumulator hand-over count)
 struct PipeState {
   int s;
   uint32_t ph;
@@ -105,52 +126,95 @@ struct PipeState {
 };
 
 struct GemmSmem {
-  uint8_t* a;
-  uint8_t* b;
+  uint8_t* ring;
   uint64_t* full;
   uint64_t* empty;
-  uint64_t* tfull;
-  uint64_t* tempty;
+  uint64_t* tfull;            // [TB_MAX_SLOTS]
+  uint64_t* tempty;           // [TB_MAX_SLOTS]
 };
 
-// One GEMM phase: work items (tile, k-slice) it = blockIdx.x, blockIdx.x + gridDim.x, ...; result into `out` (fp32) by plain
-// 16-byte stores (split_k == 1) or vector reductions (split_k > 1, `out` zero-filled).  No bias, no activation.
+struct TileAt {
+  int tw, th, mt, cls, n0;
+};
+__device__ __forceinline__ TileAt tile_at(const IgemmParams& p, int tile) {
+  const int ny = p.n_tiles_per_class * p.num_classes;
+  TileAt a;
+  const int y = tile % ny;
+  int mt = tile / ny;
+  a.tw = mt % p.tiles_w; mt /= p.tiles_w;
+  a.th = mt % p.tiles_h; mt /= p.tiles_h;
+  a.mt = mt;
+  a.cls = y / p.n_tiles_per_class;
+  a.n0 = (y - a.cls * p.n_tiles_per_class) * p.block_n;
+  return a;
+}
+
+__device__ __forceinline__ void tmem_ld32x(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld16(taddr, v);
+  tmem_ld16(taddr + 16u, v + 16);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+               "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])::"memory");
+  asm volatile("" : "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+               "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory");
+}
+
+// Column sums over the 32 lanes of a warp for 32 columns held one row per lane: five exchange-and-halve steps (31 shuffles);
+// lane l ends up with the total of column l.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; j++) {
+      const float send = upper ? v[j] : v[j + off];
+      const float keep = upper ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// One GEMM phase: work items (tile, k-slice) it = blockIdx.x, blockIdx.x + gridDim.x, ...; fp32 result into `out` (nullable)
+// by 16-byte stores (split_k == 1) or vector reductions (split_k > 1, `out` zero-filled).  No bias, no activation.
+// g.stats: the epilogue also adds every channel's sum / sum of squares over the valid rows into sums[0..C) / sums[C..2C).
 __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_a_lo,
-                                           const CUtensorMap* map_w_lo, const IgemmParams& p, float* __restrict__ out,
-                                           const GemmSmem& sm, uint32_t tmem_base, PipeState& st) {
+                                           const CUtensorMap* map_w_lo, const IgemmParams& p, const GemmCfg& g,
+                                           float* __restrict__ out, double* __restrict__ sums, int C, const GemmSmem& sm,
+                                           uint32_t tmem_base, PipeState& st) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t b_stage_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
   const int ny = p.n_tiles_per_class * p.num_classes;
   const int tiles = p.tiles_w * p.tiles_h * p.tiles_b * ny;
-  const int items = tiles * p.split_k;
-  const int num_k_total = p.ntaps * p.cchunks * p.npass;
-  const int k_per = (num_k_total + p.split_k - 1) / p.split_k;
+  const int items = tiles * g.split_k;
+  const int num_k_total = p.ntaps * p.cchunks;
+  const int k_per = (num_k_total + g.split_k - 1) / g.split_k;
+  const bool split = p.npass > 1;
+  const uint32_t a_bytes = split ? 2u * A_STAGE_BYTES : A_STAGE_BYTES;
   if (warp == 0) {
     if (lane == 0) {
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int slice = it % p.split_k, tile = it / p.split_k;
-        const int y = tile % ny;
-        int mt = tile / ny;
-        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-        const int th = mt % p.tiles_h; mt /= p.tiles_h;
-        const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = mt * p.box_b;
-        const int cls = y / p.n_tiles_per_class;
-        const int n0 = (y - cls * p.n_tiles_per_class) * p.block_n;
-        const int tap_base = p.shared_taps ? 0 : cls * p.ntaps;
-        const int chan_base = p.a_chan_base[cls];
-        const int wrow = cls * p.class_n + n0;
+        const int slice = it % g.split_k;
+        const TileAt a = tile_at(p, it / g.split_k);
+        const int w0 = a.tw * p.box_w, h0 = a.th * p.box_h, b0 = a.mt * p.box_b;
+        const int tap_base = p.shared_taps ? 0 : a.cls * p.ntaps;
+        const int chan_base = p.a_chan_base[a.cls];
+        const int wrow = a.cls * p.class_n + a.n0;
         const int k_beg = slice * k_per;
         const int k_end = min(num_k_total, k_beg + k_per);
-        for (int kg = k_beg; kg < k_end; kg++) {
+        for (int kk = k_beg; kk < k_end; kk++) {
           mbar_wait(&sm.empty[st.s], st.ph ^ 1u);
-          const int kk = kg / p.npass, pass = kg - kk * p.npass;          // split-bf16: hi*hi, hi*lo, lo*hi
           const int tap = kk / p.cchunks, cc = kk - tap * p.cchunks;
           const short* t = p.taps[tap_base + tap];
-          mbar_expect_tx(&sm.full[st.s], A_STAGE_BYTES + b_stage_bytes);
-          tma_load_5d(pass == 2 ? map_a_lo : map_a, &sm.full[st.s], sm.a + (size_t)st.s * A_STAGE_BYTES,
-                      chan_base + t[0] + cc * BLOCK_K, w0 + t[1], t[2], h0 + t[3], b0);
-          tma_load_2d(pass == 1 ? map_w_lo : map_w, &sm.full[st.s], sm.b + (size_t)st.s * TB_B_STAGE_BYTES, kk * BLOCK_K, wrow);
-          if (++st.s == TB_STAGES) { st.s = 0; st.ph ^= 1u; }
+          uint8_t* dst = sm.ring + (size_t)st.s * g.stage_bytes;
+          mbar_expect_tx(&sm.full[st.s], g.stage_bytes);
+          const int c0 = chan_base + t[0] + cc * BLOCK_K, c1 = w0 + t[1], c2 = t[2], c3 = h0 + t[3];
+          tma_load_5d(map_a, &sm.full[st.s], dst, c0, c1, c2, c3, b0);
+          tma_load_2d(map_w, &sm.full[st.s], dst + a_bytes, kk * BLOCK_K, wrow);
+          if (split) {
+            tma_load_5d(map_a_lo, &sm.full[st.s], dst + A_STAGE_BYTES, c0, c1, c2, c3, b0);
+            tma_load_2d(map_w_lo, &sm.full[st.s], dst + a_bytes + g.w_plane_bytes, kk * BLOCK_K, wrow);
+          }
+          if (++st.s == g.stages) { st.s = 0; st.ph ^= 1u; }
         }
       }
     }
@@ -158,23 +222,38 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int slice = it % p.split_k;
+        const int slice = it % g.split_k;
         const int k_beg = slice * k_per;
         const int num_k = min(num_k_total, k_beg + k_per) - k_beg;
-        mbar_wait(sm.tempty, (st.li & 1u) ^ 1u);         // the epilogue warps drained the previous item's accumulator
+        const int slot = (int)(st.li % (uint32_t)g.nslots);
+        const uint32_t use = st.li / (uint32_t)g.nslots;
+        mbar_wait(&sm.tempty[slot], (use & 1u) ^ 1u);       // the epilogue warps drained this slot's previous accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + (uint32_t)(slot * p.block_n);
         for (int ks = 0; ks < num_k; ks++) {
           mbar_wait(&sm.full[st.s], st.ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_kmajor_sw128_desc(smem_u32(sm.a + (size_t)st.s * A_STAGE_BYTES));
-          const uint64_t db = make_kmajor_sw128_desc(smem_u32(sm.b + (size_t)st.s * TB_B_STAGE_BYTES));
+          const uint32_t base = smem_u32(sm.ring + (size_t)st.s * g.stage_bytes);
+          const uint64_t da = make_kmajor_sw128_desc(base);
+          const uint64_t db = make_kmajor_sw128_desc(base + a_bytes);
+          if (split) {
+            const uint64_t da_lo = make_kmajor_sw128_desc(base + A_STAGE_BYTES);
+            const uint64_t db_lo = make_kmajor_sw128_desc(base + a_bytes + g.w_plane_bytes);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; k++)
-            umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; k++) {
+              umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+              umma_bf16(tacc, da + (uint64_t)(k * 2), db_lo + (uint64_t)(k * 2), idesc, 1u);
+              umma_bf16(tacc, da_lo + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; k++)
+              umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&sm.empty[st.s]);
-          if (++st.s == TB_STAGES) { st.s = 0; st.ph ^= 1u; }
+          if (++st.s == g.stages) { st.s = 0; st.ph ^= 1u; }
         }
-        umma_commit(sm.tfull);
+        umma_commit(&sm.tfull[slot]);
         st.li++;
       }
     }
@@ -184,42 +263,76 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
     const int wi = r % p.box_w;
     const int hi = (r / p.box_w) % p.box_h;
     const int bi = r / (p.box_w * p.box_h);
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int tile = it / p.split_k;
-      const int y = tile % ny;
-      int mt = tile / ny;
-      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-      const int th = mt % p.tiles_h; mt /= p.tiles_h;
-      const int cls = y / p.n_tiles_per_class;
-      const int n0 = (y - cls * p.n_tiles_per_class) * p.block_n;
-      const int ow = tw * p.box_w + wi, oh = th * p.box_h + hi, ob = mt * p.box_b + bi;
+      const TileAt a = tile_at(p, it / g.split_k);
+      const int ow = a.tw * p.box_w + wi, oh = a.th * p.box_h + hi, ob = a.mt * p.box_b + bi;
       const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
-      float* dst = out + (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + p.out_off[cls] + n0;
-      mbar_wait(sm.tfull, st.li & 1u);
+      const long long col0 = p.out_off[a.cls] + a.n0;
+      float* dst = out ? out + (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + col0 : nullptr;
+      const int slot = (int)(st.li % (uint32_t)g.nslots);
+      const uint32_t use = st.li / (uint32_t)g.nslots;
+      mbar_wait(&sm.tfull[slot], use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        tmem_wait_ld16(v);
-        if (valid && (n0 + c0) < p.class_n) {
-          if (p.split_k > 1) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int rem = min(p.class_n - a.n0, p.block_n) - c0;     // columns left in this tile (uniform; multiple of 16)
+        if (rem <= 0) break;
+        if (rem < 32) {
+          // trailing 16 columns (e.g. the 272-channel input gradient of the style-concatenated features); never with stats
+          uint32_t u[16];
+          tmem_ld16(taddr + (uint32_t)c0, u);
+          tmem_wait_ld16(u);
+          if (valid && dst) {
+            if (g.split_k > 1) {
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+              for (int j = 0; j < 4; j++)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j), "f"(__uint_as_float(u[4 * j])),
+                             "f"(__uint_as_float(u[4 * j + 1])), "f"(__uint_as_float(u[4 * j + 2])), "f"(__uint_as_float(u[4 * j + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; j++)
+                *reinterpret_cast<float4*>(dst + c0 + 4 * j) = make_float4(__uint_as_float(u[4 * j]), __uint_as_float(u[4 * j + 1]),
+                                                                           __uint_as_float(u[4 * j + 2]), __uint_as_float(u[4 * j + 3]));
+            }
+          }
+          break;
+        }
+        uint32_t v[32];
+        tmem_ld32x(taddr + (uint32_t)c0, v);
+        if (valid && dst) {
+          if (g.split_k > 1) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + 4 * j), "f"(__uint_as_float(v[4 * j])),
                            "f"(__uint_as_float(v[4 * j + 1])), "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
                            : "memory");
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int j = 0; j < 8; j++)
               *reinterpret_cast<float4*>(dst + c0 + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
           }
         }
+        if (g.stats) {
+          float f[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            f[j] = valid ? __uint_as_float(v[j]) : 0.f;
+            s2[j] = f[j] * f[j];
+          }
+          const float cs = warp_colsum32(f, lane);
+          const float cq = warp_colsum32(s2, lane);
+          const long long c = col0 + c0 + lane;
+          atomicAdd(sums + c, (double)cs);
+          atomicAdd(sums + C + c, (double)cq);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sm.tempty);
+      if (!g.resident) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.tempty[slot]);
+      }
       st.li++;
     }
   }
@@ -233,30 +346,141 @@ __device__ __forceinline__ void cta_rows(long long rows, long long& r0, long lon
   r1 = rows * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
 }
 
-// Column reduction helper: every thread owns one 4-channel group cg and one row lane rl; eight fp64 partials per thread
-// are combined over the row lanes through `scratch` and added to dst_a[4cg..] / dst_b[4cg..] with fp64 atomics.
-__device__ __forceinline__ void reduce_lanes_and_add(double (&acc)[8], int cg, int rl, int RL, int ncg, bool active, double* scratch,
-                                                     double* __restrict__ dst_a, double* __restrict__ dst_b) {
-  if (RL > 1) {
-    if (active) {
+// Slab decomposition of a (rows, C) matrix for the column reductions: 64-channel blocks x row blocks, one slab per CTA and
+// pass; 16 float4 channel groups x 16 row lanes of threads.  A slab's column totals cost ONE fp64 atomic per channel, and
+// an address sees (row blocks) of them instead of one per CTA.
+struct Slabs {
+  int ncb, nrb, total;
+};
+__device__ __forceinline__ Slabs slabs_of(int C, long long rows) {
+  Slabs s;
+  s.ncb = ((C >> 2) + 15) >> 4;
+  int nrb = (int)gridDim.x / s.ncb;
+  if (nrb < 1) nrb = 1;
+  if ((long long)nrb > (rows + 15) / 16) nrb = (int)((rows + 15) / 16);
+  s.nrb = nrb;
+  s.total = s.ncb * nrb;
+  return s;
+}
+
+struct SlabAt {
+  int cbi, cg;                // channel block, this thread's float4 channel group (global)
+  bool ok;                    // the group exists (4 * cg < C)
+  long long r0, r1;           // rows of the slab
+  int rbi;
+};
+__device__ __forceinline__ SlabAt slab_at(const Slabs& s, int sl, int C, long long rows) {
+  SlabAt a;
+  a.cbi = sl % s.ncb;
+  a.rbi = sl / s.ncb;
+  a.cg = a.cbi * 16 + (threadIdx.x & 15);
+  a.ok = a.cg * 4 < C;
+  a.r0 = rows * (long long)a.rbi / (long long)s.nrb;
+  a.r1 = rows * (long long)(a.rbi + 1) / (long long)s.nrb;
+  return a;
+}
+
+// Combine eight per-thread fp64 partials (acc[0..3] -> dst_a, acc[4..7] -> dst_b, four channels each) over the 16 row lanes
+// of a slab and add them to global memory: one atomic per channel and slab.  scratch: [8 warps][16 groups][8] doubles.
+__device__ __forceinline__ void slab_reduce_add(double (&acc)[8], const SlabAt& a, int C, double* scratch,
+                                                double* __restrict__ dst_a, double* __restrict__ dst_b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-      for (int j = 0; j < 8; j++) scratch[((size_t)rl * ncg + cg) * 8 + j] = acc[j];
+  for (int j = 0; j < 8; j++) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);     // the warp's two row lanes
+  if (lane < 16) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) scratch[(warp * 16 + lane) * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c_l = threadIdx.x >> 3, j = threadIdx.x & 7;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < TB_THREADS / 32; w++) v += scratch[(w * 16 + c_l) * 8 + j];
+    const int ch = (a.cbi * 16 + c_l) * 4 + (j & 3);
+    if (ch < C) atomicAdd((j < 4 ? dst_a : dst_b) + ch, v);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+// one output row segment of 32 channels: y (fp32, nullable) and operand planes (nullable) at element index e
+__device__ __forceinline__ void store_row32(float* __restrict__ y, __nv_bfloat16* __restrict__ planes, int pfmt, long long ps,
+                                            long long e, const float (&o)[32]) {
+  if (y) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(y + e + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  }
+  if (planes) {
+    uint32_t h[16];
+    float lo[32];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      __nv_bfloat162 b = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+      h[j] = *reinterpret_cast<uint32_t*>(&b);
+      lo[2 * j] = o[2 * j] - __bfloat162float(b.x);
+      lo[2 * j + 1] = o[2 * j + 1] - __bfloat162float(b.y);
     }
-    __syncthreads();
-    if (active && rl == 0) {
-      for (int l = 1; l < RL; l++) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] += scratch[((size_t)l * ncg + cg) * 8 + j];
+    for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(planes + e + 8 * j) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    if (pfmt == MS_BF16X2) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        *reinterpret_cast<uint4*>(planes + ps + e + 8 * j) =
+            make_uint4(pack_bf162(lo[8 * j], lo[8 * j + 1]), pack_bf162(lo[8 * j + 2], lo[8 * j + 3]),
+                       pack_bf162(lo[8 * j + 4], lo[8 * j + 5]), pack_bf162(lo[8 * j + 6], lo[8 * j + 7]));
+    }
+  }
+}
+
+// skip tensor (fp32 or operand planes) added to 32 channels at element index e
+__device__ __forceinline__ void add_res32(const FwdIO& io, long long e, float (&o)[32]) {
+  if (io.res) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float4 r = ldcg4(io.res + e + 4 * j);
+      o[4 * j] += r.x; o[4 * j + 1] += r.y; o[4 * j + 2] += r.z; o[4 * j + 3] += r.w;
+    }
+  } else if (io.res_pl) {
+    for (int pl = 0; pl < (io.res_fmt == MS_BF16X2 ? 2 : 1); pl++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(io.res_pl + pl * io.res_ps + e + 8 * j));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+          o[8 * j + 2 * i] += __bfloat162float(b.x);
+          o[8 * j + 2 * i + 1] += __bfloat162float(b.y);
+        }
       }
     }
-    __syncthreads();
   }
-  if (active && rl == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      atomicAdd(dst_a + 4 * cg + j, acc[j]);
-      atomicAdd(dst_b + 4 * cg + j, acc[4 + j]);
-    }
+}
+
+// per-channel finalize of training-mode BatchNorm: scale / shift for the normalise pass; `publish`: running statistics and
+// the [scale, shift, mean, rstd] table the backward reads
+__device__ __forceinline__ void bn_finalize_channel(const BnParams& bn, long long rows, int c, bool publish, float& sc, float& sh) {
+  const int C = bn.C;
+  const double sum = __ldcg(bn.sums + c), sumsq = __ldcg(bn.sums + C + c);
+  const double mean = sum / (double)rows;
+  double var = sumsq / (double)rows - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)bn.eps);
+  const double g = ms_ldp_d(bn.gamma, bn.pdt, c), b = ms_ldp_d(bn.beta, bn.pdt, c);
+  sc = (float)(g * rstd);
+  sh = (float)(b - mean * g * rstd);
+  if (publish) {
+    const double cb = bn.cbias ? ms_ldp_d(bn.cbias, bn.pdt, c) : 0.0;
+    const double unb = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
+    const double rm = ms_ldp_d(bn.rmean, bn.pdt, c), rv = ms_ldp_d(bn.rvar, bn.pdt, c);
+    ms_stp(bn.rmean, bn.pdt, c, (1.0 - (double)bn.momentum) * rm + (double)bn.momentum * (mean + cb));
+    ms_stp(bn.rvar, bn.pdt, c, (1.0 - (double)bn.momentum) * rv + (double)bn.momentum * unb);
+    bn.ss[c] = sc;
+    bn.ss[C + c] = sh;
+    bn.ss[2 * C + c] = (float)mean;
+    bn.ss[3 * C + c] = (float)rstd;
   }
 }
 
@@ -266,17 +490,20 @@ __device__ __forceinline__ void reduce_lanes_and_add(double (&acc)[8], int cg, i
 __global__ void __launch_bounds__(TB_THREADS, 1)
 conv_block_train_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                             const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
-                            const __grid_constant__ IgemmParams p, const __grid_constant__ BnParams bn,
-                            const __grid_constant__ FwdIO io) {
+                            const __grid_constant__ IgemmParams p, const __grid_constant__ GemmCfg g,
+                            const __grid_constant__ BnParams bn, const __grid_constant__ FwdIO io) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[TB_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TB_STAGES];
-  __shared__ __align__(8) uint64_t tfull_bar, tempty_bar;
+  __shared__ __align__(8) uint64_t full_bar[TB_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TB_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[TB_MAX_SLOTS];
+  __shared__ __align__(8) uint64_t tempty_bar[TB_MAX_SLOTS];
+  __shared__ __align__(16) double red_scratch[8 * 16 * 8];
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  phase_ts(io.dbg, 0);
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(g.nslots * p.block_n)) tmem_cols <<= 1;
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
@@ -284,9 +511,8 @@ conv_block_train_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
     }
-    for (int s = 0; s < TB_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tfull_bar, 1);
-    mbar_init(&tempty_bar, 4);
+    for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < g.nslots; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -298,120 +524,182 @@ conv_block_train_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
   GemmSmem sm;
-  sm.a = smem; sm.b = smem + TB_STAGES * A_STAGE_BYTES;
-  sm.full = full_bar; sm.empty = empty_bar; sm.tfull = &tfull_bar; sm.tempty = &tempty_bar;
+  sm.ring = smem; sm.full = full_bar; sm.empty = empty_bar; sm.tfull = tfull_bar; sm.tempty = tempty_bar;
   PipeState st;
   st.s = 0; st.ph = 0; st.li = 0;
+  const int C = bn.C, T = TB_THREADS, t = threadIdx.x;
+  const float slope = bn.slope;
 
-  // ---- phase 1: z = conv(x) on the tensor cores
-  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, io.z, sm, tmem_base, st);
+  // ---- phase 1: z = conv(x) on the tensor cores (+ statistics from the accumulators in the full-K training form)
+  phase_ts(io.dbg, 1);
+  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, g, io.z, bn.sums, C, sm, tmem_base, st);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  grid_barrier(io.sync, gridDim.x);
+  unsigned int bar_target = 0;
+  const bool need_bar1 = bn.training || g.split_k > 1;      // inference, full-K: every CTA normalises its own tiles at once
+  if (need_bar1) {
+    bar_target += gridDim.x;
+    grid_barrier(io.sync, bar_target, io.dbg, 2);
+  } else {
+    __syncthreads();
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  phase_ts(io.dbg, 3);
 
-  // ---- phase 2: per-channel sum and sum of squares of z over this CTA's rows (elementwise.cu: bn_stats_finalize_kernel)
-  const int C = bn.C, ncg = C >> 2, T = TB_THREADS, t = threadIdx.x;
-  const float* __restrict__ z = io.z;
-  double* scratch = reinterpret_cast<double*>(smem);
-  if (bn.training) {
-    long long r0, r1;
-    cta_rows(io.rows, r0, r1);
-    if (r1 > r0) {                                         // uniform per CTA
-      if (ncg >= T) {
-        for (int cg = t; cg < ncg; cg += T) {
-          double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          for (long long r = r0; r < r1; r++) {
-            const float4 v = ldcg4(z + r * C + 4 * cg);
-            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
-            acc[4] += (double)v.x * v.x; acc[5] += (double)v.y * v.y; acc[6] += (double)v.z * v.z; acc[7] += (double)v.w * v.w;
-          }
-          reduce_lanes_and_add(acc, cg, 0, 1, ncg, true, scratch, bn.sums, bn.sums + C);
+  // ---- phase 2 (split-K training form only): per-channel sum and sum of squares of z over slabs
+  if (bn.training && !g.stats) {
+    const Slabs sl = slabs_of(C, io.rows);
+    const float* __restrict__ z = io.z;
+    for (int s = blockIdx.x; s < sl.total; s += gridDim.x) {
+      const SlabAt a = slab_at(sl, s, C, io.rows);
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (a.ok) {
+        long long r = a.r0 + (t >> 4);
+        for (; r + 16 < a.r1; r += 32) {
+          const float4 v = ldcg4(z + r * C + 4 * a.cg), w = ldcg4(z + (r + 16) * C + 4 * a.cg);
+          acc[0] += (double)v.x + (double)w.x; acc[1] += (double)v.y + (double)w.y;
+          acc[2] += (double)v.z + (double)w.z; acc[3] += (double)v.w + (double)w.w;
+          acc[4] += (double)v.x * v.x + (double)w.x * w.x; acc[5] += (double)v.y * v.y + (double)w.y * w.y;
+          acc[6] += (double)v.z * v.z + (double)w.z * w.z; acc[7] += (double)v.w * v.w + (double)w.w * w.w;
         }
-      } else {
-        const int RL = T / ncg, rl = t / ncg, cg = t - rl * ncg;
-        const bool active = rl < RL;
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (active)
-          for (long long r = r0 + rl; r < r1; r += RL) {
-            const float4 v = ldcg4(z + r * C + 4 * cg);
-            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
-            acc[4] += (double)v.x * v.x; acc[5] += (double)v.y * v.y; acc[6] += (double)v.z * v.z; acc[7] += (double)v.w * v.w;
-          }
-        reduce_lanes_and_add(acc, cg, rl, RL, ncg, active, scratch, bn.sums, bn.sums + C);
+        for (; r < a.r1; r += 16) {
+          const float4 v = ldcg4(z + r * C + 4 * a.cg);
+          acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+          acc[4] += (double)v.x * v.x; acc[5] += (double)v.y * v.y; acc[6] += (double)v.z * v.z; acc[7] += (double)v.w * v.w;
+        }
+      }
+      slab_reduce_add(acc, a, C, red_scratch, bn.sums, bn.sums + C);
+    }
+    bar_target += gridDim.x;
+    grid_barrier(io.sync, bar_target, io.dbg, 4);
+  }
+  phase_ts(io.dbg, 5);
+
+  // ---- phase 3: finalize + normalise + LeakyReLU (+ upsample x2 + skip)
+  if (bn.training && blockIdx.x == 0 && t == 0 && bn.nbt) bn.nbt[0] += 1;
+  float* s_scale = reinterpret_cast<float*>(smem);          // the ring is idle from here on
+  if (g.resident) {
+    // the CTA's own tiles, accumulators still in TMEM: constants of each slot's columns, then TMEM -> y / planes
+    const int ny = p.n_tiles_per_class * p.num_classes;
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_b * ny;
+    int n_my = 0;
+    for (int it = blockIdx.x; it < tiles; it += gridDim.x) n_my++;
+    float* s_shift = s_scale + TB_MAX_SLOTS * 256;
+    for (int idx = t; idx < n_my * p.block_n; idx += T) {
+      const int slot = idx / p.block_n, j = idx - slot * p.block_n;
+      const TileAt a = tile_at(p, blockIdx.x + slot * gridDim.x);
+      if (a.n0 + j < p.class_n) {
+        const int c = (int)p.out_off[a.cls] + a.n0 + j;
+        float sc, sh;
+        if (bn.training) bn_finalize_channel(bn, io.rows, c, a.tw == 0 && a.th == 0 && a.mt == 0, sc, sh);
+        else { sc = __ldg(bn.ss + c); sh = __ldg(bn.ss + C + c); }
+        s_scale[idx] = sc;
+        s_shift[idx] = sh;
       }
     }
-  }
-  if (bn.training) grid_barrier(io.sync, 2u * gridDim.x);
-
-  // ---- phase 3: finalize (every CTA for itself; CTA 0 publishes) + normalise + LeakyReLU (+ upsample x2 + skip)
-  float* s_scale = reinterpret_cast<float*>(smem);
-  float* s_shift = s_scale + C;
-  if (!bn.training) {                                     // inference: BatchNorm folded by the host-side finalize
+    __syncthreads();
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    const int wi = r % p.box_w;
+    const int hi = (r / p.box_w) % p.box_h;
+    const int bi = r / (p.box_w * p.box_h);
+    for (int slot = 0; slot < n_my; slot++) {
+      const TileAt a = tile_at(p, blockIdx.x + slot * gridDim.x);
+      const int ow = a.tw * p.box_w + wi, oh = a.th * p.box_h + hi, ob = a.mt * p.box_b + bi;
+      const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
+      const long long zrow = ((long long)ob * p.out_h + oh) * p.out_w + ow;
+      const long long col0 = p.out_off[a.cls] + a.n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * p.block_n);
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+        if (a.n0 + c0 >= p.class_n) break;
+        uint32_t v[32];
+        tmem_ld32x(taddr + (uint32_t)c0, v);
+        if (!valid) continue;
+        float o[32];
+        const float* sc = s_scale + slot * p.block_n + c0;
+        const float* sh = s_shift + slot * p.block_n + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) o[j] = lrelu(fmaf(__uint_as_float(v[j]), sc[j], sh[j]), slope);
+        if (!io.up2) {
+          store_row32(io.y, io.planes, io.pfmt, io.pstride, zrow * C + col0 + c0, o);
+        } else {
+          const long long b = zrow / io.L;
+          const long long ro = b * 2 * io.L + 2 * (zrow - b * io.L);
+#pragma unroll 1
+          for (int rr = 0; rr < 2; rr++) {
+            float o2[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) o2[j] = o[j];
+            const long long e = (ro + rr) * C + col0 + c0;
+            add_res32(io, e, o2);
+            store_row32(io.y, io.planes, io.pfmt, io.pstride, e, o2);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // streaming form: constants of all channels, then this CTA's share of the rows re-read from z
+    float* s_shift = s_scale + C;
     for (int c = t; c < C; c += T) {
-      s_scale[c] = __ldg(bn.ss + c);
-      s_shift[c] = __ldg(bn.ss + C + c);
+      float sc, sh;
+      if (bn.training) bn_finalize_channel(bn, io.rows, c, blockIdx.x == 0, sc, sh);
+      else { sc = __ldg(bn.ss + c); sh = __ldg(bn.ss + C + c); }
+      s_scale[c] = sc;
+      s_shift[c] = sh;
     }
-  } else
-  for (int c = t; c < C; c += T) {
-    const double sum = __ldcg(bn.sums + c), sumsq = __ldcg(bn.sums + C + c);
-    const double mean = sum / (double)io.rows;
-    double var = sumsq / (double)io.rows - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const double rstd = 1.0 / sqrt(var + (double)bn.eps);
-    const double g = ms_ldp_d(bn.gamma, bn.pdt, c), b = ms_ldp_d(bn.beta, bn.pdt, c);
-    const float sc = (float)(g * rstd), sh = (float)(b - mean * g * rstd);
-    s_scale[c] = sc;
-    s_shift[c] = sh;
-    if (blockIdx.x == 0) {
-      const double cb = bn.cbias ? ms_ldp_d(bn.cbias, bn.pdt, c) : 0.0;
-      const double unb = io.rows > 1 ? var * ((double)io.rows / (double)(io.rows - 1)) : var;
-      const double rm = ms_ldp_d(bn.rmean, bn.pdt, c), rv = ms_ldp_d(bn.rvar, bn.pdt, c);
-      ms_stp(bn.rmean, bn.pdt, c, (1.0 - (double)bn.momentum) * rm + (double)bn.momentum * (mean + cb));
-      ms_stp(bn.rvar, bn.pdt, c, (1.0 - (double)bn.momentum) * rv + (double)bn.momentum * unb);
-      bn.ss[c] = sc;
-      bn.ss[C + c] = sh;
-      bn.ss[2 * C + c] = (float)mean;
-      bn.ss[3 * C + c] = (float)rstd;
-    }
-  }
-  if (bn.training && blockIdx.x == 0 && t == 0 && bn.nbt) bn.nbt[0] += 1;
-  __syncthreads();
-  {
+    __syncthreads();
+    const float* __restrict__ z = io.z;
+    const int ncg = C >> 2;
     const long long rows_out = io.up2 ? 2 * io.rows : io.rows;
     long long o0, o1;
     cta_rows(rows_out, o0, o1);
     const long long total = (o1 - o0) * ncg;
-    const float slope = bn.slope;
-    for (long long i = t; i < total; i += T) {
-      const long long ro = o0 + i / ncg;
-      const int cg = (int)(i % ncg);
-      long long ri = ro;
-      if (io.up2) {
-        const long long b = ro / (2 * io.L);
-        const int l2 = (int)(ro - b * 2 * io.L);
-        ri = b * io.L + (l2 >> 1);
-      }
-      const float4 v = ldcg4(z + ri * C + 4 * cg);
-      const float4 s = *reinterpret_cast<const float4*>(s_scale + 4 * cg);
-      const float4 h = *reinterpret_cast<const float4*>(s_shift + 4 * cg);
-      float4 o;
-      o.x = fmaf(v.x, s.x, h.x); o.y = fmaf(v.y, s.y, h.y); o.z = fmaf(v.z, s.z, h.z); o.w = fmaf(v.w, s.w, h.w);
-      o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
-      o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
-      if (io.res) {
-        const float4 r = ldcg4(io.res + ro * C + 4 * cg);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      } else if (io.res_pl) {
-        for (int pl = 0; pl < (io.res_fmt == MS_BF16X2 ? 2 : 1); pl++) {
-          const uint2 u = __ldcg(reinterpret_cast<const uint2*>(io.res_pl + pl * io.res_ps + ro * C + 4 * cg));
-          const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&u.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-          o.x += __bfloat162float(h0.x); o.y += __bfloat162float(h0.y); o.z += __bfloat162float(h1.x); o.w += __bfloat162float(h1.y);
+    for (long long i0 = t; i0 < total; i0 += 4 * T) {
+      float4 v[4];
+      long long ro[4];
+      int cg[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long i = i0 + (long long)u * T;
+        if (i < total) {
+          ro[u] = o0 + i / ncg;
+          cg[u] = (int)(i % ncg);
+          long long ri = ro[u];
+          if (io.up2) {
+            const long long b = ro[u] / (2 * io.L);
+            ri = b * io.L + ((ro[u] - b * 2 * io.L) >> 1);
+          }
+          v[u] = ldcg4(z + ri * C + 4 * cg[u]);
         }
       }
-      if (io.y) *reinterpret_cast<float4*>(io.y + ro * C + 4 * cg) = o;
-      if (io.planes) store_planes4(io.planes, io.pfmt, io.pstride, ro * C + 4 * cg, o);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long i = i0 + (long long)u * T;
+        if (i < total) {
+          const float4 s = *reinterpret_cast<const float4*>(s_scale + 4 * cg[u]);
+          const float4 h = *reinterpret_cast<const float4*>(s_shift + 4 * cg[u]);
+          float4 o;
+          o.x = lrelu(fmaf(v[u].x, s.x, h.x), slope); o.y = lrelu(fmaf(v[u].y, s.y, h.y), slope);
+          o.z = lrelu(fmaf(v[u].z, s.z, h.z), slope); o.w = lrelu(fmaf(v[u].w, s.w, h.w), slope);
+          const long long e = ro[u] * C + 4 * cg[u];
+          if (io.res) {
+            const float4 r4 = ldcg4(io.res + e);
+            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+          } else if (io.res_pl) {
+            for (int pl = 0; pl < (io.res_fmt == MS_BF16X2 ? 2 : 1); pl++) {
+              const uint2 w2 = __ldcg(reinterpret_cast<const uint2*>(io.res_pl + pl * io.res_ps + e));
+              const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w2.x), h1 = *reinterpret_cast<const __nv_bfloat162*>(&w2.y);
+              o.x += __bfloat162float(h0.x); o.y += __bfloat162float(h0.y); o.z += __bfloat162float(h1.x); o.w += __bfloat162float(h1.y);
+            }
+          }
+          if (io.y) *reinterpret_cast<float4*>(io.y + e) = o;
+          if (io.planes) store_planes4(io.planes, io.pfmt, io.pstride, e, o);
+        }
+      }
     }
   }
   __syncthreads();
+  phase_ts(io.dbg, 6);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -433,18 +721,21 @@ __device__ __forceinline__ float4 dy_at4(const float* __restrict__ dy, long long
 __global__ void __launch_bounds__(TB_THREADS, 1)
 conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                             const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
-                            const __grid_constant__ IgemmParams p, const __grid_constant__ BnParams bn,
-                            const __grid_constant__ BwdIO io) {
+                            const __grid_constant__ IgemmParams p, const __grid_constant__ GemmCfg g,
+                            const __grid_constant__ BnParams bn, const __grid_constant__ BwdIO io) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[TB_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TB_STAGES];
-  __shared__ __align__(8) uint64_t tfull_bar, tempty_bar;
+  __shared__ __align__(8) uint64_t full_bar[TB_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TB_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[TB_MAX_SLOTS];
+  __shared__ __align__(8) uint64_t tempty_bar[TB_MAX_SLOTS];
+  __shared__ __align__(16) double red_scratch[8 * 16 * 8];
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  phase_ts(io.dbg, 0);
   uint32_t tmem_cols = 32;
   if (io.has_gemm) {
-    while (tmem_cols < (uint32_t)p.block_n) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(g.nslots * p.block_n)) tmem_cols <<= 1;
     if (warp == 0 && lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
@@ -452,9 +743,8 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
       }
-      for (int s = 0; s < TB_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(&tfull_bar, 1);
-      mbar_init(&tempty_bar, 4);
+      for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < g.nslots; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -467,56 +757,24 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = io.has_gemm ? tmem_base_smem : 0u;
 
-  const int C = bn.C, ncg = C >> 2, T = TB_THREADS, t = threadIdx.x;
+  const int C = bn.C, t = threadIdx.x;
   const float* __restrict__ z = io.z;
   const float* __restrict__ dy = io.dy;
   const float slope = bn.slope;
-  // per-channel constants of the forward pass -> shared memory (scale, shift, mean, rstd)
-  float* s_sc = reinterpret_cast<float*>(smem);
-  float* s_sh = s_sc + C;
-  float* s_mu = s_sh + C;
-  float* s_rs = s_mu + C;
-  float* s_dg = s_rs + C;
-  float* s_db = s_dg + C;
-  double* scratch = reinterpret_cast<double*>(s_db + C);          // 6*C floats = 24*C bytes: 8-byte aligned
-  for (int c = t; c < C; c += T) {
-    s_sc[c] = __ldcg(bn.ss + c);
-    s_sh[c] = __ldcg(bn.ss + C + c);
-    s_mu[c] = __ldcg(bn.ss + 2 * C + c);
-    s_rs[c] = __ldcg(bn.ss + 3 * C + c);
-  }
-  __syncthreads();
-  long long r0, r1;
-  cta_rows(io.rows, r0, r1);
+  const Slabs sl = slabs_of(C, io.rows);
+  phase_ts(io.dbg, 1);
 
-  // ---- phase 1: dbeta = sum dz, dgamma = sum dz * xhat with dz = dy * act'(z)   (elementwise.cu: bn_act_bwd_reduce_kernel)
-  if (r1 > r0) {
-    if (ncg >= T) {
-      for (int cg = t; cg < ncg; cg += T) {
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * cg), sh = *reinterpret_cast<const float4*>(s_sh + 4 * cg);
-        const float4 mu = *reinterpret_cast<const float4*>(s_mu + 4 * cg), rs = *reinterpret_cast<const float4*>(s_rs + 4 * cg);
-        for (long long r = r0; r < r1; r++) {
-          const float4 xv = ldcg4(z + r * C + 4 * cg);
-          const float4 d = dy_at4(dy, r, cg, C, io.up2, io.L);
-          const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
-          const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
-          acc[0] += (double)g0 * (double)((xv.x - mu.x) * rs.x); acc[1] += (double)g1 * (double)((xv.y - mu.y) * rs.y);
-          acc[2] += (double)g2 * (double)((xv.z - mu.z) * rs.z); acc[3] += (double)g3 * (double)((xv.w - mu.w) * rs.w);
-          acc[4] += g0; acc[5] += g1; acc[6] += g2; acc[7] += g3;
-        }
-        reduce_lanes_and_add(acc, cg, 0, 1, ncg, true, scratch, bn.sums, bn.sums + C);
-      }
-    } else {
-      const int RL = T / ncg, rl = t / ncg, cg = t - rl * ncg;
-      const bool active = rl < RL;
+  // ---- phase 1: dbeta = sum g, dgamma = sum g * xhat with g = dy * act'(z)   (slab reductions)
+  if (bn.training) {
+    for (int s = blockIdx.x; s < sl.total; s += gridDim.x) {
+      const SlabAt a = slab_at(sl, s, C, io.rows);
       double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      if (active) {
-        const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * cg), sh = *reinterpret_cast<const float4*>(s_sh + 4 * cg);
-        const float4 mu = *reinterpret_cast<const float4*>(s_mu + 4 * cg), rs = *reinterpret_cast<const float4*>(s_rs + 4 * cg);
-        for (long long r = r0 + rl; r < r1; r += RL) {
-          const float4 xv = ldcg4(z + r * C + 4 * cg);
-          const float4 d = dy_at4(dy, r, cg, C, io.up2, io.L);
+      if (a.ok) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.ss + 4 * a.cg)), sh = __ldg(reinterpret_cast<const float4*>(bn.ss + C + 4 * a.cg));
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * a.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * a.cg));
+        for (long long r = a.r0 + (t >> 4); r < a.r1; r += 16) {
+          const float4 xv = ldcg4(z + r * C + 4 * a.cg);
+          const float4 d = dy_at4(dy, r, a.cg, C, io.up2, io.L);
           const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
           const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
           acc[0] += (double)g0 * (double)((xv.x - mu.x) * rs.x); acc[1] += (double)g1 * (double)((xv.y - mu.y) * rs.y);
@@ -524,67 +782,77 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           acc[4] += g0; acc[5] += g1; acc[6] += g2; acc[7] += g3;
         }
       }
-      reduce_lanes_and_add(acc, cg, rl, RL, ncg, active, scratch, bn.sums, bn.sums + C);
+      slab_reduce_add(acc, a, C, red_scratch, bn.sums, bn.sums + C);
     }
   }
-  grid_barrier(io.sync, gridDim.x);
+  unsigned int bar_target = gridDim.x;
+  grid_barrier(io.sync, bar_target, io.dbg, 2);
+  phase_ts(io.dbg, 3);
 
-  // ---- phase 2: dz = scale * (g - dbeta/N - xhat * dgamma/N) -> operand planes; affine gradients (elementwise.cu: bn_act_bwd_apply_kernel)
-  for (int c = t; c < C; c += T) {
-    const double dg = __ldcg(bn.sums + c), db = __ldcg(bn.sums + C + c);
-    s_dg[c] = (float)dg;
-    s_db[c] = (float)db;
-    if (blockIdx.x == 0) {
-      if (io.ggamma) ms_stp(io.ggamma, io.gdt, c, ms_ldp_d(io.ggamma, io.gdt, c) + dg);
-      if (io.gbeta) ms_stp(io.gbeta, io.gdt, c, ms_ldp_d(io.gbeta, io.gdt, c) + db);
-    }
-  }
-  __syncthreads();
+  // ---- phase 2: dz = scale * (g - dbeta/N - xhat * dgamma/N) -> operand planes; affine gradients
   {
     const float inv = 1.f / (float)io.rows;
-    const long long total = (r1 - r0) * ncg;
-    for (long long i = t; i < total; i += T) {
-      const long long r = r0 + i / ncg;
-      const int cg = (int)(i % ncg);
-      const float4 xv = ldcg4(z + r * C + 4 * cg);
-      const float4 d = dy_at4(dy, r, cg, C, io.up2, io.L);
-      const float4 sc = *reinterpret_cast<const float4*>(s_sc + 4 * cg), sh = *reinterpret_cast<const float4*>(s_sh + 4 * cg);
-      const float4 mu = *reinterpret_cast<const float4*>(s_mu + 4 * cg), rs = *reinterpret_cast<const float4*>(s_rs + 4 * cg);
-      const float4 dgv = *reinterpret_cast<const float4*>(s_dg + 4 * cg), dbv = *reinterpret_cast<const float4*>(s_db + 4 * cg);
-      const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
-      const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
-      float4 o;
+    for (int s = blockIdx.x; s < sl.total; s += gridDim.x) {
+      const SlabAt a = slab_at(sl, s, C, io.rows);
+      if (!a.ok) continue;
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.ss + 4 * a.cg)), sh = __ldg(reinterpret_cast<const float4*>(bn.ss + C + 4 * a.cg));
+      const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * a.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * a.cg));
+      float4 dgv = make_float4(0.f, 0.f, 0.f, 0.f), dbv = dgv;
       if (bn.training) {
-        o.x = sc.x * (g0 - dbv.x * inv - ((xv.x - mu.x) * rs.x) * dgv.x * inv);
-        o.y = sc.y * (g1 - dbv.y * inv - ((xv.y - mu.y) * rs.y) * dgv.y * inv);
-        o.z = sc.z * (g2 - dbv.z * inv - ((xv.z - mu.z) * rs.z) * dgv.z * inv);
-        o.w = sc.w * (g3 - dbv.w * inv - ((xv.w - mu.w) * rs.w) * dgv.w * inv);
-      } else {
-        o.x = sc.x * g0; o.y = sc.y * g1; o.z = sc.z * g2; o.w = sc.w * g3;
+        const double d0 = __ldcg(bn.sums + 4 * a.cg), d1 = __ldcg(bn.sums + 4 * a.cg + 1), d2 = __ldcg(bn.sums + 4 * a.cg + 2), d3 = __ldcg(bn.sums + 4 * a.cg + 3);
+        const double b0 = __ldcg(bn.sums + C + 4 * a.cg), b1 = __ldcg(bn.sums + C + 4 * a.cg + 1), b2 = __ldcg(bn.sums + C + 4 * a.cg + 2), b3 = __ldcg(bn.sums + C + 4 * a.cg + 3);
+        dgv = make_float4((float)d0, (float)d1, (float)d2, (float)d3);
+        dbv = make_float4((float)b0, (float)b1, (float)b2, (float)b3);
+        if (a.rbi == 0 && (t >> 4) == 0) {
+          const double dgs[4] = {d0, d1, d2, d3}, dbs[4] = {b0, b1, b2, b3};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (io.ggamma) ms_stp(io.ggamma, io.gdt, 4 * a.cg + j, ms_ldp_d(io.ggamma, io.gdt, 4 * a.cg + j) + dgs[j]);
+            if (io.gbeta) ms_stp(io.gbeta, io.gdt, 4 * a.cg + j, ms_ldp_d(io.gbeta, io.gdt, 4 * a.cg + j) + dbs[j]);
+          }
+        }
       }
-      store_planes4(io.dzp, io.pfmt, io.pstride, r * C + 4 * cg, o);
+      for (long long r = a.r0 + (t >> 4); r < a.r1; r += 16) {
+        const float4 xv = ldcg4(z + r * C + 4 * a.cg);
+        const float4 d = dy_at4(dy, r, a.cg, C, io.up2, io.L);
+        const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
+        const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
+        float4 o;
+        if (bn.training) {
+          o.x = sc.x * (g0 - dbv.x * inv - ((xv.x - mu.x) * rs.x) * dgv.x * inv);
+          o.y = sc.y * (g1 - dbv.y * inv - ((xv.y - mu.y) * rs.y) * dgv.y * inv);
+          o.z = sc.z * (g2 - dbv.z * inv - ((xv.z - mu.z) * rs.z) * dgv.z * inv);
+          o.w = sc.w * (g3 - dbv.w * inv - ((xv.w - mu.w) * rs.w) * dgv.w * inv);
+        } else {
+          o.x = sc.x * g0; o.y = sc.y * g1; o.z = sc.z * g2; o.w = sc.w * g3;
+        }
+        store_planes4(io.dzp, io.pfmt, io.pstride, r * C + 4 * a.cg, o);
+      }
     }
   }
   if (!io.has_gemm) return;
   // the planes just written (generic proxy) are read by other CTAs' TMA loads (async proxy) in the next phase
   asm volatile("fence.proxy.async;" ::: "memory");
-  grid_barrier(io.sync, 2u * gridDim.x);
+  bar_target += gridDim.x;
+  grid_barrier(io.sync, bar_target, io.dbg, 4);
   asm volatile("fence.proxy.async;" ::: "memory");
+  phase_ts(io.dbg, 5);
 
   // ---- phase 3: dx = conv^T(dz) on the tensor cores
   GemmSmem sm;
-  sm.a = smem; sm.b = smem + TB_STAGES * A_STAGE_BYTES;
-  sm.full = full_bar; sm.empty = empty_bar; sm.tfull = &tfull_bar; sm.tempty = &tempty_bar;
+  sm.ring = smem; sm.full = full_bar; sm.empty = empty_bar; sm.tfull = tfull_bar; sm.tempty = tempty_bar;
   PipeState st;
   st.s = 0; st.ph = 0; st.li = 0;
-  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, io.dx, sm, tmem_base, st);
+  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, g, io.dx, nullptr, 0, sm, tmem_base, st);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  phase_ts(io.dbg, 6);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
+
 
 // ------------------------------------------------------------------------------------------------------------------
 // weight gradient, accumulated in place
@@ -761,6 +1029,15 @@ static int launch_coop(const void* fn, dim3 grid, size_t smem, cudaStream_t cs, 
   return (int)e;
 }
 
+static int phase_dbg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MS_PHASE_TS");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
 static int fill_bn(BnParams& b, const ms_block_bn* s) {
   if (!s || s->C < 16 || s->C % 4 || !s->gamma || !s->beta || !s->sums || !s->ss) return MS_EINVAL;
   if (s->pdt != MS_F32 && s->pdt != MS_F64) return MS_EINVAL;
@@ -770,21 +1047,63 @@ static int fill_bn(BnParams& b, const ms_block_bn* s) {
   return 0;
 }
 
+// Execution shape of a GEMM phase from the descriptor: ring depth from the stage size, k-slices normalised so that every
+// slice owns at least one k-step, accumulator slots.  want_resident: keep all tiles of a CTA in TMEM when they fit.
+static int gemm_cfg(const ms_igemm_desc* d, const IgemmParams& p, int sms, bool stats, bool want_resident, GemmCfg* gp, unsigned* grid) {
+  GemmCfg& g = *gp;
+  if ((stats || want_resident) && (p.block_n % 32 || d->class_n % 32)) return MS_EINVAL;
+  if (p.block_n % 16) return MS_EINVAL;
+  const int planes = p.npass > 1 ? 2 : 1;
+  g.w_plane_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  g.stage_bytes = (uint32_t)planes * (A_STAGE_BYTES + g.w_plane_bytes);
+  g.stages = (int)(TB_RING_BYTES / g.stage_bytes);
+  if (g.stages > TB_MAX_STAGES) g.stages = TB_MAX_STAGES;
+  if (g.stages < 2) return MS_EINVAL;
+  const int num_k = d->ntaps * d->cchunks;
+  int split = d->split_k > 1 ? d->split_k : 1;
+  if (split > num_k) split = num_k;
+  const int per = (num_k + split - 1) / split;
+  g.split_k = (num_k + per - 1) / per;
+  const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * p.num_classes;
+  const long long items = tiles * g.split_k;
+  if (items < 1 || items > 0x7fffffffLL) return MS_EINVAL;
+  *grid = (unsigned)(items < sms ? items : sms);
+  g.stats = (stats && g.split_k == 1) ? 1 : 0;
+  g.resident = 0;
+  g.nslots = 2;
+  if (want_resident && g.split_k == 1) {
+    const long long per_cta = (tiles + *grid - 1) / *grid;
+    if (per_cta <= TB_MAX_SLOTS && per_cta * p.block_n <= 512) {
+      g.resident = 1;
+      g.nslots = (int)per_cta;
+    }
+  }
+  if (2 * p.block_n > 512 && !g.resident) return MS_EINVAL;
+  return 0;
+}
+
 }  // namespace
+
+extern "C" int ms_debug_phase_ts(unsigned long long* out16) {
+  if (!out16) return MS_EINVAL;
+  MS_CUDA(cudaMemcpyFromSymbol(out16, g_phase_ts, sizeof(unsigned long long) * 16));
+  return 0;
+}
 
 extern "C" int ms_conv_block_train_fwd(const ms_igemm_desc* d, const void* a, const void* w, float* z, const ms_block_bn* bn,
                                        float* y, void* planes, int pfmt, int64_t pstride, const float* res,
                                        const void* res_planes, int res_pfmt, int64_t res_pstride, int up2, void* sync,
                                        void* stream) {
-  if (!d || !a || !w || !z || !bn || !sync || (!y && !planes)) return MS_EINVAL;
+  if (!d || !a || !w || !bn || !sync || (!y && !planes)) return MS_EINVAL;
   if (d->out_dtype != MS_F32 || d->epilogue != 0) return MS_EINVAL;
-  if (bn->training && (!bn->running_mean || !bn->running_var)) return MS_EINVAL;
-  if (res_planes && (((uintptr_t)res_planes & 7) || (res_pfmt != MS_BF16 && res_pfmt != MS_BF16X2) ||
-                     (res_pfmt == MS_BF16X2 && (res_pstride <= 0 || (res_pstride * 2) % 8))))
+  if (bn->training && (!bn->running_mean || !bn->running_var || !z)) return MS_EINVAL;
+  if (!z && d->split_k > 1) return MS_EINVAL;
+  if (res_planes && (((uintptr_t)res_planes & 15) || (res_pfmt != MS_BF16 && res_pfmt != MS_BF16X2) ||
+                     (res_pfmt == MS_BF16X2 && (res_pstride <= 0 || (res_pstride * 2) % 16))))
     return MS_EINVAL;
   if (((uintptr_t)z & 15) || ((uintptr_t)y & 15) || ((uintptr_t)planes & 15) || ((uintptr_t)res & 15)) return MS_EINVAL;
   if (planes && pfmt != MS_BF16 && pfmt != MS_BF16X2) return MS_EINVAL;
-  if (planes && pfmt == MS_BF16X2 && (pstride <= 0 || (pstride * 2) % 8)) return MS_EINVAL;
+  if (planes && pfmt == MS_BF16X2 && (pstride <= 0 || (pstride * 2) % 16)) return MS_EINVAL;
   if (up2 && ((!res && !res_planes) || d->out_dims[1] != 1)) return MS_EINVAL;
   CUtensorMap maps[4];
   IgemmParams p;
@@ -795,30 +1114,32 @@ extern "C" int ms_conv_block_train_fwd(const ms_igemm_desc* d, const void* a, co
   if (rc) return rc;
   const long long rows = (long long)d->out_dims[0] * d->out_dims[1] * d->out_dims[2];
   const int C = d->num_classes * d->class_n;
-  if (C != b.C) return MS_EINVAL;
-  // z must be a dense (rows, C) matrix: the element-wise phases index it that way
+  if (C != b.C || C % 32) return MS_EINVAL;
+  // z / y are dense (rows, C) matrices: the element-wise phases index them that way
   if (d->out_strides[0] != C || d->out_strides[1] != (int64_t)C * d->out_dims[0] ||
       d->out_strides[2] != (int64_t)C * d->out_dims[0] * d->out_dims[1])
     return MS_EINVAL;
   for (int i = 0; i < d->num_classes; i++)
     if (d->out_off[i] != (int64_t)i * d->class_n) return MS_EINVAL;
-  if ((size_t)C * 8 + 8 * 8 * TB_THREADS > TB_RING_BYTES) return MS_EINVAL;
+  if ((size_t)C * 8 > TB_RING_BYTES) return MS_EINVAL;
   FwdIO io;
   io.z = z; io.y = y; io.planes = reinterpret_cast<__nv_bfloat16*>(planes); io.pfmt = pfmt; io.pstride = pstride;
   io.res = up2 ? res : nullptr; io.up2 = up2 ? 1 : 0; io.L = d->out_dims[0]; io.rows = rows;
   io.res_pl = (up2 && !res) ? reinterpret_cast<const __nv_bfloat16*>(res_planes) : nullptr; io.res_fmt = res_pfmt; io.res_ps = res_pstride;
   io.sync = reinterpret_cast<unsigned int*>(sync);
-  const long long items = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * p.num_classes * p.split_k;
-  if (items < 1 || items > 0x7fffffffLL) return MS_EINVAL;
-  const int sms = ms_num_sms();
-  const unsigned grid = (unsigned)(items < sms ? items : sms);
+  io.dbg = phase_dbg();
+  GemmCfg g;
+  unsigned grid = 0;
+  rc = gemm_cfg(d, p, ms_num_sms(), b.training != 0, true, &g, &grid);
+  if (rc) return rc;
+  if (!b.training && !g.resident && !z) return MS_EINVAL;         // the streaming normalise pass re-reads z
   const size_t smem = TB_RING_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     MS_CUDA(cudaFuncSetAttribute(conv_block_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  void* args[] = {&maps[0], &maps[1], &maps[2], &maps[3], &p, &b, &io};
+  void* args[] = {&maps[0], &maps[1], &maps[2], &maps[3], &p, &g, &b, &io};
   rc = launch_coop(reinterpret_cast<const void*>(conv_block_train_fwd_kernel), dim3(grid), smem, ms_stream(stream), args);
   if (rc) return rc;
   MS_LAUNCH_CHECK();
@@ -838,37 +1159,41 @@ extern "C" int ms_conv_block_train_bwd(const ms_igemm_desc* dg, const float* dy,
   BnParams b;
   int rc = fill_bn(b, bn);
   if (rc) return rc;
-  if ((size_t)b.C * 24 + 8 * 8 * TB_THREADS > TB_RING_BYTES) return MS_EINVAL;
   CUtensorMap maps[4];
   IgemmParams p;
+  GemmCfg g;
   BwdIO io;
   io.dy = dy; io.z = z; io.dzp = reinterpret_cast<__nv_bfloat16*>(dz_planes); io.pfmt = pfmt; io.pstride = pstride;
   io.up2 = up2 ? 1 : 0; io.L = rows_per_seq; io.rows = rows; io.ggamma = grad_gamma; io.gbeta = grad_beta; io.gdt = gdt;
   io.dx = dx; io.has_gemm = dg ? 1 : 0; io.sync = reinterpret_cast<unsigned int*>(sync);
+  io.dbg = phase_dbg();
   const int sms = ms_num_sms();
-  long long want;
+  // element-wise phases: one slab (64 channels x >= 16 rows) per CTA and pass
+  long long slabs = (long long)((b.C / 4 + 15) / 16) * ((rows + 15) / 16);
+  unsigned grid = 0;
   if (dg) {
     if (!wt || !dx || dg->out_dtype != MS_F32 || dg->epilogue != 0) return MS_EINVAL;
     rc = igemm_prepare(dg, dz_planes, wt, dg->block_n, maps, &p);
     if (rc) return rc;
-    want = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * p.num_classes * p.split_k;
-    if (want < 1 || want > 0x7fffffffLL) return MS_EINVAL;
+    rc = gemm_cfg(dg, p, sms, false, false, &g, &grid);
+    if (rc) return rc;
+    if ((long long)grid < slabs) grid = (unsigned)(slabs < sms ? slabs : sms);
   } else {
     memset(&p, 0, sizeof(p));
     memset(maps, 0, sizeof(maps));
+    memset(&g, 0, sizeof(g));
     p.block_n = 32;
-    // element-wise only: enough CTAs to spread the rows, no more than one per SM
-    want = (rows * b.C + 16383) / 16384;
-    if (want < 1) want = 1;
+    g.nslots = 1; g.stages = 2; g.split_k = 1;
+    grid = (unsigned)(slabs < sms ? slabs : sms);
   }
-  const unsigned grid = (unsigned)(want < sms ? want : sms);
+  if (grid < 1) grid = 1;
   const size_t smem = TB_RING_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     MS_CUDA(cudaFuncSetAttribute(conv_block_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  void* args[] = {&maps[0], &maps[1], &maps[2], &maps[3], &p, &b, &io};
+  void* args[] = {&maps[0], &maps[1], &maps[2], &maps[3], &p, &g, &b, &io};
   rc = launch_coop(reinterpret_cast<const void*>(conv_block_train_bwd_kernel), dim3(grid), smem, ms_stream(stream), args);
   if (rc) return rc;
   MS_LAUNCH_CHECK();

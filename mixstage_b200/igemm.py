@@ -223,6 +223,55 @@ def igemm_split(d, npass, sms=148):
     return _normalise_split(num_k, min(sms // ctas, num_k // 4))          # one wave: at most one CTA per SM
 
 
+def block_plan(d, npass, stats, sms=148):
+    """(block_n, split_k) of the GEMM phase of a fused block (csrc/conv_train.cu) by a cycle estimate.
+
+    One k-step stages A (16 KB per plane) and W (block_n * 128 B per plane) once for all MMA passes, so it is bound by
+    max(tensor time 2 * block_n * npass clk, operand bytes / (L2 -> SM rate)); the rate is ~6300 B/clk chip-wide
+    (B300_MICROARCH.md) and at most ~80 B/clk for one SM.  Full-K tiles (split 1) cost one pipeline fill per tile and ONE
+    device barrier (statistics come out of the accumulators); split-K costs the reductions into z, a second barrier and
+    the statistics pass over z, and pays when few tiles face a long K (audio encoder tail, UNet bottleneck).
+    stats: forward of a training block (full-K needs 32-column chunks); False for the input-gradient GEMM, whose split
+    form has no statistics pass."""
+    tiles_m = _tiles_m(d)
+    k_steps = d.ntaps * d.cchunks
+    planes = 2 if npass > 1 else 1
+    gran = 32 if stats else 16
+    cands = [b for b in (256, 128, 64, 32) if b <= d.class_n and b % gran == 0]
+    if min(256, d.class_n) not in cands and d.class_n % gran == 0 and d.class_n <= 256:
+        cands.insert(0, d.class_n)
+    if not cands:
+        cands = [min(256, d.class_n)]
+    best = None
+    for bn in cands:
+        tiles = tiles_m * d.num_classes * ((d.class_n + bn - 1) // bn)
+        stage = planes * (16384 + bn * 128)
+        mma = 2 * bn * npass
+        for split in sorted({1} | {_normalise_split(k_steps, s) for s in (2, 3, 4, 6, 8, 12, 16, 24) if tiles * s <= 2 * sms}):
+            items = tiles * split
+            active = min(items, sms)
+            rate = min(80.0, 6300.0 / active)
+            kclk = max(mma, stage / rate)
+            if 196608 // stage < 3:
+                kclk *= 1.4                       # a two-stage ring does not cover the TMA latency
+            waves = (items + sms - 1) // sms
+            per = (k_steps + split - 1) // split
+            cost = waves * (per * kclk + 2500)
+            if split > 1:
+                cost += waves * (128 * bn * 4 / 40.0)
+                cost += 6000 if stats else 1500
+            if best is None or cost < best[0]:
+                best = (cost, bn, split)
+    return best[1], best[2]
+
+
+def block_resident(d, block_n, sms=148):
+    """True when every CTA of a full-K fused launch keeps all of its tiles in TMEM (<= 512 columns, <= 16 tiles)."""
+    tiles = _tiles_m(d) * d.num_classes * ((d.class_n + block_n - 1) // block_n)
+    per_cta = (tiles + min(tiles, sms) - 1) // min(tiles, sms)
+    return per_cta <= 16 and per_cta * block_n <= 512
+
+
 def wgrad_split(d, sms=148, npass=1):
     """(split, c_tile) of a weight-gradient launch.  Tiles are (128 output channels) x (c_tile input channels) per
     (class, tap); the 64-pixel-row tiles are sliced `split` ways and every slice writes its own partial dWp.

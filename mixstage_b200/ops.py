@@ -391,7 +391,7 @@ class PackedWeight:
             pd = igemm.make_dgrad(*geo, out_row_stride=rs if rs != Cin else None) if need_dgrad else None
             for p_ in (pf, pd):
                 if p_ is not None:
-                    p_.desc.block_n = igemm.pick_block_n(p_.desc, npass)
+                    p_.desc.block_n = p_.block_n0 = igemm.pick_block_n(p_.desc, npass)
             pl[key] = (pf, pd)
         return pl[key]
 
@@ -701,12 +701,14 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     global last_gemm_flops
     last_gemm_flops = ctx.flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
     # training-mode BatchNorm blocks: GEMM + statistics + normalise in ONE cooperative launch (csrc/conv_train.cu)
-    fused = FUSED_BLOCKS and cfg.has_bn and training and Cout % 16 == 0 and Cout <= 8192
+    fused = FUSED_BLOCKS and cfg.has_bn and training and (Cout // cfg.groups) % 32 == 0 and Cout <= 8192
     zshape = (B, desc.Ho, desc.Wo, Cout)
     if fused:
+        d.block_n, d.split_k = _block_plan(pf, 3 if split else 1, True)
         z = arena.take_f32(zshape, dev) if d.split_k > 1 else torch.empty(zshape, dtype=torch.float32, device=dev)
     else:
         z = torch.empty(zshape, dtype=torch.float32, device=dev)
+        d.block_n = pf.block_n0
         d.out_numel = z.numel()
         call("ms_igemm_bf16", d, ptr(xp.t), ptr(wp), ptr(b32), None, None, ptr(z), st)
     ctx.tc, ctx.fmt = True, fmt
@@ -734,6 +736,15 @@ def _tc_forward(ctx, x, weight, bias, gamma, beta, residual, cfg, packed, bn_buf
     if yp is not None and carrier is not None:
         carrier.planes = yp           # attached to the output by conv_block (autograd returns a fresh tensor object)
     return y
+
+
+def _block_plan(plan, npass, stats):
+    """(block_n, split_k) of a fused-block GEMM phase, cached on the plan."""
+    key = ("_bp", npass, stats)
+    cache = plan.__dict__.setdefault("_bp_cache", {})
+    if key not in cache:
+        cache[key] = igemm.block_plan(plan.desc, npass, stats)
+    return cache[key]
 
 
 def _block_bn(C, gamma, beta, cbias, bn_buffers, cfg, training, sums, ss):
@@ -809,7 +820,7 @@ def _tc_backward(ctx, dy):
         if need_x:
             wt, wtps = ctx.wt
             igemm.set_planes(pd, split, dzp.ps, wtps, 0)
-            pd.desc.split_k = igemm.igemm_split(pd.desc, 3 if split else 1)
+            pd.desc.block_n, pd.desc.split_k = _block_plan(pd, 3 if split else 1, False)
             dshape = (B, H, W, xrs)
             dxf = arena.take_f32(dshape, dev) if pd.desc.split_k > 1 else torch.empty(dshape, dtype=torch.float32, device=dev)
             dgd, wtp = pd.desc, wt
@@ -878,6 +889,7 @@ def _tc_backward(ctx, dy):
         wt, wtps = ctx.wt
         igemm.set_planes(pd, split, dzp.ps, wtps, 0)
         dxf = torch.empty((B, H, W, xrs), dtype=torch.float32, device=dev)
+        pd.desc.block_n = pd.block_n0
         pd.desc.split_k = igemm.igemm_split(pd.desc, 3 if split else 1)
         pd.desc.out_numel = dxf.numel()
         call("ms_igemm_bf16", pd.desc, ptr(dzp.t), ptr(wt), None, None, None, ptr(dxf), st)
@@ -920,13 +932,17 @@ def _tc_eval(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, up
     y32 = torch.empty(oshape, dtype=torch.float32, device=dev) if want != "planes" else None
     yp = alloc_planes(rows_out, Cout, fmt, dev) if want != "f32" else None
     global last_gemm_flops
-    ksplit = igemm.igemm_split(d, 3 if split else 1) if (FUSED_BLOCKS and cfg.has_bn and row_w is None and Cout <= 8192) else 1
-    if ksplit > 1:
-        # small batch: fewer tiles than SMs.  k-slices over the whole machine reduce into an fp32 tile in L2, one device-wide
-        # barrier, then the folded BatchNorm + LeakyReLU (+ upsample/skip) -> planes / fp32: still ONE launch (conv_train.cu)
-        d.epilogue, d.split_k, d.out_dtype = 0, ksplit, _lib.MS_F32
+    small = False
+    if FUSED_BLOCKS and cfg.has_bn and row_w is None and Cout <= 8192 and (Cout // cfg.groups) % 32 == 0:
+        bn_, ksplit = _block_plan(pf, 3 if split else 1, True)
+        small = ksplit > 1 or (igemm.block_resident(d, bn_) and igemm._tiles_m(d) * d.num_classes * ((d.class_n + bn_ - 1) // bn_) <= 148)
+    if small:
+        # small batch: at most one tile per SM.  Full-K tiles normalise straight out of TMEM (no barrier at all); long-K
+        # layers with few tiles run k-slices over the whole machine, reduce into an fp32 tile in L2, one device-wide barrier,
+        # then the folded BatchNorm + LeakyReLU (+ upsample/skip) -> planes / fp32: ONE launch either way (conv_train.cu)
+        d.epilogue, d.block_n, d.split_k, d.out_dtype = 0, bn_, ksplit, _lib.MS_F32
         igemm.set_planes(pf, split, xp.ps, wps, 0)
-        z = arena.take_f32((B, Ho, Wo, Cout), dev)
+        z = arena.take_f32((B, Ho, Wo, Cout), dev) if ksplit > 1 else None
         sync = arena.take((2,), dev)
         bn = _block_bn(Cout, gamma, beta, None, None, cfg, False, None, ss)
         bn.sums = ptr(sync)                  # unused in inference form; non-NULL for the argument check
@@ -941,6 +957,7 @@ def _tc_eval(x, weight, bias, gamma, beta, residual, cfg, packed, bn_buffers, up
         return planes_view(yp, oshape)
     igemm.set_planes(pf, split, xp.ps, wps, yp.ps if yp is not None else 0)
     d.out_dtype = fmt if yp is not None else _lib.MS_F32
+    d.block_n = pf.block_n0
     last_gemm_flops = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
     if row_w is not None:
         # soft cluster weight of every row applied in the epilogue (classes = clusters): the mixture moves into the GEMMs

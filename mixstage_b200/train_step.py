@@ -460,15 +460,15 @@ class TrainStep:
             self._pver = (self.fG.p._version, self.fD.p._version)
             self.eager_steps += 1
             return self.fake, self.losses
+        if self._pver != (self.fG.p._version, self.fD.p._version):
+            self.refresh()           # someone wrote the parameters between steps (load_state_dict, ...); may drop graphs
         if key not in self.graphs:
             self._capture(key, batch)
         for s, t in zip(self.static, batch):
             s.copy_(t, non_blocking=True)
-        if self._pver != (self.fG.p._version, self.fD.p._version):
-            self.refresh()           # someone wrote the parameters between steps (load_state_dict, ...)
         g, self.fake, self.losses = self.graphs[key]
         g.replay()
         self.replays += 1
-        self.launched += self.kernels_per_graph[key]
+        self.launched += self.kernels_per_graph.get(key, 0)
         ops.bump_weight_epoch()
         return self.fake, self.losses

@@ -541,6 +541,10 @@ def ms_conv_block_train_fwd(desc, a, w, z, bn, y, planes, pfmt, pstride, res, re
     Wo, Ho, Bo = d.out_dims
     rows = Wo * Ho * Bo
     assert b.C == C and d.epilogue == 0 and d.out_dtype == 0
+    if not z:                       # inference form, full-K: the accumulators never leave TMEM, z is not materialised
+        assert not b.training
+        keep_z = torch.zeros(rows * C, dtype=torch.float32)
+        z = keep_z.data_ptr()
     f32(z, rows * C).zero_()
     _igemm(desc, a, w, None, None, None, z, None, None, 0, 0, 0)
     ss = _ptr(b.ss)

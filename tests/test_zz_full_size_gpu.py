@@ -53,7 +53,10 @@ def test_full_size_eval_batch_independence_and_cache(precision, tol):
         assert _rel(soft_full[:n], soft_sub) < tol
         agree = float((soft_full[:n].argmax(-1) == soft_sub.argmax(-1)).double().mean())
         assert agree >= 0.995, agree
-        assert _rel(full2, full2_nc) < 1e-6                                    # cache on/off: same kernels on the same data
+        # cache on/off: the same kernels on the same data, but the split-K layers (fewer tiles than SMs: UNet bottleneck)
+        # reduce their k-slices with red.global.add in arrival order, so two runs agree to fp32 reduction-order noise
+        # amplified by the operand rounding of the next layer -- a tenth of the mode's own tolerance, not bit-equal
+        assert _rel(full2, full2_nc) < 0.1 * tol, _rel(full2, full2_nc)
         assert _rel(full2, full) > 1e-3                                        # another target style is another gesture
         s = soft_full.sum(-1)
         assert float((s - 1).abs().max()) < 1e-4 and float(soft_full.min()) >= 0.0

@@ -8,6 +8,11 @@ for w in $what; do
   case $w in
     pytest) timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" ;;
     pytestall) timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" ;;
+    fused) timeout 900 python -m pytest tests/test_fused_blocks_gpu.py -q --timeout 600 > gpurun_out/${tag}_fused.log 2>&1; echo "fused rc=$?" ;;
+    benchunfused) MS_FUSED_BLOCKS=0 timeout 600 python bench.py --workload train > gpurun_out/${tag}_bench_train_unfused.json 2> gpurun_out/${tag}_bench_train_unfused.err; echo "benchunfused rc=$?" ;;
+    bench3) timeout 900 python bench.py --workload config3 --steps 10 > gpurun_out/${tag}_bench_c3.json 2> gpurun_out/${tag}_bench_c3.err; echo "bench3 rc=$?" ;;
+    breakdown) timeout 600 python tools/step_breakdown.py --order > gpurun_out/${tag}_breakdown.txt 2>&1; echo "breakdown rc=$?" ;;
+    breakdown128) timeout 600 python tools/step_breakdown.py --batch 128 --speakers 8 > gpurun_out/${tag}_breakdown128.txt 2>&1; echo "breakdown128 rc=$?" ;;
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" ;;
     bench) timeout 1200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" ;;
     benchtrain) timeout 600 python bench.py --workload train > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; echo "benchtrain rc=$?" ;;

@@ -94,7 +94,9 @@ def test_fused_block_equals_three_kernel_path(name, precision):
         assert a[k] is not None, k
         # identical arithmetic up to the order of fp32 split-K / atomic reductions; dz planes are bf16-rounded from values
         # that may differ in the last fp32 bit, which moves dx / dw by ~1e-6 in split-bf16 mode and ~1e-3 of an ulp-flip in bf16
-        tol = 2e-5 if precision == "bf16x3" else 2e-3
+        # (the full-K forward reduces the statistics from fp32 warp partials of the accumulators instead of an fp64 pass over
+        # z: mean / rstd move in the 7th digit, dgamma of a 2048-channel layer by 3e-5)
+        tol = 1e-4 if precision == "bf16x3" else 2e-3
         assert _rel(a[k], b[k]) < tol, (name, k, _rel(a[k], b[k]))
 
 

@@ -222,9 +222,66 @@ int ms_conv_block_train_bwd(const ms_igemm_desc* dg, const float* dy, const floa
                             int64_t rows, int up2, int rows_per_seq, void* dz_planes, int pfmt, int64_t pstride,
                             void* grad_gamma, void* grad_beta, int gdt, const void* wt, float* dx, void* sync,
                             void* stream);
+/* CHAINS: up to MS_CHAIN_MAX consecutive blocks in ONE cooperative launch (block i+1 reads the operand planes block i
+ * wrote; a device-wide barrier separates them).  At batch 16 a train step is bound by the ~280 dependent launches it is
+ * made of, not by their arithmetic; a chain turns the 6-12 launches of a conv stack (UNet1D, ClusterClassify, the grouped
+ * sub-decoders, AudioEncoder, PoseStyleEncoder -- layers.py:80-157,159-199,246-289,446-467) into one.
+ * Forward layer = the arguments of ms_conv_block_train_fwd; `sync` (4 zero-filled bytes) is shared by the chain. */
+#define MS_CHAIN_MAX 16
+typedef struct ms_chain_fwd_layer {
+  const ms_igemm_desc* d;
+  const void* a;
+  const void* w;
+  float* z;
+  const ms_block_bn* bn;
+  float* y;
+  void* planes;
+  int32_t pfmt;
+  int64_t pstride;
+  const float* res;
+  const void* res_planes;
+  int32_t res_pfmt;
+  int64_t res_pstride;
+  int32_t up2;
+} ms_chain_fwd_layer;
+int ms_conv_chain_fwd(const ms_chain_fwd_layer* layers, int n, void* sync, void* stream);
+/* Backward layers in EXECUTION order (last block of the forward chain first) = the arguments of ms_conv_block_train_bwd
+ * plus dy2 (nullable): a second addend of the incoming gradient, laid out like dy -- the gradient a later block of the
+ * chain received for an output that used this block's output as its skip tensor (UNet1D, layers.py:150-152). */
+typedef struct ms_chain_bwd_layer {
+  const ms_igemm_desc* dg;
+  const float* dy;
+  const float* dy2;
+  const float* z;
+  const ms_block_bn* bn;
+  int64_t rows;
+  int32_t up2, rows_per_seq;
+  void* dz_planes;
+  int32_t pfmt;
+  int64_t pstride;
+  void* grad_gamma;
+  void* grad_beta;
+  int32_t gdt;
+  const void* wt;
+  float* dx;
+} ms_chain_bwd_layer;
+int ms_conv_chain_bwd(const ms_chain_bwd_layer* layers, int n, void* sync, void* stream);
+/* The weight gradients of up to MS_CHAIN_MAX blocks (arguments of ms_wgrad_bf16_acc each) in ONE launch. */
+typedef struct ms_wgrad_item {
+  const ms_igemm_desc* d;
+  const void* x;
+  const void* dz;
+  float* acc;
+} ms_wgrad_item;
+int ms_wgrad_bf16_acc_multi(const ms_wgrad_item* items, int n, void* stream);
 /* Timing experiments only (MS_PHASE_TS=1 in the environment when the library is first used): %globaltimer stamps of
- * CTA 0 at the phase boundaries of the LAST fused-block launch, 16 values copied to host memory. */
+ * CTA 0 at the phase boundaries of the LAST fused launch, 8 per block of the chain (8 * MS_CHAIN_MAX values) copied to host
+ * memory. */
 int ms_debug_phase_ts(unsigned long long* out16);
+/* Debugging aid (MS_PHASE_TS=1): where a bounded spin inside a chain launch gave up, from mapped host memory (readable after
+ * the context died): [0] site (1 producer/empty, 2 MMA/accumulator free, 3 MMA/operands, 4 epilogue/accumulator full,
+ * 5 producer drain, 6 device barrier), [1] CTA, [2] thread, [3] block of the chain (+100: backward), [4..5] site data. */
+int ms_debug_trap_info(int* out8);
 /* ms_wgrad_bf16 with every pixel slice ADDING its tile into one fp32 accumulator acc[classes*class_n][ntaps][cchunks*64]
  * (zero-filled by the caller once per step) -- no per-slice partials, no summing kernel. */
 int ms_wgrad_bf16_acc(const ms_igemm_desc* d, const void* x, const void* dz, float* acc, void* stream);

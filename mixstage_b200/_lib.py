@@ -53,6 +53,31 @@ class BlockBn(ctypes.Structure):
                 ("sums", ctypes.c_void_p), ("ss", ctypes.c_void_p)]
 
 
+CHAIN_MAX = 16
+
+
+class ChainFwdLayer(ctypes.Structure):
+    """ms_chain_fwd_layer (include/mixstage_b200.h)."""
+    _fields_ = [("d", ctypes.POINTER(IgemmDesc)), ("a", ctypes.c_void_p), ("w", ctypes.c_void_p), ("z", ctypes.c_void_p),
+                ("bn", ctypes.POINTER(BlockBn)), ("y", ctypes.c_void_p), ("planes", ctypes.c_void_p), ("pfmt", ctypes.c_int32),
+                ("pstride", ctypes.c_int64), ("res", ctypes.c_void_p), ("res_planes", ctypes.c_void_p),
+                ("res_pfmt", ctypes.c_int32), ("res_pstride", ctypes.c_int64), ("up2", ctypes.c_int32)]
+
+
+class ChainBwdLayer(ctypes.Structure):
+    """ms_chain_bwd_layer (include/mixstage_b200.h)."""
+    _fields_ = [("dg", ctypes.POINTER(IgemmDesc)), ("dy", ctypes.c_void_p), ("dy2", ctypes.c_void_p), ("z", ctypes.c_void_p),
+                ("bn", ctypes.POINTER(BlockBn)), ("rows", ctypes.c_int64), ("up2", ctypes.c_int32),
+                ("rows_per_seq", ctypes.c_int32), ("dz_planes", ctypes.c_void_p), ("pfmt", ctypes.c_int32),
+                ("pstride", ctypes.c_int64), ("grad_gamma", ctypes.c_void_p), ("grad_beta", ctypes.c_void_p),
+                ("gdt", ctypes.c_int32), ("wt", ctypes.c_void_p), ("dx", ctypes.c_void_p)]
+
+
+class WgradItem(ctypes.Structure):
+    """ms_wgrad_item (include/mixstage_b200.h)."""
+    _fields_ = [("d", ctypes.POINTER(IgemmDesc)), ("x", ctypes.c_void_p), ("dz", ctypes.c_void_p), ("acc", ctypes.c_void_p)]
+
+
 class WgradEntry(ctypes.Structure):
     """ms_wgrad_entry (include/mixstage_b200.h)."""
     _fields_ = [("acc", ctypes.c_void_p), ("dw", ctypes.c_void_p)] + [
@@ -87,6 +112,10 @@ PROTOTYPES = {
     "ms_conv_block_train_fwd": [_GD, _P, _P, _P, _BN, _P, _P, _I, _L, _P, _P, _I, _L, _I, _P, _P],
     "ms_conv_block_train_bwd": [_GD, _P, _P, _BN, _L, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P],
     "ms_debug_phase_ts": [_P],
+    "ms_debug_trap_info": [_P],
+    "ms_conv_chain_fwd": [_P, _I, _P, _P],
+    "ms_conv_chain_bwd": [_P, _I, _P, _P],
+    "ms_wgrad_bf16_acc_multi": [_P, _I, _P],
     "ms_wgrad_bf16_acc": [_GD, _P, _P, _P, _P],
     "ms_unpack_wgrad_multi": [_P, _I, _I, _P],
     "ms_unpack_igemm_wgrad": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],

@@ -32,7 +32,7 @@ constexpr int TB_THREADS = 256;       // warp 0: TMA producer, warp 1: MMA issue
 constexpr uint32_t TB_RING_BYTES = 196608;      // operand ring (192 KB); reused as scratch by the element-wise phases
 constexpr int TB_MAX_STAGES = 8;
 constexpr int TB_MAX_SLOTS = 16;      // TMEM accumulator slots per CTA (resident tiles)
-constexpr uint32_t GRID_SPIN_LIMIT = 1u << 26;
+constexpr uint32_t GRID_SPIN_LIMIT = 1u << 22;
 
 // BatchNorm side of a block
 struct BnParams {
@@ -77,6 +77,7 @@ struct FwdIO {
 
 struct BwdIO {
   const float* dy;            // (rows_out, C)
+  const float* dy2;           // nullable second addend of the incoming gradient (a skip connection's contribution)
   const float* z;             // (rows, C)
   __nv_bfloat16* dzp;         // operand planes of dz, row stride C
   int pfmt;
@@ -92,13 +93,63 @@ struct BwdIO {
   int dbg;
 };
 
+// One block of a chain launch: tensor maps (A, W, A lo, W lo), GEMM geometry, execution shape, BatchNorm side, tensors
+struct FwdLayer {
+  CUtensorMap map_a, map_w, map_a_lo, map_w_lo;
+  IgemmParams p;
+  GemmCfg g;
+  BnParams bn;
+  FwdIO io;
+};
+struct BwdLayer {
+  CUtensorMap map_a, map_w, map_a_lo, map_w_lo;
+  IgemmParams p;
+  GemmCfg g;
+  BnParams bn;
+  BwdIO io;
+};
+constexpr int CHAIN_MAX = MS_CHAIN_MAX;
+struct FwdChain {
+  int n, dbg;
+  unsigned int* sync;
+  FwdLayer L[CHAIN_MAX];
+};
+struct BwdChain {
+  int n, dbg;
+  unsigned int* sync;
+  BwdLayer L[CHAIN_MAX];
+};
+static_assert(sizeof(FwdChain) <= 32000 && sizeof(BwdChain) <= 32000, "chain parameter block exceeds the kernel parameter space");
+
+// Where a bounded spin gave up (pipeline deadlock): written to MAPPED HOST memory right before the trap, so the host can
+// still read it from a dead context (ms_debug_trap_info).  [0] site, [1] CTA, [2] thread, [3] block of the chain, [4..5] extra
+__device__ int* g_trap_info = nullptr;
+__device__ int g_trap_layer = 0;
+__device__ __noinline__ void trap_report(int site, int x0, int x1) {
+  int* q = g_trap_info;
+  if (q) {
+    if (atomicCAS(reinterpret_cast<unsigned int*>(q), 0u, (unsigned int)site) == 0u) {
+      q[1] = (int)blockIdx.x; q[2] = (int)threadIdx.x; q[3] = g_trap_layer; q[4] = x0; q[5] = x1;
+      __threadfence_system();
+    }
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, int site, int x0 = 0) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) trap_report(site, x0, (int)parity);
+  }
+}
+
 // MS_PHASE_TS=1 (timing experiments only): CTA 0 stamps %globaltimer at the phase boundaries of the last fused launch
-__device__ unsigned long long g_phase_ts[16];
+__device__ unsigned long long g_phase_ts[8 * MS_CHAIN_MAX];
+// dbg = 0: off; else 1 + 8 * (layer index in the chain)
 __device__ __forceinline__ void phase_ts(int dbg, int i) {
   if (dbg && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_phase_ts[i] = t;
+    g_phase_ts[(dbg - 1) + i] = t;
   }
 }
 
@@ -113,16 +164,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
     while (true) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
       if (v >= target) break;
-      if (++spins > GRID_SPIN_LIMIT) __trap();       // a CTA that never arrives must not hang the GPU
+      if (++spins > GRID_SPIN_LIMIT) trap_report(6, (int)v, (int)target);       // a CTA that never arrives must not hang the GPU
     }
   }
   __syncthreads();
 }
 
-struct PipeState {
-  int s;
-  uint32_t ph;
-  uint32_t li;
+// Phase parity of every pipeline barrier as each role thread has consumed it (bit s = uses so far of barrier s, mod 2).
+// The barriers are initialised once per launch; the bits travel from block to block of a chain, so nothing is ever
+// re-initialised (re-initialising between blocks raced with arrivals still in flight: observed deadlocks).
+struct PipeBits {
+  uint32_t e, f, te, tf;       // empty (producer), full (MMA), accumulator free (MMA), accumulator full (epilogue)
 };
 
 struct GemmSmem {
@@ -181,7 +233,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUtensorMap* map_w, const CUtensorMap* map_a_lo,
                                            const CUtensorMap* map_w_lo, const IgemmParams& p, const GemmCfg& g,
                                            float* __restrict__ out, double* __restrict__ sums, int C, const GemmSmem& sm,
-                                           uint32_t tmem_base, PipeState& st) {
+                                           uint32_t tmem_base, PipeBits& pb, float* stat_part = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ny = p.n_tiles_per_class * p.num_classes;
   const int tiles = p.tiles_w * p.tiles_h * p.tiles_b * ny;
@@ -192,6 +244,7 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
   const uint32_t a_bytes = split ? 2u * A_STAGE_BYTES : A_STAGE_BYTES;
   if (warp == 0) {
     if (lane == 0) {
+      int s = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int slice = it % g.split_k;
         const TileAt a = tile_at(p, it / g.split_k);
@@ -202,38 +255,48 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
         const int k_beg = slice * k_per;
         const int k_end = min(num_k_total, k_beg + k_per);
         for (int kk = k_beg; kk < k_end; kk++) {
-          mbar_wait(&sm.empty[st.s], st.ph ^ 1u);
+          mbar_wait_at(&sm.empty[s], ((pb.e >> s) & 1u) ^ 1u, 1, kk);     // the release of this stage's previous use
+          pb.e ^= 1u << s;
           const int tap = kk / p.cchunks, cc = kk - tap * p.cchunks;
           const short* t = p.taps[tap_base + tap];
-          uint8_t* dst = sm.ring + (size_t)st.s * g.stage_bytes;
-          mbar_expect_tx(&sm.full[st.s], g.stage_bytes);
+          uint8_t* dst = sm.ring + (size_t)s * g.stage_bytes;
+          mbar_expect_tx(&sm.full[s], g.stage_bytes);
           const int c0 = chan_base + t[0] + cc * BLOCK_K, c1 = w0 + t[1], c2 = t[2], c3 = h0 + t[3];
-          tma_load_5d(map_a, &sm.full[st.s], dst, c0, c1, c2, c3, b0);
-          tma_load_2d(map_w, &sm.full[st.s], dst + a_bytes, kk * BLOCK_K, wrow);
+          tma_load_5d(map_a, &sm.full[s], dst, c0, c1, c2, c3, b0);
+          tma_load_2d(map_w, &sm.full[s], dst + a_bytes, kk * BLOCK_K, wrow);
           if (split) {
-            tma_load_5d(map_a_lo, &sm.full[st.s], dst + A_STAGE_BYTES, c0, c1, c2, c3, b0);
-            tma_load_2d(map_w_lo, &sm.full[st.s], dst + a_bytes + g.w_plane_bytes, kk * BLOCK_K, wrow);
+            tma_load_5d(map_a_lo, &sm.full[s], dst + A_STAGE_BYTES, c0, c1, c2, c3, b0);
+            tma_load_2d(map_w_lo, &sm.full[s], dst + a_bytes + g.w_plane_bytes, kk * BLOCK_K, wrow);
           }
-          if (++st.s == g.stages) { st.s = 0; st.ph ^= 1u; }
+          if (++s == g.stages) s = 0;
         }
       }
+      // drain: the MMA thread's commits on the `empty` barriers of the last k-steps have nobody waiting for them; they must
+      // have landed before this phase ends, so that the phase bits every role carries from block to block of a chain
+      // (the barriers are initialised ONCE per launch) stay in step with the barriers
+      for (int i = 0; i < TB_MAX_STAGES; i++) mbar_wait_at(&sm.empty[i], ((pb.e >> i) & 1u) ^ 1u, 5, i);
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      int s = 0;
+      uint32_t li = 0;
       for (int it = blockIdx.x; it < items; it += gridDim.x) {
         const int slice = it % g.split_k;
         const int k_beg = slice * k_per;
         const int num_k = min(num_k_total, k_beg + k_per) - k_beg;
-        const int slot = (int)(st.li % (uint32_t)g.nslots);
-        const uint32_t use = st.li / (uint32_t)g.nslots;
-        mbar_wait(&sm.tempty[slot], (use & 1u) ^ 1u);       // the epilogue warps drained this slot's previous accumulator
+        const int slot = (int)(li % (uint32_t)g.nslots);
+        if (!g.resident) {
+          mbar_wait_at(&sm.tempty[slot], ((pb.te >> slot) & 1u) ^ 1u, 2, slot);   // the epilogue warps drained this slot's previous accumulator
+          pb.te ^= 1u << slot;
+        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(slot * p.block_n);
         for (int ks = 0; ks < num_k; ks++) {
-          mbar_wait(&sm.full[st.s], st.ph);
+          mbar_wait_at(&sm.full[s], (pb.f >> s) & 1u, 3, ks);
+          pb.f ^= 1u << s;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t base = smem_u32(sm.ring + (size_t)st.s * g.stage_bytes);
+          const uint32_t base = smem_u32(sm.ring + (size_t)s * g.stage_bytes);
           const uint64_t da = make_kmajor_sw128_desc(base);
           const uint64_t db = make_kmajor_sw128_desc(base + a_bytes);
           if (split) {
@@ -250,12 +313,15 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
             for (int k = 0; k < BLOCK_K / UMMA_K; k++)
               umma_bf16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (ks | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&sm.empty[st.s]);
-          if (++st.s == g.stages) { st.s = 0; st.ph ^= 1u; }
+          umma_commit(&sm.empty[s]);
+          if (++s == g.stages) s = 0;
         }
         umma_commit(&sm.tfull[slot]);
-        st.li++;
+        li++;
       }
+      // drain (streaming accumulators): the epilogue's hand-back of the last use of every slot
+      if (!g.resident)
+        for (int i = 0; i < g.nslots; i++) mbar_wait_at(&sm.tempty[i], ((pb.te >> i) & 1u) ^ 1u, 7, i);
     }
   } else if (warp < 6) {
     const int q = warp & 3;
@@ -263,15 +329,16 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
     const int wi = r % p.box_w;
     const int hi = (r / p.box_w) % p.box_h;
     const int bi = r / (p.box_w * p.box_h);
+    uint32_t li = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       const TileAt a = tile_at(p, it / g.split_k);
       const int ow = a.tw * p.box_w + wi, oh = a.th * p.box_h + hi, ob = a.mt * p.box_b + bi;
       const bool valid = ow < p.out_w && oh < p.out_h && ob < p.out_b;
       const long long col0 = p.out_off[a.cls] + a.n0;
       float* dst = out ? out + (long long)ob * p.os_b + (long long)oh * p.os_h + (long long)ow * p.os_w + col0 : nullptr;
-      const int slot = (int)(st.li % (uint32_t)g.nslots);
-      const uint32_t use = st.li / (uint32_t)g.nslots;
-      mbar_wait(&sm.tfull[slot], use & 1u);
+      const int slot = (int)(li % (uint32_t)g.nslots);
+      mbar_wait_at(&sm.tfull[slot], (pb.tf >> slot) & 1u, 4, slot);
+      pb.tf ^= 1u << slot;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * p.block_n);
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
@@ -323,9 +390,16 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
           }
           const float cs = warp_colsum32(f, lane);
           const float cq = warp_colsum32(s2, lane);
-          const long long c = col0 + c0 + lane;
-          atomicAdd(sums + c, (double)cs);
-          atomicAdd(sums + C + c, (double)cq);
+          if (stat_part) {
+            // resident tiles: the four epilogue warps' partials meet in shared memory, ONE atomic per channel and CTA later
+            float* sp = stat_part + ((size_t)(slot * p.block_n + c0 + lane) * 4 + q) * 2;
+            sp[0] = cs;
+            sp[1] = cq;
+          } else {
+            const long long c = col0 + c0 + lane;
+            atomicAdd(sums + c, (double)cs);
+            atomicAdd(sums + C + c, (double)cq);
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -333,7 +407,7 @@ __device__ __forceinline__ void gemm_phase(const CUtensorMap* map_a, const CUten
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.tempty[slot]);
       }
-      st.li++;
+      li++;
     }
   }
 }
@@ -459,94 +533,133 @@ __device__ __forceinline__ void add_res32(const FwdIO& io, long long e, float (&
   }
 }
 
-// per-channel finalize of training-mode BatchNorm: scale / shift for the normalise pass; `publish`: running statistics and
-// the [scale, shift, mean, rstd] table the backward reads
-__device__ __forceinline__ void bn_finalize_channel(const BnParams& bn, long long rows, int c, bool publish, float& sc, float& sh) {
+// per-channel finalize of training-mode BatchNorm in two parts: the parameter loads do not depend on the statistics and are
+// issued BEFORE the device barrier (bn_pre); after it only the two sums are fetched.  `publish`: running statistics and the
+// [scale, shift, mean, rstd] table the backward reads
+struct BnPre {
+  double g, b, cb, rm, rv;
+};
+__device__ __forceinline__ BnPre bn_pre(const BnParams& bn, int c, bool publish) {
+  BnPre q;
+  q.g = ms_ldp_d(bn.gamma, bn.pdt, c);
+  q.b = ms_ldp_d(bn.beta, bn.pdt, c);
+  q.cb = 0.0; q.rm = 0.0; q.rv = 0.0;
+  if (publish) {
+    if (bn.cbias) q.cb = ms_ldp_d(bn.cbias, bn.pdt, c);
+    q.rm = ms_ldp_d(bn.rmean, bn.pdt, c);
+    q.rv = ms_ldp_d(bn.rvar, bn.pdt, c);
+  }
+  return q;
+}
+__device__ __forceinline__ void bn_finish(const BnParams& bn, const BnPre& q, long long rows, int c, bool publish, float& sc, float& sh) {
   const int C = bn.C;
   const double sum = __ldcg(bn.sums + c), sumsq = __ldcg(bn.sums + C + c);
   const double mean = sum / (double)rows;
   double var = sumsq / (double)rows - mean * mean;
   if (var < 0.0) var = 0.0;
   const double rstd = 1.0 / sqrt(var + (double)bn.eps);
-  const double g = ms_ldp_d(bn.gamma, bn.pdt, c), b = ms_ldp_d(bn.beta, bn.pdt, c);
-  sc = (float)(g * rstd);
-  sh = (float)(b - mean * g * rstd);
+  sc = (float)(q.g * rstd);
+  sh = (float)(q.b - mean * q.g * rstd);
   if (publish) {
-    const double cb = bn.cbias ? ms_ldp_d(bn.cbias, bn.pdt, c) : 0.0;
     const double unb = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
-    const double rm = ms_ldp_d(bn.rmean, bn.pdt, c), rv = ms_ldp_d(bn.rvar, bn.pdt, c);
-    ms_stp(bn.rmean, bn.pdt, c, (1.0 - (double)bn.momentum) * rm + (double)bn.momentum * (mean + cb));
-    ms_stp(bn.rvar, bn.pdt, c, (1.0 - (double)bn.momentum) * rv + (double)bn.momentum * unb);
+    ms_stp(bn.rmean, bn.pdt, c, (1.0 - (double)bn.momentum) * q.rm + (double)bn.momentum * (mean + q.cb));
+    ms_stp(bn.rvar, bn.pdt, c, (1.0 - (double)bn.momentum) * q.rv + (double)bn.momentum * unb);
     bn.ss[c] = sc;
     bn.ss[C + c] = sh;
     bn.ss[2 * C + c] = (float)mean;
     bn.ss[3 * C + c] = (float)rstd;
   }
 }
+__device__ __forceinline__ void bn_finalize_channel(const BnParams& bn, long long rows, int c, bool publish, float& sc, float& sh) {
+  const BnPre q = bn_pre(bn, c, publish);
+  bn_finish(bn, q, rows, c, publish, sc, sh);
+}
+
+// inference: BatchNorm over the running statistics folded to (scale, shift), the conv bias inside the shift (the GEMM output
+// excludes it) -- the arithmetic of ms_bn_finalize's inference form, per channel, inside the launch
+__device__ __forceinline__ void bn_fold_channel(const BnParams& bn, int c, float& sc, float& sh) {
+  const double g = ms_ldp_d(bn.gamma, bn.pdt, c), b = ms_ldp_d(bn.beta, bn.pdt, c);
+  const double rm = ms_ldp_d(bn.rmean, bn.pdt, c), rv = ms_ldp_d(bn.rvar, bn.pdt, c);
+  const double cb = bn.cbias ? ms_ldp_d(bn.cbias, bn.pdt, c) : 0.0;
+  const double rstd = 1.0 / sqrt(rv + (double)bn.eps);
+  sc = (float)(g * rstd);
+  sh = (float)(b + (cb - rm) * g * rstd);
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward block
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TB_THREADS, 1)
-conv_block_train_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                            const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
-                            const __grid_constant__ IgemmParams p, const __grid_constant__ GemmCfg g,
-                            const __grid_constant__ BnParams bn, const __grid_constant__ FwdIO io) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[TB_MAX_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TB_MAX_STAGES];
-  __shared__ __align__(8) uint64_t tfull_bar[TB_MAX_SLOTS];
-  __shared__ __align__(8) uint64_t tempty_bar[TB_MAX_SLOTS];
-  __shared__ __align__(16) double red_scratch[8 * 16 * 8];
-  __shared__ uint32_t tmem_base_smem;
+// One forward block inside a chain launch.  Barriers are already initialised and TMEM allocated by the caller; bar_target is
+// the running target of the device-wide barrier counter (all CTAs walk the same sequence of barriers).
+__device__ __forceinline__ void fwd_layer(const FwdLayer& L, uint8_t* smem, const GemmSmem& sm, double* red_scratch,
+                                          float* stat_part, uint32_t tmem_base, unsigned int* sync, unsigned int& bar_target,
+                                          PipeBits& pb, int dbg) {
+  const CUtensorMap& map_a = L.map_a;
+  const CUtensorMap& map_w = L.map_w;
+  const CUtensorMap& map_a_lo = L.map_a_lo;
+  const CUtensorMap& map_w_lo = L.map_w_lo;
+  const IgemmParams& p = L.p;
+  const GemmCfg& g = L.g;
+  const BnParams& bn = L.bn;
+  const FwdIO& io = L.io;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  phase_ts(io.dbg, 0);
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(g.nslots * p.block_n)) tmem_cols <<= 1;
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-    if (p.npass > 1) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
-    }
-    for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < g.nslots; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_smem;
-  GemmSmem sm;
-  sm.ring = smem; sm.full = full_bar; sm.empty = empty_bar; sm.tfull = tfull_bar; sm.tempty = tempty_bar;
-  PipeState st;
-  st.s = 0; st.ph = 0; st.li = 0;
   const int C = bn.C, T = TB_THREADS, t = threadIdx.x;
   const float slope = bn.slope;
+  const bool train = bn.training == 1;     // 0: inference, folded constants in bn.ss; 2: inference, folded here from the running statistics
 
   // ---- phase 1: z = conv(x) on the tensor cores (+ statistics from the accumulators in the full-K training form)
-  phase_ts(io.dbg, 1);
-  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, g, io.z, bn.sums, C, sm, tmem_base, st);
+  phase_ts(dbg, 1);
+  const bool smem_stats = g.resident && g.stats;
+  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, g, io.z, bn.sums, C, sm, tmem_base, pb, smem_stats ? stat_part : nullptr);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  unsigned int bar_target = 0;
-  const bool need_bar1 = bn.training || g.split_k > 1;      // inference, full-K: every CTA normalises its own tiles at once
+  // resident form: at most 512 accumulator columns per CTA = two (slot, column) entries per thread.  Their channel, the
+  // BatchNorm parameters (independent of the statistics: fetched BEFORE the barrier) and the CTA-level statistics atomics
+  int n_my = 0;
+  int my_c[2] = {-1, -1};
+  bool my_pub[2] = {false, false};
+  BnPre my_pre[2];
+  if (g.resident) {
+    const int tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * p.num_classes;
+    for (int it = blockIdx.x; it < tiles; it += gridDim.x) n_my++;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int idx = t + k * T;
+      if (idx < n_my * p.block_n) {
+        const int slot = idx / p.block_n, j = idx - slot * p.block_n;
+        const TileAt a = tile_at(p, blockIdx.x + slot * gridDim.x);
+        if (a.n0 + j < p.class_n) {
+          my_c[k] = (int)p.out_off[a.cls] + a.n0 + j;
+          my_pub[k] = a.tw == 0 && a.th == 0 && a.mt == 0;
+          if (train) my_pre[k] = bn_pre(bn, my_c[k], my_pub[k]);
+        }
+      }
+    }
+    if (smem_stats) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        if (my_c[k] >= 0) {
+          const float* sp = stat_part + (size_t)(t + k * T) * 8;
+          const double cs = (double)sp[0] + (double)sp[2] + (double)sp[4] + (double)sp[6];
+          const double cq = (double)sp[1] + (double)sp[3] + (double)sp[5] + (double)sp[7];
+          atomicAdd(bn.sums + my_c[k], cs);
+          atomicAdd(bn.sums + C + my_c[k], cq);
+        }
+      }
+    }
+  }
+  const bool need_bar1 = train || g.split_k > 1;      // inference, full-K: every CTA normalises its own tiles at once
   if (need_bar1) {
     bar_target += gridDim.x;
-    grid_barrier(io.sync, bar_target, io.dbg, 2);
+    grid_barrier(sync, bar_target, dbg, 2);
   } else {
     __syncthreads();
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  phase_ts(io.dbg, 3);
+  phase_ts(dbg, 3);
 
   // ---- phase 2 (split-K training form only): per-channel sum and sum of squares of z over slabs
-  if (bn.training && !g.stats) {
+  if (train && !g.stats) {
     const Slabs sl = slabs_of(C, io.rows);
     const float* __restrict__ z = io.z;
     for (int s = blockIdx.x; s < sl.total; s += gridDim.x) {
@@ -570,30 +683,26 @@ conv_block_train_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       slab_reduce_add(acc, a, C, red_scratch, bn.sums, bn.sums + C);
     }
     bar_target += gridDim.x;
-    grid_barrier(io.sync, bar_target, io.dbg, 4);
+    grid_barrier(sync, bar_target, dbg, 4);
   }
-  phase_ts(io.dbg, 5);
+  phase_ts(dbg, 5);
 
   // ---- phase 3: finalize + normalise + LeakyReLU (+ upsample x2 + skip)
-  if (bn.training && blockIdx.x == 0 && t == 0 && bn.nbt) bn.nbt[0] += 1;
+  if (train && blockIdx.x == 0 && t == 0 && bn.nbt) bn.nbt[0] += 1;
   float* s_scale = reinterpret_cast<float*>(smem);          // the ring is idle from here on
   if (g.resident) {
     // the CTA's own tiles, accumulators still in TMEM: constants of each slot's columns, then TMEM -> y / planes
-    const int ny = p.n_tiles_per_class * p.num_classes;
-    const int tiles = p.tiles_w * p.tiles_h * p.tiles_b * ny;
-    int n_my = 0;
-    for (int it = blockIdx.x; it < tiles; it += gridDim.x) n_my++;
-    float* s_shift = s_scale + TB_MAX_SLOTS * 256;
-    for (int idx = t; idx < n_my * p.block_n; idx += T) {
-      const int slot = idx / p.block_n, j = idx - slot * p.block_n;
-      const TileAt a = tile_at(p, blockIdx.x + slot * gridDim.x);
-      if (a.n0 + j < p.class_n) {
-        const int c = (int)p.out_off[a.cls] + a.n0 + j;
+    float* s_shift = s_scale + 512;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (my_c[k] >= 0) {
+        const int c = my_c[k];
         float sc, sh;
-        if (bn.training) bn_finalize_channel(bn, io.rows, c, a.tw == 0 && a.th == 0 && a.mt == 0, sc, sh);
+        if (train) bn_finish(bn, my_pre[k], io.rows, c, my_pub[k], sc, sh);
+        else if (bn.training == 2) bn_fold_channel(bn, c, sc, sh);
         else { sc = __ldg(bn.ss + c); sh = __ldg(bn.ss + C + c); }
-        s_scale[idx] = sc;
-        s_shift[idx] = sh;
+        s_scale[t + k * T] = sc;
+        s_shift[t + k * T] = sh;
       }
     }
     __syncthreads();
@@ -642,7 +751,8 @@ conv_block_train_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     float* s_shift = s_scale + C;
     for (int c = t; c < C; c += T) {
       float sc, sh;
-      if (bn.training) bn_finalize_channel(bn, io.rows, c, blockIdx.x == 0, sc, sh);
+      if (train) bn_finalize_channel(bn, io.rows, c, blockIdx.x == 0, sc, sh);
+      else if (bn.training == 2) bn_fold_channel(bn, c, sc, sh);
       else { sc = __ldg(bn.ss + c); sh = __ldg(bn.ss + C + c); }
       s_scale[c] = sc;
       s_shift[c] = sh;
@@ -698,31 +808,28 @@ conv_block_train_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       }
     }
   }
+  (void)warp; (void)lane;
   __syncthreads();
-  phase_ts(io.dbg, 6);
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  phase_ts(dbg, 6);
+}
+
+// initialise every pipeline barrier of a chain launch, once (thread 0; callers sync after it)
+__device__ __forceinline__ void chain_init_barriers(const GemmSmem& sm) {
+  if (threadIdx.x != 0) return;
+  for (int s = 0; s < TB_MAX_STAGES; s++) {
+    mbar_init(&sm.full[s], 1);
+    mbar_init(&sm.empty[s], 1);
   }
+  for (int s = 0; s < TB_MAX_SLOTS; s++) {
+    mbar_init(&sm.tfull[s], 1);
+    mbar_init(&sm.tempty[s], 4);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// backward block
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 dy_at4(const float* __restrict__ dy, long long r, int cg, int C, int up2, int L) {
-  if (!up2) return ldcg4(dy + r * C + 4 * cg);
-  const long long b = r / L;
-  const int l = (int)(r - b * L);
-  const long long ro = b * 2 * L + 2 * l;
-  const float4 a = ldcg4(dy + ro * C + 4 * cg), c = ldcg4(dy + (ro + 1) * C + 4 * cg);
-  return make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
-}
-
-__global__ void __launch_bounds__(TB_THREADS, 1)
-conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                            const __grid_constant__ CUtensorMap map_a_lo, const __grid_constant__ CUtensorMap map_w_lo,
-                            const __grid_constant__ IgemmParams p, const __grid_constant__ GemmCfg g,
-                            const __grid_constant__ BnParams bn, const __grid_constant__ BwdIO io) {
+// A chain of forward blocks in ONE launch: block i+1 reads the operand planes block i wrote (a device-wide barrier with
+// generic -> async proxy fences in between); TMEM (512 columns) is allocated once.
+__global__ void __launch_bounds__(TB_THREADS, 1) conv_chain_fwd_kernel(const __grid_constant__ FwdChain ch) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[TB_MAX_STAGES];
@@ -730,42 +837,134 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   __shared__ __align__(8) uint64_t tfull_bar[TB_MAX_SLOTS];
   __shared__ __align__(8) uint64_t tempty_bar[TB_MAX_SLOTS];
   __shared__ __align__(16) double red_scratch[8 * 16 * 8];
+  __shared__ __align__(16) float stat_part[512 * 4 * 2];      // [accumulator column][epilogue warp][sum, sum of squares]
   __shared__ uint32_t tmem_base_smem;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  phase_ts(io.dbg, 0);
-  uint32_t tmem_cols = 32;
-  if (io.has_gemm) {
-    while (tmem_cols < (uint32_t)(g.nslots * p.block_n)) tmem_cols <<= 1;
-    if (warp == 0 && lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-      if (p.npass > 1) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_lo)) : "memory");
-      }
-      for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int s = 0; s < g.nslots; s++) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(tmem_cols) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  const int warp = threadIdx.x >> 5;
+  GemmSmem sm;
+  sm.ring = smem; sm.full = full_bar; sm.empty = empty_bar; sm.tfull = tfull_bar; sm.tempty = tempty_bar;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  unsigned int bar_target = 0;
+  uint32_t tmem_base = 0;
+  PipeBits pb;
+  pb.e = pb.f = pb.te = pb.tf = 0u;
+  for (int li = 0; li < ch.n; li++) {
+    const FwdLayer& L = ch.L[li];
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_trap_layer = li;
+    phase_ts(ch.dbg ? 1 + 8 * li : 0, 0);
+    if (li > 0) {
+      // this block's TMA loads (async proxy, any CTA) read the planes the previous block's normalise pass wrote
+      asm volatile("fence.proxy.async;" ::: "memory");
+      bar_target += gridDim.x;
+      grid_barrier(ch.sync, bar_target);
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_a)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_w)) : "memory");
+      if (L.p.npass > 1) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_a_lo)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_w_lo)) : "memory");
+      }
+    }
+    if (li == 0) chain_init_barriers(sm);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_base = tmem_base_smem;
+    fwd_layer(L, smem, sm, red_scratch, stat_part, tmem_base, ch.sync, bar_target, pb, ch.dbg ? 1 + 8 * li : 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = io.has_gemm ? tmem_base_smem : 0u;
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward block
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 dy_at4(const float* __restrict__ dy, const float* __restrict__ dy2, long long r, int cg, int C,
+                                         int up2, int L) {
+  if (!up2) {
+    float4 a = ldcg4(dy + r * C + 4 * cg);
+    if (dy2) {
+      const float4 b = ldcg4(dy2 + r * C + 4 * cg);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    return a;
+  }
+  const long long b = r / L;
+  const int l = (int)(r - b * L);
+  const long long ro = b * 2 * L + 2 * l;
+  float4 a = ldcg4(dy + ro * C + 4 * cg);
+  const float4 c = ldcg4(dy + (ro + 1) * C + 4 * cg);
+  a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+  if (dy2) {
+    const float4 e = ldcg4(dy2 + ro * C + 4 * cg), f = ldcg4(dy2 + (ro + 1) * C + 4 * cg);
+    a.x += e.x + f.x; a.y += e.y + f.y; a.z += e.z + f.z; a.w += e.w + f.w;
+  }
+  return a;
+}
+
+__device__ __forceinline__ void bwd_layer(const BwdLayer& L, uint8_t* smem, const GemmSmem& sm, double* red_scratch,
+                                          uint32_t tmem_base, unsigned int* sync, unsigned int& bar_target, PipeBits& pb, int dbg) {
+  const CUtensorMap& map_a = L.map_a;
+  const CUtensorMap& map_w = L.map_w;
+  const CUtensorMap& map_a_lo = L.map_a_lo;
+  const CUtensorMap& map_w_lo = L.map_w_lo;
+  const IgemmParams& p = L.p;
+  const GemmCfg& g = L.g;
+  const BnParams& bn = L.bn;
+  const BwdIO& io = L.io;
 
   const int C = bn.C, t = threadIdx.x;
   const float* __restrict__ z = io.z;
   const float* __restrict__ dy = io.dy;
   const float slope = bn.slope;
   const Slabs sl = slabs_of(C, io.rows);
-  phase_ts(io.dbg, 1);
+  phase_ts(dbg, 1);
 
   // ---- phase 1: dbeta = sum g, dgamma = sum g * xhat with g = dy * act'(z)   (slab reductions)
-  if (bn.training) {
+  // Fast form (one slab per CTA, <= 4 rows per thread: every small-batch layer): g and xhat stay in registers across the
+  // barrier, so the apply phase re-reads nothing but the two column totals.
+  constexpr int RMAX = 4;
+  const bool fast = sl.total <= (int)gridDim.x && (io.rows / sl.nrb + 1) <= 16 * RMAX;
+  float4 kg[RMAX], kx[RMAX];
+  float4 ksc = make_float4(0.f, 0.f, 0.f, 0.f);
+  SlabAt fa;
+  fa.ok = false; fa.r0 = fa.r1 = 0; fa.cg = 0; fa.cbi = 0; fa.rbi = 0;
+  if (fast) {
+    if ((int)blockIdx.x < sl.total) {
+      fa = slab_at(sl, blockIdx.x, C, io.rows);
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (fa.ok) {
+        ksc = __ldg(reinterpret_cast<const float4*>(bn.ss + 4 * fa.cg));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(bn.ss + C + 4 * fa.cg));
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * fa.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * fa.cg));
+#pragma unroll
+        for (int k = 0; k < RMAX; k++) {
+          const long long r = fa.r0 + (t >> 4) + 16 * k;
+          if (r < fa.r1) {
+            const float4 xv = ldcg4(z + r * C + 4 * fa.cg);
+            const float4 d = dy_at4(dy, io.dy2, r, fa.cg, C, io.up2, io.L);
+            float4 gq, xh;
+            gq.x = fmaf(xv.x, ksc.x, sh.x) > 0.f ? d.x : d.x * slope; gq.y = fmaf(xv.y, ksc.y, sh.y) > 0.f ? d.y : d.y * slope;
+            gq.z = fmaf(xv.z, ksc.z, sh.z) > 0.f ? d.z : d.z * slope; gq.w = fmaf(xv.w, ksc.w, sh.w) > 0.f ? d.w : d.w * slope;
+            xh.x = (xv.x - mu.x) * rs.x; xh.y = (xv.y - mu.y) * rs.y; xh.z = (xv.z - mu.z) * rs.z; xh.w = (xv.w - mu.w) * rs.w;
+            kg[k] = gq; kx[k] = xh;
+            acc[0] += (double)gq.x * (double)xh.x; acc[1] += (double)gq.y * (double)xh.y;
+            acc[2] += (double)gq.z * (double)xh.z; acc[3] += (double)gq.w * (double)xh.w;
+            acc[4] += gq.x; acc[5] += gq.y; acc[6] += gq.z; acc[7] += gq.w;
+          }
+        }
+      }
+      if (bn.training) slab_reduce_add(acc, fa, C, red_scratch, bn.sums, bn.sums + C);
+    }
+  } else if (bn.training) {
     for (int s = blockIdx.x; s < sl.total; s += gridDim.x) {
       const SlabAt a = slab_at(sl, s, C, io.rows);
       double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -774,7 +973,7 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * a.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * a.cg));
         for (long long r = a.r0 + (t >> 4); r < a.r1; r += 16) {
           const float4 xv = ldcg4(z + r * C + 4 * a.cg);
-          const float4 d = dy_at4(dy, r, a.cg, C, io.up2, io.L);
+          const float4 d = dy_at4(dy, io.dy2, r, a.cg, C, io.up2, io.L);
           const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
           const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
           acc[0] += (double)g0 * (double)((xv.x - mu.x) * rs.x); acc[1] += (double)g1 * (double)((xv.y - mu.y) * rs.y);
@@ -785,18 +984,18 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       slab_reduce_add(acc, a, C, red_scratch, bn.sums, bn.sums + C);
     }
   }
-  unsigned int bar_target = gridDim.x;
-  grid_barrier(io.sync, bar_target, io.dbg, 2);
-  phase_ts(io.dbg, 3);
+  bar_target += gridDim.x;
+  grid_barrier(sync, bar_target, dbg, 2);
+  phase_ts(dbg, 3);
 
   // ---- phase 2: dz = scale * (g - dbeta/N - xhat * dgamma/N) -> operand planes; affine gradients
   {
     const float inv = 1.f / (float)io.rows;
-    for (int s = blockIdx.x; s < sl.total; s += gridDim.x) {
-      const SlabAt a = slab_at(sl, s, C, io.rows);
+    const int s_beg = fast ? ((int)blockIdx.x < sl.total ? (int)blockIdx.x : sl.total) : (int)blockIdx.x;
+    const int s_step = fast ? sl.total : (int)gridDim.x;
+    for (int s = s_beg; s < sl.total; s += s_step) {
+      const SlabAt a = fast ? fa : slab_at(sl, s, C, io.rows);
       if (!a.ok) continue;
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.ss + 4 * a.cg)), sh = __ldg(reinterpret_cast<const float4*>(bn.ss + C + 4 * a.cg));
-      const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * a.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * a.cg));
       float4 dgv = make_float4(0.f, 0.f, 0.f, 0.f), dbv = dgv;
       if (bn.training) {
         const double d0 = __ldcg(bn.sums + 4 * a.cg), d1 = __ldcg(bn.sums + 4 * a.cg + 1), d2 = __ldcg(bn.sums + 4 * a.cg + 2), d3 = __ldcg(bn.sums + 4 * a.cg + 3);
@@ -812,9 +1011,30 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           }
         }
       }
+      if (fast) {
+#pragma unroll
+        for (int k = 0; k < RMAX; k++) {
+          const long long r = a.r0 + (t >> 4) + 16 * k;
+          if (r < a.r1) {
+            float4 o;
+            if (bn.training) {
+              o.x = ksc.x * (kg[k].x - dbv.x * inv - kx[k].x * dgv.x * inv);
+              o.y = ksc.y * (kg[k].y - dbv.y * inv - kx[k].y * dgv.y * inv);
+              o.z = ksc.z * (kg[k].z - dbv.z * inv - kx[k].z * dgv.z * inv);
+              o.w = ksc.w * (kg[k].w - dbv.w * inv - kx[k].w * dgv.w * inv);
+            } else {
+              o.x = ksc.x * kg[k].x; o.y = ksc.y * kg[k].y; o.z = ksc.z * kg[k].z; o.w = ksc.w * kg[k].w;
+            }
+            store_planes4(io.dzp, io.pfmt, io.pstride, r * C + 4 * a.cg, o);
+          }
+        }
+        continue;
+      }
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.ss + 4 * a.cg)), sh = __ldg(reinterpret_cast<const float4*>(bn.ss + C + 4 * a.cg));
+      const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * a.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * a.cg));
       for (long long r = a.r0 + (t >> 4); r < a.r1; r += 16) {
         const float4 xv = ldcg4(z + r * C + 4 * a.cg);
-        const float4 d = dy_at4(dy, r, a.cg, C, io.up2, io.L);
+        const float4 d = dy_at4(dy, io.dy2, r, a.cg, C, io.up2, io.L);
         const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
         const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
         float4 o;
@@ -830,26 +1050,77 @@ conv_block_train_bwd_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       }
     }
   }
-  if (!io.has_gemm) return;
+  if (!io.has_gemm) {
+    __syncthreads();
+    return;
+  }
   // the planes just written (generic proxy) are read by other CTAs' TMA loads (async proxy) in the next phase
   asm volatile("fence.proxy.async;" ::: "memory");
   bar_target += gridDim.x;
-  grid_barrier(io.sync, bar_target, io.dbg, 4);
+  grid_barrier(sync, bar_target, dbg, 4);
   asm volatile("fence.proxy.async;" ::: "memory");
-  phase_ts(io.dbg, 5);
+  phase_ts(dbg, 5);
 
   // ---- phase 3: dx = conv^T(dz) on the tensor cores
-  GemmSmem sm;
-  sm.ring = smem; sm.full = full_bar; sm.empty = empty_bar; sm.tfull = tfull_bar; sm.tempty = tempty_bar;
-  PipeState st;
-  st.s = 0; st.ph = 0; st.li = 0;
-  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, g, io.dx, nullptr, 0, sm, tmem_base, st);
+  gemm_phase(&map_a, &map_w, &map_a_lo, &map_w_lo, p, g, io.dx, nullptr, 0, sm, tmem_base, pb);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  phase_ts(io.dbg, 6);
+  phase_ts(dbg, 6);
+}
+
+// A chain of backward blocks in ONE launch, last block of the forward chain first: block i's incoming gradient is the input
+// gradient block i+1 just produced (plus, for a UNet skip source, the gradient of the block that consumed the skip).
+__global__ void __launch_bounds__(TB_THREADS, 1) conv_chain_bwd_kernel(const __grid_constant__ BwdChain ch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[TB_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TB_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[TB_MAX_SLOTS];
+  __shared__ __align__(8) uint64_t tempty_bar[TB_MAX_SLOTS];
+  __shared__ __align__(16) double red_scratch[8 * 16 * 8];
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5;
+  GemmSmem sm;
+  sm.ring = smem; sm.full = full_bar; sm.empty = empty_bar; sm.tfull = tfull_bar; sm.tempty = tempty_bar;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  unsigned int bar_target = 0;
+  uint32_t tmem_base = 0;
+  PipeBits pb;
+  pb.e = pb.f = pb.te = pb.tf = 0u;
+  for (int li = 0; li < ch.n; li++) {
+    const BwdLayer& L = ch.L[li];
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_trap_layer = 100 + li;
+    phase_ts(ch.dbg ? 1 + 8 * li : 0, 0);
+    if (li > 0) {
+      // the previous block's input gradient (this block's dy) must be complete and visible
+      bar_target += gridDim.x;
+      grid_barrier(ch.sync, bar_target);
+    }
+    if (threadIdx.x == 0) {
+      if (L.io.has_gemm) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_w)) : "memory");
+        if (L.p.npass > 1) {
+          asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_a_lo)) : "memory");
+          asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&L.map_w_lo)) : "memory");
+        }
+      }
+    }
+    if (li == 0) chain_init_barriers(sm);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_base = tmem_base_smem;
+    bwd_layer(L, smem, sm, red_scratch, tmem_base, ch.sync, bar_target, pb, ch.dbg ? 1 + 8 * li : 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -883,10 +1154,9 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc2(uint32_t saddr) {
   return d;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-wgrad_acc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z,
-                 const __grid_constant__ CUtensorMap map_x_lo, const __grid_constant__ CUtensorMap map_z_lo,
-                 const __grid_constant__ WgradAccParams p, float* __restrict__ acc) {
+__device__ __forceinline__ void wgrad_acc_body(const CUtensorMap& map_x, const CUtensorMap& map_z, const CUtensorMap& map_x_lo,
+                                               const CUtensorMap& map_z_lo, const WgradAccParams& p, float* __restrict__ acc,
+                                               const int bx, const int by, const int bz) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[WGA_STAGES];
@@ -894,15 +1164,15 @@ wgrad_acc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = blockIdx.z / p.ntaps, tap = blockIdx.z - cls * p.ntaps;
-  const int nt = blockIdx.y / p.c_tiles, ct = blockIdx.y - nt * p.c_tiles;
+  const int cls = bz / p.ntaps, tap = bz - cls * p.ntaps;
+  const int nt = by / p.c_tiles, ct = by - nt * p.c_tiles;
   const int n0 = nt * 128, c0 = ct * p.c_tile;
   const int nc = min(p.c_tile, p.kpad - c0);
   const int xchunks = nc / 64;
   const uint32_t stage_bytes = (2 + xchunks) * WGA_CHUNK_BYTES;
   const int total_rt = p.tiles_w * p.tiles_h * p.tiles_b;
   const int per = (total_rt + p.split - 1) / p.split;
-  const int rt_beg = blockIdx.x * per, rt_end = min(total_rt, rt_beg + per);
+  const int rt_beg = bx * per, rt_end = min(total_rt, rt_beg + per);
   const int num_k = max(0, rt_end - rt_beg) * p.npass;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + WGA_STAGES * 2 * WGA_CHUNK_BYTES;
@@ -997,6 +1267,34 @@ wgrad_acc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   }
 }
 
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_acc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z,
+                 const __grid_constant__ CUtensorMap map_x_lo, const __grid_constant__ CUtensorMap map_z_lo,
+                 const __grid_constant__ WgradAccParams p, float* __restrict__ acc) {
+  wgrad_acc_body(map_x, map_z, map_x_lo, map_z_lo, p, acc, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
+}
+
+// The weight gradients of every block of a chain in ONE launch: CTA ranges per layer, the same tile program inside.
+struct WgradLayer {
+  CUtensorMap map_x, map_z, map_x_lo, map_z_lo;
+  WgradAccParams p;
+  float* acc;
+  int gx, gy, gz, first;
+};
+struct WgradMulti {
+  int n;
+  WgradLayer L[CHAIN_MAX];
+};
+static_assert(sizeof(WgradMulti) <= 32000, "multi-wgrad parameter block exceeds the kernel parameter space");
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_acc_multi_kernel(const __grid_constant__ WgradMulti m) {
+  int li = 0;
+  while (li + 1 < m.n && (int)blockIdx.x >= m.L[li + 1].first) li++;
+  const WgradLayer& L = m.L[li];
+  const int local = (int)blockIdx.x - L.first;
+  const int bx = local % L.gx, by = (local / L.gx) % L.gy, bz = local / (L.gx * L.gy);
+  wgrad_acc_body(L.map_x, L.map_z, L.map_x_lo, L.map_z_lo, L.p, L.acc, bx, by, bz);
+}
+
 // every accumulator of a sub-network -> its parameter-gradient buffer (dw += unpack(acc)), one launch
 __global__ void unpack_wgrad_multi_kernel(const ms_wgrad_entry* __restrict__ table) {
   const ms_wgrad_entry& e = table[blockIdx.y];
@@ -1039,7 +1337,9 @@ static int phase_dbg() {
 }
 
 static int fill_bn(BnParams& b, const ms_block_bn* s) {
-  if (!s || s->C < 16 || s->C % 4 || !s->gamma || !s->beta || !s->sums || !s->ss) return MS_EINVAL;
+  if (!s || s->C < 16 || s->C % 4 || !s->gamma || !s->beta) return MS_EINVAL;
+  if (s->training == 1 && (!s->sums || !s->ss)) return MS_EINVAL;
+  if (s->training == 0 && !s->ss) return MS_EINVAL;
   if (s->pdt != MS_F32 && s->pdt != MS_F64) return MS_EINVAL;
   b.C = s->C; b.pdt = s->pdt; b.training = s->training; b.momentum = s->momentum; b.eps = s->eps; b.slope = s->slope;
   b.gamma = s->gamma; b.beta = s->beta; b.cbias = s->conv_bias; b.rmean = s->running_mean; b.rvar = s->running_var;
@@ -1047,9 +1347,21 @@ static int fill_bn(BnParams& b, const ms_block_bn* s) {
   return 0;
 }
 
-// Execution shape of a GEMM phase from the descriptor: ring depth from the stage size, k-slices normalised so that every
-// slice owns at least one k-step, accumulator slots.  want_resident: keep all tiles of a CTA in TMEM when they fit.
-static int gemm_cfg(const ms_igemm_desc* d, const IgemmParams& p, int sms, bool stats, bool want_resident, GemmCfg* gp, unsigned* grid) {
+// k-slices of a GEMM phase normalised so that every slice owns at least one k-step; work items = tiles x slices
+static int gemm_split(const ms_igemm_desc* d) {
+  const int num_k = d->ntaps * d->cchunks;
+  int split = d->split_k > 1 ? d->split_k : 1;
+  if (split > num_k) split = num_k;
+  const int per = (num_k + split - 1) / split;
+  return (num_k + per - 1) / per;
+}
+static long long gemm_tiles(const IgemmParams& p) {
+  return (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * p.num_classes;
+}
+
+// Execution shape of a GEMM phase on a launch of `grid` CTAs: ring depth from the stage size, accumulator slots.
+// want_resident: keep all tiles of a CTA in TMEM when they fit (forward blocks).
+static int gemm_cfg(const ms_igemm_desc* d, const IgemmParams& p, unsigned grid, bool stats, bool want_resident, GemmCfg* gp) {
   GemmCfg& g = *gp;
   if ((stats || want_resident) && (p.block_n % 32 || d->class_n % 32)) return MS_EINVAL;
   if (p.block_n % 16) return MS_EINVAL;
@@ -1059,20 +1371,14 @@ static int gemm_cfg(const ms_igemm_desc* d, const IgemmParams& p, int sms, bool 
   g.stages = (int)(TB_RING_BYTES / g.stage_bytes);
   if (g.stages > TB_MAX_STAGES) g.stages = TB_MAX_STAGES;
   if (g.stages < 2) return MS_EINVAL;
-  const int num_k = d->ntaps * d->cchunks;
-  int split = d->split_k > 1 ? d->split_k : 1;
-  if (split > num_k) split = num_k;
-  const int per = (num_k + split - 1) / split;
-  g.split_k = (num_k + per - 1) / per;
-  const long long tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles_per_class * p.num_classes;
-  const long long items = tiles * g.split_k;
-  if (items < 1 || items > 0x7fffffffLL) return MS_EINVAL;
-  *grid = (unsigned)(items < sms ? items : sms);
+  g.split_k = gemm_split(d);
+  const long long tiles = gemm_tiles(p);
+  if (tiles < 1 || tiles * g.split_k > 0x7fffffffLL) return MS_EINVAL;
   g.stats = (stats && g.split_k == 1) ? 1 : 0;
   g.resident = 0;
   g.nslots = 2;
   if (want_resident && g.split_k == 1) {
-    const long long per_cta = (tiles + *grid - 1) / *grid;
+    const long long per_cta = (tiles + grid - 1) / grid;
     if (per_cta <= TB_MAX_SLOTS && per_cta * p.block_n <= 512) {
       g.resident = 1;
       g.nslots = (int)per_cta;
@@ -1082,39 +1388,29 @@ static int gemm_cfg(const ms_igemm_desc* d, const IgemmParams& p, int sms, bool 
   return 0;
 }
 
-}  // namespace
-
-extern "C" int ms_debug_phase_ts(unsigned long long* out16) {
-  if (!out16) return MS_EINVAL;
-  MS_CUDA(cudaMemcpyFromSymbol(out16, g_phase_ts, sizeof(unsigned long long) * 16));
-  return 0;
-}
-
-extern "C" int ms_conv_block_train_fwd(const ms_igemm_desc* d, const void* a, const void* w, float* z, const ms_block_bn* bn,
-                                       float* y, void* planes, int pfmt, int64_t pstride, const float* res,
-                                       const void* res_planes, int res_pfmt, int64_t res_pstride, int up2, void* sync,
-                                       void* stream) {
-  if (!d || !a || !w || !bn || !sync || (!y && !planes)) return MS_EINVAL;
+static int fill_fwd_layer(const ms_chain_fwd_layer* e, FwdLayer* L, long long* want) {
+  const ms_igemm_desc* d = e->d;
+  if (!d || !e->a || !e->w || !e->bn || (!e->y && !e->planes)) return MS_EINVAL;
   if (d->out_dtype != MS_F32 || d->epilogue != 0) return MS_EINVAL;
-  if (bn->training && (!bn->running_mean || !bn->running_var || !z)) return MS_EINVAL;
-  if (!z && d->split_k > 1) return MS_EINVAL;
-  if (res_planes && (((uintptr_t)res_planes & 15) || (res_pfmt != MS_BF16 && res_pfmt != MS_BF16X2) ||
-                     (res_pfmt == MS_BF16X2 && (res_pstride <= 0 || (res_pstride * 2) % 16))))
+  if (e->bn->training && (!e->bn->running_mean || !e->bn->running_var)) return MS_EINVAL;
+  if (e->bn->training == 1 && !e->z) return MS_EINVAL;
+  if (!e->z && d->split_k > 1) return MS_EINVAL;
+  if (e->res_planes && (((uintptr_t)e->res_planes & 15) || (e->res_pfmt != MS_BF16 && e->res_pfmt != MS_BF16X2) ||
+                        (e->res_pfmt == MS_BF16X2 && (e->res_pstride <= 0 || (e->res_pstride * 2) % 16))))
     return MS_EINVAL;
-  if (((uintptr_t)z & 15) || ((uintptr_t)y & 15) || ((uintptr_t)planes & 15) || ((uintptr_t)res & 15)) return MS_EINVAL;
-  if (planes && pfmt != MS_BF16 && pfmt != MS_BF16X2) return MS_EINVAL;
-  if (planes && pfmt == MS_BF16X2 && (pstride <= 0 || (pstride * 2) % 16)) return MS_EINVAL;
-  if (up2 && ((!res && !res_planes) || d->out_dims[1] != 1)) return MS_EINVAL;
+  if (((uintptr_t)e->z & 15) || ((uintptr_t)e->y & 15) || ((uintptr_t)e->planes & 15) || ((uintptr_t)e->res & 15)) return MS_EINVAL;
+  if (e->planes && e->pfmt != MS_BF16 && e->pfmt != MS_BF16X2) return MS_EINVAL;
+  if (e->planes && e->pfmt == MS_BF16X2 && (e->pstride <= 0 || (e->pstride * 2) % 16)) return MS_EINVAL;
+  if (e->up2 && ((!e->res && !e->res_planes) || d->out_dims[1] != 1)) return MS_EINVAL;
   CUtensorMap maps[4];
-  IgemmParams p;
-  int rc = igemm_prepare(d, a, w, d->block_n, maps, &p);
+  int rc = igemm_prepare(d, e->a, e->w, d->block_n, maps, &L->p);
   if (rc) return rc;
-  BnParams b;
-  rc = fill_bn(b, bn);
+  L->map_a = maps[0]; L->map_w = maps[1]; L->map_a_lo = maps[2]; L->map_w_lo = maps[3];
+  rc = fill_bn(L->bn, e->bn);
   if (rc) return rc;
   const long long rows = (long long)d->out_dims[0] * d->out_dims[1] * d->out_dims[2];
   const int C = d->num_classes * d->class_n;
-  if (C != b.C || C % 32) return MS_EINVAL;
+  if (C != L->bn.C || C % 32) return MS_EINVAL;
   // z / y are dense (rows, C) matrices: the element-wise phases index them that way
   if (d->out_strides[0] != C || d->out_strides[1] != (int64_t)C * d->out_dims[0] ||
       d->out_strides[2] != (int64_t)C * d->out_dims[0] * d->out_dims[1])
@@ -1122,25 +1418,149 @@ extern "C" int ms_conv_block_train_fwd(const ms_igemm_desc* d, const void* a, co
   for (int i = 0; i < d->num_classes; i++)
     if (d->out_off[i] != (int64_t)i * d->class_n) return MS_EINVAL;
   if ((size_t)C * 8 > TB_RING_BYTES) return MS_EINVAL;
-  FwdIO io;
-  io.z = z; io.y = y; io.planes = reinterpret_cast<__nv_bfloat16*>(planes); io.pfmt = pfmt; io.pstride = pstride;
-  io.res = up2 ? res : nullptr; io.up2 = up2 ? 1 : 0; io.L = d->out_dims[0]; io.rows = rows;
-  io.res_pl = (up2 && !res) ? reinterpret_cast<const __nv_bfloat16*>(res_planes) : nullptr; io.res_fmt = res_pfmt; io.res_ps = res_pstride;
-  io.sync = reinterpret_cast<unsigned int*>(sync);
-  io.dbg = phase_dbg();
-  GemmCfg g;
-  unsigned grid = 0;
-  rc = gemm_cfg(d, p, ms_num_sms(), b.training != 0, true, &g, &grid);
-  if (rc) return rc;
-  if (!b.training && !g.resident && !z) return MS_EINVAL;         // the streaming normalise pass re-reads z
+  FwdIO& io = L->io;
+  io.z = e->z; io.y = e->y; io.planes = reinterpret_cast<__nv_bfloat16*>(e->planes); io.pfmt = e->pfmt; io.pstride = e->pstride;
+  io.res = e->up2 ? e->res : nullptr; io.up2 = e->up2 ? 1 : 0; io.L = d->out_dims[0]; io.rows = rows;
+  io.res_pl = (e->up2 && !e->res) ? reinterpret_cast<const __nv_bfloat16*>(e->res_planes) : nullptr;
+  io.res_fmt = e->res_pfmt; io.res_ps = e->res_pstride;
+  io.sync = nullptr; io.dbg = 0;
+  *want = gemm_tiles(L->p) * gemm_split(d);
+  return 0;
+}
+
+static FwdChain g_fwd_chain;      // host staging of the parameter blocks (one launch at a time per process: the C-ABI is
+static BwdChain g_bwd_chain;      // called from the single Python thread that owns the device)
+static WgradMulti g_wgrad_multi;
+
+}  // namespace
+
+static int* g_trap_host = nullptr;
+static int trap_buffer_init() {
+  if (g_trap_host) return 0;
+  int* h = nullptr;
+  MS_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h), 64, cudaHostAllocMapped));
+  memset(h, 0, 64);
+  int* d = nullptr;
+  MS_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0));
+  MS_CUDA(cudaMemcpyToSymbol(g_trap_info, &d, sizeof(d)));
+  g_trap_host = h;
+  return 0;
+}
+
+extern "C" int ms_debug_trap_info(int* out8) {
+  if (!out8) return MS_EINVAL;
+  for (int i = 0; i < 8; i++) out8[i] = g_trap_host ? g_trap_host[i] : 0;
+  return 0;
+}
+
+extern "C" int ms_debug_phase_ts(unsigned long long* out16) {
+  if (!out16) return MS_EINVAL;
+  MS_CUDA(cudaMemcpyFromSymbol(out16, g_phase_ts, sizeof(unsigned long long) * 8 * MS_CHAIN_MAX));
+  return 0;
+}
+
+extern "C" int ms_conv_chain_fwd(const ms_chain_fwd_layer* layers, int n, void* sync, void* stream) {
+  if (!layers || n < 1 || n > CHAIN_MAX || !sync) return MS_EINVAL;
+  FwdChain& ch = g_fwd_chain;
+  if (phase_dbg()) { int rc0 = trap_buffer_init(); if (rc0) return rc0; }
+  ch.n = n; ch.dbg = phase_dbg(); ch.sync = reinterpret_cast<unsigned int*>(sync);
+  const int sms = ms_num_sms();
+  long long want = 1;
+  for (int i = 0; i < n; i++) {
+    long long w = 0;
+    int rc = fill_fwd_layer(&layers[i], &ch.L[i], &w);
+    if (rc) return rc;
+    if (w > want) want = w;
+  }
+  const unsigned grid = (unsigned)(want < sms ? want : sms);
+  for (int i = 0; i < n; i++) {
+    int rc = gemm_cfg(layers[i].d, ch.L[i].p, grid, ch.L[i].bn.training == 1, true, &ch.L[i].g);
+    if (rc) return rc;
+    if (ch.L[i].bn.training != 1 && !ch.L[i].g.resident && !ch.L[i].io.z) return MS_EINVAL;   // the streaming normalise pass re-reads z
+  }
   const size_t smem = TB_RING_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    MS_CUDA(cudaFuncSetAttribute(conv_block_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MS_CUDA(cudaFuncSetAttribute(conv_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  void* args[] = {&maps[0], &maps[1], &maps[2], &maps[3], &p, &g, &b, &io};
-  rc = launch_coop(reinterpret_cast<const void*>(conv_block_train_fwd_kernel), dim3(grid), smem, ms_stream(stream), args);
+  void* args[] = {&ch};
+  int rc = launch_coop(reinterpret_cast<const void*>(conv_chain_fwd_kernel), dim3(grid), smem, ms_stream(stream), args);
+  if (rc) return rc;
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_conv_block_train_fwd(const ms_igemm_desc* d, const void* a, const void* w, float* z, const ms_block_bn* bn,
+                                       float* y, void* planes, int pfmt, int64_t pstride, const float* res,
+                                       const void* res_planes, int res_pfmt, int64_t res_pstride, int up2, void* sync,
+                                       void* stream) {
+  ms_chain_fwd_layer e;
+  memset(&e, 0, sizeof(e));
+  e.d = d; e.a = a; e.w = w; e.z = z; e.bn = bn; e.y = y; e.planes = planes; e.pfmt = pfmt; e.pstride = pstride;
+  e.res = res; e.res_planes = res_planes; e.res_pfmt = res_pfmt; e.res_pstride = res_pstride; e.up2 = up2;
+  return ms_conv_chain_fwd(&e, 1, sync, stream);
+}
+
+extern "C" int ms_conv_chain_bwd(const ms_chain_bwd_layer* layers, int n, void* sync, void* stream) {
+  if (!layers || n < 1 || n > CHAIN_MAX || !sync) return MS_EINVAL;
+  BwdChain& ch = g_bwd_chain;
+  if (phase_dbg()) { int rc0 = trap_buffer_init(); if (rc0) return rc0; }
+  ch.n = n; ch.dbg = phase_dbg(); ch.sync = reinterpret_cast<unsigned int*>(sync);
+  const int sms = ms_num_sms();
+  long long want = 1;
+  for (int i = 0; i < n; i++) {
+    const ms_chain_bwd_layer* e = &layers[i];
+    BwdLayer& L = ch.L[i];
+    if (!e->dy || !e->z || !e->bn || !e->dz_planes || e->rows < 1) return MS_EINVAL;
+    if (e->pfmt != MS_BF16 && e->pfmt != MS_BF16X2) return MS_EINVAL;
+    if (e->pfmt == MS_BF16X2 && (e->pstride <= 0 || (e->pstride * 2) % 8)) return MS_EINVAL;
+    if (((uintptr_t)e->dy & 15) || ((uintptr_t)e->dy2 & 15) || ((uintptr_t)e->z & 15) || ((uintptr_t)e->dz_planes & 15) ||
+        ((uintptr_t)e->dx & 15))
+      return MS_EINVAL;
+    if (e->gdt != MS_F32 && e->gdt != MS_F64) return MS_EINVAL;
+    if (e->up2 && e->rows_per_seq < 1) return MS_EINVAL;
+    int rc = fill_bn(L.bn, e->bn);
+    if (rc) return rc;
+    BwdIO& io = L.io;
+    io.dy = e->dy; io.dy2 = e->dy2; io.z = e->z; io.dzp = reinterpret_cast<__nv_bfloat16*>(e->dz_planes); io.pfmt = e->pfmt;
+    io.pstride = e->pstride; io.up2 = e->up2 ? 1 : 0; io.L = e->rows_per_seq; io.rows = e->rows; io.ggamma = e->grad_gamma;
+    io.gbeta = e->grad_beta; io.gdt = e->gdt; io.dx = e->dx; io.has_gemm = e->dg ? 1 : 0; io.sync = nullptr; io.dbg = 0;
+    // element-wise phases: one slab (64 channels x >= 16 rows) per CTA and pass
+    long long w = (long long)((L.bn.C / 4 + 15) / 16) * ((e->rows + 15) / 16);
+    if (e->dg) {
+      if (!e->wt || !e->dx || e->dg->out_dtype != MS_F32 || e->dg->epilogue != 0) return MS_EINVAL;
+      CUtensorMap maps[4];
+      rc = igemm_prepare(e->dg, e->dz_planes, e->wt, e->dg->block_n, maps, &L.p);
+      if (rc) return rc;
+      L.map_a = maps[0]; L.map_w = maps[1]; L.map_a_lo = maps[2]; L.map_w_lo = maps[3];
+      const long long items = gemm_tiles(L.p) * gemm_split(e->dg);
+      if (items > w) w = items;
+    } else {
+      memset(&L.p, 0, sizeof(L.p));
+      memset(&L.map_a, 0, 4 * sizeof(CUtensorMap));
+      L.p.block_n = 32;
+    }
+    if (w > want) want = w;
+  }
+  const unsigned grid = (unsigned)(want < sms ? want : sms);
+  for (int i = 0; i < n; i++) {
+    if (layers[i].dg) {
+      int rc = gemm_cfg(layers[i].dg, ch.L[i].p, grid, false, false, &ch.L[i].g);
+      if (rc) return rc;
+    } else {
+      memset(&ch.L[i].g, 0, sizeof(GemmCfg));
+      ch.L[i].g.nslots = 1; ch.L[i].g.stages = 2; ch.L[i].g.split_k = 1;
+    }
+  }
+  const size_t smem = TB_RING_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MS_CUDA(cudaFuncSetAttribute(conv_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  void* args[] = {&ch};
+  int rc = launch_coop(reinterpret_cast<const void*>(conv_chain_bwd_kernel), dim3(grid), smem, ms_stream(stream), args);
   if (rc) return rc;
   MS_LAUNCH_CHECK();
   return 0;
@@ -1150,54 +1570,12 @@ extern "C" int ms_conv_block_train_bwd(const ms_igemm_desc* dg, const float* dy,
                                        int64_t rows, int up2, int rows_per_seq, void* dz_planes, int pfmt, int64_t pstride,
                                        void* grad_gamma, void* grad_beta, int gdt, const void* wt, float* dx, void* sync,
                                        void* stream) {
-  if (!dy || !z || !bn || !dz_planes || !sync || rows < 1) return MS_EINVAL;
-  if (pfmt != MS_BF16 && pfmt != MS_BF16X2) return MS_EINVAL;
-  if (pfmt == MS_BF16X2 && (pstride <= 0 || (pstride * 2) % 8)) return MS_EINVAL;
-  if (((uintptr_t)dy & 15) || ((uintptr_t)z & 15) || ((uintptr_t)dz_planes & 15) || ((uintptr_t)dx & 15)) return MS_EINVAL;
-  if (gdt != MS_F32 && gdt != MS_F64) return MS_EINVAL;
-  if (up2 && rows_per_seq < 1) return MS_EINVAL;
-  BnParams b;
-  int rc = fill_bn(b, bn);
-  if (rc) return rc;
-  CUtensorMap maps[4];
-  IgemmParams p;
-  GemmCfg g;
-  BwdIO io;
-  io.dy = dy; io.z = z; io.dzp = reinterpret_cast<__nv_bfloat16*>(dz_planes); io.pfmt = pfmt; io.pstride = pstride;
-  io.up2 = up2 ? 1 : 0; io.L = rows_per_seq; io.rows = rows; io.ggamma = grad_gamma; io.gbeta = grad_beta; io.gdt = gdt;
-  io.dx = dx; io.has_gemm = dg ? 1 : 0; io.sync = reinterpret_cast<unsigned int*>(sync);
-  io.dbg = phase_dbg();
-  const int sms = ms_num_sms();
-  // element-wise phases: one slab (64 channels x >= 16 rows) per CTA and pass
-  long long slabs = (long long)((b.C / 4 + 15) / 16) * ((rows + 15) / 16);
-  unsigned grid = 0;
-  if (dg) {
-    if (!wt || !dx || dg->out_dtype != MS_F32 || dg->epilogue != 0) return MS_EINVAL;
-    rc = igemm_prepare(dg, dz_planes, wt, dg->block_n, maps, &p);
-    if (rc) return rc;
-    rc = gemm_cfg(dg, p, sms, false, false, &g, &grid);
-    if (rc) return rc;
-    if ((long long)grid < slabs) grid = (unsigned)(slabs < sms ? slabs : sms);
-  } else {
-    memset(&p, 0, sizeof(p));
-    memset(maps, 0, sizeof(maps));
-    memset(&g, 0, sizeof(g));
-    p.block_n = 32;
-    g.nslots = 1; g.stages = 2; g.split_k = 1;
-    grid = (unsigned)(slabs < sms ? slabs : sms);
-  }
-  if (grid < 1) grid = 1;
-  const size_t smem = TB_RING_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MS_CUDA(cudaFuncSetAttribute(conv_block_train_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  void* args[] = {&maps[0], &maps[1], &maps[2], &maps[3], &p, &g, &b, &io};
-  rc = launch_coop(reinterpret_cast<const void*>(conv_block_train_bwd_kernel), dim3(grid), smem, ms_stream(stream), args);
-  if (rc) return rc;
-  MS_LAUNCH_CHECK();
-  return 0;
+  ms_chain_bwd_layer e;
+  memset(&e, 0, sizeof(e));
+  e.dg = dg; e.dy = dy; e.dy2 = nullptr; e.z = z; e.bn = bn; e.rows = rows; e.up2 = up2; e.rows_per_seq = rows_per_seq;
+  e.dz_planes = dz_planes; e.pfmt = pfmt; e.pstride = pstride; e.grad_gamma = grad_gamma; e.grad_beta = grad_beta; e.gdt = gdt;
+  e.wt = wt; e.dx = dx;
+  return ms_conv_chain_bwd(&e, 1, sync, stream);
 }
 
 static int encode_5d_acc(EncodeTiledFn enc, CUtensorMap* m, const void* base, const int32_t* dims, const int64_t* strides_el,
@@ -1214,13 +1592,14 @@ static int encode_5d_acc(EncodeTiledFn enc, CUtensorMap* m, const void* base, co
   return r == CUDA_SUCCESS ? 0 : MS_EINVAL;
 }
 
-extern "C" int ms_wgrad_bf16_acc(const ms_igemm_desc* d, const void* x, const void* dz, float* acc, void* stream) {
+// tensor maps, tile program and CTA grid (gx pixel slices, gy output x input channel tiles, gz class x tap) of one weight gradient
+static int fill_wgrad_layer(const ms_igemm_desc* d, const void* x, const void* dz, float* acc, WgradLayer* L) {
   if (!d || !x || !dz || !acc) return MS_EINVAL;
   if (d->num_classes < 1 || d->num_classes > MS_IGEMM_MAX_CLASSES || d->ntaps < 1 || d->cchunks < 1) return MS_EINVAL;
   if (((uintptr_t)x & 15) || ((uintptr_t)dz & 15) || ((uintptr_t)acc & 15)) return MS_EINVAL;
   EncodeTiledFn enc = get_encode();
   if (!enc) return MS_ENOTSUP;
-  WgradAccParams p;
+  WgradAccParams& p = L->p;
   p.ntaps = d->ntaps; p.cchunks = d->cchunks; p.shared_taps = d->shared_taps;
   p.num_classes = d->num_classes; p.class_n = d->class_n;
   int bw = d->box[1], bh = d->box[3], bb = d->box[4];
@@ -1247,30 +1626,61 @@ extern "C" int ms_wgrad_bf16_acc(const ms_igemm_desc* d, const void* x, const vo
   p.npass = d->planes == 2 ? 3 : 1;
   if (d->planes == 2 && (d->a_plane_stride <= 0 || d->out_plane_stride <= 0 || (d->a_plane_stride * 2) % 16 || (d->out_plane_stride * 2) % 16))
     return MS_EINVAL;
-  CUtensorMap map_x, map_z, map_x_lo, map_z_lo;
   int box[5] = {64, bw, 1, bh, bb};
   const int32_t zdims[5] = {(int32_t)d->out_strides[0], Wo, 1, Ho, Bo};
   const int64_t zstr[5] = {1, d->out_strides[0], d->out_strides[1], d->out_strides[1], d->out_strides[2]};
-  int rc = encode_5d_acc(enc, &map_x, x, d->a_dims, d->a_strides, box);
+  int rc = encode_5d_acc(enc, &L->map_x, x, d->a_dims, d->a_strides, box);
   if (rc) return rc;
-  rc = encode_5d_acc(enc, &map_z, dz, zdims, zstr, box);
+  rc = encode_5d_acc(enc, &L->map_z, dz, zdims, zstr, box);
   if (rc) return rc;
   if (d->planes == 2) {
-    rc = encode_5d_acc(enc, &map_x_lo, reinterpret_cast<const __nv_bfloat16*>(x) + d->a_plane_stride, d->a_dims, d->a_strides, box);
+    rc = encode_5d_acc(enc, &L->map_x_lo, reinterpret_cast<const __nv_bfloat16*>(x) + d->a_plane_stride, d->a_dims, d->a_strides, box);
     if (rc) return rc;
-    rc = encode_5d_acc(enc, &map_z_lo, reinterpret_cast<const __nv_bfloat16*>(dz) + d->out_plane_stride, zdims, zstr, box);
+    rc = encode_5d_acc(enc, &L->map_z_lo, reinterpret_cast<const __nv_bfloat16*>(dz) + d->out_plane_stride, zdims, zstr, box);
     if (rc) return rc;
   } else {
-    map_x_lo = map_x; map_z_lo = map_z;
+    L->map_x_lo = L->map_x; L->map_z_lo = L->map_z;
   }
-  const size_t smem = (size_t)WGA_STAGES * 6 * WGA_CHUNK_BYTES + 1024;
+  L->acc = acc;
+  L->gx = p.split; L->gy = p.n_tiles * p.c_tiles; L->gz = d->num_classes * d->ntaps; L->first = 0;
+  return 0;
+}
+
+static const size_t WGA_SMEM = (size_t)WGA_STAGES * 6 * WGA_CHUNK_BYTES + 1024;
+
+extern "C" int ms_wgrad_bf16_acc(const ms_igemm_desc* d, const void* x, const void* dz, float* acc, void* stream) {
+  WgradLayer& L = g_wgrad_multi.L[0];
+  int rc = fill_wgrad_layer(d, x, dz, acc, &L);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     MS_CUDA(cudaFuncSetAttribute(wgrad_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
     attr_set = true;
   }
-  dim3 grid((unsigned)p.split, (unsigned)(p.n_tiles * p.c_tiles), (unsigned)(d->num_classes * d->ntaps));
-  wgrad_acc_kernel<<<grid, NUM_THREADS, smem, ms_stream(stream)>>>(map_x, map_z, map_x_lo, map_z_lo, p, acc);
+  dim3 grid((unsigned)L.gx, (unsigned)L.gy, (unsigned)L.gz);
+  wgrad_acc_kernel<<<grid, NUM_THREADS, WGA_SMEM, ms_stream(stream)>>>(L.map_x, L.map_z, L.map_x_lo, L.map_z_lo, L.p, acc);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int ms_wgrad_bf16_acc_multi(const ms_wgrad_item* items, int n, void* stream) {
+  if (!items || n < 1 || n > CHAIN_MAX) return MS_EINVAL;
+  WgradMulti& m = g_wgrad_multi;
+  m.n = n;
+  long long total = 0;
+  for (int i = 0; i < n; i++) {
+    int rc = fill_wgrad_layer(items[i].d, items[i].x, items[i].dz, items[i].acc, &m.L[i]);
+    if (rc) return rc;
+    m.L[i].first = (int)total;
+    total += (long long)m.L[i].gx * m.L[i].gy * m.L[i].gz;
+    if (total > 0x7fffffffLL) return MS_EINVAL;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MS_CUDA(cudaFuncSetAttribute(wgrad_acc_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    attr_set = true;
+  }
+  wgrad_acc_multi_kernel<<<dim3((unsigned)total), NUM_THREADS, WGA_SMEM, ms_stream(stream)>>>(m);
   MS_LAUNCH_CHECK();
   return 0;
 }

@@ -228,7 +228,7 @@ def block_plan(d, npass, stats, sms=148):
 
     One k-step stages A (16 KB per plane) and W (block_n * 128 B per plane) once for all MMA passes, so it is bound by
     max(tensor time 2 * block_n * npass clk, operand bytes / (L2 -> SM rate)); the rate is ~6300 B/clk chip-wide
-    (B300_MICROARCH.md) and at most ~80 B/clk for one SM.  Full-K tiles (split 1) cost one pipeline fill per tile and ONE
+    (B300_MICROARCH.md) and ~40 B/clk for one SM (measured).  Full-K tiles (split 1) cost one pipeline fill per tile and ONE
     device barrier (statistics come out of the accumulators); split-K costs the reductions into z, a second barrier and
     the statistics pass over z, and pays when few tiles face a long K (audio encoder tail, UNet bottleneck).
     stats: forward of a training block (full-K needs 32-column chunks); False for the input-gradient GEMM, whose split
@@ -250,7 +250,7 @@ def block_plan(d, npass, stats, sms=148):
         for split in sorted({1} | {_normalise_split(k_steps, s) for s in (2, 3, 4, 6, 8, 12, 16, 24) if tiles * s <= 2 * sms}):
             items = tiles * split
             active = min(items, sms)
-            rate = min(80.0, 6300.0 / active)
+            rate = min(40.0, 6300.0 / active)      # measured: one SM's TMA path sustains ~40 B/clk (tools/chain_phases.py)
             kclk = max(mma, stage / rate)
             if 196608 // stage < 3:
                 kclk *= 1.4                       # a two-stage ring does not cover the TMA latency
@@ -270,6 +270,12 @@ def block_resident(d, block_n, sms=148):
     tiles = _tiles_m(d) * d.num_classes * ((d.class_n + block_n - 1) // block_n)
     per_cta = (tiles + min(tiles, sms) - 1) // min(tiles, sms)
     return per_cta <= 16 and per_cta * block_n <= 512
+
+
+def wgrad_tiles(d, c_tile=256):
+    """(128 output channels) x (c_tile input channels) tiles per (class, tap) of a weight gradient."""
+    kpad = d.cchunks * BLOCK_K
+    return ((d.class_n + 127) // 128) * ((kpad + c_tile - 1) // c_tile) * d.num_classes * d.ntaps
 
 
 def wgrad_split(d, sms=148, npass=1):

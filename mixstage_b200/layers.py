@@ -83,13 +83,17 @@ class PlainConv(object):
         return ops.conv_block(x, conv.weight, conv.bias, None, None, self.cfg, self.packed, None, False, want="f32")
 
 
-def _run(blocks, x, last="f32"):
-    """A chain of blocks: every intermediate activation is only read by the next convolution (operand planes suffice
-    on the inference fast path); the last one is wanted as `last`."""
-    n = len(blocks)
-    for i, b in enumerate(blocks):
-        x = b(x, want="planes" if i < n - 1 else last)
-    return x
+def _chain_block(m):
+    n = m.norm
+    return ops.ChainBlock(m.conv.weight, m.conv.bias, n.weight, n.bias, m.cfg, m._packed,
+                          (n.running_mean, n.running_var, n.num_batches_tracked))
+
+
+def _run(blocks, x, last="f32", res_from=None):
+    """A chain of ConvNormRelu blocks: every intermediate activation is only read by the next convolution (operand planes
+    suffice); the last one is wanted as `last`.  Runs of blocks that qualify leave as ONE launch (ops.conv_chain)."""
+    blocks = list(blocks)
+    return ops.conv_chain([_chain_block(b) for b in blocks], x, blocks[0].training, res_from=res_from, last=last)
 
 
 class UNet1D(nn.Module):
@@ -116,22 +120,16 @@ class UNet1D(nn.Module):
             'Input size is {}. It must be >= {}'.format(T, 2 ** (self.max_depth - 1))
         assert num_powers_of_two(T) >= self.max_depth, \
             'Input size is {}. It must be a multiple of 2^(max_depth) = 2^{} = {}'.format(T, self.max_depth, 2 ** self.max_depth)
-        x = _run(self.pre_downsampling_conv, x, last="planes")
-        residuals = [x]
+        # the whole UNet as one chain: pre (2), down (5), up (5).  The last down block and the first four up blocks produce
+        # `upconv(x) + residual` directly (layers.py:150-151): block i with res_from[i] = j adds the output of block j
         d = self.max_depth
-        # the last down block feeds `upconv(x) + residual` directly (layers.py:150-151): fuse it
-        for i, conv1 in enumerate(self.conv1):
-            if i < d - 1:
-                x = conv1(x, want="planes")
-                residuals.append(x)
-            else:
-                x = conv1(x, residual=residuals[d - 1], up2=True, want="planes")
-        for i, conv2 in enumerate(self.conv2):
-            if i < d - 1:
-                x = conv2(x, residual=residuals[d - i - 2], up2=True, want="planes")   # output already holds next step's input
-            else:
-                x = conv2(x, want="f32")
-        return x
+        blocks = list(self.pre_downsampling_conv) + list(self.conv1) + list(self.conv2)
+        res_from = [None] * len(blocks)
+        res_idx = [1] + [2 + i for i in range(d - 1)]          # residuals[0] = pre output, residuals[i + 1] = conv1[i] output
+        res_from[2 + d - 1] = res_idx[d - 1]
+        for i in range(d - 1):
+            res_from[2 + d + i] = res_idx[d - i - 2]
+        return _run(blocks, x, last="f32", res_from=res_from)
 
 
 class AudioEncoder(nn.Module):

@@ -6,6 +6,8 @@ torch stream.  Activations are channels-last fp32: (B, L, C) or (B, H, W, C).
 There is no CPU path: CPU tensors raise MixStageError."""
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib, igemm
@@ -1339,3 +1341,433 @@ class _L1Mean(torch.autograd.Function):
 def l1_mean(a, b=None, const=0.0):
     """mean |a - b| (b tensor) or mean |a - const|: L1Loss(reduction='none') + mean (gan.py:64-75)."""
     return _L1Mean.apply(a, b, const)
+
+
+# ---------------------------------------------------------------------------- chains of blocks in one launch
+# At batch 16 the train step is bound by the number of dependent launches, not by their arithmetic: a conv stack (UNet1D,
+# ClusterClassify, the grouped sub-decoders, AudioEncoder.conv.1-7, PoseStyleEncoder) runs as ONE cooperative launch per
+# direction (csrc/conv_train.cu: conv_chain_fwd_kernel / conv_chain_bwd_kernel) and its weight gradients as one more.
+CHAINS = _os.environ.get("MS_CHAINS", "1") != "0"
+
+
+class ChainBlock:
+    """What a chain needs of one ConvNormRelu: parameters, static geometry, packed-weight cache, BatchNorm buffers."""
+    __slots__ = ("weight", "bias", "gamma", "beta", "cfg", "packed", "bn_buffers")
+
+    def __init__(self, weight, bias, gamma, beta, cfg, packed, bn_buffers):
+        self.weight, self.bias, self.gamma, self.beta = weight, bias, gamma, beta
+        self.cfg, self.packed, self.bn_buffers = cfg, packed, bn_buffers
+
+
+class _ChainSpec:
+    __slots__ = ("blocks", "res_from", "fmt", "sinks", "out_planes")
+
+
+def _chain_shapes(blocks, x_shape, res_from):
+    """Input shape of every block and the output shape of the chain; None when a block cannot take the tensor-core path."""
+    shapes = []
+    cur = tuple(x_shape)
+    for i, b in enumerate(blocks):
+        cfg = b.cfg
+        B, H, W, Cin = cur
+        w = b.weight
+        Cout = w.shape[0]
+        if w.shape[1] * cfg.groups != Cin or not cfg.has_bn:
+            return None
+        if not tc_eligible(cfg, B, H, W, Cin, Cout, True):
+            return None
+        if (Cout // cfg.groups) % 32 or Cout > 8192:
+            return None
+        if i > 0 and pad8(Cin) != Cin:
+            return None
+        Ho, Wo = conv_out(H, cfg.kh, cfg.sh, cfg.ph), conv_out(W, cfg.kw, cfg.sw, cfg.pw)
+        shapes.append(cur)
+        if res_from[i] is not None:
+            if Ho != 1:
+                return None
+            cur = (B, 1, 2 * Wo, Cout)
+        else:
+            cur = (B, Ho, Wo, Cout)
+    shapes.append(cur)
+    return shapes
+
+
+class _ConvChain(torch.autograd.Function):
+    """y = block_{n-1}(... block_0(x)) for training-mode ConvNormRelu blocks; block i with res_from[i] = j produces
+    upsample2(act(bn(conv(.)))) + output of block j (UNet1D, layers.py:150-152).  One launch forward, one backward (+ one
+    for all weight gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, spec, *params):
+        blocks, res_from, fmt = spec.blocks, spec.res_from, spec.fmt
+        n = len(blocks)
+        split = fmt == MS_BF16X2
+        npass = 3 if split else 1
+        dev = x.device
+        if x.dtype != torch.bfloat16:
+            x = _f32c(x)
+        need_dx0 = ctx.needs_input_grad[0]
+        cur = tuple(x.shape)
+        xp = planes_of(x, fmt, pad8(cur[3]))
+        layers = (_lib.ChainFwdLayer * n)()
+        keep, rec = [], []
+        flops = 0.0
+        global _stats_epoch, last_gemm_flops
+        for i, b in enumerate(blocks):
+            weight = params[4 * i]
+            cfg, packed = b.cfg, b.packed
+            B, H, W, Cin = cur
+            Cout = weight.shape[0]
+            rs = pad8(Cin)
+            desc = make_desc(cur, Cout, cfg.kh, cfg.kw, cfg.sh, cfg.sw, cfg.ph, cfg.pw, cfg.groups)
+            pf, pd = packed.tc_plans(cur, Cout, cfg, rs, need_dx0 if i == 0 else True, npass)
+            wp, wps = packed.get_tc(weight, pf, fmt, cfg.groups)
+            wt = packed.get_tc(weight, pd, fmt, cfg.groups) if pd is not None else None
+            d = pf.desc
+            igemm.set_planes(pf, split, xp.ps, wps, 0)
+            d.out_dtype, d.epilogue, d.slope, d.out_numel = _lib.MS_F32, 0, cfg.slope, 0
+            d.block_n, d.split_k = _block_plan(pf, npass, True)
+            rows = B * desc.Ho * desc.Wo
+            zshape = (B, desc.Ho, desc.Wo, Cout)
+            z = arena.take_f32(zshape, dev) if d.split_k > 1 else torch.empty(zshape, dtype=torch.float32, device=dev)
+            up2 = res_from[i] is not None
+            oshape = (B, 1, 2 * desc.Wo, Cout) if up2 else zshape
+            rows_out = 2 * rows if up2 else rows
+            y = torch.empty(oshape, dtype=torch.float32, device=dev) if i == n - 1 else None
+            yp = alloc_planes(rows_out, Cout, fmt, dev)
+            ss = torch.empty(4, Cout, dtype=torch.float32, device=dev)
+            acc = arena.take((2 * Cout + 2,), dev)
+            gamma, beta, cbias = params[4 * i + 2], params[4 * i + 3], params[4 * i + 1]
+            if cbias is not None and cbias.dtype != gamma.dtype:
+                raise MixStageError("conv bias and BatchNorm parameters must share a dtype")
+            bn = _block_bn(Cout, gamma, beta, cbias, b.bn_buffers, cfg, True, acc, ss)
+            _stats_epoch += 1
+            packed.stats_epoch += 1
+            L = layers[i]
+            L.d, L.a, L.w, L.z = ctypes.pointer(d), ptr(xp.t), ptr(wp), ptr(z)
+            L.bn, L.y, L.planes, L.pfmt, L.pstride = ctypes.pointer(bn), ptr(y), ptr(yp.t), yp.fmt, yp.ps
+            L.up2 = 1 if up2 else 0
+            if up2:
+                rp = rec[res_from[i]]["yp"]
+                if rec[res_from[i]]["oshape"] != oshape:
+                    raise MixStageError("skip tensor shape %s != %s" % (rec[res_from[i]]["oshape"], oshape))
+                L.res, L.res_planes, L.res_pfmt, L.res_pstride = None, ptr(rp.t), rp.fmt, rp.ps
+            keep.append((bn, acc))
+            fl = 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
+            flops += fl
+            rec.append(dict(xp=xp, z=z, ss=ss, desc=desc, pf=pf, pd=pd, wt=wt, rows=rows, Cout=Cout, oshape=oshape, yp=yp,
+                            in_shape=cur, rs=rs, up2=up2, flops=fl, gamma_dtype=gamma.dtype,
+                            wdt=weight.dtype, bdt=None if cbias is None else cbias.dtype))
+            xp, cur = yp, oshape
+        sync = arena.take((2,), dev)
+        last_gemm_flops = flops
+        call("ms_conv_chain_fwd", ctypes.cast(layers, ctypes.c_void_p), n, ptr(sync), stream())
+        ctx.spec, ctx.rec, ctx.n = spec, rec, n
+        ctx.flops = flops
+        spec.out_planes = rec[-1]["yp"]
+        # tensors the backward reads stay referenced through ctx.rec (they are not autograd inputs / outputs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec, rec, n = ctx.spec, ctx.rec, ctx.n
+        blocks, res_from, fmt = spec.blocks, spec.res_from, spec.fmt
+        split = fmt == MS_BF16X2
+        npass = 3 if split else 1
+        dy = dy.contiguous()
+        dev = dy.device
+        st = stream()
+        need = ctx.needs_input_grad
+        layers = (_lib.ChainBwdLayer * n)()
+        keep = []
+        grads = [None] * (4 * n)
+        dyin = [None] * n                  # incoming gradient of every block's OUTPUT (its main consumer's input gradient)
+        dxs = [None] * n
+        consumers = {}                     # block j -> blocks whose skip tensor is block j's output
+        for i, j in enumerate(res_from):
+            if j is not None:
+                consumers.setdefault(j, []).append(i)
+        global last_gemm_flops
+        flops = 0.0
+        wg_items = []
+        for k, i in enumerate(range(n - 1, -1, -1)):
+            r, b = rec[i], blocks[i]
+            cfg = b.cfg
+            Cout, rows = r["Cout"], r["rows"]
+            need_w, need_g, need_be = need[2 + 4 * i], need[2 + 4 * i + 2], need[2 + 4 * i + 3]
+            sinks = spec.sinks[i]
+            dyin[i] = dy if i == n - 1 else dxs[i + 1]
+            dy2 = None
+            cons = consumers.get(i, [])
+            if len(cons) > 1:
+                raise MixStageError("internal: a block's output feeds more than one skip connection")
+            if cons:
+                dy2 = dyin[cons[0]]
+            dzp = alloc_planes(rows, Cout, fmt, dev)
+            red = arena.take((2 * Cout + 2,), dev)
+            bn = _lib.BlockBn()
+            bn.C, bn.pdt, bn.training = Cout, dt_code(r["gamma_dtype"]), 1
+            bn.momentum, bn.eps, bn.slope = cfg.momentum, cfg.eps, (cfg.slope if cfg.act else 1.0)
+            bn.sums, bn.ss = ptr(red), ptr(r["ss"])
+            bn.gamma = bn.beta = ptr(r["ss"])              # not read by the backward; non-NULL for the argument check
+            sg = sb = None
+            if need_g and need_be:
+                sg, sb = sinks[2], sinks[3]
+                if sg is None or sb is None:
+                    sg = torch.zeros(Cout, dtype=r["gamma_dtype"], device=dev)
+                    sb = torch.zeros(Cout, dtype=r["gamma_dtype"], device=dev)
+                    grads[4 * i + 2], grads[4 * i + 3] = sg, sb
+            elif need_g or need_be:
+                raise MixStageError("chain: BatchNorm weight and bias must both (or neither) require gradients")
+            B, H, W, Cin = r["in_shape"]
+            xrs = r["rs"]
+            need_dx = (i > 0) or need[0]
+            L = layers[k]
+            L.dy, L.dy2, L.z, L.bn = ptr(dyin[i]), ptr(dy2), ptr(r["z"]), ctypes.pointer(bn)
+            L.rows, L.up2, L.rows_per_seq = rows, 1 if r["up2"] else 0, r["desc"].Wo
+            L.dz_planes, L.pfmt, L.pstride = ptr(dzp.t), fmt, dzp.ps
+            L.grad_gamma, L.grad_beta, L.gdt = ptr(sg), ptr(sb), dt_code(r["gamma_dtype"])
+            if need_dx:
+                pd = r["pd"]
+                wt, wtps = r["wt"]
+                igemm.set_planes(pd, split, dzp.ps, wtps, 0)
+                pd.desc.out_numel = 0
+                pd.desc.block_n, pd.desc.split_k = _block_plan(pd, npass, False)
+                dshape = (B, H, W, xrs)
+                dxf = arena.take_f32(dshape, dev) if pd.desc.split_k > 1 else torch.empty(dshape, dtype=torch.float32, device=dev)
+                dxs[i] = dxf
+                L.dg, L.wt, L.dx = ctypes.pointer(pd.desc), ptr(wt), ptr(dxf)
+                flops += r["flops"]
+            keep.append((bn, red, dzp))
+            r["dzp"] = dzp
+            # d(conv bias) is identically zero under batch-statistics BatchNorm
+            if need[2 + 4 * i + 1] and r["bdt"] is not None and sinks[1] is None:
+                grads[4 * i + 1] = torch.zeros(Cout, dtype=r["bdt"], device=dev)
+            if need_w:
+                wg_items.append(i)
+        sync = arena.take((2,), dev)
+        last_gemm_flops = flops
+        call("ms_conv_chain_bwd", ctypes.cast(layers, ctypes.c_void_p), n, ptr(sync), st)
+        # ---- weight gradients: dW = dz^T x, every block of the chain in one launch beside the main stream
+        direct = [i for i in wg_items if spec.sinks[i][0] is not None and WACC is not None]
+        if direct:
+            items = (_lib.WgradItem * len(direct))()
+            fl = 0.0
+            # the blocks share ONE launch: every block gets its share of ~two waves of CTAs for its pixel slices (slicing a
+            # block as if it had the machine to itself multiplies the 128 KB-per-CTA accumulator reductions instead)
+            total_tiles = sum(igemm.wgrad_tiles(rec[i]["pf"].desc) for i in direct)
+            for k, i in enumerate(direct):
+                r, b = rec[i], blocks[i]
+                pf = r["pf"]
+                B, H, W, Cin = r["in_shape"]
+                igemm.set_planes(pf, split, r["xp"].ps, 0, r["dzp"].ps)
+                share = max(4, int(148.0 * igemm.wgrad_tiles(pf.desc) / total_tiles))
+                nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc, sms=share, npass=npass)
+                pf.desc.split_k = nsplit
+                acc = WACC.acc_for(b.packed, pf.wp_numel, dev)
+                WACC.note(acc, spec.sinks[i][0], r["Cout"], Cin // b.cfg.groups, b.cfg.kh * b.cfg.kw, pf.kpad, r["wdt"])
+                it = items[k]
+                # the descriptor is shared, mutable plan state: the launch below copies it, so one COPY per item
+                dcopy = _lib.IgemmDesc.from_buffer_copy(pf.desc)
+                keep.append(dcopy)
+                it.d, it.x, it.dz, it.acc = ctypes.pointer(dcopy), ptr(r["xp"].t), ptr(r["dzp"].t), ptr(acc)
+                fl += r["flops"]
+            last_gemm_flops = fl
+            if SIDE is not None:
+                with SIDE.fork(*([rec[i]["xp"].t for i in direct] + [rec[i]["dzp"].t for i in direct])):
+                    call("ms_wgrad_bf16_acc_multi", ctypes.cast(items, ctypes.c_void_p), len(direct), stream())
+            else:
+                call("ms_wgrad_bf16_acc_multi", ctypes.cast(items, ctypes.c_void_p), len(direct), st)
+        for i in wg_items:
+            if i in direct:
+                continue
+            r, b = rec[i], blocks[i]
+            pf = r["pf"]
+            B, H, W, Cin = r["in_shape"]
+            Cin_g = Cin // b.cfg.groups
+            igemm.set_planes(pf, split, r["xp"].ps, 0, r["dzp"].ps)
+            nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc, npass=npass)
+            pf.desc.split_k = nsplit
+            last_gemm_flops = r["flops"]
+            dwp = torch.empty(nsplit * pf.wp_numel, dtype=torch.float32, device=dev)
+            call("ms_wgrad_bf16", pf.desc, ptr(r["xp"].t), ptr(r["dzp"].t), ptr(dwp), st)
+            sink = spec.sinks[i][0]
+            taps = b.cfg.kh * b.cfg.kw
+            if sink is not None:
+                call("ms_unpack_igemm_wgrad", ptr(dwp), r["Cout"], Cin_g, taps, pf.desc.ntaps, pf.kpad, ptr(sink),
+                     dt_code(r["wdt"]), nsplit, 1, st)
+            else:
+                dw = torch.empty((r["Cout"], Cin_g, b.cfg.kh, b.cfg.kw), dtype=r["wdt"], device=dev)
+                call("ms_unpack_igemm_wgrad", ptr(dwp), r["Cout"], Cin_g, taps, pf.desc.ntaps, pf.kpad, ptr(dw),
+                     dt_code(r["wdt"]), nsplit, 0, st)
+                grads[4 * i] = dw
+        dx0 = None
+        if need[0]:
+            Cin0 = rec[0]["in_shape"][3]
+            dx0 = dxs[0] if rec[0]["rs"] == Cin0 else dxs[0][..., :Cin0]
+        ctx.rec = None
+        return (dx0, None) + tuple(grads)
+
+
+def _chain_eval(blocks, x, shapes, res_from, fmt, last):
+    """Inference form of a chain (eval mode, no autograd, small batch): BatchNorm folded from the running statistics inside
+    the launch, no statistics, accumulators normalised straight out of TMEM."""
+    n = len(blocks)
+    split = fmt == MS_BF16X2
+    npass = 3 if split else 1
+    dev = x.device
+    cur = tuple(x.shape)
+    xp = planes_of(x, fmt, pad8(cur[3]))
+    layers = (_lib.ChainFwdLayer * n)()
+    keep, outs = [], []
+    flops = 0.0
+    for i, b in enumerate(blocks):
+        cfg, packed = b.cfg, b.packed
+        w4 = b.weight.detach()
+        if w4.dim() == 3:
+            w4 = w4.unsqueeze(2)
+        B, H, W, Cin = cur
+        Cout = w4.shape[0]
+        pf, _ = packed.tc_plans(cur, Cout, cfg, pad8(Cin), False, npass)
+        wp, wps = packed.get_tc(w4, pf, fmt, cfg.groups)
+        d = pf.desc
+        igemm.set_planes(pf, split, xp.ps, wps, 0)
+        d.out_dtype, d.epilogue, d.slope, d.out_numel = _lib.MS_F32, 0, cfg.slope, 0
+        d.block_n, d.split_k = _block_plan(pf, npass, True)
+        Ho, Wo = conv_out(H, cfg.kh, cfg.sh, cfg.ph), conv_out(W, cfg.kw, cfg.sw, cfg.pw)
+        rows = B * Ho * Wo
+        up2 = res_from[i] is not None
+        oshape = (B, 1, 2 * Wo, Cout) if up2 else (B, Ho, Wo, Cout)
+        z = arena.take_f32((B, Ho, Wo, Cout), dev) if d.split_k > 1 else None
+        is_last = i == n - 1
+        y = torch.empty(oshape, dtype=torch.float32, device=dev) if (is_last and last != "planes") else None
+        yp = alloc_planes(2 * rows if up2 else rows, Cout, fmt, dev) if not (is_last and last == "f32") else None
+        rm, rv, _ = b.bn_buffers
+        bn = _lib.BlockBn()
+        bn.C, bn.pdt, bn.training = Cout, dt_code(b.gamma.dtype), 2
+        bn.momentum, bn.eps, bn.slope = cfg.momentum, cfg.eps, (cfg.slope if cfg.act else 1.0)
+        bn.gamma, bn.beta, bn.conv_bias = ptr(b.gamma), ptr(b.beta), ptr(b.bias)
+        bn.running_mean, bn.running_var = ptr(rm), ptr(rv)
+        L = layers[i]
+        L.d, L.a, L.w, L.z, L.bn = ctypes.pointer(d), ptr(xp.t), ptr(wp), ptr(z), ctypes.pointer(bn)
+        L.y, L.planes, L.pfmt, L.pstride = ptr(y), (ptr(yp.t) if yp is not None else None), fmt, (yp.ps if yp is not None else 0)
+        L.up2 = 1 if up2 else 0
+        if up2:
+            rp = outs[res_from[i]][1]
+            L.res, L.res_planes, L.res_pfmt, L.res_pstride = None, ptr(rp.t), rp.fmt, rp.ps
+        keep.append((bn, z))
+        outs.append((y, yp, oshape))
+        flops += 2.0 * rows * Cout * (Cin // cfg.groups) * cfg.kh * cfg.kw
+        xp, cur = yp, oshape
+    sync = arena.take((2,), dev)
+    global last_gemm_flops
+    last_gemm_flops = flops
+    call("ms_conv_chain_fwd", ctypes.cast(layers, ctypes.c_void_p), n, ptr(sync), stream())
+    y, yp, oshape = outs[-1]
+    if y is not None:
+        if yp is not None:
+            y._ms_planes = yp
+        return y
+    return planes_view(yp, oshape)
+
+
+def _chain_small(blocks, shapes, fmt):
+    """True when every block of an inference chain fits the small-batch form (all tiles of a launch resident in TMEM, or
+    split-K)."""
+    npass = 3 if fmt == MS_BF16X2 else 1
+    for b, shp in zip(blocks, shapes[:-1]):
+        w = b.weight
+        pf, _ = b.packed.tc_plans(shp, w.shape[0], b.cfg, pad8(shp[3]), False, npass)
+        bn_, ks = _block_plan(pf, npass, True)
+        d = pf.desc
+        tiles = igemm._tiles_m(d) * d.num_classes * ((d.class_n + bn_ - 1) // bn_)
+        if ks == 1 and not (tiles <= 148 and igemm.block_resident(d, bn_)):
+            return False
+    return True
+
+
+def _block_chainable(b, shape, first):
+    cfg, w = b.cfg, b.weight
+    B, H, W, Cin = shape
+    Cout = w.shape[0]
+    if not cfg.has_bn or w.shape[1] * cfg.groups != Cin:
+        return False
+    if not tc_eligible(cfg, B, H, W, Cin, Cout, True):
+        return False
+    if (Cout // cfg.groups) % 32 or Cout > 8192:
+        return False
+    return first or pad8(Cin) == Cin
+
+
+def _out_shape(b, shape):
+    cfg = b.cfg
+    B, H, W, _ = shape
+    return (B, conv_out(H, cfg.kh, cfg.sh, cfg.ph), conv_out(W, cfg.kw, cfg.sw, cfg.pw), b.weight.shape[0])
+
+
+def _run_chain(blocks, x, training, res_from, fmt, last):
+    """One launch for `blocks` (all chainable); None when the inference form does not fit (caller goes block by block)."""
+    if training:
+        spec = _ChainSpec()
+        spec.blocks, spec.res_from, spec.fmt = blocks, res_from, fmt
+        spec.sinks = [(_sink(b.weight), _sink(b.bias), _sink(b.gamma), _sink(b.beta)) for b in blocks]
+        spec.out_planes = None
+        params = []
+        for b in blocks:
+            w = b.weight
+            params += [w.unsqueeze(2) if w.dim() == 3 else w, b.bias, b.gamma, b.beta]
+        y = _ConvChain.apply(x, spec, *params)
+        if spec.out_planes is not None:
+            y._ms_planes = spec.out_planes
+        return y
+    shapes = _chain_shapes(blocks, x.shape, res_from)
+    if shapes is not None and not torch.is_grad_enabled() and _chain_small(blocks, shapes, fmt):
+        return _chain_eval(blocks, x, shapes, res_from, fmt, last)
+    return None
+
+
+def conv_chain(blocks, x, training, res_from=None, last="f32", precision=None):
+    """Run ChainBlocks one after the other.  Maximal runs of blocks that qualify (tensor-core precision and geometry;
+    training-mode BatchNorm, or small-batch inference under no_grad) go out as ONE launch per direction, the rest block by
+    block through conv_block.  res_from[i] = j: block i is a UNet decoder step, upsample2(.) + output of block j.
+    `last`: form of the final activation on the inference fast path ("planes" | "f32" | "both")."""
+    prec = precision or _precision
+    n = len(blocks)
+    skips = res_from is not None and any(r is not None for r in res_from)
+    res_from = list(res_from) if res_from is not None else [None] * n
+    _need_cuda(x)
+    can_chain = CHAINS and FUSED_BLOCKS and prec != "fp32" and x.dim() == 4 and (training or not torch.is_grad_enabled())
+    fmt = _fmt(prec) if prec != "fp32" else None
+    if can_chain and skips:
+        if n <= _lib.CHAIN_MAX and _chain_shapes(blocks, x.shape, res_from) is not None:
+            y = _run_chain(blocks, x, training, res_from, fmt, last)
+            if y is not None:
+                return y
+        can_chain = False
+    outs = []
+    i = 0
+    while i < n:
+        j = i
+        if can_chain:
+            # longest run of chainable blocks starting at i
+            shape = tuple(x.shape)
+            while j < n and j - i < _lib.CHAIN_MAX and _block_chainable(blocks[j], shape, j == i):
+                shape = _out_shape(blocks[j], shape)
+                j += 1
+        if j - i >= 2:
+            y = _run_chain(blocks[i:j], x, training, [None] * (j - i), fmt, "planes" if j < n else last)
+            if y is not None:
+                x = y
+                outs += [None] * (j - i - 1) + [x]
+                i = j
+                continue
+        b = blocks[i]
+        want = "planes" if i < n - 1 else last
+        if res_from[i] is not None:
+            x = conv_block(x, b.weight, b.bias, b.gamma, b.beta, b.cfg, b.packed, b.bn_buffers, training,
+                           residual=outs[res_from[i]], up2=True, precision=prec, want=want)
+        else:
+            x = conv_block(x, b.weight, b.bias, b.gamma, b.beta, b.cfg, b.packed, b.bn_buffers, training, precision=prec, want=want)
+        outs.append(x)
+        i += 1
+    return x

@@ -84,9 +84,7 @@ class Speech2Gesture_D(nn.Module):
         B, T, P = x.shape
         h = ops.cast(x, torch.float32).contiguous().view(B, 1, T, P)
         h = self._conv1(self.conv1[0], h)
-        for blk in self.conv2:
-            h = blk(h)
-        h = self.conv3(h)
+        h = _run(list(self.conv2) + [self.conv3], h, last="f32")
         h = self._logits(self.logits, h)                  # (B,1,L',out_shape)
         out = h.reshape(B, h.shape[2], h.shape[3])
         if out.shape[-1] == 1:

@@ -542,13 +542,18 @@ def ms_conv_block_train_fwd(desc, a, w, z, bn, y, planes, pfmt, pstride, res, re
     rows = Wo * Ho * Bo
     assert b.C == C and d.epilogue == 0 and d.out_dtype == 0
     if not z:                       # inference form, full-K: the accumulators never leave TMEM, z is not materialised
-        assert not b.training
+        assert b.training != 1
         keep_z = torch.zeros(rows * C, dtype=torch.float32)
         z = keep_z.data_ptr()
     f32(z, rows * C).zero_()
     _igemm(desc, a, w, None, None, None, z, None, None, 0, 0, 0)
     ss = _ptr(b.ss)
-    if b.training:
+    if b.training == 2:             # inference, BatchNorm folded from the running statistics inside the launch
+        keep_ss = torch.zeros(4 * C, dtype=torch.float32)
+        ss = keep_ss.data_ptr()
+        ms_bn_finalize(None, None, rows, C, _ptr(b.gamma), _ptr(b.beta), _ptr(b.conv_bias) or None, _ptr(b.running_mean),
+                       _ptr(b.running_var), b.pdt, 0, b.momentum, b.eps, ss, ss + 4 * C, ss + 8 * C, ss + 12 * C, st)
+    elif b.training:
         sums = _ptr(b.sums)
         ms_bn_stats_finalize(z, rows, C, sums, sums + 8 * C, None, _ptr(b.gamma), _ptr(b.beta), _ptr(b.conv_bias) or None,
                              _ptr(b.running_mean), _ptr(b.running_var), _ptr(b.num_batches_tracked) or None, b.pdt, b.momentum, b.eps,
@@ -577,6 +582,37 @@ def ms_conv_block_train_bwd(dg, dy, z, bn, rows, up2, L, dzp, pfmt, pstride, gga
         d = _d(dg)
         Wo, Ho, Bo = d.out_dims
         _igemm(dg, dzp, wt, None, None, None, dx, None, None, 0, 0, 0)
+
+
+def ms_conv_chain_fwd(layers, n, sync, st):
+    """A chain = its blocks one after the other."""
+    from mixstage_b200 import _lib
+    arr = (_lib.ChainFwdLayer * n).from_address(_ptr(layers))
+    for L in arr:
+        ms_conv_block_train_fwd(L.d.contents, L.a, L.w, L.z, L.bn.contents, L.y, L.planes, L.pfmt, L.pstride, L.res, L.res_planes,
+                                L.res_pfmt, L.res_pstride, L.up2, sync, st)
+
+
+def ms_conv_chain_bwd(layers, n, sync, st):
+    from mixstage_b200 import _lib
+    arr = (_lib.ChainBwdLayer * n).from_address(_ptr(layers))
+    for L in arr:
+        dy = L.dy
+        keep = None
+        if L.dy2:
+            C = L.bn.contents.C
+            m = (2 if L.up2 else 1) * L.rows * C
+            keep = (f32(L.dy, m) + f32(L.dy2, m)).contiguous()
+            dy = keep.data_ptr()
+        ms_conv_block_train_bwd(L.dg.contents if L.dg else None, dy, L.z, L.bn.contents, L.rows, L.up2, L.rows_per_seq, L.dz_planes,
+                                L.pfmt, L.pstride, L.grad_gamma, L.grad_beta, L.gdt, L.wt, L.dx, sync, st)
+
+
+def ms_wgrad_bf16_acc_multi(items, n, st):
+    from mixstage_b200 import _lib
+    arr = (_lib.WgradItem * n).from_address(_ptr(items))
+    for it in arr:
+        ms_wgrad_bf16_acc(it.d.contents, it.x, it.dz, it.acc, st)
 
 
 def ms_wgrad_bf16_acc(desc, x, dz, acc, st):

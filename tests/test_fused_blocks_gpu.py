@@ -97,6 +97,10 @@ def test_fused_block_equals_three_kernel_path(name, precision):
         # (the full-K forward reduces the statistics from fp32 warp partials of the accumulators instead of an fp64 pass over
         # z: mean / rstd move in the 7th digit, dgamma of a 2048-channel layer by 3e-5)
         tol = 1e-4 if precision == "bf16x3" else 2e-3
+        if k in ("dgamma", "dbeta", "dx", "dw", "dres"):
+            # a handful of LeakyReLU masks (pre-activations within 1e-6 of the corner, ~2 of the 2 M elements of a sub-decoder
+            # block) flip with the 7th digit of scale / shift: each moves the backward by 0.8 * dy at that element
+            tol = max(tol, 1e-3)
         assert _rel(a[k], b[k]) < tol, (name, k, _rel(a[k], b[k]))
 
 

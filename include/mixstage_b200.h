@@ -175,7 +175,8 @@ typedef struct ms_pack_entry {
   int32_t pdt, Cout, Cin_g, taps_total, groups, mode, num_classes, class_n, ntaps, kpad;
   int16_t srctap[MS_IGEMM_MAX_TAPS];
 } ms_pack_entry;
-int ms_pack_igemm_weight_multi(const ms_pack_entry* table_dev, int n_entries, int blocks_per_entry, void* stream);
+/* blocks: CTAs of the launch (<= 0: 8 per SM); work units are spread over the entries in proportion to their size. */
+int ms_pack_igemm_weight_multi(const ms_pack_entry* table_dev, int n_entries, int blocks, void* stream);
 
 /* Weight gradient on tcgen05 (aten::convolution_backward, weight grad): with d the FORWARD descriptor,
  *   dwp[q*class_n + n][t][c] = sum_{b,h,w} dz[b,h,w, off[q] + n] * A5[base[q] + taps[t].chan + c, w + dw, par, h + dh, b]
@@ -292,7 +293,7 @@ typedef struct ms_wgrad_entry {
   void* dw;
   int32_t pdt, Cout, Cin_g, taps, kpad, accumulate;
 } ms_wgrad_entry;
-int ms_unpack_wgrad_multi(const ms_wgrad_entry* table_dev, int n_entries, int blocks_per_entry, void* stream);
+int ms_unpack_wgrad_multi(const ms_wgrad_entry* table_dev, int n_entries, int blocks, void* stream);
 
 /* ---- BatchNorm (+LeakyReLU) pieces, nn.BatchNorm1d/2d at layers.py:64,70 and
  * nn.LeakyReLU(0.2) at layers.py:72-73, applied as in ConvNormRelu.forward (:78) ------ */

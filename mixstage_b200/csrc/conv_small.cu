@@ -496,8 +496,10 @@ int ms_small_conv_wgrad(const float* x, const float* dy, float* dwf, const ms_co
   }
   if (d->Cout <= NMAX && d->Cin > 1) {
     int cb = (d->Cin + 127) / 128;
-    int chunks = (ms_num_sms() + cb * p.taps - 1) / (cb * p.taps);
-    int maxc = (M + 63) / 64;
+    // every thread walks its chunk's pixels serially with dependent L2 loads (~0.4 us each): short chunks (>= 8 pixels) over
+    // ~four waves of CTAs instead of 64-pixel chunks (25 us for the 1024-pixel classifier logits at batch 16)
+    int chunks = (4 * ms_num_sms() + cb * p.taps - 1) / (cb * p.taps);
+    int maxc = (M + 7) / 8;
     if (chunks > maxc) chunks = maxc;
     if (chunks < 1) chunks = 1;
     if (chunks > 1 && cudaMemsetAsync(dwf, 0, sizeof(float) * (size_t)p.taps * d->Cin * d->Cout, st) != cudaSuccess) return -1;

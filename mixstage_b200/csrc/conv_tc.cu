@@ -1145,41 +1145,70 @@ __global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, Pa
   }
 }
 
-// Table-driven form: blockIdx.y selects the entry, so ONE launch re-tiles every weight of a sub-network (the train step
-// refreshes all packed copies right after the optimiser update instead of ~80 separate launches).
-__global__ void pack_igemm_weight_multi_kernel(const ms_pack_entry* __restrict__ table) {
-  const ms_pack_entry& e = table[blockIdx.y];
-  const long long total = (long long)e.num_classes * e.class_n * e.ntaps * e.kpad;
-  const int Cout_g = e.Cout / e.groups;
-  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(e.wp);
-  __nv_bfloat16* wp_lo = reinterpret_cast<__nv_bfloat16*>(e.wp_lo);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int kc = (int)(i % e.kpad);
-    long long t2 = i / e.kpad;
-    int t = (int)(t2 % e.ntaps);
-    long long row = t2 / e.ntaps;
-    int cls = (int)(row / e.class_n), r = (int)(row - (long long)cls * e.class_n);
-    float v = 0.f;
-    if (e.mode == 0) {
-      if (row < e.Cout && kc < e.Cin_g) v = ms_ldp(e.w, e.pdt, (row * e.Cin_g + kc) * e.taps_total + e.srctap[t]);
-    } else {
-      int g = e.groups > 1 ? cls : 0;
-      if (kc < Cout_g && r < e.Cin_g)
-        v = ms_ldp(e.w, e.pdt, ((long long)(g * Cout_g + kc) * e.Cin_g + r) * e.taps_total + e.srctap[cls * e.ntaps + t]);
+// Table-driven form: ONE launch re-tiles every weight of a sub-network (the train step refreshes all packed copies right after
+// the optimiser update instead of ~80 separate launches).  Work units of ~PACK_UNIT packed elements are spread over the
+// entries in proportion to their size; a thread converts two adjacent k positions and stores bf16 pairs.
+constexpr int PACK_UNIT = 16384;
+constexpr int PACK_MAX_ENTRIES = 256;
+__global__ void __launch_bounds__(256) pack_igemm_weight_multi_kernel(const ms_pack_entry* __restrict__ table, int n_entries) {
+  __shared__ int s_units[PACK_MAX_ENTRIES];
+  __shared__ int s_total;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_entries; i += blockDim.x) {
+    const long long tot = (long long)table[i].num_classes * table[i].class_n * table[i].ntaps * table[i].kpad;
+    s_units[i] = (int)((tot + PACK_UNIT - 1) / PACK_UNIT);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+    for (int i = 0; i < n_entries; i++) tot += s_units[i];
+    s_total = tot;
+  }
+  __syncthreads();
+  const int total_units = s_total;
+  for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+    int ei = 0, local = u;
+    while (ei < n_entries && local >= s_units[ei]) { local -= s_units[ei]; ei++; }
+    const ms_pack_entry& e = table[ei];
+    const int nu = s_units[ei];
+    const long long pairs = ((long long)e.num_classes * e.class_n * e.ntaps * e.kpad) >> 1;     // kpad is a multiple of 64
+    const long long p0 = pairs * local / nu, p1 = pairs * (local + 1) / nu;
+    const int Cout_g = e.Cout / e.groups;
+    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(e.wp);
+    __nv_bfloat16* wp_lo = reinterpret_cast<__nv_bfloat16*>(e.wp_lo);
+    for (long long pi = p0 + tid; pi < p1; pi += blockDim.x) {
+      const long long i = pi << 1;
+      const int kc = (int)(i % e.kpad);
+      const long long t2 = i / e.kpad;
+      const int t = (int)(t2 % e.ntaps);
+      const long long row = t2 / e.ntaps;
+      const int cls = (int)(row / e.class_n), r = (int)(row - (long long)cls * e.class_n);
+      float v[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int k = kc + j;
+        if (e.mode == 0) {
+          if (row < e.Cout && k < e.Cin_g) v[j] = ms_ldp(e.w, e.pdt, (row * e.Cin_g + k) * e.taps_total + e.srctap[t]);
+        } else {
+          const int g = e.groups > 1 ? cls : 0;
+          if (k < Cout_g && r < e.Cin_g)
+            v[j] = ms_ldp(e.w, e.pdt, ((long long)(g * Cout_g + k) * e.Cin_g + r) * e.taps_total + e.srctap[cls * e.ntaps + t]);
+        }
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
+      *reinterpret_cast<__nv_bfloat162*>(wp + i) = h;
+      if (wp_lo)
+        *reinterpret_cast<__nv_bfloat162*>(wp_lo + i) = __floats2bfloat162_rn(v[0] - __bfloat162float(h.x), v[1] - __bfloat162float(h.y));
     }
-    __nv_bfloat16 h = __float2bfloat16(v);
-    wp[i] = h;
-    if (wp_lo) wp_lo[i] = __float2bfloat16(v - __bfloat162float(h));
   }
 }
 
 }  // namespace
 
-extern "C" int ms_pack_igemm_weight_multi(const ms_pack_entry* table_dev, int n_entries, int blocks_per_entry, void* stream) {
-  if (!table_dev || n_entries < 1 || n_entries > 65535) return MS_EINVAL;
-  if (blocks_per_entry < 1) blocks_per_entry = 64;
-  dim3 grid((unsigned)blocks_per_entry, (unsigned)n_entries);
-  pack_igemm_weight_multi_kernel<<<grid, 256, 0, ms_stream(stream)>>>(table_dev);
+extern "C" int ms_pack_igemm_weight_multi(const ms_pack_entry* table_dev, int n_entries, int blocks, void* stream) {
+  if (!table_dev || n_entries < 1 || n_entries > PACK_MAX_ENTRIES) return MS_EINVAL;
+  if (blocks < 1) blocks = 8 * ms_num_sms();
+  pack_igemm_weight_multi_kernel<<<dim3((unsigned)blocks), 256, 0, ms_stream(stream)>>>(table_dev, n_entries);
   MS_LAUNCH_CHECK();
   return 0;
 }

@@ -1295,18 +1295,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_acc_multi_kernel(const _
   wgrad_acc_body(L.map_x, L.map_z, L.map_x_lo, L.map_z_lo, L.p, L.acc, bx, by, bz);
 }
 
-// every accumulator of a sub-network -> its parameter-gradient buffer (dw += unpack(acc)), one launch
-__global__ void unpack_wgrad_multi_kernel(const ms_wgrad_entry* __restrict__ table) {
-  const ms_wgrad_entry& e = table[blockIdx.y];
-  const long long total = (long long)e.Cout * e.Cin_g * e.taps;
-  const float* __restrict__ acc = reinterpret_cast<const float*>(e.acc);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % e.taps);
-    const long long t2 = i / e.taps;
-    const int c = (int)(t2 % e.Cin_g);
-    const long long o = t2 / e.Cin_g;
-    const double v = (double)acc[(o * e.taps + tap) * e.kpad + c];
-    ms_stp(e.dw, e.pdt, i, v + (e.accumulate ? ms_ldp_d(e.dw, e.pdt, i) : 0.0));
+// every accumulator of a sub-network -> its parameter-gradient buffer (dw += unpack(acc)), one launch.
+// Work is cut into units of ~MULTI_UNIT elements spread over the entries in proportion to their size (every CTA derives
+// the same unit -> (entry, output-channel range) map from the table), and every output channel goes through shared memory:
+// its accumulator row [tap][kpad] is read contiguously, its gradient row [c][tap] written contiguously.
+constexpr int MULTI_UNIT = 16384;
+constexpr int MULTI_MAX_ENTRIES = 256;
+constexpr int UNPACK_SMEM_FLOATS = 10240;      // 40 KB: rows of up to 48 taps x 192 padded channels; longer rows go direct
+
+__device__ __forceinline__ int multi_units(long long elems) { return (int)((elems + MULTI_UNIT - 1) / MULTI_UNIT); }
+
+// unit u -> entry index and the unit's position inside the entry; *nu = units of that entry.  All threads get the same answer.
+__device__ __forceinline__ int multi_find(const int* __restrict__ s_units, int n_entries, int u, int* local, int* nu) {
+  int e = 0;
+  while (e < n_entries && u >= s_units[e]) { u -= s_units[e]; e++; }
+  *local = u;
+  *nu = e < n_entries ? s_units[e] : 1;
+  return e;
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const ms_wgrad_entry* __restrict__ table, int n_entries) {
+  __shared__ int s_units[MULTI_MAX_ENTRIES];
+  __shared__ int s_total;
+  __shared__ __align__(16) float s_row[UNPACK_SMEM_FLOATS];
+  const int t = threadIdx.x;
+  for (int i = t; i < n_entries; i += blockDim.x) s_units[i] = multi_units((long long)table[i].Cout * table[i].Cin_g * table[i].taps);
+  __syncthreads();
+  if (t == 0) {
+    int tot = 0;
+    for (int i = 0; i < n_entries; i++) tot += s_units[i];
+    s_total = tot;
+  }
+  __syncthreads();
+  const int total = s_total;
+  for (int u = blockIdx.x; u < total; u += gridDim.x) {
+    int local, nu;
+    const int ei = multi_find(s_units, n_entries, u, &local, &nu);
+    const ms_wgrad_entry e = table[ei];
+    const int o0 = (int)((long long)e.Cout * local / nu), o1 = (int)((long long)e.Cout * (local + 1) / nu);
+    const float* __restrict__ acc = reinterpret_cast<const float*>(e.acc);
+    const int row_in = e.taps * e.kpad, row_out = e.Cin_g * e.taps;
+    if (row_in <= UNPACK_SMEM_FLOATS) {
+      // as many output channels per pass as fit in shared memory: contiguous reads, contiguous writes, two syncs per pass
+      const int R = UNPACK_SMEM_FLOATS / row_in;
+      for (int ob0 = o0; ob0 < o1; ob0 += R) {
+        const int nr = min(R, o1 - ob0);
+        const float* src = acc + (long long)ob0 * row_in;
+        __syncthreads();
+        for (int i = 4 * t; i < nr * row_in; i += 4 * blockDim.x) *reinterpret_cast<float4*>(s_row + i) = *reinterpret_cast<const float4*>(src + i);
+        __syncthreads();
+        const long long ob = (long long)ob0 * row_out;
+        for (int i = t; i < nr * row_out; i += blockDim.x) {
+          const int rr = i / row_out, j = i - rr * row_out;
+          const int c = j / e.taps, tap = j - c * e.taps;
+          const double v = (double)s_row[rr * row_in + tap * e.kpad + c];
+          ms_stp(e.dw, e.pdt, ob + i, v + (e.accumulate ? ms_ldp_d(e.dw, e.pdt, ob + i) : 0.0));
+        }
+      }
+    } else {
+      for (int o = o0; o < o1; o++) {
+        const float* src = acc + (long long)o * row_in;
+        const long long ob = (long long)o * row_out;
+        for (int i = t; i < row_out; i += blockDim.x) {
+          const int c = i / e.taps, tap = i - c * e.taps;
+          const double v = (double)src[tap * e.kpad + c];
+          ms_stp(e.dw, e.pdt, ob + i, v + (e.accumulate ? ms_ldp_d(e.dw, e.pdt, ob + i) : 0.0));
+        }
+      }
+    }
   }
 }
 
@@ -1685,11 +1741,10 @@ extern "C" int ms_wgrad_bf16_acc_multi(const ms_wgrad_item* items, int n, void* 
   return 0;
 }
 
-extern "C" int ms_unpack_wgrad_multi(const ms_wgrad_entry* table_dev, int n_entries, int blocks_per_entry, void* stream) {
-  if (!table_dev || n_entries < 1 || n_entries > 65535) return MS_EINVAL;
-  if (blocks_per_entry < 1) blocks_per_entry = 32;
-  dim3 grid((unsigned)blocks_per_entry, (unsigned)n_entries);
-  unpack_wgrad_multi_kernel<<<grid, 256, 0, ms_stream(stream)>>>(table_dev);
+extern "C" int ms_unpack_wgrad_multi(const ms_wgrad_entry* table_dev, int n_entries, int blocks, void* stream) {
+  if (!table_dev || n_entries < 1 || n_entries > MULTI_MAX_ENTRIES) return MS_EINVAL;
+  if (blocks < 1) blocks = 8 * ms_num_sms();
+  unpack_wgrad_multi_kernel<<<dim3((unsigned)blocks), 256, 0, ms_stream(stream)>>>(table_dev, n_entries);
   MS_LAUNCH_CHECK();
   return 0;
 }

@@ -278,6 +278,38 @@ def wgrad_tiles(d, c_tile=256):
     return ((d.class_n + 127) // 128) * ((kpad + c_tile - 1) // c_tile) * d.num_classes * d.ntaps
 
 
+def wgrad_row_tiles(d):
+    """64-pixel-row tiles (the k-steps) of a weight gradient."""
+    bw, bh, bb = d.box[1], d.box[3], d.box[4]
+    if bb > 1:
+        bb //= 2
+    elif bh > 1:
+        bh //= 2
+    else:
+        bw //= 2
+    return _tiles_m(d, (bw, bh, bb))
+
+
+def wgrad_multi_splits(descs, sms=148):
+    """Pixel-slice counts (and c_tile = 256) for the weight gradients of a chain that share ONE launch: about two waves of
+    CTAs in total, every CTA with roughly the same operand bytes to stream, at least two k-steps per CTA (each CTA ends with
+    a 128 x c_tile fp32 reduction into the accumulator, which more slicing only multiplies)."""
+    per_tile = []
+    for d in descs:
+        kpad = d.cchunks * BLOCK_K
+        ct = min(256, kpad)
+        rt = wgrad_row_tiles(d)
+        per_tile.append((wgrad_tiles(d, 256), rt, rt * (128 + ct) * 128.0))
+    total = sum(t * w for t, _, w in per_tile)
+    target = max(total / (2.0 * sms), 1.0)
+    out = []
+    for t, rt, w in per_tile:
+        split = int(round(w / target))
+        split = max(1, min(split, max(1, rt // 2)))
+        out.append((_normalise_split(rt, split), 256))
+    return out
+
+
 def wgrad_split(d, sms=148, npass=1):
     """(split, c_tile) of a weight-gradient launch.  Tiles are (128 output channels) x (c_tile input channels) per
     (class, tap); the 64-pixel-row tiles are sliced `split` ways and every slice writes its own partial dWp.

@@ -1199,7 +1199,7 @@ class _SoftmaxCE(torch.autograd.Function):
             target = target.contiguous()
             if target.dtype != torch.int64 or target.numel() * trep != rows:
                 raise MixStageError("CE target must be int64 with rows/trep entries")
-            acc = torch.zeros(1, dtype=torch.float64, device=dev)
+            acc = arena.take((1,), dev)
             call("ms_softmax_ce_fwd_f32", ptr(score), rows, K, ptr(target), trep, ptr(soft), ptr(amax), ptr(acc), st)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             call("ms_scalar_finish", ptr(acc), 1.0 / rows, ptr(loss), st)
@@ -1319,7 +1319,7 @@ class _L1Mean(torch.autograd.Function):
                 raise MixStageError("l1: shape mismatch")
         n = a.numel()
         dev = a.device
-        acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        acc = arena.take((1,), dev)
         sgn = torch.empty_like(a)
         st = stream()
         call("ms_l1_fwd_f32", ptr(a), ptr(b), float(const), n, ptr(acc), ptr(sgn), st)
@@ -1553,16 +1553,15 @@ class _ConvChain(torch.autograd.Function):
         if direct:
             items = (_lib.WgradItem * len(direct))()
             fl = 0.0
-            # the blocks share ONE launch: every block gets its share of ~two waves of CTAs for its pixel slices (slicing a
+            # the blocks share ONE launch: pixel slices chosen so that ~two waves of CTAs carry equal operand bytes (slicing a
             # block as if it had the machine to itself multiplies the 128 KB-per-CTA accumulator reductions instead)
-            total_tiles = sum(igemm.wgrad_tiles(rec[i]["pf"].desc) for i in direct)
+            splits = igemm.wgrad_multi_splits([rec[i]["pf"].desc for i in direct])
             for k, i in enumerate(direct):
                 r, b = rec[i], blocks[i]
                 pf = r["pf"]
                 B, H, W, Cin = r["in_shape"]
                 igemm.set_planes(pf, split, r["xp"].ps, 0, r["dzp"].ps)
-                share = max(4, int(148.0 * igemm.wgrad_tiles(pf.desc) / total_tiles))
-                nsplit, pf.desc.wgrad_c_tile = igemm.wgrad_split(pf.desc, sms=share, npass=npass)
+                nsplit, pf.desc.wgrad_c_tile = splits[k]
                 pf.desc.split_k = nsplit
                 acc = WACC.acc_for(b.packed, pf.wp_numel, dev)
                 WACC.note(acc, spec.sinks[i][0], r["Cout"], Cin // b.cfg.groups, b.cfg.kh * b.cfg.kw, pf.kpad, r["wdt"])

@@ -353,7 +353,7 @@ class TrainStep:
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             cur = (sig, host.to(self.fG.device), len(entries))
             self._tables[kind] = cur
-        call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 48, stream())
+        call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 0, stream())
 
     def _flush_wgrads(self, kind):
         """Every weight-gradient accumulator of this step -> the flat gradient buffers, one launch."""
@@ -375,7 +375,7 @@ class TrainStep:
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             cur = (sig, host.to(self.fG.device), len(ents))
             self._wtables[kind] = cur
-        call("ms_unpack_wgrad_multi", ptr(cur[1]), cur[2], 32, stream())
+        call("ms_unpack_wgrad_multi", ptr(cur[1]), cur[2], 0, stream())
 
     def refresh(self):
         """Call after changing parameters or BatchNorm buffers from outside (load_state_dict, manual edits)."""

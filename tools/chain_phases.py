@@ -40,6 +40,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--eval", action="store_true", help="inference chains (eval mode, no_grad)")
     a = ap.parse_args()
     from mixstage_b200 import layers, ops
     import torch.nn as nn
@@ -54,8 +55,8 @@ def main():
         "pose_style.conv.0-5": (nn.Sequential(*list(layers.PoseStyleEncoder().conv)[:6]), (B, 1, 64, 96)),
     }
     for name, (m, shape) in mods.items():
-        m = m.to("cuda", torch.float64).train()
-        x = torch.randn(*shape, device="cuda", requires_grad=True)
+        m = m.to("cuda", torch.float64).train(not a.eval)
+        x = torch.randn(*shape, device="cuda", requires_grad=not a.eval)
         rec = {}
         orig = ops.call
 
@@ -75,11 +76,13 @@ def main():
         for it in range(3):
             ops.call = timed if it == 2 else orig
             try:
-                if isinstance(m, layers.UNet1D):
-                    y = m(x)
-                else:
-                    y = layers._run(list(m), x)
-                y.backward(torch.randn_like(y))
+                with torch.set_grad_enabled(not a.eval):
+                    if isinstance(m, layers.UNet1D):
+                        y = m(x)
+                    else:
+                        y = layers._run(list(m), x)
+                if not a.eval:
+                    y.backward(torch.randn_like(y))
             finally:
                 ops.call = orig
             torch.cuda.synchronize()

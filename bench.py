@@ -47,6 +47,18 @@ TRAIN_WORKLOADS = {
 }
 
 
+def train_workload_name(label, B, T, S, K, am):
+    """Canonical name of a train workload: the SAME string on the CUDA arm and on the reference arm (the driver compares
+    the two `config` objects); implementation details (precision, graphs, exchange) go to `config_detail`."""
+    return ("%s: GAN train step (G on even, D on odd iterations), B=%d per GPU, T=%d, S=%d, K=%d, %s style, gan=1, L1Loss, "
+            "fp64 master params/inputs" % (label, B, T, S, K, "argmax" if am else "soft"))
+
+
+def infer_workload_name(B, S):
+    return ("configs[2]: inference sweep, B=%d windows per GPU x S=%d target styles per step (sample_all_styles), T=64, K=8, "
+            "eval mode, fp64 parameters/inputs/outputs" % (B, S))
+
+
 def ncu_traffic(workload):
     """dram bytes per launch of the dominant kernel family from the committed ncu --set full capture (profiles/), or None."""
     for name in ("r02_traffic.json", "r01_traffic.json"):
@@ -273,27 +285,33 @@ def reference_line(args):
     steps, warmup = args.steps, args.warmup
     cores = os.cpu_count()
     if wl == "infer":
-        B, S = args.batch or 16, 4
+        B, S = args.batch or 1024, 4
+        cb = 16                                  # bounded sample: the CPU sweeps B=16 windows per step, same shapes otherwise
         spec = _spec(S)
-        dt, kind, what = cpu_infer_sweep(spec, B, 64, steps, warmup)
-        val = steps * B * S / dt
+        dt, kind, what = cpu_infer_sweep(spec, cb, 64, steps, warmup)
+        val = steps * cb * S / dt
         metric = "pose sequences/sec (64-frame windows), inference style sweep"
-        workload = "configs[2]: inference sweep, B=%d x S=%d styles per step, T=64, K=8, fp64" % (B, S)
-        sample = "%d sweeps of B=%d x S=%d styles after %d warm-up, %s, %d threads" % (steps, B, S, warmup, what, cores)
+        workload = infer_workload_name(B, S)
+        sample = "%d sweeps of B=%d x S=%d styles after %d warm-up, %s, %d threads" % (steps, cb, S, warmup, what, cores)
+        gb = B * args.gpus
     else:
         label, B0, S0, K, am, T, _ = TRAIN_WORKLOADS[wl]
-        B = args.batch or (B0 if wl == "train" else min(B0, 16))
+        B = args.batch or B0
+        cb = min(B, 16)                          # bounded sample of the same workload: at most 16 sequences per CPU step
         S = args.speakers or S0
         spec = _spec(S, K, am, T)
-        dt, kind, what = cpu_train_steps(spec, B, T, steps, warmup)
-        val = steps * B / dt
+        dt, kind, what = cpu_train_steps(spec, cb, T, steps, warmup)
+        val = steps * cb / dt
         metric = "pose sequences/sec (%d-frame windows), GAN train step" % T
-        workload = "%s: GAN train step (alternating G/D), B=%d, T=%d, S=%d, K=%d, fp64" % (label, B, T, S, K)
-        sample = "%d train steps (G/D alternating) B=%d after %d warm-up, %s, %d threads" % (steps, B, warmup, what, cores)
+        workload = train_workload_name(label if (B, S) == (B0, S0) else "variant of " + label, B, T, S, K, am)
+        sample = "%d train steps (G/D alternating) B=%d after %d warm-up, %s, %d threads" % (steps, cb, warmup, what, cores)
+        gb = B * args.gpus
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * dt / max(1, steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": gb, "parallelism": "dp%d" % args.gpus},
+        "config_detail": {"arm": "reference algorithm on the host cores (rank 0 only), fp64, %d threads" % cores},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -378,7 +396,8 @@ def _instrument(ops, names, run, busy_ms=60):
 
 
 GEMM_ENTRY_POINTS = ("ms_igemm_bf16", "ms_igemm_bf16_fused", "ms_igemm_bf16_mix", "ms_wgrad_bf16", "ms_conv_block_train_fwd",
-                     "ms_conv_block_train_bwd", "ms_wgrad_bf16_acc")
+                     "ms_conv_block_train_bwd", "ms_wgrad_bf16_acc", "ms_conv_chain_fwd", "ms_conv_chain_bwd",
+                     "ms_wgrad_bf16_acc_multi")
 
 
 def _roofline(ctx, recs, kernel_desc, traffic_key):
@@ -471,23 +490,23 @@ def bench_train(ctx, args, wl, steps, warmup, headline):
         "metric": "pose sequences/sec (%d-frame windows), GAN train step" % T, "value": total / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": steps, "warmup": nwarm, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[prec], "data": "synthetic",
-        "config": {"workload": "%s: GAN train step (G on even, D on odd iterations), B=%d per GPU, T=%d, S=%d, K=%d, %s style, "
-                               "gan=1, L1Loss, fp64 master params/inputs, precision=%s, %s%s" % (
-                                   label if (B, S) == (B0, S0) else "variant of " + label, B, T, S, K,
-                                   "argmax" if am else "soft", prec, "CUDA-graph replay" if ts.use_graphs else "eager launches",
-                                   "" if world == 1 else ", gradients exchanged as %s in %s" % (
-                                       args.exchange_dtype, "4 buckets overlapped with backward" if not args.no_overlap
-                                       else "one all-reduce after backward")),
-                   "global_batch": B * world, "parallelism": "dp%d" % world,
-                   "l2": "no explicit flush: per-step working set (master params + packed weights + grads + Adam state "
-                         "~0.9 GB) exceeds the 126 MB L2"},
+        "config": {"workload": train_workload_name(label if (B, S) == (B0, S0) else "variant of " + label, B, T, S, K, am),
+                   "global_batch": B * world, "parallelism": "dp%d" % world},
+        "config_detail": {"precision": prec, "launch": "CUDA-graph replay" if ts.use_graphs else "eager launches",
+                          "exchange": None if world == 1 else "gradients exchanged as %s in %s" % (
+                              args.exchange_dtype, "4 buckets overlapped with backward" if not args.no_overlap
+                              else "one all-reduce after backward"),
+                          "l2": "no explicit flush: per-step working set (master params + packed weights + grads + Adam state "
+                                "~0.9 GB) exceeds the 126 MB L2"},
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "mixstage_b200.TrainStep.step(pinned host batch); every step's losses and generated poses copied to "
                        "pinned host memory and read one step behind the launch (%d reads)" % len(log)},
         "gpu_launches": launches, "kernels_per_graph": per_graph,
         "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
-        "roofline": _roofline(ctx, recs, "tcgen05 implicit-GEMM family (fwd / dgrad / wgrad, fused train blocks), %d launches per "
-                              "G+D step pair; algorithmic FLOPs" + (", split-bf16 issues 3x the MMAs" if prec == "bf16x3" else ""),
+        "roofline": _roofline(ctx, recs, "tcgen05 chain kernels (conv_chain_fwd / conv_chain_bwd: implicit GEMM + BatchNorm "
+                              "statistics / normalise / backward of up to 12 blocks per launch) + chain weight-gradient launches, "
+                              "%d launches per G+D step pair; algorithmic GEMM FLOPs over the WHOLE launch time (element-wise "
+                              "phases and device barriers included)" + (", split-bf16 issues 3x the MMAs" if prec == "bf16x3" else ""),
                               "train"),
     }
     # whole-step fraction: algorithmic FLOPs of the alternating G/D loop / device-timed step
@@ -614,12 +633,10 @@ def bench_infer(ctx, args, steps, warmup, headline):
         "metric": "pose sequences/sec (64-frame windows), inference style sweep", "value": total / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": steps, "warmup": nwarm, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[prec], "data": "synthetic",
-        "config": {"workload": "configs[2]: inference sweep, B=%d windows per GPU x S=%d target styles per step "
-                               "(sample_all_styles), T=64, K=8, eval mode, fp64 parameters/inputs/outputs, precision=%s, "
-                               "encoder+UNet computed once per batch and reused across styles, %s" % (
-                                   B, S, prec, "one CUDA graph per input buffer" if use_graphs else "eager launches"),
-                   "global_batch": B * world, "parallelism": "dp%d (no collective)" % world,
-                   "l2": "two alternating input batches; per-step activations (>1 GB at B=1024) exceed the 126 MB L2"},
+        "config": {"workload": infer_workload_name(B, S), "global_batch": B * world, "parallelism": "dp%d" % world},
+        "config_detail": {"precision": prec, "collective": "none", "cache": "encoder+UNet computed once per batch and reused across styles",
+                          "launch": "one CUDA graph per input buffer" if use_graphs else "eager launches",
+                          "l2": "two alternating input batches; per-step activations (>1 GB at B=1024) exceed the 126 MB L2"},
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "G.forward per style on a batch copied from pinned host memory + fp64 pose outputs copied back to pinned host memory"},
         "gpu_launches": launches,

@@ -971,14 +971,27 @@ __device__ __forceinline__ void bwd_layer(const BwdLayer& L, uint8_t* smem, cons
       if (a.ok) {
         const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.ss + 4 * a.cg)), sh = __ldg(reinterpret_cast<const float4*>(bn.ss + C + 4 * a.cg));
         const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * a.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * a.cg));
-        for (long long r = a.r0 + (t >> 4); r < a.r1; r += 16) {
-          const float4 xv = ldcg4(z + r * C + 4 * a.cg);
-          const float4 d = dy_at4(dy, io.dy2, r, a.cg, C, io.up2, io.L);
-          const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
-          const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
-          acc[0] += (double)g0 * (double)((xv.x - mu.x) * rs.x); acc[1] += (double)g1 * (double)((xv.y - mu.y) * rs.y);
-          acc[2] += (double)g2 * (double)((xv.z - mu.z) * rs.z); acc[3] += (double)g3 * (double)((xv.w - mu.w) * rs.w);
-          acc[4] += g0; acc[5] += g1; acc[6] += g2; acc[7] += g3;
+        // four rows in flight per thread (large batches: this pass is HBM-bound, one row at a time left it latency-bound)
+        for (long long r = a.r0 + (t >> 4); r < a.r1; r += 64) {
+          float4 xv[4], d[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const long long ru = r + 16 * u;
+            if (ru < a.r1) {
+              xv[u] = ldcg4(z + ru * C + 4 * a.cg);
+              d[u] = dy_at4(dy, io.dy2, ru, a.cg, C, io.up2, io.L);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (r + 16 * u < a.r1) {
+              const float g0 = fmaf(xv[u].x, sc.x, sh.x) > 0.f ? d[u].x : d[u].x * slope, g1 = fmaf(xv[u].y, sc.y, sh.y) > 0.f ? d[u].y : d[u].y * slope;
+              const float g2 = fmaf(xv[u].z, sc.z, sh.z) > 0.f ? d[u].z : d[u].z * slope, g3 = fmaf(xv[u].w, sc.w, sh.w) > 0.f ? d[u].w : d[u].w * slope;
+              acc[0] += (double)g0 * (double)((xv[u].x - mu.x) * rs.x); acc[1] += (double)g1 * (double)((xv[u].y - mu.y) * rs.y);
+              acc[2] += (double)g2 * (double)((xv[u].z - mu.z) * rs.z); acc[3] += (double)g3 * (double)((xv[u].w - mu.w) * rs.w);
+              acc[4] += g0; acc[5] += g1; acc[6] += g2; acc[7] += g3;
+            }
+          }
         }
       }
       slab_reduce_add(acc, a, C, red_scratch, bn.sums, bn.sums + C);
@@ -1032,21 +1045,35 @@ __device__ __forceinline__ void bwd_layer(const BwdLayer& L, uint8_t* smem, cons
       }
       const float4 sc = __ldg(reinterpret_cast<const float4*>(bn.ss + 4 * a.cg)), sh = __ldg(reinterpret_cast<const float4*>(bn.ss + C + 4 * a.cg));
       const float4 mu = __ldg(reinterpret_cast<const float4*>(bn.ss + 2 * C + 4 * a.cg)), rs = __ldg(reinterpret_cast<const float4*>(bn.ss + 3 * C + 4 * a.cg));
-      for (long long r = a.r0 + (t >> 4); r < a.r1; r += 16) {
-        const float4 xv = ldcg4(z + r * C + 4 * a.cg);
-        const float4 d = dy_at4(dy, io.dy2, r, a.cg, C, io.up2, io.L);
-        const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
-        const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
-        float4 o;
-        if (bn.training) {
-          o.x = sc.x * (g0 - dbv.x * inv - ((xv.x - mu.x) * rs.x) * dgv.x * inv);
-          o.y = sc.y * (g1 - dbv.y * inv - ((xv.y - mu.y) * rs.y) * dgv.y * inv);
-          o.z = sc.z * (g2 - dbv.z * inv - ((xv.z - mu.z) * rs.z) * dgv.z * inv);
-          o.w = sc.w * (g3 - dbv.w * inv - ((xv.w - mu.w) * rs.w) * dgv.w * inv);
-        } else {
-          o.x = sc.x * g0; o.y = sc.y * g1; o.z = sc.z * g2; o.w = sc.w * g3;
+      for (long long r = a.r0 + (t >> 4); r < a.r1; r += 64) {
+        float4 xq[4], dq[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const long long ru = r + 16 * u;
+          if (ru < a.r1) {
+            xq[u] = ldcg4(z + ru * C + 4 * a.cg);
+            dq[u] = dy_at4(dy, io.dy2, ru, a.cg, C, io.up2, io.L);
+          }
         }
-        store_planes4(io.dzp, io.pfmt, io.pstride, r * C + 4 * a.cg, o);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const long long ru = r + 16 * u;
+          if (ru < a.r1) {
+            const float4 xv = xq[u], d = dq[u];
+            const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
+            const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
+            float4 o;
+            if (bn.training) {
+              o.x = sc.x * (g0 - dbv.x * inv - ((xv.x - mu.x) * rs.x) * dgv.x * inv);
+              o.y = sc.y * (g1 - dbv.y * inv - ((xv.y - mu.y) * rs.y) * dgv.y * inv);
+              o.z = sc.z * (g2 - dbv.z * inv - ((xv.z - mu.z) * rs.z) * dgv.z * inv);
+              o.w = sc.w * (g3 - dbv.w * inv - ((xv.w - mu.w) * rs.w) * dgv.w * inv);
+            } else {
+              o.x = sc.x * g0; o.y = sc.y * g1; o.z = sc.z * g2; o.w = sc.w * g3;
+            }
+            store_planes4(io.dzp, io.pfmt, io.pstride, ru * C + 4 * a.cg, o);
+          }
+        }
       }
     }
   }

@@ -334,6 +334,8 @@ class Ctx:
 
     def init_dist(self):
         if self.world > 1 and not self.dist.is_initialized():
+            # the overlapped gradient exchange runs beside persistent chain launches on the SMs TrainStep leaves free
+            os.environ.setdefault("NCCL_MAX_CTAS", "16")
             self.dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
@@ -493,9 +495,12 @@ def bench_train(ctx, args, wl, steps, warmup, headline):
         "config": {"workload": train_workload_name(label if (B, S) == (B0, S0) else "variant of " + label, B, T, S, K, am),
                    "global_batch": B * world, "parallelism": "dp%d" % world},
         "config_detail": {"precision": prec, "launch": "CUDA-graph replay" if ts.use_graphs else "eager launches",
-                          "exchange": None if world == 1 else "gradients exchanged as %s in %s" % (
-                              args.exchange_dtype, "4 buckets overlapped with backward" if not args.no_overlap
-                              else "one all-reduce after backward"),
+                          "exchange": None if world == 1 else (
+                              "fp32 weight-gradient accumulators all-reduced (NCCL AVG) %s; the ~1 %% of gradients outside them "
+                              "gathered into one %s vector" % (
+                                  "in buckets sent from backward hooks on a communication stream while the chain launches "
+                                  "leave 16 SMs free" if not args.no_overlap else "after backward",
+                                  "fp32" if args.exchange_dtype == "fp32" else "fp64")),
                           "l2": "no explicit flush: per-step working set (master params + packed weights + grads + Adam state "
                                 "~0.9 GB) exceeds the 126 MB L2"},
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -511,6 +516,12 @@ def bench_train(ctx, args, wl, steps, warmup, headline):
     }
     # whole-step fraction: algorithmic FLOPs of the alternating G/D loop / device-timed step
     out["roofline"]["whole_step_frac"] = (_step_gflop(spec, T) * B / (ms / steps * 1e-3) / 1e3) / out["roofline"]["peak"]
+    if world > 1:
+        # data-parallel replicas must hold bit-identical parameters after the timed steps (same reduced gradients, same update)
+        chk = torch.stack([ts.fG.p.sum(), ts.fG.p.abs().sum(), ts.fD.p.sum(), ts.fD.p.abs().sum()]).to(torch.float64)
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        ctx.dist.all_gather(allc, chk)
+        out["replicas_in_sync"] = bool(all(torch.equal(allc[0], c) for c in allc))
     out["cpu_baseline"] = _cpu_leg_train(ctx, spec, B, T)
     del ts, G, D, gan
     torch.cuda.empty_cache()

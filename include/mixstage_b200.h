@@ -267,6 +267,10 @@ typedef struct ms_chain_bwd_layer {
   float* dx;
 } ms_chain_bwd_layer;
 int ms_conv_chain_bwd(const ms_chain_bwd_layer* layers, int n, void* sync, void* stream);
+/* SM budget of the chain launches (0 = whole device).  Data-parallel training sets it a little below the SM count so that the
+ * NCCL kernels of the overlapped gradient exchange find free SMs beside a chain launch (which is persistent and would
+ * otherwise hold all of them until it ends). */
+int ms_set_chain_sm_budget(int sms);
 /* The weight gradients of up to MS_CHAIN_MAX blocks (arguments of ms_wgrad_bf16_acc each) in ONE launch. */
 typedef struct ms_wgrad_item {
   const ms_igemm_desc* d;

@@ -111,6 +111,7 @@ PROTOTYPES = {
     "ms_wgrad_bf16": [_GD, _P, _P, _P, _P],
     "ms_conv_block_train_fwd": [_GD, _P, _P, _P, _BN, _P, _P, _I, _L, _P, _P, _I, _L, _I, _P, _P],
     "ms_conv_block_train_bwd": [_GD, _P, _P, _BN, _L, _I, _I, _P, _I, _L, _P, _P, _I, _P, _P, _P, _P],
+    "ms_set_chain_sm_budget": [_I],
     "ms_debug_phase_ts": [_P],
     "ms_debug_trap_info": [_P],
     "ms_conv_chain_fwd": [_P, _I, _P, _P],

@@ -1410,6 +1410,14 @@ static int launch_coop(const void* fn, dim3 grid, size_t smem, cudaStream_t cs, 
   return (int)e;
 }
 
+// SM budget of the cooperative chain launches (0 = the whole device).  Data-parallel training leaves a few SMs to the NCCL
+// kernels of the overlapped gradient exchange: a chain launch that holds every SM would serialise them behind itself.
+static int g_sm_budget = 0;
+static int chain_sms() {
+  const int n = ms_num_sms();
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+}
+
 static int phase_dbg() {
   static int v = -1;
   if (v < 0) {
@@ -1530,6 +1538,12 @@ static int trap_buffer_init() {
   return 0;
 }
 
+extern "C" int ms_set_chain_sm_budget(int sms) {
+  if (sms < 0) return MS_EINVAL;
+  g_sm_budget = sms;
+  return 0;
+}
+
 extern "C" int ms_debug_trap_info(int* out8) {
   if (!out8) return MS_EINVAL;
   for (int i = 0; i < 8; i++) out8[i] = g_trap_host ? g_trap_host[i] : 0;
@@ -1547,7 +1561,7 @@ extern "C" int ms_conv_chain_fwd(const ms_chain_fwd_layer* layers, int n, void* 
   FwdChain& ch = g_fwd_chain;
   if (phase_dbg()) { int rc0 = trap_buffer_init(); if (rc0) return rc0; }
   ch.n = n; ch.dbg = phase_dbg(); ch.sync = reinterpret_cast<unsigned int*>(sync);
-  const int sms = ms_num_sms();
+  const int sms = chain_sms();
   long long want = 1;
   for (int i = 0; i < n; i++) {
     long long w = 0;
@@ -1590,7 +1604,7 @@ extern "C" int ms_conv_chain_bwd(const ms_chain_bwd_layer* layers, int n, void* 
   BwdChain& ch = g_bwd_chain;
   if (phase_dbg()) { int rc0 = trap_buffer_init(); if (rc0) return rc0; }
   ch.n = n; ch.dbg = phase_dbg(); ch.sync = reinterpret_cast<unsigned int*>(sync);
-  const int sms = ms_num_sms();
+  const int sms = chain_sms();
   long long want = 1;
   for (int i = 0; i < n; i++) {
     const ms_chain_bwd_layer* e = &layers[i];

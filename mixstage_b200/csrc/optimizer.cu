@@ -12,10 +12,18 @@
 
 namespace {
 
+// Sum of squares in a FIXED order (block partials, summed by the last block to finish): data-parallel replicas compute the
+// clip coefficient from bit-identical gradients and must get bit-identical coefficients -- floating-point atomics in
+// arrival order would let the parameters of the replicas drift apart by an ulp per step.
+constexpr int SQNORM_MAX_BLOCKS = 2048;
+__device__ double g_sqnorm_part[SQNORM_MAX_BLOCKS];
+__device__ unsigned int g_sqnorm_ticket = 0;
+
 template <typename T>
 __global__ void __launch_bounds__(256) sqnorm_kernel(const T* __restrict__ g, int64_t n, double* __restrict__ acc,
                                                      long long* __restrict__ step) {
   __shared__ double part[8];
+  __shared__ bool last;
   double a = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double v = (double)g[i];
@@ -27,8 +35,23 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const T* __restrict__ g, in
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < (blockDim.x >> 5); i++) t += part[i];
-    atomicAdd(acc, t);
-    if (blockIdx.x == 0 && step) step[0] += 1;
+    g_sqnorm_part[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&g_sqnorm_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    // one warp, fixed tree
+    if (threadIdx.x < 32) {
+      double t = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += __ldcg(&g_sqnorm_part[i]);
+      t = ms_warp_sum_d(t);
+      if (threadIdx.x == 0) {
+        acc[0] = t;
+        g_sqnorm_ticket = 0;
+        if (step) step[0] += 1;
+      }
+    }
   }
 }
 
@@ -58,6 +81,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(T* __restrict__ p, const
 inline int opt_blocks(int64_t n) {
   int64_t b = ms_cdiv(n, 256 * 4);
   int64_t cap = (int64_t)ms_num_sms() * 8;
+  if (cap > SQNORM_MAX_BLOCKS) cap = SQNORM_MAX_BLOCKS;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -67,7 +91,6 @@ inline int opt_blocks(int64_t n) {
 
 extern "C" int ms_grad_sqnorm(const void* g, int dt, int64_t n, double* acc, int64_t* step, void* stream) {
   if (!g || !acc || n < 1 || (dt != MS_F32 && dt != MS_F64)) return MS_EINVAL;
-  MS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), ms_stream(stream)));
   if (dt == MS_F64)
     sqnorm_kernel<double><<<opt_blocks(n), 256, 0, ms_stream(stream)>>>((const double*)g, n, acc, (long long*)step);
   else

@@ -172,27 +172,52 @@ class WgradAccum:
     def __init__(self):
         self.chunks, self.off = [], 0
         self.slots = {}         # id(PackedWeight) -> accumulator
+        self.where = {}         # id(PackedWeight) -> (chunk index, begin, end) incl. alignment padding
+        self.touched = []       # accumulators used so far in the running step, in order (data-parallel exchange buckets)
         self.entries = {}       # (acc ptr, sink ptr) -> WgradEntry fields
 
     def acc_for(self, packed, n, device):
         t = self.slots.get(id(packed))
         if t is not None and t.numel() == n and t.device == device:
+            if id(packed) not in self._touched_set:
+                self._touched_set.add(id(packed))
+                self.touched.append(id(packed))
             return t
         n_al = (n + 63) // 64 * 64
         if not self.chunks or self.chunks[-1].device != device or self.off + n_al > self.chunks[-1].numel():
             self.chunks.append(torch.zeros(max(self.CHUNK, n_al), dtype=torch.float32, device=device))
             self.off = 0
         t = self.chunks[-1][self.off:self.off + n]
+        self.where[id(packed)] = (len(self.chunks) - 1, self.off, self.off + n_al)
         self.off += n_al
         self.slots[id(packed)] = t
+        self._touched_set.add(id(packed))
+        self.touched.append(id(packed))
         return t
+
+    def begin_step(self):
+        self.touched, self._touched_set = [], set()
+
+    def ranges(self, keys):
+        """Contiguous slices of the chunks covering the accumulators `keys` (adjacent allocations merged)."""
+        spans = sorted(self.where[k] for k in keys)
+        out = []
+        for ci, b, e in spans:
+            if out and out[-1][0] == ci and out[-1][2] == b:
+                out[-1][2] = e
+            else:
+                out.append([ci, b, e])
+        return [self.chunks[ci][b:e] for ci, b, e in out]
 
     def note(self, acc, sink, Cout, Cin_g, taps, kpad, dtype):
         self.entries[(acc.data_ptr(), sink.data_ptr())] = (acc.data_ptr(), sink.data_ptr(), dt_code(dtype), Cout, Cin_g, taps, kpad, 1)
 
+    _touched_set = frozenset()
+
     def zero(self):
         for c in self.chunks:
             c.zero_()
+        self.begin_step()
 
 
 WACC = None                  # WgradAccum of the running train step (set by TrainStep), else None: per-slice partials

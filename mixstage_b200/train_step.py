@@ -96,8 +96,11 @@ class FlatState:
             stage = self.x32[beg:end]
             call("ms_scale_cast", ptr(chunk), _lib.MS_F64, ptr(stage), _lib.MS_F32, n, 1.0 / ws, st)
             w = dist.all_reduce(stage, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-            if w is not None and self.device.type != "cuda":
-                w.wait()            # gloo: the widening below runs on the host right away
+            if w is not None:
+                # the widening below must see the REDUCED staging range.  NCCL runs the collective on its own stream: wait()
+                # makes the launching (communication) stream wait for it -- a stream-level dependency, the host does not
+                # block and the compute stream is not involved.  (gloo: a host wait; the widening runs on the host.)
+                w.wait()
                 w = None
             call("ms_scale_cast", ptr(stage), _lib.MS_F32, ptr(chunk), _lib.MS_F64, n, 1.0, st)
             return w
@@ -128,7 +131,7 @@ class TrainStep:
 
     def __init__(self, gan, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, use_graphs=True, group=None,
                  input_modalities=("audio/log_mel_400",), description="train", overlap_allreduce=True,
-                 exchange_dtype="fp32", rng_seed=None, check_agreement=False):
+                 exchange_dtype="fp32", rng_seed=None, check_agreement=False, comm_sms=16):
         """One TrainStep (and one CUDA device) per process: the scratch arena, the direct-gradient switch and the
         side stream are module-level state of mixstage_b200.ops, and the kernels' lazily set function attributes are
         per process.
@@ -137,6 +140,7 @@ class TrainStep:
         launched from backward hooks on a communication stream (decoder + logits + classifier first, ... audio encoder
         last) while backward is still running, as fp32 ("fp32", default: half the bytes of the fp64 master gradients)
         or in the master dtype ("native").
+        comm_sms: SMs left free beside the chain launches for the NCCL kernels of the overlapped exchange (multi-rank only).
         rng_seed: seed of the generator the D/G coin and the curriculum draw come from.  None = the process-global CPU
         generator in a single-process run (the reference's own RNG consumption, gan.py:105 / jlcss.py:127) and a
         dedicated generator seeded with the reference's seed 11212 on every rank of a data-parallel run: ranks then
@@ -174,7 +178,18 @@ class TrainStep:
             raise MixStageError("exchange_dtype must be 'fp32' or 'native'")
         self.exchange_fp32 = exchange_dtype == "fp32"
         self.comm = torch.cuda.Stream(device=dev) if (self.overlap and dev.type == "cuda") else None
+        # the chain launches are persistent and would hold every SM: leave a few to the NCCL kernels of the overlapped
+        # exchange (set NCCL_MAX_CTAS accordingly before the process group is created; bench.py does)
+        self.comm_sms = int(comm_sms)
+        if self.comm is not None and self._world() > 1 and self.comm_sms > 0:
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            call("ms_set_chain_sm_budget", max(16, n_sm - self.comm_sms))
         self._reduced, self._works = [], []
+        self._flushed = set()
+        # tensor-core modes: the conv weight gradients are exchanged as their fp32 accumulators (see _exchange_acc)
+        self._acc_plan = {}          # (kind, curriculum branch) -> [(stage, accumulator keys), ...] learned in the first body
+        self._acc_marks = None       # learning pass: [(stage, accumulators touched so far)]
+        self._small_idx = {}         # kind -> (entries seen, indices of the flat gradient elements outside the accumulators)
         if rng_seed is None and self._world() > 1:
             rng_seed = 11212
         self.rng = None if rng_seed is None else torch.Generator().manual_seed(int(rng_seed))
@@ -241,6 +256,10 @@ class TrainStep:
         ops.WACC = wacc
         overlap = self.overlap and kind == "G" and self._world() > 1
         self._reduced, self._works = [], []
+        self._flushed = set()
+        self._step_key = (kind, bool(use_pose))
+        self._acc_marks = []
+        self._acc_mode = None        # decided at the first hook / at the end: accumulators exist <=> tensor-core mode
         G.grad_ready_hook = self._on_ready if overlap else None
         try:
             fake, losses, _ = gan([audio, labels], pose, input_modalities=self.mod, style=style, sample_flag=0,
@@ -257,11 +276,17 @@ class TrainStep:
             ops.arena.end()
             if self.side is not None:
                 self.side.join()
-        self._flush_wgrads(kind)
         f = self.fG if kind == "G" else self.fD
-        if overlap:
+        if self._world() > 1 and self.wacc[kind].touched:
+            # tensor-core mode: exchange the fp32 accumulators (+ the few gradients that live only in the flat buffer), THEN
+            # convert everything into the flat buffer with the whole machine
+            self._exchange_acc_finish(kind, overlap)
+            self._flush_wgrads(kind)
+        elif overlap:
             self._finish_overlapped()
+            self._flush_wgrads(kind, None, "tail")      # nothing left unless a gap-free layout skipped the "rest" bucket
         else:
+            self._flush_wgrads(kind)
             f.allreduce_mean(self.group, self.exchange_fp32)
         f.clip_adam(self.lr, self.lr_dev, self.betas, self.eps, self.max_norm)
         if self.use_graphs:
@@ -276,10 +301,14 @@ class TrainStep:
             return 1
         return dist.get_world_size(self.group)
 
-    def _reduce_range(self, beg, end):
+    def _reduce_range(self, beg, end, tops=None, tag=None):
+        """Mean of the generator's flat gradient [beg, end) over the ranks on the communication stream.  The conv weight
+        gradients of the range still sit in their fp32 accumulators (the weight-gradient launches add into them on the side
+        stream): they are converted into the flat buffer FIRST, on the communication stream, behind both other streams."""
         if end <= beg:
             return
         if self.comm is None:                       # CPU (gloo): no streams
+            self._flush_wgrads("G", tops, tag)
             self.fG.reduce_range(beg, end, self.group, self.exchange_fp32)
             return
         cur = torch.cuda.current_stream()
@@ -287,23 +316,137 @@ class TrainStep:
         if self.side is not None:
             self.comm.wait_stream(self.side.stream) # weight gradients on the side stream
         with torch.cuda.stream(self.comm):
+            self._flush_wgrads("G", tops, tag)
             w = self.fG.reduce_range(beg, end, self.group, self.exchange_fp32, async_op=True)
             if w is not None:
                 self._works.append(w)
 
+    # ------------------------------------------------------------------ exchange through the weight-gradient accumulators
+    # In the tensor-core modes 99 % of the gradient bytes sit in the fp32 accumulators of the chain weight-gradient launches
+    # until the conversion launch at the end of backward.  They are all-reduced THERE (mean, NCCL AVG): no fp64 -> fp32
+    # staging pass, no widening pass, no per-bucket conversion squeezed onto the SMs the chain launches leave free.  The
+    # buckets are "the accumulators touched since the previous hook", learned in the first body of every (kind, branch).
+    def _reduce_tensors(self, tensors):
+        ws = self._world()
+        nccl = self.fG.device.type == "cuda"
+        for t in tensors:
+            if nccl:
+                self._works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.mul_(1.0 / ws)
+
+    def _acc_bucket(self, keys):
+        """All-reduce the accumulators `keys` on the communication stream, behind the side stream's weight-gradient launches."""
+        wacc = self.wacc[self._step_key[0]]
+        tensors = wacc.ranges(keys)
+        if not tensors:
+            return
+        if self.comm is None:
+            self._reduce_tensors(tensors)
+            return
+        if self.side is not None:
+            self.comm.wait_stream(self.side.stream)
+        with torch.cuda.stream(self.comm):
+            self._reduce_tensors(tensors)
+
+    def _small_indices(self, kind):
+        """Indices of the flat gradient elements that no accumulator feeds (BatchNorm affine parameters, biases, the style
+        embedding, the few convolutions on the CUDA-core kernels): ~1 % of the buffer, exchanged as one gathered vector."""
+        f = self.fG if kind == "G" else self.fD
+        ents = self.wacc[kind].entries
+        cur = self._small_idx.get(kind)
+        if cur is not None and cur[0] == len(ents):
+            return cur[1]
+        base, isz = f.g.data_ptr(), f.g.element_size()
+        mask = torch.ones(f.numel, dtype=torch.bool)
+        for e in ents.values():
+            off = (e[1] - base) // isz
+            if 0 <= off < f.numel:
+                mask[off:off + e[3] * e[4] * e[5]] = False        # Cout * Cin_g * taps
+        idx = mask.nonzero().flatten().to(f.device)
+        if torch.cuda.is_available() and f.device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            raise MixStageError("internal: exchange index table changed during graph capture")
+        if cur is not None:
+            self._old_tables.append(cur)
+        self._small_idx[kind] = (len(ents), idx)
+        return idx
+
+    def _exchange_acc_finish(self, kind, overlap):
+        """End of backward: the buckets not sent from hooks (all of them when not overlapping or still learning), the
+        gathered small gradients, then join.  Runs after the side stream has been joined."""
+        wacc = self.wacc[kind]
+        f = self.fG if kind == "G" else self.fD
+        plan = self._acc_plan.get(self._step_key) if overlap else None
+        sent = set()
+        if plan is not None and self._acc_mode == "plan":
+            for _, keys in plan:
+                sent.update(keys)
+        rest = [k for k in wacc.touched if k not in sent]
+        if overlap and self._acc_mode != "plan":
+            # learning pass: remember which accumulators every hook could have sent
+            marks, prev, plan = self._acc_marks, 0, []
+            for stage, m in marks:
+                plan.append((stage, tuple(wacc.touched[prev:m])))
+                prev = m
+            self._acc_plan[self._step_key] = [p_ for p_ in plan if p_[1]]
+        idx = self._small_indices(kind)
+        ws = self._world()
+        ctxm = torch.cuda.stream(self.comm) if self.comm is not None else None
+        if self.comm is not None:
+            self.comm.wait_stream(torch.cuda.current_stream())
+        if ctxm is not None:
+            ctxm.__enter__()
+        try:
+            self._reduce_tensors(wacc.ranges(rest))
+            if idx.numel():
+                small = f.g.index_select(0, idx)
+                if self.exchange_fp32 and small.dtype == torch.float64:
+                    small = small.float()
+                small.mul_(1.0 / ws)
+                w = dist.all_reduce(small, op=dist.ReduceOp.SUM, group=self.group, async_op=self.comm is not None)
+                if w is not None:
+                    w.wait()
+                f.g.index_copy_(0, idx, small.to(f.g.dtype))
+        finally:
+            if ctxm is not None:
+                ctxm.__exit__(None, None, None)
+        for w in self._works:
+            w.wait()
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
+        self._works = []
+
     def _on_ready(self, stage):
+        wacc = self.wacc[self._step_key[0]]
+        if wacc.touched or self._acc_mode is not None:
+            # tensor-core mode
+            plan = self._acc_plan.get(self._step_key)
+            if self._acc_mode is None:
+                self._acc_mode = "plan" if plan is not None else "learn"
+            if self._acc_mode == "learn":
+                self._acc_marks.append((stage, len(wacc.touched)))
+            else:
+                for st_, keys in plan:
+                    if st_ == stage:
+                        self._acc_bucket(keys)
+            return
         for top in self.READY.get(stage, ()):
             seg = self.fG.segments.get(top)
             if seg is not None and seg not in self._reduced:
                 self._reduced.append(seg)
-                self._reduce_range(*seg)
+                self._reduce_range(*seg, tops=(top,), tag=top)
 
     def _finish_overlapped(self):
         """Everything not exchanged from a hook (audio / pose encoder, pose-style encoder, gaps), then join."""
         done = sorted(self._reduced)
         pos = 0
+        first = True
         for beg, end in done + [(self.fG.numel, self.fG.numel)]:
-            self._reduce_range(pos, beg)
+            if beg > pos:
+                # the remaining accumulators (all of them, whichever gap they fall in) go out with the first gap
+                self._reduce_range(pos, beg, tops=None, tag="rest") if first else self._reduce_range(pos, beg, tops=(), tag=None)
+                first = False
             pos = max(pos, end)
         for w in self._works:
             w.wait()
@@ -355,13 +498,26 @@ class TrainStep:
             self._tables[kind] = cur
         call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 0, stream())
 
-    def _flush_wgrads(self, kind):
-        """Every weight-gradient accumulator of this step -> the flat gradient buffers, one launch."""
-        ents = list(self.wacc[kind].entries.values())
+    def _flush_wgrads(self, kind, tops=None, tag="all"):
+        """Weight-gradient accumulators of this step -> the flat gradient buffers, one launch.  tops: only the accumulators
+        of these top-level sub-modules (the overlapped exchange converts a bucket's accumulators right before it reduces
+        the bucket); None: everything not converted yet in this step."""
+        f = self.fG if kind == "G" else self.fD
+        base, isz = f.g.data_ptr(), f.g.element_size()
+        ents = []
+        for key, e in self.wacc[kind].entries.items():
+            if key in self._flushed:
+                continue
+            if tops is not None:
+                off = (e[1] - base) // isz
+                if not any(f.segments[t][0] <= off < f.segments[t][1] for t in tops if t in f.segments):
+                    continue
+            ents.append(e)
+            self._flushed.add(key)
         if not ents:
             return
         sig = tuple(ents)
-        cur = self._wtables.get(kind)
+        cur = self._wtables.get((kind, tag))
         if cur is None or cur[0] != sig:
             if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
                 raise MixStageError("internal: weight-gradient table changed during graph capture")
@@ -374,7 +530,7 @@ class TrainStep:
                 (arr[i].acc, arr[i].dw, arr[i].pdt, arr[i].Cout, arr[i].Cin_g, arr[i].taps, arr[i].kpad, arr[i].accumulate) = e
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             cur = (sig, host.to(self.fG.device), len(ents))
-            self._wtables[kind] = cur
+            self._wtables[(kind, tag)] = cur
         call("ms_unpack_wgrad_multi", ptr(cur[1]), cur[2], 0, stream())
 
     def refresh(self):

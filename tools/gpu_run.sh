@@ -18,6 +18,7 @@ for w in $what; do
     bench) timeout 1200 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?" ;;
     benchtrain) timeout 600 python bench.py --workload train > gpurun_out/${tag}_bench_train.json 2> gpurun_out/${tag}_bench_train.err; echo "benchtrain rc=$?" ;;
     benchref) timeout 900 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "benchref rc=$?" ;;
+    ncufull) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"conv_chain|wgrad_acc_multi" --launch-skip 60 -c 22 -f -o gpurun_out/${tag}_chain_full python bench.py --workload train --no-graphs --steps 2 --warmup 4 > gpurun_out/${tag}_ncufull.log 2>&1; echo "ncufull rc=$?" ;;
     launchesg) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none --graph-profiling node -c 6000 --csv --log-file gpurun_out/${tag}_launches_graph.csv python bench.py --workload train --steps 2 --warmup 4 > gpurun_out/${tag}_launches_graph.log 2>&1; echo "launchesg rc=$?" ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 4000 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --workload train --no-graphs --steps 2 --warmup 4 > gpurun_out/${tag}_launches.log 2>&1; echo "launches rc=$?" ;;
     *) echo "unknown $w" ;;

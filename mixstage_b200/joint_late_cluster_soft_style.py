@@ -51,6 +51,8 @@ class JointLateClusterSoftStyle4_G(nn.Module):
     # jlcss.py:117-209), concat_encoder (text only) and smoothen (unused).  TrainStep leaves them out of its flat buffers.
     UNUSED_PARAMETER_PREFIXES = ("text_encoder.", "style_dec.", "style_dec_gr.", "concat_encoder.", "smoothen.")
 
+    MIX_IN_GEMM_MIN_ROWS = 8192      # frames per forward from which the cluster mixture rides inside the decoder GEMMs
+
     def __init__(self, time_steps=64, in_channels=256, out_feats=104, p=0, num_clusters=8, cluster=None,
                  style_dict={}, style_dim=10, lambda_id=1, train_only=0, softmax=1, argmax=0,
                  some_grad_flag=False, **kwargs):
@@ -252,8 +254,10 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         self.labels_cap_soft = ops.cast(soft_c.view(Bx, T, K), out_dtype)
 
         # K sub-decoders (grouped) + grouped 1x1 logits + soft mixture (jlcss.py:190-194)
+        # (small batches: the persistent one-CTA-per-tile GEMMs of the mixture path cost ~40 us each on a 1024-row problem;
+        # the sub-decoders then run as one inference chain and the mixture as its own few-microsecond kernel)
         if (not self.training and ops.fast_eval() and ops.MixedLogits.eligible(self.out_feats, K, self.in_channels)
-                and self.decoder[-1].cfg.groups == K):
+                and self.decoder[-1].cfg.groups == K and Bx * T >= self.MIX_IN_GEMM_MIN_ROWS):
             # inference: the mixture rides inside the GEMMs -- cluster weights in the last sub-decoder epilogue, the grouped
             # logits as one dense GEMM accumulating sum_k w_k * logits_k; (B,T,K*P) is never materialised
             d = _run(self.decoder[:-1], hc, last="planes")

@@ -210,7 +210,9 @@ class WgradAccum:
         return [self.chunks[ci][b:e] for ci, b, e in out]
 
     def note(self, acc, sink, Cout, Cin_g, taps, kpad, dtype):
-        self.entries[(acc.data_ptr(), sink.data_ptr())] = (acc.data_ptr(), sink.data_ptr(), dt_code(dtype), Cout, Cin_g, taps, kpad, 1)
+        # accumulate = 0: the conversion launch is the ONLY writer of a conv weight's gradient in a step (every use of the weight
+        # adds into the same accumulator; the flat buffer is zero-filled before the step), so it stores instead of read-add-store
+        self.entries[(acc.data_ptr(), sink.data_ptr())] = (acc.data_ptr(), sink.data_ptr(), dt_code(dtype), Cout, Cin_g, taps, kpad, 0)
 
     _touched_set = frozenset()
 
@@ -1779,7 +1781,13 @@ def conv_chain(blocks, x, training, res_from=None, last="f32", precision=None):
                 shape = _out_shape(blocks[j], shape)
                 j += 1
         if j - i >= 2:
-            y = _run_chain(blocks[i:j], x, training, [None] * (j - i), fmt, "planes" if j < n else last)
+            seg_last = last
+            if j < n:
+                # the next block runs on its own: operand planes if it is a tensor-core block, fp32 if it is a CUDA-core one
+                nb = blocks[j]
+                B_, H_, W_, C_ = shape
+                seg_last = "planes" if tc_eligible(nb.cfg, B_, H_, W_, C_, nb.weight.shape[0], False) else "f32"
+            y = _run_chain(blocks[i:j], x, training, [None] * (j - i), fmt, seg_last)
             if y is not None:
                 x = y
                 outs += [None] * (j - i - 1) + [x]

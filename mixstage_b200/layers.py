@@ -144,11 +144,45 @@ class AudioEncoder(nn.Module):
             self.conv.append(ConvNormRelu(ci, co, downsample=down, **kw))
         self.conv.append(ConvNormRelu(256, 256, type='2d', leaky=True, downsample=False,
                                       kernel_size=(3, 8), stride=1, p=p, groups=groups))
+        self.prune_eval_columns = True      # inference: only the output column the bilinear resize reads (see _pruned_last)
+        self._alt = {}                      # input width -> (pruned ConvCfg, its PackedWeight)
+
+    def _pruned_last(self, W):
+        """Eval only.  The bilinear resize to width 1 (layers.py:197) reads exactly the CENTRE output column of the last
+        block (kernel (3, 8), padding (1, 3) on 8 mel columns -> 7 output columns, column 3 selected with weight 1: probe in
+        SURVEY.md Appendix A note 4), so inference computes that column only: the same convolution with the width padding
+        reduced until one output column is left -- 1/7 of the block's MACs, every tap still inside the input.  (Training
+        needs all columns: they enter the BatchNorm statistics.)  Returns a ChainBlock or None when the geometry does not
+        reduce to a single exact column."""
+        m = self.conv[-1]
+        c = m.cfg
+        if c.sw != 1 or W > c.kw or (c.kw - W) % 2:
+            return None
+        pw = (c.kw - W) // 2
+        wo_full = W + 2 * c.pw - c.kw + 1
+        if pw > c.pw or wo_full % 2 == 0 or c.pw - pw != (wo_full - 1) // 2:
+            return None
+        alt = self._alt.get(W)
+        if alt is None:
+            cfg = ops.ConvCfg(c.kh, c.kw, c.sh, c.sw, c.ph, pw, c.groups, c.slope, has_bn=c.has_bn, act=c.act)
+            alt = self._alt[W] = (cfg, ops.PackedWeight())
+        n = m.norm
+        return ops.ChainBlock(m.conv.weight, m.conv.bias, n.weight, n.bias, alt[0], alt[1],
+                              (n.running_mean, n.running_var, n.num_batches_tracked))
 
     def forward(self, x, time_steps=None):
         if time_steps is None:
             time_steps = x.shape[1]
-        x = _run(self.conv, x)
+        blocks = [_chain_block(b) for b in self.conv]
+        if not self.training and not torch.is_grad_enabled() and self.prune_eval_columns:
+            # width of the last block's input: the mel axis halves at every stride-2 block
+            W = x.shape[2]
+            for b in list(self.conv)[:-1]:
+                W = ops.conv_out(W, b.cfg.kw, b.cfg.sw, b.cfg.pw)
+            last = self._pruned_last(W)
+            if last is not None:
+                blocks[-1] = last
+        x = ops.conv_chain(blocks, x, self.training, last="f32")
         return ops.bilinear_to_T(x, time_steps)
 
 

@@ -467,6 +467,8 @@ class TrainStep:
                     out.append(v.packed)
                 elif isinstance(v, ops.MixedLogits):
                     out.append(v.packed)
+            for cfg_pw in getattr(m, "_alt", {}).values():       # AudioEncoder: the pruned inference form of its last block
+                out.append(cfg_pw[1])
         return out
 
     def _refresh(self, kind):

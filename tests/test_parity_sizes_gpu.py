@@ -266,3 +266,30 @@ def test_generator_gradients_without_gan_term(precision, mult):
     # orders); bf16x3: activations 7e-5 off instead of 1e-5, sqrt law -> ~2.5x the fp32 figure
     assert vals[-1] < mult * cal[-1], (worst, vals[-1], cal[-1])
     assert vals[len(vals) // 2] < mult * cal[len(cal) // 2]
+
+
+# ------------------------------------------------------------------------------------------ eval-only column pruning
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 2e-5), ("bf16", 2e-3)])
+def test_audio_encoder_last_block_column_pruning_is_exact(precision, tol):
+    """Inference computes only the output column of audio_encoder.conv.7 that the bilinear resize reads (layers.py:185,
+    195-198: width 7 -> 1 selects column 3 with weight 1).  Same taps, same products: the pruned forward must agree with the
+    full one to the order of the fp32 reductions (the two use different tile / k-slice plans), and with the oracle."""
+    B, T, spec = 16, 64, CFG2
+    with _precision(precision):
+        G, D, gan = build(spec, T, "cuda", torch.float64)
+        G.eval()
+        G.thresh.value, G.thresh.iters = 1.0, 1000
+        audio, pose, labels, style = O.synth_inputs(B, T, spec)
+        dev = [t.cuda() for t in (audio, labels, pose, style)]
+        outs = []
+        for prune in (True, False):
+            G.audio_encoder.prune_eval_columns = prune
+            G.cache_encoder = False
+            with torch.no_grad():
+                out, _ = G([dev[0], dev[1]], dev[2], input_modalities=MOD, style=dev[3], sample_flag=1, description="test")
+            outs.append(out.clone())
+        torch.cuda.synchronize()
+        assert G.audio_encoder._alt, "the pruned form was never built"
+    e = _rel(outs[0], outs[1].cpu())
+    _log(case="conv7_column_pruning", precision=precision, pruned_vs_full=e)
+    assert e < tol, e

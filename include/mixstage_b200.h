@@ -365,6 +365,12 @@ int ms_bilinear_to_T_bwd_f32(const float* dy, int B, int Hi, int Wi, int C, int 
  * rep = T when the style is constant over the sequence and given per sequence, else 1. */
 int ms_style_concat_fwd_f32(const float* x, int64_t rows, int C, const int64_t* idx, const float* soft,
                             int rep, const void* emb, int pdt, int S, int sd, float* out, void* stream);
+/* Warp-per-row form of the same concat (C % 128 == 0, sd <= 32): 16-byte loads, 8-byte stores, and the row is ALSO emitted as
+ * bf16 operand planes (nullable; row stride rs >= C + sd elements, padding zero-filled, hi [+ lo at pstride]) for the
+ * tensor-core consumers (ClusterClassify.conv.0 / decoder.0), so no separate fp32 -> planes pass runs over the features. */
+int ms_style_concat_planes_fwd_f32(const float* x, int64_t rows, int C, const int64_t* idx, const float* soft, int rep,
+                                   const void* emb, int pdt, int S, int sd, float* out, void* planes, int pfmt,
+                                   int64_t pstride, int rs, void* stream);
 /* backward: dx[r,:] = dout[r,:C]; demb[s,:] += sum_{r: idx=s} dout[r,C:] (fp32 table, caller
  * zeroes; 'lin': demb += soft^T dout_style, dsoft[q,:] = sum_{r in q} dout_style[r,:] @ emb^T). */
 int ms_style_concat_bwd_f32(const float* dout, int64_t rows, int C, const int64_t* idx, const float* soft,
@@ -396,6 +402,9 @@ int ms_velocity_bwd_f32(const float* dv, int B, int T, int P, float* dx, void* s
 int ms_l1_fwd_f32(const float* a, const float* b, float c, int64_t n, double* loss_sum, float* sgn, void* stream);
 /* da = g[0] * sgn / n  (g device scalar) */
 int ms_l1_bwd_f32(const float* sgn, const float* g, int64_t n, float* da, void* stream);
+/* The same backward WITHOUT a stored sign tensor (ms_l1_fwd_f32 with sgn = NULL): da = sign(a - b) * g[0] / n recomputed from
+ * the operands (b NULL: constant c) -- 12 B of traffic per element instead of 16 B and no (n,) fp32 temporary. */
+int ms_l1_bwd_ab_f32(const float* a, const float* b, float c, const float* g, int64_t n, float* da, void* stream);
 /* out[0] = (float)(scale * in[0]) : turns a double accumulator into a loss scalar. */
 int ms_scalar_finish(const double* in, double scale, float* out, void* stream);
 

@@ -133,6 +133,7 @@ PROTOTYPES = {
     "ms_bilinear_to_T_fwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ms_bilinear_to_T_bwd_f32": [_P, _I, _I, _I, _I, _I, _P, _P],
     "ms_style_concat_fwd_f32": [_P, _L, _I, _P, _P, _I, _P, _I, _I, _I, _P, _P],
+    "ms_style_concat_planes_fwd_f32": [_P, _L, _I, _P, _P, _I, _P, _I, _I, _I, _P, _P, _I, _L, _I, _P],
     "ms_style_concat_bwd_f32": [_P, _L, _I, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P],
     "ms_softmax_ce_fwd_f32": [_P, _L, _I, _P, _I, _P, _P, _P, _P],
     "ms_softmax_ce_bwd_f32": [_P, _L, _I, _P, _I, _P, _P, _P, _P],
@@ -144,6 +145,7 @@ PROTOTYPES = {
     "ms_velocity_bwd_f32": [_P, _I, _I, _I, _P, _P],
     "ms_l1_fwd_f32": [_P, _P, _F, _L, _P, _P, _P],
     "ms_l1_bwd_f32": [_P, _P, _L, _P, _P],
+    "ms_l1_bwd_ab_f32": [_P, _P, _F, _P, _L, _P, _P],
     "ms_scalar_finish": [_P, _D, _P, _P],
     "ms_grad_sqnorm": [_P, _I, _L, _P, _P, _P],
     "ms_clip_adam": [_P, _P, _P, _P, _I, _L, _P, _P, _D, _D, _D, _D, _D, _P, _P],

@@ -449,6 +449,42 @@ __global__ void style_concat_fwd_kernel(const float* __restrict__ x, int64_t row
   }
 }
 
+// Warp-per-row form (C % 128 == 0, sd <= 32): a lane moves the row's content channels as float4 loads / 8-byte stores (output rows
+// are C + sd floats: 8-byte aligned only), lanes 0..sd-1 fetch the style row (index gather or soft S x sd product) and the warp
+// also emits the row as bf16 operand planes (row stride rs >= C + sd, padding zero-filled) for the tensor-core consumers -- the
+// separate fp32 -> planes pass over the concatenated features is gone.
+__global__ void __launch_bounds__(256) style_concat_rows_kernel(const float* __restrict__ x, int64_t rows, int C,
+                                                                const int64_t* __restrict__ idx, const float* __restrict__ soft,
+                                                                int rep, const void* __restrict__ emb, int pdt, int S, int sd,
+                                                                float* __restrict__ out, __nv_bfloat16* __restrict__ planes, int pfmt,
+                                                                int64_t pstride, int rs) {
+  const int lane = threadIdx.x & 31;
+  const int Co = C + sd;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    float sv = 0.f;
+    if (lane < sd) {
+      const int64_t q = r / rep;
+      if (idx) {
+        const int64_t s_ = idx[q];
+        sv = (s_ >= 0 && s_ < S) ? ms_ldp(emb, pdt, s_ * sd + lane) : 0.f;
+      } else {
+        for (int s_ = 0; s_ < S; s_++) sv = fmaf(__ldg(soft + q * S + s_), ms_ldp(emb, pdt, (int64_t)s_ * sd + lane), sv);
+      }
+    }
+    const float* xr = x + r * C;
+    float* orow = out + r * Co;
+    for (int c0 = 4 * lane; c0 < C; c0 += 128) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c0));
+      *reinterpret_cast<float2*>(orow + c0) = make_float2(v.x, v.y);
+      *reinterpret_cast<float2*>(orow + c0 + 2) = make_float2(v.z, v.w);
+      if (planes) store_planes4(planes, pfmt, pstride, r * rs + c0, v);
+    }
+    if (lane < sd) orow[C + lane] = sv;
+    if (planes && lane < rs - C) store_planes1(planes, pfmt, pstride, r * rs + C + lane, lane < sd ? sv : 0.f);
+  }
+}
+
 // dx = dout[:, :C]
 __global__ void slice_cols_kernel(const float* __restrict__ dout, int64_t rows, int C, int Co, float* __restrict__ dx) {
   int64_t total = rows * C;
@@ -488,6 +524,50 @@ __global__ void __launch_bounds__(256) style_scatter_kernel(const float* __restr
   __syncthreads();
   for (int i = threadIdx.x; i < S * sd; i += blockDim.x)
     if (tab[i] != 0.f) atomicAdd(demb + i, tab[i]);
+}
+
+// Warp-per-row backward of the concat in ONE pass over dout ('emb' mode, C % 128 == 0, sd <= 32): the content part of a row goes
+// to dx (8-byte loads: rows of C + sd floats are 8-byte aligned; 16-byte stores), the style part is summed in the lanes over
+// the warp's consecutive rows while they share a style row (rows of a sequence do) and leaves as sd shared-memory atomics
+// per run, then one global atomic per table entry and block -- the scatter-add of the embedding gradient.
+__global__ void __launch_bounds__(256) style_concat_rows_bwd_kernel(const float* __restrict__ dout, int64_t rows, int C,
+                                                                    const int64_t* __restrict__ idx, int rep, int S, int sd,
+                                                                    float* __restrict__ dx, float* __restrict__ demb) {
+  extern __shared__ float tab[];   // S*sd
+  const int Co = C + sd;
+  for (int i = threadIdx.x; i < S * sd; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // contiguous chunk of rows per warp
+  const int64_t warps_total = (int64_t)gridDim.x * nw, wid = (int64_t)blockIdx.x * nw + warp;
+  const int64_t per = (rows + warps_total - 1) / warps_total;
+  const int64_t r0 = wid * per, r1 = min(rows, r0 + per);
+  float acc = 0.f;
+  int64_t cur = -1;
+  for (int64_t r = r0; r < r1; r++) {
+    const float* dr = dout + r * Co;
+    if (dx) {
+      float* xr = dx + r * C;
+      for (int c0 = 4 * lane; c0 < C; c0 += 128) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(dr + c0)), b = __ldg(reinterpret_cast<const float2*>(dr + c0 + 2));
+        *reinterpret_cast<float4*>(xr + c0) = make_float4(a.x, a.y, b.x, b.y);
+      }
+    }
+    if (demb) {
+      const int64_t s_ = idx[r / rep];
+      if (s_ != cur) {
+        if (cur >= 0 && cur < S && lane < sd) atomicAdd(&tab[cur * sd + lane], acc);
+        acc = 0.f;
+        cur = s_;
+      }
+      if (lane < sd) acc += __ldg(dr + C + lane);
+    }
+  }
+  if (demb && cur >= 0 && cur < S && lane < sd) atomicAdd(&tab[cur * sd + lane], acc);
+  __syncthreads();
+  if (demb)
+    for (int i = threadIdx.x; i < S * sd; i += blockDim.x)
+      if (tab[i] != 0.f) atomicAdd(demb + i, tab[i]);
 }
 
 // dsoft[q, s] = sum_{r in q} sum_j dstyle[r, j] * emb[s, j]
@@ -610,6 +690,29 @@ __global__ void mean_rows_bwd_kernel(const float* __restrict__ dy, int B, int L,
 }
 
 // ------------------------------------------------------------------ velocity / L1
+// 16-byte form (P % 4 == 0): a thread owns four features of one frame; the previous frame's four sit P floats earlier
+__global__ void velocity_fwd4_kernel(const float4* __restrict__ x, int B, int T, int P4, float4* __restrict__ v) {
+  const int64_t total = (int64_t)B * T * P4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)((i / P4) % T);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t) {
+      const float4 a = __ldg(x + i), b = __ldg(x + i - P4);
+      o = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    }
+    v[i] = o;
+  }
+}
+__global__ void velocity_bwd4_kernel(const float4* __restrict__ dv, int B, int T, int P4, float4* __restrict__ dx) {
+  const int64_t total = (int64_t)B * T * P4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)((i / P4) % T);
+    const float4 a = t >= 1 ? __ldg(dv + i) : zero;
+    const float4 b = t + 1 < T ? __ldg(dv + i + P4) : zero;
+    dx[i] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+  }
+}
 __global__ void velocity_fwd_kernel(const float* __restrict__ x, int B, int T, int P, float* __restrict__ v) {
   int64_t total = (int64_t)B * T * P;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -631,7 +734,18 @@ __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ a
                                                      double* __restrict__ loss_sum, float* __restrict__ sgn) {
   __shared__ double part[8];
   double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  int64_t start = 0;
+  if (!sgn && ((((uintptr_t)a | (uintptr_t)b) & 15) == 0)) {
+    // no sign tensor to write: 16-byte loads, fp32 partial of four elements before the fp64 accumulation
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i);
+      const float4 bv = b ? __ldg(reinterpret_cast<const float4*>(b) + i) : make_float4(c, c, c, c);
+      acc += (double)fabsf(av.x - bv.x) + (double)fabsf(av.y - bv.y) + (double)fabsf(av.z - bv.z) + (double)fabsf(av.w - bv.w);
+    }
+    start = n4 << 2;
+  }
+  for (int64_t i = start + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float d = __ldg(a + i) - (b ? __ldg(b + i) : c);
     acc += fabsf(d);
     if (sgn) sgn[i] = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
@@ -643,6 +757,28 @@ __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ a
     double t = 0.0;
     for (int i = 0; i < (blockDim.x >> 5); i++) t += part[i];
     atomicAdd(loss_sum, t);
+  }
+}
+// backward without a stored sign tensor: da = sign(a - b) * g / n recomputed from the operands (8 B read + 4 B written per
+// element instead of 4 B written forward + 4 B read + 4 B written backward)
+__global__ void l1_bwd_ab_kernel(const float* __restrict__ a, const float* __restrict__ b, float c, const float* __restrict__ g,
+                                 int64_t n, float* __restrict__ da) {
+  const float s = g[0] / (float)n;
+  const int64_t n4 = n >> 2;
+  const bool vec = (((uintptr_t)a | (uintptr_t)da | (uintptr_t)b) & 15) == 0;
+  if (vec) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i);
+      const float4 bv = b ? __ldg(reinterpret_cast<const float4*>(b) + i) : make_float4(c, c, c, c);
+      float4 o;
+      o.x = av.x > bv.x ? s : (av.x < bv.x ? -s : 0.f); o.y = av.y > bv.y ? s : (av.y < bv.y ? -s : 0.f);
+      o.z = av.z > bv.z ? s : (av.z < bv.z ? -s : 0.f); o.w = av.w > bv.w ? s : (av.w < bv.w ? -s : 0.f);
+      reinterpret_cast<float4*>(da)[i] = o;
+    }
+  }
+  for (int64_t i = (vec ? (n4 << 2) : 0) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = __ldg(a + i) - (b ? __ldg(b + i) : c);
+    da[i] = d > 0.f ? s : (d < 0.f ? -s : 0.f);
   }
 }
 __global__ void l1_bwd_kernel(const float* __restrict__ sgn, const float* __restrict__ g, int64_t n, float* __restrict__ da) {
@@ -864,10 +1000,35 @@ extern "C" int ms_style_concat_fwd_f32(const float* x, int64_t rows, int C, cons
   return 0;
 }
 
+extern "C" int ms_style_concat_planes_fwd_f32(const float* x, int64_t rows, int C, const int64_t* idx, const float* soft, int rep,
+                                              const void* emb, int pdt, int S, int sd, float* out, void* planes, int pfmt,
+                                              int64_t pstride, int rs, void* stream) {
+  if (!x || !emb || !out || (!idx && !soft) || rows < 1 || rep < 1 || rows % rep || S < 1 || sd < 1) return MS_EINVAL;
+  if (C % 128 || sd > 32 || ((uintptr_t)x & 15) || ((uintptr_t)out & 7) || (C + sd) % 2) return MS_EINVAL;
+  if (planes && (rs < C + sd || rs - C > 32 || rs % 4 || ((uintptr_t)planes & 7) || !planes_ok(planes, pfmt, pstride))) return MS_EINVAL;
+  int64_t blocks = ms_cdiv(rows, 8);
+  const int64_t cap = (int64_t)ms_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  style_concat_rows_kernel<<<(unsigned)blocks, 256, 0, ST>>>(x, rows, C, idx, soft, rep, emb, pdt, S, sd, out,
+                                                             reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride, rs);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int ms_style_concat_bwd_f32(const float* dout, int64_t rows, int C, const int64_t* idx, const float* soft, int rep,
                                        const void* emb, int pdt, int S, int sd, float* dx, float* demb, float* dsoft,
                                        void* stream) {
   if (!dout || (!idx && !soft) || rows < 1 || rep < 1 || rows % rep || S < 1 || sd < 1) return MS_EINVAL;
+  if (idx && !soft && C % 128 == 0 && sd <= 32 && (C + sd) % 2 == 0 && !(((uintptr_t)dout) & 7) && !(((uintptr_t)dx) & 15) &&
+      (size_t)S * sd * sizeof(float) <= 40 * 1024) {
+    int64_t blocks = ms_cdiv(rows, 8 * 8);
+    const int64_t cap = (int64_t)ms_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    style_concat_rows_bwd_kernel<<<(unsigned)blocks, 256, sizeof(float) * S * sd, ST>>>(dout, rows, C, idx, rep, S, sd, dx, demb);
+    MS_LAUNCH_CHECK();
+    return 0;
+  }
   if (dx) {
     slice_cols_kernel<<<ew_blocks(rows * C), EW_THREADS, 0, ST>>>(dout, rows, C, C + sd, dx);
     MS_LAUNCH_CHECK();
@@ -929,12 +1090,24 @@ extern "C" int ms_mean_rows_bwd_f32(const float* dy, int B, int L, int C, float*
 
 extern "C" int ms_velocity_fwd_f32(const float* x, int B, int T, int P, float* v, void* stream) {
   if (!x || !v || B < 1 || T < 1 || P < 1) return MS_EINVAL;
+  if (P % 4 == 0 && !(((uintptr_t)x | (uintptr_t)v) & 15)) {
+    velocity_fwd4_kernel<<<ew_blocks((int64_t)B * T * (P / 4)), EW_THREADS, 0, ST>>>(reinterpret_cast<const float4*>(x), B, T, P / 4,
+                                                                                   reinterpret_cast<float4*>(v));
+    MS_LAUNCH_CHECK();
+    return 0;
+  }
   velocity_fwd_kernel<<<ew_blocks((int64_t)B * T * P), EW_THREADS, 0, ST>>>(x, B, T, P, v);
   MS_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int ms_velocity_bwd_f32(const float* dv, int B, int T, int P, float* dx, void* stream) {
   if (!dv || !dx || B < 1 || T < 1 || P < 1) return MS_EINVAL;
+  if (P % 4 == 0 && !(((uintptr_t)dv | (uintptr_t)dx) & 15)) {
+    velocity_bwd4_kernel<<<ew_blocks((int64_t)B * T * (P / 4)), EW_THREADS, 0, ST>>>(reinterpret_cast<const float4*>(dv), B, T, P / 4,
+                                                                                   reinterpret_cast<float4*>(dx));
+    MS_LAUNCH_CHECK();
+    return 0;
+  }
   velocity_bwd_kernel<<<ew_blocks((int64_t)B * T * P), EW_THREADS, 0, ST>>>(dv, B, T, P, dx);
   MS_LAUNCH_CHECK();
   return 0;
@@ -950,6 +1123,12 @@ extern "C" int ms_l1_fwd_f32(const float* a, const float* b, float c, int64_t n,
 extern "C" int ms_l1_bwd_f32(const float* sgn, const float* g, int64_t n, float* da, void* stream) {
   if (!sgn || !g || !da || n < 1) return MS_EINVAL;
   l1_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, ST>>>(sgn, g, n, da);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_l1_bwd_ab_f32(const float* a, const float* b, float c, const float* g, int64_t n, float* da, void* stream) {
+  if (!a || !g || !da || n < 1) return MS_EINVAL;
+  l1_bwd_ab_kernel<<<ew_blocks((n + 3) / 4), EW_THREADS, 0, ST>>>(a, b, c, g, n, da);
   MS_LAUNCH_CHECK();
   return 0;
 }

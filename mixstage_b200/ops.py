@@ -1168,7 +1168,7 @@ def bilinear_to_T(x, T):
 # ---------------------------------------------------------------------------- style embedding + concat
 class _StyleConcat(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, idx, soft, emb, rep):
+    def forward(ctx, x, idx, soft, emb, rep, carrier=None):
         x = _f32c(x)
         rows, C = x.numel() // x.shape[-1], x.shape[-1]
         S, sd = emb.shape
@@ -1184,8 +1184,18 @@ class _StyleConcat(torch.autograd.Function):
             soft = _f32c(soft)
             if soft.numel() // S * rep != rows:
                 raise MixStageError("soft style rows mismatch")
-        call("ms_style_concat_fwd_f32", ptr(x), rows, C, ptr(idx), ptr(soft), rep, ptr(e), dt_code(e.dtype), S, sd,
-             ptr(out), stream())
+        if C % 128 == 0 and sd <= 32 and (C + sd) % 2 == 0:
+            # warp-per-row kernel; in the tensor-core modes it also emits the operand planes the conv stacks read
+            pl = None
+            rs = pad8(C + sd)
+            if carrier is not None and _precision != "fp32" and rs - C <= 32:
+                pl = alloc_planes(rows, rs, _fmt(_precision), x.device)
+                carrier.planes = pl
+            call("ms_style_concat_planes_fwd_f32", ptr(x), rows, C, ptr(idx), ptr(soft), rep, ptr(e), dt_code(e.dtype), S, sd,
+                 ptr(out), ptr(pl.t) if pl else None, pl.fmt if pl else 0, pl.ps if pl else 0, rs, stream())
+        else:
+            call("ms_style_concat_fwd_f32", ptr(x), rows, C, ptr(idx), ptr(soft), rep, ptr(e), dt_code(e.dtype), S, sd,
+                 ptr(out), stream())
         ctx.save_for_backward(idx, soft, e)
         ctx.meta = (rows, C, S, sd, rep, x.shape, emb.dtype)
         return out
@@ -1202,13 +1212,17 @@ class _StyleConcat(torch.autograd.Function):
         call("ms_style_concat_bwd_f32", ptr(dout), rows, C, ptr(idx), ptr(soft), rep, ptr(e), dt_code(e.dtype), S, sd,
              ptr(dx), ptr(demb32), ptr(dsoft), stream())
         demb = None if demb32 is None else cast_raw(demb32, edt)
-        return dx, None, dsoft, demb, None
+        return dx, None, dsoft, demb, None, None
 
 
 def style_concat(x, emb_weight, idx=None, soft=None, rep=1):
     """cat([x, style_emb(pose_style)], -1) (jlcss.py:175-180).  idx int64 ('emb') or soft fp32 ('lin');
     one style row per `rep` consecutive rows of x."""
-    return _StyleConcat.apply(x, idx, soft, emb_weight, rep)
+    carrier = _Carrier()
+    out = _StyleConcat.apply(x, idx, soft, emb_weight, rep, carrier)
+    if carrier.planes is not None:
+        out._ms_planes = carrier.planes
+    return out
 
 
 # ---------------------------------------------------------------------------- softmax + CE + argmax
@@ -1347,20 +1361,19 @@ class _L1Mean(torch.autograd.Function):
         n = a.numel()
         dev = a.device
         acc = arena.take((1,), dev)
-        sgn = torch.empty_like(a)
         st = stream()
-        call("ms_l1_fwd_f32", ptr(a), ptr(b), float(const), n, ptr(acc), ptr(sgn), st)
+        call("ms_l1_fwd_f32", ptr(a), ptr(b), float(const), n, ptr(acc), None, st)       # no sign tensor: backward re-derives it
         loss = torch.empty((), dtype=torch.float32, device=dev)
         call("ms_scalar_finish", ptr(acc), 1.0 / n, ptr(loss), st)
-        ctx.save_for_backward(sgn)
-        ctx.n = n
+        ctx.save_for_backward(a, b)
+        ctx.n, ctx.const = n, float(const)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        (sgn,) = ctx.saved_tensors
-        da = torch.empty_like(sgn)
-        call("ms_l1_bwd_f32", ptr(sgn), ptr(g.to(torch.float32).contiguous()), ctx.n, ptr(da), stream())
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a)
+        call("ms_l1_bwd_ab_f32", ptr(a), ptr(b), ctx.const, ptr(g.to(torch.float32).contiguous()), ctx.n, ptr(da), stream())
         db = -da if ctx.needs_input_grad[1] else None
         return da, db, None
 

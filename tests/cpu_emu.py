@@ -279,6 +279,18 @@ def ms_style_concat_fwd_f32(x, rows, C, idx, soft, rep, emb, pdt, S, sd, out, st
     f32(out, rows * (C + sd)).copy_(torch.cat([X, sty], 1).reshape(-1))
 
 
+def ms_style_concat_planes_fwd_f32(x, rows, C, idx, soft, rep, emb, pdt, S, sd, out, planes, pfmt, pstride, rs, st):
+    ms_style_concat_fwd_f32(x, rows, C, idx, soft, rep, emb, pdt, S, sd, out, st)
+    if planes:
+        ms_to_planes(out, rows, C + sd, rs, planes, pfmt, pstride, st)
+
+
+def ms_l1_bwd_ab_f32(a, b, c, g, n, da, st):
+    A = f32(a, n)
+    d = A - (f32(b, n) if b else c)
+    f32(da, n).copy_(torch.sign(d) * (f32(g, 1)[0] / n))
+
+
 def ms_style_concat_bwd_f32(dout, rows, C, idx, soft, rep, emb, pdt, S, sd, dx, demb, dsoft, st):
     D = f32(dout, rows * (C + sd)).view(rows, C + sd)
     E = param(emb, S * sd, pdt).float().view(S, sd)

@@ -251,6 +251,17 @@ def test_small_ops():
     (og,), (oc,) = run_both("ms_style_concat_fwd_f32", [(x, "in"), rows, C, (idx2, "in"), (None, "in"), 1, (emb, "in"), 1, S, sd,
                                                         (torch.zeros(rows, C + sd), "out")])
     close(og, oc, 1e-6)
+    # warp-per-row form with operand planes (row stride 272 for the 266 concatenated channels), both plane formats
+    if C % 128 == 0:
+        rs = (C + sd + 7) // 8 * 8
+        ps = rows * rs
+        for (i, s_) in ((idx, None), (None, soft)):
+            for pfmt in (2, 3):
+                g, c = run_both("ms_style_concat_planes_fwd_f32",
+                                [(x, "in"), rows, C, (i, "in"), (s_, "in"), T, (emb, "in"), 1, S, sd, (torch.zeros(rows, C + sd), "out"),
+                                 (torch.full(((2 if pfmt == 3 else 1) * ps,), 7.0, dtype=torch.bfloat16), "out"), pfmt, ps, rs])
+                close(g[0], c[0], 1e-6)
+                assert torch.equal(g[1].float(), c[1].float())            # planes: same roundings, zero-filled padding columns
     # softmax / CE / argmax
     for Kk, r, trep in ((8, rows, 1), (25, B, 1), (4, 64, 16)):
         score = torch.randn(r, Kk) * 3
@@ -291,6 +302,14 @@ def test_small_ops():
         assert torch.equal(g[1], c[1])
     (og,), (oc,) = run_both("ms_l1_bwd_f32", [(c[1], "in"), (torch.tensor([0.3]), "in"), n, (torch.zeros(n), "out")])
     close(og, oc, 1e-6)
+    # forward without the sign tensor (vector loads) and the backward that re-derives the sign from the operands
+    for b_, cst in ((torch.randn(n), 0.0), (None, 1.0)):
+        g, c = run_both("ms_l1_fwd_f32", [(xp.reshape(-1), "in"), (b_, "in"), cst, n, (torch.zeros(1, dtype=torch.float64), "inout"),
+                                          (None, "out")])
+        close(g[0], c[0], 1e-9)
+        (og,), (oc,) = run_both("ms_l1_bwd_ab_f32", [(xp.reshape(-1), "in"), (b_, "in"), cst, (torch.tensor([0.3]), "in"), n,
+                                                     (torch.zeros(n), "out")])
+        assert torch.equal(og, oc)
     # casts
     src = torch.randn(1000, dtype=torch.float64)
     (og,), (oc,) = run_both("ms_cast", [(src, "in"), 1, (torch.zeros(1000), "out"), 0, 1000])

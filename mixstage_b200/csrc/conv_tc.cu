@@ -1176,13 +1176,18 @@ __global__ void __launch_bounds__(256) pack_igemm_weight_multi_kernel(const ms_p
     const int Cout_g = e.Cout / e.groups;
     __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(e.wp);
     __nv_bfloat16* wp_lo = reinterpret_cast<__nv_bfloat16*>(e.wp_lo);
+    // 32-bit index arithmetic (a packed weight has far fewer than 2^31 elements: the largest here is 2 M): the 64-bit
+    // divisions of the first version cost more than the loads
+    const unsigned kpad = (unsigned)e.kpad, ntaps = (unsigned)e.ntaps, class_n = (unsigned)e.class_n;
     for (long long pi = p0 + tid; pi < p1; pi += blockDim.x) {
-      const long long i = pi << 1;
-      const int kc = (int)(i % e.kpad);
-      const long long t2 = i / e.kpad;
-      const int t = (int)(t2 % e.ntaps);
-      const long long row = t2 / e.ntaps;
-      const int cls = (int)(row / e.class_n), r = (int)(row - (long long)cls * e.class_n);
+      const unsigned iu = (unsigned)(pi << 1);
+      const long long i = (long long)iu;
+      const unsigned t2 = iu / kpad;
+      const int kc = (int)(iu - t2 * kpad);
+      const unsigned rowu = t2 / ntaps;
+      const int t = (int)(t2 - rowu * ntaps);
+      const long long row = (long long)rowu;
+      const int cls = (int)(rowu / class_n), r = (int)(rowu - (unsigned)cls * class_n);
       float v[2] = {0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 2; j++) {

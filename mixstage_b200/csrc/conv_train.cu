@@ -1196,13 +1196,21 @@ __device__ __forceinline__ void wgrad_acc_body(const CUtensorMap& map_x, const C
   const int n0 = nt * 128, c0 = ct * p.c_tile;
   const int nc = min(p.c_tile, p.kpad - c0);
   const int xchunks = nc / 64;
-  const uint32_t stage_bytes = (2 + xchunks) * WGA_CHUNK_BYTES;
+  // One k-step = one tile of 64 pixel rows.  Split-bf16 stages dz_hi, dz_lo, x_hi, x_lo ONCE and issues the three passes from
+  // them (4 tile loads per 3 passes instead of 6: this GEMM streams its operands from L2 and is bound by that traffic);
+  // stage = [dz hi (2 chunks)][dz lo (2)][x hi (xchunks)][x lo (xchunks)], ring depth = what fits in 192 KB.
+  const bool split = p.npass > 1;
+  const int stage_chunks = split ? (4 + 2 * xchunks) : (2 + xchunks);
+  const uint32_t stage_bytes = (uint32_t)stage_chunks * WGA_CHUNK_BYTES;
+  int nstages = (WGA_STAGES * 6) / stage_chunks;
+  if (nstages > WGA_STAGES) nstages = WGA_STAGES;
   const int total_rt = p.tiles_w * p.tiles_h * p.tiles_b;
   const int per = (total_rt + p.split - 1) / p.split;
   const int rt_beg = bx * per, rt_end = min(total_rt, rt_beg + per);
-  const int num_k = max(0, rt_end - rt_beg) * p.npass;
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + WGA_STAGES * 2 * WGA_CHUNK_BYTES;
+  const int num_k = max(0, rt_end - rt_beg);
+  const uint32_t zlo_off = 2 * WGA_CHUNK_BYTES;
+  const uint32_t x_off = (split ? 4 : 2) * WGA_CHUNK_BYTES;
+  const uint32_t xlo_off = x_off + (uint32_t)xchunks * WGA_CHUNK_BYTES;
   uint32_t tmem_cols = 64;
   while (tmem_cols < (uint32_t)nc) tmem_cols <<= 1;
   if (warp == 0 && lane == 0) {
@@ -1227,23 +1235,25 @@ __device__ __forceinline__ void wgrad_acc_body(const CUtensorMap& map_x, const C
         const int xc = p.a_chan_base[cls] + t[0] + c0;
         const int zc = p.z_chan_base[cls] + n0;
         for (int ks = 0; ks < num_k; ks++) {
-          const int s = ks % WGA_STAGES;
-          const uint32_t ph = (uint32_t)(ks / WGA_STAGES) & 1u;
+          const int s = ks % nstages;
+          const uint32_t ph = (uint32_t)(ks / nstages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          const int pass = ks % p.npass;              // split-bf16: x_hi*z_hi, x_hi*z_lo, x_lo*z_hi
-          int rt = rt_beg + ks / p.npass;
-          const CUtensorMap* mz = pass == 1 ? &map_z_lo : &map_z;
-          const CUtensorMap* mx = pass == 2 ? &map_x_lo : &map_x;
+          int rt = rt_beg + ks;
           const int tw = rt % p.tiles_w; rt /= p.tiles_w;
           const int th = rt % p.tiles_h; rt /= p.tiles_h;
           const int w0 = tw * p.box_w, h0 = th * p.box_h, b0 = rt * p.box_b;
           mbar_expect_tx(&full_bar[s], stage_bytes);
-          uint8_t* sa = smem_a + (size_t)s * 2 * WGA_CHUNK_BYTES;
-          uint8_t* sb = smem_b + (size_t)s * 4 * WGA_CHUNK_BYTES;
-          tma_load_5d(mz, &full_bar[s], sa, zc, w0, 0, h0, b0);
-          tma_load_5d(mz, &full_bar[s], sa + WGA_CHUNK_BYTES, zc + 64, w0, 0, h0, b0);
+          uint8_t* st_ = smem + (size_t)s * stage_bytes;
+          tma_load_5d(&map_z, &full_bar[s], st_, zc, w0, 0, h0, b0);
+          tma_load_5d(&map_z, &full_bar[s], st_ + WGA_CHUNK_BYTES, zc + 64, w0, 0, h0, b0);
           for (int i = 0; i < xchunks; i++)
-            tma_load_5d(mx, &full_bar[s], sb + (size_t)i * WGA_CHUNK_BYTES, xc + 64 * i, w0 + t[1], t[2], h0 + t[3], b0);
+            tma_load_5d(&map_x, &full_bar[s], st_ + x_off + (size_t)i * WGA_CHUNK_BYTES, xc + 64 * i, w0 + t[1], t[2], h0 + t[3], b0);
+          if (split) {
+            tma_load_5d(&map_z_lo, &full_bar[s], st_ + zlo_off, zc, w0, 0, h0, b0);
+            tma_load_5d(&map_z_lo, &full_bar[s], st_ + zlo_off + WGA_CHUNK_BYTES, zc + 64, w0, 0, h0, b0);
+            for (int i = 0; i < xchunks; i++)
+              tma_load_5d(&map_x_lo, &full_bar[s], st_ + xlo_off + (size_t)i * WGA_CHUNK_BYTES, xc + 64 * i, w0 + t[1], t[2], h0 + t[3], b0);
+          }
         }
       }
     } else if (warp == 1) {
@@ -1251,15 +1261,27 @@ __device__ __forceinline__ void wgrad_acc_body(const CUtensorMap& map_x, const C
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                ((uint32_t)(nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         for (int ks = 0; ks < num_k; ks++) {
-          const int s = ks % WGA_STAGES;
-          const uint32_t ph = (uint32_t)(ks / WGA_STAGES) & 1u;
+          const int s = ks % nstages;
+          const uint32_t ph = (uint32_t)(ks / nstages) & 1u;
           mbar_wait(&full_bar[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t da = make_mnmajor_sw128_desc2(smem_u32(smem_a + (size_t)s * 2 * WGA_CHUNK_BYTES));
-          const uint64_t db = make_mnmajor_sw128_desc2(smem_u32(smem_b + (size_t)s * 4 * WGA_CHUNK_BYTES));
+          const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t da = make_mnmajor_sw128_desc2(base);
+          const uint64_t db = make_mnmajor_sw128_desc2(base + x_off);
 #pragma unroll
           for (int k = 0; k < WGA_ROWS / UMMA_K; k++)
             umma_bf16(tmem_base, da + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, (ks | k) != 0 ? 1u : 0u);
+          if (split) {
+            // same pass order as pass-by-pass staging: x_hi * dz_hi, x_hi * dz_lo, x_lo * dz_hi
+            const uint64_t da_lo = make_mnmajor_sw128_desc2(base + zlo_off);
+            const uint64_t db_lo = make_mnmajor_sw128_desc2(base + xlo_off);
+#pragma unroll
+            for (int k = 0; k < WGA_ROWS / UMMA_K; k++)
+              umma_bf16(tmem_base, da_lo + (uint64_t)(k * 128), db + (uint64_t)(k * 128), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < WGA_ROWS / UMMA_K; k++)
+              umma_bf16(tmem_base, da + (uint64_t)(k * 128), db_lo + (uint64_t)(k * 128), idesc, 1u);
+          }
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full_bar);

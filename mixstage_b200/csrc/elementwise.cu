@@ -323,6 +323,96 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dy, const floa
   }
 }
 
+// 16-byte form of the apply pass (C % 4 == 0, no upsampling): a thread owns four channels of one row -- one index division per
+// four elements, per-channel constants as float4, 16-byte loads and stores.  (The scalar form above ran at ~1.3 TB/s on the
+// 134 MB tensors of audio_encoder.conv.0 at batch 128: 300 us per call.)
+__global__ void bn_act_bwd_apply4_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                                         const float* __restrict__ scale, const float* __restrict__ shift,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd, float slope,
+                                         int64_t rows, int C4, const double* __restrict__ dgamma,
+                                         const double* __restrict__ dbeta, int training, float4* __restrict__ dx,
+                                         __nv_bfloat16* __restrict__ planes, int pfmt, int64_t pstride,
+                                         void* __restrict__ ggamma, void* __restrict__ gbeta, int gdt) {
+  const int64_t total = rows * C4;
+  const float inv = 1.f / (float)rows;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (stride % C4 == 0) {
+    // the thread's four channels never change along its grid-stride walk: constants in registers, a pure streaming loop
+    const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int c = 4 * (int)(i0 % C4);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, kb = mu, kg = mu;
+    if (training) {
+      mu = *reinterpret_cast<const float4*>(mean + c);
+      rs = *reinterpret_cast<const float4*>(rstd + c);
+      kb = make_float4((float)dbeta[c] * inv, (float)dbeta[c + 1] * inv, (float)dbeta[c + 2] * inv, (float)dbeta[c + 3] * inv);
+      kg = make_float4((float)dgamma[c], (float)dgamma[c + 1], (float)dgamma[c + 2], (float)dgamma[c + 3]);
+    }
+    if (i0 < C4) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (ggamma) ms_stp(ggamma, gdt, c + j, ms_ldp_d(ggamma, gdt, c + j) + dgamma[c + j]);
+        if (gbeta) ms_stp(gbeta, gdt, c + j, ms_ldp_d(gbeta, gdt, c + j) + dbeta[c + j]);
+      }
+    }
+    for (int64_t i = i0; i < total; i += 2 * stride) {
+      const int64_t i2 = i + stride;
+      const bool two = i2 < total;
+      const float4 xa = __ldg(x + i), da = __ldg(dy + i);
+      float4 xb = xa, db = da;
+      if (two) { xb = __ldg(x + i2); db = __ldg(dy + i2); }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        if (u == 1 && !two) break;
+        const float4 xv = u ? xb : xa, d = u ? db : da;
+        const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
+        const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
+        float4 o;
+        if (training) {
+          // (same expression order as the general form below: identical results)
+          o.x = sc.x * (g0 - kb.x - ((xv.x - mu.x) * rs.x) * kg.x * inv);
+          o.y = sc.y * (g1 - kb.y - ((xv.y - mu.y) * rs.y) * kg.y * inv);
+          o.z = sc.z * (g2 - kb.z - ((xv.z - mu.z) * rs.z) * kg.z * inv);
+          o.w = sc.w * (g3 - kb.w - ((xv.w - mu.w) * rs.w) * kg.w * inv);
+        } else {
+          o.x = sc.x * g0; o.y = sc.y * g1; o.z = sc.z * g2; o.w = sc.w * g3;
+        }
+        const int64_t io = u ? i2 : i;
+        if (dx) dx[io] = o;
+        if (planes) store_planes4(planes, pfmt, pstride, 4 * io, o);
+      }
+    }
+    return;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C4;
+    const int c = 4 * (int)(i - r * C4);
+    if (r == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (ggamma) ms_stp(ggamma, gdt, c + j, ms_ldp_d(ggamma, gdt, c + j) + dgamma[c + j]);
+        if (gbeta) ms_stp(gbeta, gdt, c + j, ms_ldp_d(gbeta, gdt, c + j) + dbeta[c + j]);
+      }
+    }
+    const float4 xv = __ldg(x + i), d = __ldg(dy + i);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    const float g0 = fmaf(xv.x, sc.x, sh.x) > 0.f ? d.x : d.x * slope, g1 = fmaf(xv.y, sc.y, sh.y) > 0.f ? d.y : d.y * slope;
+    const float g2 = fmaf(xv.z, sc.z, sh.z) > 0.f ? d.z : d.z * slope, g3 = fmaf(xv.w, sc.w, sh.w) > 0.f ? d.w : d.w * slope;
+    float4 o;
+    if (training) {
+      const float4 mu = *reinterpret_cast<const float4*>(mean + c), rs = *reinterpret_cast<const float4*>(rstd + c);
+      o.x = sc.x * (g0 - (float)dbeta[c] * inv - ((xv.x - mu.x) * rs.x) * (float)dgamma[c] * inv);
+      o.y = sc.y * (g1 - (float)dbeta[c + 1] * inv - ((xv.y - mu.y) * rs.y) * (float)dgamma[c + 1] * inv);
+      o.z = sc.z * (g2 - (float)dbeta[c + 2] * inv - ((xv.z - mu.z) * rs.z) * (float)dgamma[c + 2] * inv);
+      o.w = sc.w * (g3 - (float)dbeta[c + 3] * inv - ((xv.w - mu.w) * rs.w) * (float)dgamma[c + 3] * inv);
+    } else {
+      o.x = sc.x * g0; o.y = sc.y * g1; o.z = sc.z * g2; o.w = sc.w * g3;
+    }
+    if (dx) dx[i] = o;
+    if (planes) store_planes4(planes, pfmt, pstride, 4 * i, o);
+  }
+}
+
 // x (rows, C) fp32 -> bf16 planes with row stride rs >= C (pad columns zero-filled)
 __global__ void to_planes_kernel(const float* __restrict__ x, int64_t rows, int C, int rs, __nv_bfloat16* __restrict__ planes,
                                  int pfmt, int64_t pstride) {
@@ -962,6 +1052,15 @@ extern "C" int ms_bn_act_bwd_apply_f32(const float* dy, const float* x, const fl
   if (training && (!dgamma || !dbeta)) return MS_EINVAL;
   if ((grad_gamma || grad_beta) && (!dgamma || !dbeta || (gdt != MS_F32 && gdt != MS_F64))) return MS_EINVAL;
   if (!planes_ok(planes, pfmt, pstride)) return MS_EINVAL;
+  if (!up2 && C % 4 == 0 && !(((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)scale | (uintptr_t)shift | (uintptr_t)mean |
+                                (uintptr_t)rstd) & 15)) {
+    bn_act_bwd_apply4_kernel<<<ew_blocks(rows * (C / 4)), EW_THREADS, 0, ST>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), scale, shift, mean, rstd, slope, rows, C / 4, dgamma,
+        dbeta, training, reinterpret_cast<float4*>(dx), reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride, grad_gamma, grad_beta,
+        gdt);
+    MS_LAUNCH_CHECK();
+    return 0;
+  }
   bn_act_bwd_apply_kernel<<<ew_blocks(rows * C), EW_THREADS, 0, ST>>>(dy, x, scale, shift, mean, rstd, slope, rows, C, up2,
                                                                       rows_per_seq, dgamma, dbeta, training, dx,
                                                                       reinterpret_cast<__nv_bfloat16*>(planes), pfmt, pstride,

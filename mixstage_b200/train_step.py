@@ -18,6 +18,8 @@ touch stay zero, which reproduces the reference's torch-1.5 `zero_grad()` (zero-
 """
 from __future__ import annotations
 
+import os as _os
+
 import torch
 import torch.distributed as dist
 
@@ -131,7 +133,7 @@ class TrainStep:
 
     def __init__(self, gan, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, use_graphs=True, group=None,
                  input_modalities=("audio/log_mel_400",), description="train", overlap_allreduce=True,
-                 exchange_dtype="fp32", rng_seed=None, check_agreement=False, comm_sms=16):
+                 exchange_dtype="fp32", rng_seed=None, check_agreement=False, comm_sms=16, side_sms=None):
         """One TrainStep (and one CUDA device) per process: the scratch arena, the direct-gradient switch and the
         side stream are module-level state of mixstage_b200.ops, and the kernels' lazily set function attributes are
         per process.
@@ -141,6 +143,8 @@ class TrainStep:
         last) while backward is still running, as fp32 ("fp32", default: half the bytes of the fp64 master gradients)
         or in the master dtype ("native").
         comm_sms: SMs left free beside the chain launches for the NCCL kernels of the overlapped exchange (multi-rank only).
+        side_sms: SMs left free beside the chain launches for the side stream's weight-gradient launches (default: the
+        MS_SIDE_SMS environment variable, else 0).
         rng_seed: seed of the generator the D/G coin and the curriculum draw come from.  None = the process-global CPU
         generator in a single-process run (the reference's own RNG consumption, gan.py:105 / jlcss.py:127) and a
         dedicated generator seeded with the reference's seed 11212 on every rank of a data-parallel run: ranks then
@@ -181,9 +185,12 @@ class TrainStep:
         # the chain launches are persistent and would hold every SM: leave a few to the NCCL kernels of the overlapped
         # exchange (set NCCL_MAX_CTAS accordingly before the process group is created; bench.py does)
         self.comm_sms = int(comm_sms)
-        if self.comm is not None and self._world() > 1 and self.comm_sms > 0:
+        if side_sms is None:
+            side_sms = int(_os.environ.get("MS_SIDE_SMS", "0"))
+        free = max(self.comm_sms if (self.comm is not None and self._world() > 1) else 0, int(side_sms))
+        if dev.type == "cuda" and free > 0:
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-            call("ms_set_chain_sm_budget", max(16, n_sm - self.comm_sms))
+            call("ms_set_chain_sm_budget", max(16, n_sm - free))
         self._reduced, self._works = [], []
         self._flushed = set()
         # tensor-core modes: the conv weight gradients are exchanged as their fp32 accumulators (see _exchange_acc)

@@ -12,6 +12,7 @@ for w in $what; do
     benchunfused) MS_FUSED_BLOCKS=0 timeout 600 python bench.py --workload train > gpurun_out/${tag}_bench_train_unfused.json 2> gpurun_out/${tag}_bench_train_unfused.err; echo "benchunfused rc=$?" ;;
     bench3) timeout 900 python bench.py --workload config3 --steps 10 > gpurun_out/${tag}_bench_c3.json 2> gpurun_out/${tag}_bench_c3.err; echo "bench3 rc=$?" ;;
     phases) MS_PHASE_TS=1 timeout 300 python tools/chain_phases.py > gpurun_out/${tag}_chain_phases.txt 2>&1; MS_PHASE_TS=1 timeout 300 python tools/chain_phases.py --eval > gpurun_out/${tag}_chain_phases_eval.txt 2>&1; echo "phases rc=$?" ;;
+    breakdownside) for n in 8 16 24; do echo "MS_SIDE_SMS=$n"; MS_SIDE_SMS=$n timeout 600 python tools/step_breakdown.py 2>&1 | grep "graph replay"; done > gpurun_out/${tag}_breakdown_side.txt 2>&1; echo "breakdownside rc=$?" ;;
     breakdown) timeout 600 python tools/step_breakdown.py --order > gpurun_out/${tag}_breakdown.txt 2>&1; echo "breakdown rc=$?" ;;
     breakdown128) timeout 600 python tools/step_breakdown.py --batch 128 --speakers 8 > gpurun_out/${tag}_breakdown128.txt 2>&1; echo "breakdown128 rc=$?" ;;
     smoke) timeout 600 python __graft_entry__.py smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" ;;

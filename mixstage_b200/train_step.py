@@ -171,7 +171,8 @@ class TrainStep:
         self.eager_steps = 0         # steps whose batch shape differed from the captured one (run eagerly)
         self.warmup_iters = 2
         self.side = ops.SideWork(dev) if dev.type == "cuda" else None      # weight-gradient GEMMs beside the dgrad chain
-        self._tables = {}            # kind -> (signature, device table, n): entries of the batched weight re-tiling
+        self._tables = {}            # (kind, tag) -> (signature, device table, n): entries of the batched weight re-tiling
+        self.defer_dgrad_pack = _os.environ.get("MS_DEFER_DGRAD_PACK", "1") != "0"
         for pw in self._packed_of(self.G) + self._packed_of(self.D):
             pw._src.clear()          # recipes recorded before the parameters moved into the flat buffers are stale
         self._pver = None            # flat-parameter versions seen by the last refresh
@@ -247,8 +248,22 @@ class TrainStep:
     # ------------------------------------------------------------------ the step body (eager, and what gets captured)
     def _body(self, kind, use_pose, audio, labels, pose, style):
         gan, G = self.gan, self.G
-        self.fG.zero_grad()
-        self.fD.zero_grad()
+        wacc = self.wacc[kind]
+        # Work the FORWARD does not depend on runs beside it on the side stream: zero-filling the flat gradient buffers and
+        # the weight-gradient accumulators (first touched by backward) and, in a graphed generator step, the re-tiling of the
+        # input-gradient copies of the weights (only this step's backward reads them).  Joined right before backward.
+        pre = self.side is not None
+        if pre:
+            with self.side.fork():
+                self.fG.zero_grad()
+                self.fD.zero_grad()
+                wacc.zero()
+                if self.use_graphs and kind == "G" and self.defer_dgrad_pack:
+                    self._refresh("G", "dgrad")
+        else:
+            self.fG.zero_grad()
+            self.fD.zero_grad()
+            wacc.zero()
         old_force, old_lam = gan.force_step, gan.lambda_dev
         gan.force_step = kind
         gan.lambda_dev = self.lambda_dev
@@ -258,8 +273,6 @@ class TrainStep:
         ops.arena.begin(self.fG.device)
         ops.DIRECT_GRADS = True
         ops.SIDE = self.side
-        wacc = self.wacc[kind]
-        wacc.zero()
         ops.WACC = wacc
         overlap = self.overlap and kind == "G" and self._world() > 1
         self._reduced, self._works = [], []
@@ -272,6 +285,8 @@ class TrainStep:
             fake, losses, _ = gan([audio, labels], pose, input_modalities=self.mod, style=style, sample_flag=0,
                                   description=self.description, desc=self.description)
             loss = sum(losses)
+            if pre:
+                torch.cuda.current_stream().wait_stream(self.side.stream)
             loss.backward()
         finally:
             G.force_branch = None
@@ -299,7 +314,7 @@ class TrainStep:
         if self.use_graphs:
             # keep every packed copy (bf16 re-tilings, fp32 biases, folded eval BatchNorm) of the sub-network that just
             # stepped in sync with its parameters, so that no forward has to re-pack anything
-            self._refresh(kind)
+            self._refresh(kind, "fwd" if (kind == "G" and self.defer_dgrad_pack) else "all")
         return fake.detach(), torch.stack([l.detach().to(fake.dtype) for l in losses])
 
     # ------------------------------------------------------------------ overlapped gradient exchange (opt-in)
@@ -478,9 +493,18 @@ class TrainStep:
                 out.append(cfg_pw[1])
         return out
 
-    def _refresh(self, kind):
+    def _refresh(self, kind, which="all"):
+        """Re-derive the packed copies of sub-network `kind` from its parameters.  which: "all", or for the generator of a
+        graphed run "fwd" (everything but the input-gradient tilings: what the NEXT forward of either step kind reads) /
+        "dgrad" (the input-gradient tilings: only a generator step's backward reads them, so a generator step re-tiles them
+        at its START on the side stream, beside its forward, instead of at the end of the previous one)."""
         mod = self.G if kind == "G" else self.D
         entries = []
+        if which == "dgrad":
+            cur = self._tables.get((kind, "dgrad"))
+            if cur is not None:
+                call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 0, stream())
+            return
         for m in mod.modules():
             for v in vars(m).values():
                 if isinstance(v, ops.MixedLogits):
@@ -489,8 +513,17 @@ class TrainStep:
             pw.refresh(entries)
         if not entries:
             return
+        groups = [("all", entries)]
+        if kind == "G" and self.defer_dgrad_pack:
+            groups = [("fwd", [e for e in entries if e.mode == 0]), ("dgrad", [e for e in entries if e.mode != 0])]
+        for tag, ents in groups:
+            self._refresh_table(kind, tag, ents, launch=(which == "all" or tag == which or tag == "all"))
+
+    def _refresh_table(self, kind, tag, entries, launch):
+        if not entries:
+            return
         sig = tuple((e.w, e.wp, e.wp_lo, e.mode, e.num_classes, e.class_n, e.ntaps, e.kpad) for e in entries)
-        cur = self._tables.get(kind)
+        cur = self._tables.get((kind, tag))
         if cur is None or cur[0] != sig:
             if torch.cuda.is_current_stream_capturing():
                 raise MixStageError("internal: packed-weight table changed during graph capture")
@@ -504,8 +537,9 @@ class TrainStep:
             arr = (_lib.PackEntry * len(entries))(*entries)
             host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
             cur = (sig, host.to(self.fG.device), len(entries))
-            self._tables[kind] = cur
-        call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 0, stream())
+            self._tables[(kind, tag)] = cur
+        if launch:
+            call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 0, stream())
 
     def _flush_wgrads(self, kind, tops=None, tag="all"):
         """Weight-gradient accumulators of this step -> the flat gradient buffers, one launch.  tops: only the accumulators

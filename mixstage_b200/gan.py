@@ -75,13 +75,13 @@ class GAN(nn.Module):
 
     @staticmethod
     def _l1(a, b=None, const=0.0, dtype=None):
-        a32 = ops.cast(a, torch.float32).contiguous()
-        b32 = None if b is None else ops.cast(b, torch.float32).contiguous()
+        a32 = ops.f32_of(a).contiguous()
+        b32 = None if b is None else ops.f32_of(b).contiguous()
         return ops.cast(ops.l1_mean(a32, b32, const), dtype or a.dtype)
 
     def _score(self, pose):
         """D(velocity(pose)) without leaving fp32."""
-        v = ops.velocity(ops.cast(pose, torch.float32).contiguous())
+        v = ops.velocity(ops.f32_of(pose).contiguous())
         s, _ = self.D(v)
         return s
 
@@ -109,7 +109,11 @@ class GAN(nn.Module):
                     args = args[0] if len(args) > 0 else {}
                 self.G.train(self.training)
                 self.fake_flag = True
-                fake_score = self._score(fake_pose.detach())
+                f32 = getattr(fake_pose, "_ms_f32", None)
+                fake_d = fake_pose.detach()
+                if f32 is not None:
+                    fake_d._ms_f32 = f32.detach()
+                fake_score = self._score(fake_d)
                 fake_D_loss = lam_D * self._l1(fake_score, None, 0.0, dt)
                 real_score = self._score(y_pose)
                 real_D_loss = self._l1(real_score, None, 1.0, dt)

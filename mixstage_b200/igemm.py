@@ -10,6 +10,7 @@ descriptors against F.conv2d through the CPU specification of the kernel."""
 from __future__ import annotations
 
 import ctypes
+import os as _os
 
 from ._lib import MS_BF16, MS_F32, MixStageError
 
@@ -223,6 +224,10 @@ def igemm_split(d, npass, sms=148):
     return _normalise_split(num_k, min(sms // ctas, num_k // 4))          # one wave: at most one CTA per SM
 
 
+_PLAN_RATE = float(_os.environ.get("MS_PLAN_RATE", "40"))
+_PLAN_SPLIT_COST = float(_os.environ.get("MS_PLAN_SPLIT_COST", "4500"))
+
+
 def block_plan(d, npass, stats, sms=148):
     """(block_n, split_k) of the GEMM phase of a fused block (csrc/conv_train.cu) by a cycle estimate.
 
@@ -237,6 +242,7 @@ def block_plan(d, npass, stats, sms=148):
     k_steps = d.ntaps * d.cchunks
     planes = 2 if npass > 1 else 1
     gran = 32 if stats else 16
+    force = _os.environ.get("MS_BLOCK_FORCE", "")        # experiments: "full" / "split" forward form whatever the estimate says
     cands = [b for b in (256, 128, 64, 32) if b <= d.class_n and b % gran == 0]
     if min(256, d.class_n) not in cands and d.class_n % gran == 0 and d.class_n <= 256:
         cands.insert(0, d.class_n)
@@ -250,7 +256,7 @@ def block_plan(d, npass, stats, sms=148):
         for split in sorted({1} | {_normalise_split(k_steps, s) for s in (2, 3, 4, 6, 8, 12, 16, 24) if tiles * s <= 2 * sms}):
             items = tiles * split
             active = min(items, sms)
-            rate = min(40.0, 6300.0 / active)      # measured: one SM's TMA path sustains ~40 B/clk (tools/chain_phases.py)
+            rate = min(_PLAN_RATE, 6300.0 / active)      # measured: one SM's TMA path sustains ~40 B/clk (tools/chain_phases.py)
             kclk = max(mma, stage / rate)
             if 196608 // stage < 3:
                 kclk *= 1.4                       # a two-stage ring does not cover the TMA latency
@@ -259,7 +265,11 @@ def block_plan(d, npass, stats, sms=148):
             cost = waves * (per * kclk + 2500)
             if split > 1:
                 cost += waves * (128 * bn * 4 / 40.0)
-                cost += 6000 if stats else 1500
+                cost += _PLAN_SPLIT_COST if stats else 1500
+            if stats and force == "full" and split > 1:
+                continue
+            if stats and force == "split" and split == 1 and k_steps >= 4:
+                cost += 1e9
             if best is None or cost < best[0]:
                 best = (cost, bn, split)
     return best[1], best[2]

@@ -278,4 +278,7 @@ class JointLateClusterSoftStyle4_G(nn.Module):
 
         internal_losses.append(ops.cast(id_in_loss, out_dtype) * self.lambda_id)
         internal_losses.append(ops.cast(id_out_loss, out_dtype) * self.lambda_id)
-        return ops.cast(pose, out_dtype), internal_losses
+        out = ops.cast(pose, out_dtype)
+        if out is not pose:
+            out._ms_f32 = pose            # consumers that compute in fp32 (GAN: velocity + D, L1) take it from here
+        return out, internal_losses

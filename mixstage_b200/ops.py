@@ -351,10 +351,30 @@ class _Cast(torch.autograd.Function):
         return cast_raw(g, ctx.src_dtype), None
 
 
+CAST_CACHE = None            # TrainStep sets a fresh dict for the duration of one step body (also while it is being captured)
+
+
 def cast(x, dtype):
+    """x in another floating dtype.  Inside a TrainStep body an input that takes no gradient (audio, ground-truth pose: read
+    by several consumers of the step) is narrowed once: the copy is kept for the rest of that body (and of that capture)."""
     if x.dtype == dtype:
         return x
+    if CAST_CACHE is not None and dtype == torch.float32 and not x.requires_grad:
+        key = (x.data_ptr(), x._version, tuple(x.shape), x.dtype)
+        y = CAST_CACHE.get(key)
+        if y is None:
+            y = CAST_CACHE[key] = cast_raw(x, dtype)
+        return y
     return _Cast.apply(x, dtype)
+
+
+def f32_of(x):
+    """fp32 form of a module output: the fp32 tensor it was widened from when the producer left it on the object (the
+    generator's pose, still connected to the autograd graph), else a cast."""
+    src = getattr(x, "_ms_f32", None)
+    if src is not None and src.shape == x.shape:
+        return src
+    return cast(x, torch.float32)
 
 
 # ---------------------------------------------------------------------------- conv block

@@ -272,6 +272,7 @@ class TrainStep:
         # one arena cleared by a single memset (ops.py)
         ops.arena.begin(self.fG.device)
         ops.DIRECT_GRADS = True
+        ops.CAST_CACHE = {}
         ops.SIDE = self.side
         ops.WACC = wacc
         overlap = self.overlap and kind == "G" and self._world() > 1
@@ -293,6 +294,7 @@ class TrainStep:
             G.grad_ready_hook = None
             gan.force_step, gan.lambda_dev = old_force, old_lam       # a direct gan(...) call draws its own coin again
             ops.DIRECT_GRADS = False
+            ops.CAST_CACHE = None
             ops.SIDE = None
             ops.WACC = None
             ops.arena.end()

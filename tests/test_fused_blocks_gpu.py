@@ -194,3 +194,80 @@ def test_train_step_fused_equals_unfused(kind, lam_gan):
     bound = 5e-2
     assert eg < bound, eg
     assert ed < bound, ed
+
+
+@pytest.mark.parametrize("which", ["unet", "classify", "audio", "pose_style"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_chain_equals_block_by_block(which, mode):
+    """A conv stack as ONE chain launch per direction (ms_conv_chain_fwd / _bwd + one weight-gradient launch; UNet1D with
+    its skip connections resolved inside the chain: block i adds the output of block res_from[i], the backward adds the
+    skip consumer's gradient as a second addend) against the same blocks launched one by one: outputs, input gradient,
+    every parameter gradient and the running statistics."""
+    from mixstage_b200 import layers, ops
+    import torch.nn as nn
+    torch.manual_seed(7)
+    B = 16
+    mk = {
+        "unet": (lambda: layers.UNet1D(256, 256), (B, 1, 64, 256)),
+        "classify": (lambda: nn.Sequential(*list(layers.ClusterClassify(input_channels=266).conv)), (B, 1, 64, 266)),
+        "audio": (lambda: nn.Sequential(*list(layers.AudioEncoder().conv)[1:]), (B, 64, 64, 64)),
+        "pose_style": (lambda: nn.Sequential(*list(layers.PoseStyleEncoder().conv)[:6]), (B, 1, 64, 96)),
+    }[which]
+    res = {}
+    old_c, old_p = ops.CHAINS, ops.get_precision()
+    ops.set_precision("bf16x3")
+    try:
+        for chains in (True, False):
+            ops.CHAINS = chains
+            torch.manual_seed(7)
+            m = mk[0]().to("cuda", torch.float64)
+            with torch.no_grad():
+                for mod in m.modules():
+                    if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                        mod.weight.uniform_(0.5, 1.5)
+                        mod.bias.uniform_(-0.5, 0.5)
+                        mod.running_mean.uniform_(-0.2, 0.2)
+                        mod.running_var.uniform_(0.5, 2.0)
+            m.train(mode == "train")
+            torch.manual_seed(9)
+            x = torch.randn(*mk[1], device="cuda", requires_grad=(mode == "train"))
+            seen = []
+            orig = ops.call
+            ops.call = lambda n, *a: (seen.append(n), orig(n, *a))[1]
+            try:
+                with torch.set_grad_enabled(mode == "train"):
+                    y = m(x) if which == "unet" else layers._run(list(m), x)
+                    y = ops.as_f32(y)
+                if mode == "train":
+                    torch.manual_seed(10)
+                    y.backward(torch.randn_like(y))
+            finally:
+                ops.call = orig
+            torch.cuda.synchronize()
+            assert ("ms_conv_chain_fwd" in seen) == chains, seen[:8]
+            out = {"y": y.detach().clone()}
+            if mode == "train":
+                assert ("ms_conv_chain_bwd" in seen) == chains
+                out["dx"] = x.grad.clone()
+                for n, p in m.named_parameters():
+                    if p.grad is not None:
+                        out["g:" + n] = p.grad.clone()
+                for n, b in m.named_buffers():
+                    if "running" in n:
+                        out["b:" + n] = b.clone()
+            res[chains] = out
+    finally:
+        ops.CHAINS = old_c
+        ops.set_precision(old_p)
+    a, b = res[True], res[False]
+    assert a.keys() == b.keys()
+    worst = ("", 0.0)
+    for k in a:
+        e = _rel(a[k], b[k])
+        if e > worst[1]:
+            worst = (k, e)
+        # forward quantities agree to the order of the fp32 reductions (and, for the UNet, to the 16-bit skip planes the
+        # chain adds instead of fp32 skips); gradients additionally see a few flipped LeakyReLU masks (see the test above)
+        tol = 2e-4 if (k == "y" or k.startswith("b:")) else 5e-3
+        assert e < tol, (which, mode, k, e)
+    print({"case": "chain_vs_blocks", "which": which, "mode": mode, "worst": worst})

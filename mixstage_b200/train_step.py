@@ -26,6 +26,7 @@ import torch.distributed as dist
 from . import _lib, ops
 from ._lib import MixStageError, call, dt_code, ptr, stream
 
+_DP_DEBUG = _os.environ.get("MS_DP_DEBUG", "")     # timing experiments: "skip_acc", "skip_small" (results are then wrong)
 ALIGN = 4       # parameter offsets in elements: 16-byte aligned for fp32, 32-byte for fp64
 
 
@@ -351,6 +352,8 @@ class TrainStep:
     # staging pass, no widening pass, no per-bucket conversion squeezed onto the SMs the chain launches leave free.  The
     # buckets are "the accumulators touched since the previous hook", learned in the first body of every (kind, branch).
     def _reduce_tensors(self, tensors):
+        if "skip_acc" in _DP_DEBUG:                # timing experiments only: replicas diverge
+            return
         ws = self._world()
         nccl = self.fG.device.type == "cuda"
         for t in tensors:
@@ -423,7 +426,7 @@ class TrainStep:
             ctxm.__enter__()
         try:
             self._reduce_tensors(wacc.ranges(rest))
-            if idx.numel():
+            if idx.numel() and "skip_small" not in _DP_DEBUG:
                 small = f.g.index_select(0, idx)
                 if self.exchange_fp32 and small.dtype == torch.float64:
                     small = small.float()

@@ -8,6 +8,7 @@ reached through the C-ABI in include/mixstage_b200.h; there is no CPU/PyTorch fa
 from __future__ import annotations
 
 import contextlib
+import os
 import weakref
 
 import torch
@@ -36,6 +37,8 @@ def some_grad(module):
         for p, r in zip(module.parameters(), saved):
             p.requires_grad_(r)
 
+
+_SPLIT_ENC_BUCKET = os.environ.get("MS_SPLIT_ENC_BUCKET", "1") != "0"   # see AudioEncoder.mid_mark
 
 class JointLateClusterSoftStyle4_G(nn.Module):
     '''
@@ -204,7 +207,12 @@ class JointLateClusterSoftStyle4_G(nn.Module):
                         a = a.squeeze(1)
                     Bt, T, F = a.shape
                     a = self._as_f32_cl(a, Bt, T).view(Bt, T, F, 1)     # NHWC with C=1
-                    feats.append(self.audio_encoder(a, time_steps if time_steps is not None else T))
+                    hooked = getattr(self, 'grad_ready_hook', None) is not None and _SPLIT_ENC_BUCKET
+                    self.audio_encoder.mid_mark = (lambda t: self._mark(t, 'audio_mid')) if hooked else None
+                    try:
+                        feats.append(self.audio_encoder(a, time_steps if time_steps is not None else T))
+                    finally:
+                        self.audio_encoder.mid_mark = None
             if len(feats) != 1:
                 raise NotImplementedError("mixstage_b200: exactly one (audio) input modality is accelerated")
             h = self.unet(self._mark(feats[0], 'encoder_out'))           # (B,1,T,256)

@@ -146,6 +146,7 @@ class AudioEncoder(nn.Module):
                                       kernel_size=(3, 8), stride=1, p=p, groups=groups))
         self.prune_eval_columns = True      # inference: only the output column the bilinear resize reads (see _pruned_last)
         self._alt = {}                      # input width -> (pruned ConvCfg, its PackedWeight)
+        self.mid_mark = None                # set by the generator while a gradient-exchange hook is active (G._mark)
 
     def _pruned_last(self, W):
         """Eval only.  The bilinear resize to width 1 (layers.py:197) reads exactly the CENTRE output column of the last
@@ -182,7 +183,14 @@ class AudioEncoder(nn.Module):
             last = self._pruned_last(W)
             if last is not None:
                 blocks[-1] = last
-        x = ops.conv_chain(blocks, x, self.training, last="f32")
+        mark = self.mid_mark
+        if mark is not None and self.training and torch.is_grad_enabled():
+            # data-parallel training: the four late blocks hold 93 % of the encoder's weights; a hook on the activation
+            # between the halves lets their gradients travel while the early (large-map) blocks still run backward
+            x = mark(ops.conv_chain(blocks[:4], x, True, last="f32"))
+            x = ops.conv_chain(blocks[4:], x, True, last="f32")
+        else:
+            x = ops.conv_chain(blocks, x, self.training, last="f32")
         return ops.bilinear_to_T(x, time_steps)
 
 

@@ -26,7 +26,7 @@ import torch.distributed as dist
 from . import _lib, ops
 from ._lib import MixStageError, call, dt_code, ptr, stream
 
-_DP_DEBUG = _os.environ.get("MS_DP_DEBUG", "")     # timing experiments: "skip_acc", "skip_small" (results are then wrong)
+_DP_DEBUG = _os.environ.get("MS_DP_DEBUG", "")     # timing experiments: "skip_acc", "skip_small" (results are then wrong), "serial_tail"
 ALIGN = 4       # parameter offsets in elements: 16-byte aligned for fp32, 32-byte for fp64
 
 
@@ -186,7 +186,7 @@ class TrainStep:
         self.comm = torch.cuda.Stream(device=dev) if (self.overlap and dev.type == "cuda") else None
         # the chain launches are persistent and would hold every SM: leave a few to the NCCL kernels of the overlapped
         # exchange (set NCCL_MAX_CTAS accordingly before the process group is created; bench.py does)
-        self.comm_sms = int(comm_sms)
+        self.comm_sms = int(_os.environ.get("MS_COMM_SMS", comm_sms))
         if side_sms is None:
             side_sms = int(_os.environ.get("MS_SIDE_SMS", "0"))
         free = max(self.comm_sms if (self.comm is not None and self._world() > 1) else 0, int(side_sms))
@@ -305,8 +305,17 @@ class TrainStep:
         if self._world() > 1 and self.wacc[kind].touched:
             # tensor-core mode: exchange the fp32 accumulators (+ the few gradients that live only in the flat buffer), THEN
             # convert everything into the flat buffer with the whole machine
-            self._exchange_acc_finish(kind, overlap)
-            self._flush_wgrads(kind)
+            # The tail after backward: the accumulators already reduced from hooks are converted while the last bucket is
+            # still travelling, that bucket's accumulators right after it, and the gathered small gradients (disjoint
+            # elements of the flat buffer) travel beside both conversion launches.
+            late, late_works = self._exchange_acc_finish(kind, overlap)
+            if late_works:
+                self._flush_wgrads(kind, None, ("early",) + self._step_key, exclude=late)
+                for w in late_works:
+                    w.wait()
+            self._flush_wgrads(kind, None, ("late",) + self._step_key if late_works else "all")
+            if self.comm is not None:
+                torch.cuda.current_stream().wait_stream(self.comm)
         elif overlap:
             self._finish_overlapped()
             self._flush_wgrads(kind, None, "tail")      # nothing left unless a gap-free layout skipped the "rest" bucket
@@ -425,7 +434,9 @@ class TrainStep:
         if ctxm is not None:
             ctxm.__enter__()
         try:
+            acc_works, self._works = self._works, []
             self._reduce_tensors(wacc.ranges(rest))
+            late_works, self._works = self._works, []
             if idx.numel() and "skip_small" not in _DP_DEBUG:
                 small = f.g.index_select(0, idx)
                 if self.exchange_fp32 and small.dtype == torch.float64:
@@ -438,11 +449,21 @@ class TrainStep:
         finally:
             if ctxm is not None:
                 ctxm.__exit__(None, None, None)
-        for w in self._works:
+        # the compute stream continues as soon as the buckets sent from hooks have arrived; the caller waits for the last
+        # bucket between its two conversion launches and joins the communication stream (small gradients) after them
+        for w in acc_works:
             w.wait()
-        if self.comm is not None:
+        if self.comm is not None and "serial_tail" in _DP_DEBUG:
+            for w in late_works:
+                w.wait()
             torch.cuda.current_stream().wait_stream(self.comm)
-        self._works = []
+            return set(), []
+        if not acc_works or not late_works:
+            # nothing was sent early (learning pass, no overlap) or nothing is left: one conversion launch
+            for w in late_works:
+                w.wait()
+            return set(), []
+        return {wacc.slots[k].data_ptr() for k in rest}, late_works
 
     def _on_ready(self, stage):
         wacc = self.wacc[self._step_key[0]]
@@ -546,15 +567,18 @@ class TrainStep:
         if launch:
             call("ms_pack_igemm_weight_multi", ptr(cur[1]), cur[2], 0, stream())
 
-    def _flush_wgrads(self, kind, tops=None, tag="all"):
+    def _flush_wgrads(self, kind, tops=None, tag="all", exclude=None):
         """Weight-gradient accumulators of this step -> the flat gradient buffers, one launch.  tops: only the accumulators
         of these top-level sub-modules (the overlapped exchange converts a bucket's accumulators right before it reduces
-        the bucket); None: everything not converted yet in this step."""
+        the bucket); None: everything not converted yet in this step.  exclude: accumulator addresses to leave for a later
+        call (their all-reduce is still in flight)."""
         f = self.fG if kind == "G" else self.fD
         base, isz = f.g.data_ptr(), f.g.element_size()
         ents = []
         for key, e in self.wacc[kind].entries.items():
             if key in self._flushed:
+                continue
+            if exclude is not None and key[0] in exclude:
                 continue
             if tops is not None:
                 off = (e[1] - base) // isz

@@ -175,7 +175,8 @@ typedef struct ms_pack_entry {
   int32_t pdt, Cout, Cin_g, taps_total, groups, mode, num_classes, class_n, ntaps, kpad;
   int16_t srctap[MS_IGEMM_MAX_TAPS];
 } ms_pack_entry;
-/* blocks: CTAs of the launch (<= 0: 8 per SM); work units are spread over the entries in proportion to their size. */
+/* blocks: CTAs of the launch (<= 0: 8 per SM); work units are spread over the entries in proportion to their size.
+ * wp / wp_lo are 16-byte aligned (a thread converts eight adjacent k positions and stores them at once). */
 int ms_pack_igemm_weight_multi(const ms_pack_entry* table_dev, int n_entries, int blocks, void* stream);
 
 /* Weight gradient on tcgen05 (aten::convolution_backward, weight grad): with d the FORWARD descriptor,
@@ -418,6 +419,13 @@ int ms_grad_sqnorm(const void* g, int dt, int64_t n, double* acc, int64_t* step,
 int ms_clip_adam(void* p, const void* g, void* m, void* v, int dt, int64_t n, const double* sqnorm, const int64_t* step,
                  double lr, double beta1, double beta2, double eps, double max_norm, const double* lr_dev, void* stream);
 /* lr_dev (nullable, device double): overrides lr, so a captured CUDA graph follows a learning-rate schedule. */
+/* The same update, 4 elements per thread, with the moments m / v stored as state_dt (MS_F32 or dt) while p / g are dt:
+ * fp64 master parameters with fp32 moments move 40 instead of 56 bytes per element.  Arithmetic in fp64 as above.
+ * All four buffers 32-byte aligned.  (torch.optim.Adam keeps its state in the parameter dtype, trainer.py:262-287: with
+ * state_dt == dt this is that update.) */
+int ms_clip_adam_mixed(void* p, const void* g, void* m, void* v, int dt, int state_dt, int64_t n, const double* sqnorm,
+                       const int64_t* step, double lr, double beta1, double beta2, double eps, double max_norm,
+                       const double* lr_dev, void* stream);
 
 /* ---- the step before the hot path: pose preprocessing on the device, fp64 like the reference.
  * Replaces, per batch, trainer.py:1290-1308 = KMeans.predict(RemoveJoints(pose)) (src/data/transform.py:352-410, 463-510)

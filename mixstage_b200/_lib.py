@@ -149,6 +149,7 @@ PROTOTYPES = {
     "ms_scalar_finish": [_P, _D, _P, _P],
     "ms_grad_sqnorm": [_P, _I, _L, _P, _P, _P],
     "ms_clip_adam": [_P, _P, _P, _P, _I, _L, _P, _P, _D, _D, _D, _D, _D, _P, _P],
+    "ms_clip_adam_mixed": [_P, _P, _P, _P, _I, _I, _L, _P, _P, _D, _D, _D, _D, _D, _P, _P],
     "ms_pose_prepare": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _S32, _I, _D, _P, _P, _P, _P],
     "ms_inv_znorm": [_P, _P, _P, _L, _I, _P, _P],
     "ms_pose_metrics": [_P, _P, _P, _P, _P, _I, _I, _I, ctypes.POINTER(ctypes.c_double), _I, _P, _P, _P],

@@ -1171,39 +1171,60 @@ __global__ void __launch_bounds__(256) pack_igemm_weight_multi_kernel(const ms_p
     while (ei < n_entries && local >= s_units[ei]) { local -= s_units[ei]; ei++; }
     const ms_pack_entry& e = table[ei];
     const int nu = s_units[ei];
-    const long long pairs = ((long long)e.num_classes * e.class_n * e.ntaps * e.kpad) >> 1;     // kpad is a multiple of 64
-    const long long p0 = pairs * local / nu, p1 = pairs * (local + 1) / nu;
-    const int Cout_g = e.Cout / e.groups;
-    __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(e.wp);
-    __nv_bfloat16* wp_lo = reinterpret_cast<__nv_bfloat16*>(e.wp_lo);
-    // 32-bit index arithmetic (a packed weight has far fewer than 2^31 elements: the largest here is 2 M): the 64-bit
-    // divisions of the first version cost more than the loads
-    const unsigned kpad = (unsigned)e.kpad, ntaps = (unsigned)e.ntaps, class_n = (unsigned)e.class_n;
-    for (long long pi = p0 + tid; pi < p1; pi += blockDim.x) {
-      const unsigned iu = (unsigned)(pi << 1);
-      const long long i = (long long)iu;
-      const unsigned t2 = iu / kpad;
-      const int kc = (int)(iu - t2 * kpad);
+    // Eight adjacent k positions per thread: one index decomposition, eight strided loads, one 16-byte store per plane.
+    // The entry's fields are copied to registers first (the stores go through pointers read from the table, so the
+    // compiler would otherwise re-read every field after every store); 32-bit index arithmetic (a packed weight has far
+    // fewer than 2^31 elements).
+    const int Cout = e.Cout, Cin_g = e.Cin_g, taps_total = e.taps_total, mode = e.mode, pdt = e.pdt;
+    const int Cout_g = Cout / e.groups, grouped = e.groups > 1;
+    const unsigned kpad8 = (unsigned)e.kpad >> 3, ntaps = (unsigned)e.ntaps, class_n = (unsigned)e.class_n;      // kpad % 64 == 0
+    const long long octs = ((long long)e.num_classes * e.class_n * e.ntaps * e.kpad) >> 3;
+    const long long q0 = octs * local / nu, q1 = octs * (local + 1) / nu;
+    const void* __restrict__ w = e.w;
+    uint4* __restrict__ wp = reinterpret_cast<uint4*>(e.wp);
+    uint4* __restrict__ wp_lo = reinterpret_cast<uint4*>(e.wp_lo);
+    const short* __restrict__ srctap = e.srctap;
+    if (((uintptr_t)wp | (uintptr_t)wp_lo) & 15) __trap();          // 16-byte stores
+    for (long long qi = q0 + tid; qi < q1; qi += blockDim.x) {
+      const unsigned qu = (unsigned)qi;
+      const unsigned t2 = qu / kpad8;
+      const int kc = (int)(qu - t2 * kpad8) << 3;
       const unsigned rowu = t2 / ntaps;
       const int t = (int)(t2 - rowu * ntaps);
-      const long long row = (long long)rowu;
-      const int cls = (int)(rowu / class_n), r = (int)(rowu - (unsigned)cls * class_n);
-      float v[2] = {0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        const int k = kc + j;
-        if (e.mode == 0) {
-          if (row < e.Cout && k < e.Cin_g) v[j] = ms_ldp(e.w, e.pdt, (row * e.Cin_g + k) * e.taps_total + e.srctap[t]);
-        } else {
-          const int g = e.groups > 1 ? cls : 0;
-          if (k < Cout_g && r < e.Cin_g)
-            v[j] = ms_ldp(e.w, e.pdt, ((long long)(g * Cout_g + k) * e.Cin_g + r) * e.taps_total + e.srctap[cls * e.ntaps + t]);
+      long long base = 0, stride = 0;
+      int nvalid = 0;
+      if (mode == 0) {
+        if ((int)rowu < Cout && kc < Cin_g) {
+          base = ((long long)rowu * Cin_g + kc) * taps_total + __ldg(&srctap[t]);
+          stride = taps_total;
+          nvalid = min(8, Cin_g - kc);
+        }
+      } else {
+        const int cls = (int)(rowu / class_n), r = (int)(rowu - (unsigned)cls * class_n);
+        if (kc < Cout_g && r < Cin_g) {
+          base = ((long long)((grouped ? cls : 0) * Cout_g + kc) * Cin_g + r) * taps_total + __ldg(&srctap[cls * (int)ntaps + t]);
+          stride = (long long)Cin_g * taps_total;
+          nvalid = min(8, Cout_g - kc);
         }
       }
-      const __nv_bfloat162 h = __floats2bfloat162_rn(v[0], v[1]);
-      *reinterpret_cast<__nv_bfloat162*>(wp + i) = h;
-      if (wp_lo)
-        *reinterpret_cast<__nv_bfloat162*>(wp_lo + i) = __floats2bfloat162_rn(v[0] - __bfloat162float(h.x), v[1] - __bfloat162float(h.y));
+      float v[8];
+      if (pdt == MS_F64) {
+        const double* __restrict__ wd = reinterpret_cast<const double*>(w) + base;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = j < nvalid ? (float)__ldg(wd + j * stride) : 0.f;
+      } else {
+        const float* __restrict__ wf = reinterpret_cast<const float*>(w) + base;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = j < nvalid ? __ldg(wf + j * stride) : 0.f;
+      }
+      __nv_bfloat162 h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        l[j] = __floats2bfloat162_rn(v[2 * j] - __bfloat162float(h[j].x), v[2 * j + 1] - __bfloat162float(h[j].y));
+      }
+      wp[qi] = *reinterpret_cast<const uint4*>(h);
+      if (wp_lo) wp_lo[qi] = *reinterpret_cast<const uint4*>(l);
     }
   }
 }

@@ -1394,11 +1394,29 @@ __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const ms_wgrad_
         for (int i = 4 * t; i < nr * row_in; i += 4 * blockDim.x) *reinterpret_cast<float4*>(s_row + i) = *reinterpret_cast<const float4*>(src + i);
         __syncthreads();
         const long long ob = (long long)ob0 * row_out;
-        for (int i = t; i < nr * row_out; i += blockDim.x) {
-          const int rr = i / row_out, j = i - rr * row_out;
-          const int c = j / e.taps, tap = j - c * e.taps;
-          const double v = (double)s_row[rr * row_in + tap * e.kpad + c];
-          ms_stp(e.dw, e.pdt, ob + i, v + (e.accumulate ? ms_ldp_d(e.dw, e.pdt, ob + i) : 0.0));
+        if (e.pdt == MS_F64 && !e.accumulate && !(row_out & 1) && !((uintptr_t)e.dw & 15)) {
+          // store-only fp64 sink: two adjacent (channel, tap) positions per thread and 16-byte stores, the channel index
+          // and the row by multiplies (i < 2^14, row_out < 2^13, taps <= 64: exact)
+          const unsigned inv = (unsigned)((0x100000000ULL + (unsigned)e.taps - 1) / (unsigned)e.taps);
+          const unsigned inv_ro = (unsigned)((0x100000000ULL + (unsigned)row_out - 1) / (unsigned)row_out);
+          double* __restrict__ dw = reinterpret_cast<double*>(e.dw) + ob;
+          for (int i = 2 * t; i < nr * row_out; i += 2 * blockDim.x) {      // i, row_out even: a pair never straddles two rows
+            const int rr = (int)__umulhi((unsigned)i, inv_ro);
+            const int j = i - rr * row_out;
+            const float* sr = s_row + rr * row_in;
+            const int c0 = e.taps == 1 ? j : (int)__umulhi((unsigned)j, inv);      // (taps == 1: the multiplier would be 2^32)
+            const int tap0 = j - c0 * e.taps;
+            int c1 = c0, tap1 = tap0 + 1;
+            if (tap1 == e.taps) { tap1 = 0; c1++; }
+            *reinterpret_cast<double2*>(dw + i) = make_double2((double)sr[tap0 * e.kpad + c0], (double)sr[tap1 * e.kpad + c1]);
+          }
+        } else {
+          for (int i = t; i < nr * row_out; i += blockDim.x) {
+            const int rr = i / row_out, j = i - rr * row_out;
+            const int c = j / e.taps, tap = j - c * e.taps;
+            const double v = (double)s_row[rr * row_in + tap * e.kpad + c];
+            ms_stp(e.dw, e.pdt, ob + i, v + (e.accumulate ? ms_ldp_d(e.dw, e.pdt, ob + i) : 0.0));
+          }
         }
       }
     } else {

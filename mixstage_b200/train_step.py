@@ -33,8 +33,9 @@ ALIGN = 4       # parameter offsets in elements: 16-byte aligned for fp32, 32-by
 class FlatState:
     """Flat parameter / gradient / Adam-moment buffers of one sub-network."""
 
-    def __init__(self, module, skip=()):
-        """skip: name prefixes of parameters that no forward of `module` ever touches (parameter holders kept for
+    def __init__(self, module, skip=(), moment_dtype=None):
+        """moment_dtype: storage type of Adam's m / v (None: the parameter dtype, as torch.optim.Adam keeps them).
+        skip: name prefixes of parameters that no forward of `module` ever touches (parameter holders kept for
         state_dict compatibility).  Their gradient is identically zero, so Adam never moves them (m = v = 0 gives a zero
         update): leaving them out of the flat buffers changes nothing but the bytes zeroed, normed, all-reduced and
         stepped over."""
@@ -65,8 +66,11 @@ class FlatState:
             if e0 != beg and top in self.segments:
                 raise ValueError("parameters of %s are not contiguous in registration order" % top)
             self.segments[top] = (b0, end)
-        mk = lambda: torch.zeros(self.numel, dtype=self.dtype, device=self.device)       # noqa: E731
-        self.p, self.g, self.m, self.v = mk(), mk(), mk(), mk()
+        mk = lambda dt=self.dtype: torch.zeros(self.numel, dtype=dt, device=self.device)       # noqa: E731
+        self.moment_dtype = moment_dtype or self.dtype
+        if self.moment_dtype not in (torch.float32, self.dtype):
+            raise MixStageError("Adam moments are stored in fp32 or in the parameter dtype")
+        self.p, self.g, self.m, self.v = mk(), mk(), mk(self.moment_dtype), mk(self.moment_dtype)
         for p, o in zip(self.params, self.offsets):
             n = p.numel()
             self.p[o:o + n].copy_(p.data.reshape(-1))
@@ -121,8 +125,9 @@ class FlatState:
         st = stream()
         dt = dt_code(self.dtype)
         call("ms_grad_sqnorm", ptr(self.g), dt, self.numel, ptr(self.sqnorm), ptr(self.step_count), st)
-        call("ms_clip_adam", ptr(self.p), ptr(self.g), ptr(self.m), ptr(self.v), dt, self.numel, ptr(self.sqnorm),
-             ptr(self.step_count), float(lr), float(betas[0]), float(betas[1]), float(eps), float(max_norm), ptr(lr_dev), st)
+        call("ms_clip_adam_mixed", ptr(self.p), ptr(self.g), ptr(self.m), ptr(self.v), dt, dt_code(self.moment_dtype), self.numel,
+             ptr(self.sqnorm), ptr(self.step_count), float(lr), float(betas[0]), float(betas[1]), float(eps), float(max_norm),
+             ptr(lr_dev), st)
 
 
 class TrainStep:
@@ -134,7 +139,8 @@ class TrainStep:
 
     def __init__(self, gan, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, use_graphs=True, group=None,
                  input_modalities=("audio/log_mel_400",), description="train", overlap_allreduce=True,
-                 exchange_dtype="fp32", rng_seed=None, check_agreement=False, comm_sms=16, side_sms=None):
+                 exchange_dtype="fp32", rng_seed=None, check_agreement=False, comm_sms=16, side_sms=None,
+                 moment_dtype="fp32"):
         """One TrainStep (and one CUDA device) per process: the scratch arena, the direct-gradient switch and the
         side stream are module-level state of mixstage_b200.ops, and the kernels' lazily set function attributes are
         per process.
@@ -143,6 +149,9 @@ class TrainStep:
         launched from backward hooks on a communication stream (decoder + logits + classifier first, ... audio encoder
         last) while backward is still running, as fp32 ("fp32", default: half the bytes of the fp64 master gradients)
         or in the master dtype ("native").
+        moment_dtype: storage of Adam's m / v: "fp32" (default: 40 instead of 56 bytes per fp64 parameter and step; the
+        update itself is computed in fp64 from them, relative rounding 6e-8 per step) or "native" (the parameter dtype, as
+        torch.optim.Adam keeps them in the reference, trainer.py:262-287).
         comm_sms: SMs left free beside the chain launches for the NCCL kernels of the overlapped exchange (multi-rank only).
         side_sms: SMs left free beside the chain launches for the side stream's weight-gradient launches (default: the
         MS_SIDE_SMS environment variable, else 0).
@@ -152,8 +161,11 @@ class TrainStep:
         choose the same (kind, branch) graphs whatever else consumes the global generator.
         check_agreement: debug aid, all-gathers (kind, branch) every step and raises on disagreement (host sync)."""
         self.gan, self.G, self.D = gan, gan.G, gan.D
-        self.fG = FlatState(self.G, skip=getattr(self.G, "UNUSED_PARAMETER_PREFIXES", ()))
-        self.fD = FlatState(self.D)
+        if moment_dtype not in ("fp32", "native"):
+            raise MixStageError("moment_dtype must be 'fp32' or 'native'")
+        mdt = torch.float32 if moment_dtype == "fp32" else None
+        self.fG = FlatState(self.G, skip=getattr(self.G, "UNUSED_PARAMETER_PREFIXES", ()), moment_dtype=mdt)
+        self.fD = FlatState(self.D, moment_dtype=mdt)
         self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
         dev = self.fG.device
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float64, device=dev)

@@ -674,6 +674,22 @@ def ms_clip_adam(p, g, m, v, dt, n, sqnorm, step, lr, b1, b2, eps, max_norm, lr_
     P.copy_((P.double() - lr / (1 - b1 ** t) * md / denom).to(P.dtype))
 
 
+def ms_clip_adam_mixed(p, g, m, v, dt, sdt, n, sqnorm, step, lr, b1, b2, eps, max_norm, lr_dev, st):
+    if lr_dev:
+        lr = float(f64(lr_dev, 1)[0])
+    P, G = param(p, n, dt), param(g, n, dt)
+    M, V = param(m, n, sdt), param(v, n, sdt)
+    total = float(f64(sqnorm, 1)[0]) ** 0.5
+    coef = min(1.0, max_norm / (total + 1e-6)) if max_norm > 0 else 1.0
+    t = int(i64(step, 1)[0])
+    gd = G.double() * coef
+    md = b1 * M.double() + (1 - b1) * gd
+    vd = b2 * V.double() + (1 - b2) * gd * gd
+    denom = vd.sqrt() / (1 - b2 ** t) ** 0.5 + eps
+    M.copy_(md.to(M.dtype))
+    V.copy_(vd.to(V.dtype))
+    P.copy_((P.double() - lr / (1 - b1 ** t) * md / denom).to(P.dtype))
+
 
 # ---- the rows either side of the hot path (csrc/preprocess.cu)
 def _i32(p, n):

@@ -314,3 +314,80 @@ def test_small_ops():
     src = torch.randn(1000, dtype=torch.float64)
     (og,), (oc,) = run_both("ms_cast", [(src, "in"), 1, (torch.zeros(1000), "out"), 0, 1000])
     assert torch.equal(og, oc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,sdt", [(1, 1), (1, 0), (0, 0)])
+def test_clip_adam_mixed(dt, sdt):
+    """The vectorised update (optionally fp32 moments beside fp64 parameters) against the host specification and, with
+    native moments, against the scalar entry point; a length that leaves a tail after the 4-wide body."""
+    torch.manual_seed(5)
+    n = 4 * 50_000 + 3
+    T = torch.float64 if dt == 1 else torch.float32
+    S = torch.float64 if sdt == 1 else torch.float32
+    p, g = torch.randn(n, dtype=T), torch.randn(n, dtype=T) * 1e-2
+    m, v = (torch.randn(n, dtype=torch.float64) * 1e-3).to(S), (torch.rand(n, dtype=torch.float64) * 1e-5).to(S)
+    sq = (g.double() ** 2).sum().reshape(1)
+    step = torch.tensor([3], dtype=torch.int64)
+    lr = torch.tensor([2e-4], dtype=torch.float64)
+    args = [(p, "inout"), (g, "in"), (m, "inout"), (v, "inout"), dt, sdt, n, (sq, "in"), (step, "in"), 1e-4, 0.9, 0.999, 1e-8, 1.0,
+            (lr, "in")]
+    gpu, cpu = run_both("ms_clip_adam_mixed", args)
+    tol = 1e-12 if dt == 1 else 1e-6
+    close(gpu[0], cpu[0], tol)
+    close(gpu[1], cpu[1], 1e-12 if sdt == 1 else 1e-6)
+    close(gpu[2], cpu[2], 1e-12 if sdt == 1 else 1e-6)
+    assert float((gpu[0] - p).abs().max()) > 1e-5            # it moved
+    if dt == sdt:
+        old, _ = run_both("ms_clip_adam", [(p, "inout"), (g, "in"), (m, "inout"), (v, "inout"), dt, n, (sq, "in"), (step, "in"), 1e-4, 0.9,
+                                           0.999, 1e-8, 1.0, (lr, "in")])
+        for a, b in zip(gpu, old):
+            close(a, b, 1e-14 if dt == 1 else 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [0, 1])
+def test_grad_sqnorm(dt):
+    """Fixed-order sum of squares (4 elements per thread + tail) and the step counter it advances; two launches agree bit
+    for bit (the data-parallel replicas rely on that)."""
+    torch.manual_seed(6)
+    n = 4 * 300_000 + 1
+    g = torch.randn(n, dtype=torch.float64 if dt == 1 else torch.float32)
+    args = [(g, "in"), dt, n, (torch.zeros(1, dtype=torch.float64), "out"), (torch.tensor([4], dtype=torch.int64), "inout")]
+    gpu, cpu = run_both("ms_grad_sqnorm", args)
+    close(gpu[0], cpu[0], 1e-12)
+    assert int(gpu[1]) == 5 and int(cpu[1]) == 5
+    gpu2, _ = run_both("ms_grad_sqnorm", args)
+    assert torch.equal(gpu[0], gpu2[0])
+
+
+@pytest.mark.gpu
+def test_unpack_wgrad_multi_layouts():
+    """The conversion launch on a table that mixes every store path: fp64 store-only sinks with an even row (the 16-byte
+    path; taps 1, 3, 16, 24), an odd row (scalar path), an accumulating sink, an fp32 sink, and a row too long for shared
+    memory."""
+    import ctypes
+    torch.manual_seed(8)
+    #        Cout Cin_g taps kpad pdt acc
+    cases = [(256, 256, 3, 256, 1, 0), (64, 64, 16, 64, 1, 0), (256, 256, 24, 256, 1, 0), (96, 256, 1, 256, 1, 0),
+             (40, 33, 3, 64, 1, 0), (64, 64, 3, 64, 1, 1), (128, 128, 3, 128, 0, 0), (32, 266, 3, 320, 1, 0), (8, 512, 24, 512, 1, 0)]
+    accs = [torch.randn(co * t * kp) for co, ci, t, kp, _, _ in cases]
+    sinks = [torch.randn(co * ci * t, dtype=torch.float64 if pdt == 1 else torch.float32) for co, ci, t, _, pdt, _ in cases]
+    outs = []
+    for dev in ("cuda", "cpu"):
+        a_ = [a.to(dev).contiguous() for a in accs]
+        s_ = [s.clone().to(dev).contiguous() for s in sinks]
+        arr = (_lib.WgradEntry * len(cases))()
+        for i, (co, ci, t, kp, pdt, ac) in enumerate(cases):
+            arr[i].acc, arr[i].dw = a_[i].data_ptr(), s_[i].data_ptr()
+            arr[i].pdt, arr[i].Cout, arr[i].Cin_g, arr[i].taps, arr[i].kpad, arr[i].accumulate = pdt, co, ci, t, kp, ac
+        tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        if dev == "cuda":
+            tab = tab.cuda()
+            _lib.call("ms_unpack_wgrad_multi", ptr(tab), len(cases), 0, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        else:
+            cpu_emu.ms_unpack_wgrad_multi(tab.data_ptr(), len(cases), 0, None)
+        outs.append([s.cpu() for s in s_])
+    for i, (g, c) in enumerate(zip(*outs)):
+        assert torch.equal(g, c), cases[i]

@@ -103,6 +103,13 @@ def main():
     us = timed(lambda: call("ms_clip_adam", ptr(p), ptr(gr), ptr(m), ptr(v), 1, npar, ptr(sq), ptr(stepc), 1e-4, 0.9, 0.999, 1e-8, 1.0,
                             ptr(lr), st()))
     report("clip_adam (fp64 p, g, m, v)", us, npar * 56)
+    us = timed(lambda: call("ms_clip_adam_mixed", ptr(p), ptr(gr), ptr(m), ptr(v), 1, 1, npar, ptr(sq), ptr(stepc), 1e-4, 0.9, 0.999,
+                            1e-8, 1.0, ptr(lr), st()))
+    report("clip_adam_mixed (fp64 p, g, m, v; 4 per thread)", us, npar * 56)
+    m32, v32 = m.float(), v.float()
+    us = timed(lambda: call("ms_clip_adam_mixed", ptr(p), ptr(gr), ptr(m32), ptr(v32), 1, 0, npar, ptr(sq), ptr(stepc), 1e-4, 0.9,
+                            0.999, 1e-8, 1.0, ptr(lr), st()))
+    report("clip_adam_mixed (fp64 p, g; fp32 m, v)", us, npar * 40)
 
 
 if __name__ == "__main__":

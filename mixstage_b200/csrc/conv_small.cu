@@ -267,6 +267,85 @@ __global__ void wgrad_cin1_rows(P p, const float* __restrict__ x, const float* _
   atomicAdd(dwf + (size_t)tap * p.Cout + n, acc);
 }
 
+// ---- C_in = 1, 3x3, stride 1, pad 1, 64 output channels (audio_encoder.conv.0): dW[tap][n] = sum over pixels of
+// x[pixel + tap] * dz[pixel][n].  A "stream" of 16 threads walks 16-pixel segments of output rows; thread cg of a stream
+// owns four channels: per pixel ONE 16-byte load of dz (the 16 threads read the pixel's 256 contiguous bytes), three
+// broadcast loads of the input column entering the sliding 3x3 window, 36 FMAs into register accumulators.  dz is read
+// once (the row-wise kernel above reads it once per tap and spends ~10 instructions per FMA: 49 us at batch 16, 350 us at
+// batch 128 -- on the critical path at the very end of backward).  Streams are combined in shared memory: 576 atomics
+// per CTA.
+constexpr int CIN1_SEG = 16;
+__global__ void __launch_bounds__(256) wgrad_cin1_k3c64(int B, int H, int W, const float* __restrict__ x,
+                                                        const float* __restrict__ dy, float* __restrict__ dwf) {
+  __shared__ float s_part[8][16][36];
+  const int cg = threadIdx.x & 15, stream = threadIdx.x >> 4;
+  const int segs = (W + CIN1_SEG - 1) / CIN1_SEG;
+  const long long units = (long long)B * H * segs;
+  float acc[9][4];
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[t][j] = 0.f;
+  for (long long u = (long long)blockIdx.x * 16 + stream; u < units; u += (long long)gridDim.x * 16) {
+    const int row = (int)(u / segs), seg = (int)(u - (long long)row * segs);
+    const int h = row % H;
+    const int w0 = seg * CIN1_SEG, w1 = min(W, w0 + CIN1_SEG);
+    const float* xr = x + (size_t)row * W;                      // input row h of image b (C_in = 1: (B, H, W))
+    const bool up = h > 0, dn = h + 1 < H;
+    const float* dr = dy + ((size_t)row * W) * 64 + 4 * cg;
+    float xw[3][3];                                             // [input row h-1..h+1][column w-1..w+1]
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const bool okr = r == 1 || (r == 0 ? up : dn);
+      const float* xp = xr + (r - 1) * W;
+      xw[r][1] = (okr && w0 > 0) ? __ldg(xp + w0 - 1) : 0.f;
+      xw[r][2] = okr ? __ldg(xp + w0) : 0.f;
+    }
+#pragma unroll 4
+    for (int w = w0; w < w1; w++) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dr + (size_t)w * 64));
+      const bool okc = w + 1 < W;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const bool okr = r == 1 || (r == 0 ? up : dn);
+        xw[r][0] = xw[r][1];
+        xw[r][1] = xw[r][2];
+        xw[r][2] = (okr && okc) ? __ldg(xr + (r - 1) * W + w + 1) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float xv = xw[r][c];
+          acc[r * 3 + c][0] = fmaf(xv, d.x, acc[r * 3 + c][0]);
+          acc[r * 3 + c][1] = fmaf(xv, d.y, acc[r * 3 + c][1]);
+          acc[r * 3 + c][2] = fmaf(xv, d.z, acc[r * 3 + c][2]);
+          acc[r * 3 + c][3] = fmaf(xv, d.w, acc[r * 3 + c][3]);
+        }
+    }
+  }
+  // the two streams of a warp, then the eight warps
+#pragma unroll
+  for (int t = 0; t < 9; t++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[t][j] += __shfl_xor_sync(0xffffffffu, acc[t][j], 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 16) {
+#pragma unroll
+    for (int t = 0; t < 9; t++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) s_part[warp][lane][t * 4 + j] = acc[t][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+    const int t = i >> 6, n = i & 63;
+    float v = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) v += s_part[wv][n >> 2][t * 4 + (n & 3)];
+    atomicAdd(dwf + (size_t)t * 64 + n, v);
+  }
+}
+
 P make(const ms_conv_desc* d) {
   P p;
   p.B = d->B; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.Cout = d->Cout;
@@ -391,11 +470,19 @@ __global__ void __launch_bounds__(256) fwd_small_n_k1c256(int M, int Cout, const
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  // the 256 x N weights reach the registers through shared memory: one coalesced pass per CTA (every lane fetching its own
+  // 64 values from global memory cost 32 sectors per load instruction -- 67 us at 8192 pixels, one pixel per warp)
+  __shared__ __align__(16) float s_w[32 * (8 * N + 4)];
+  for (int i = threadIdx.x; i < 256 * N; i += blockDim.x) {
+    const int c = i / N, n = i - c * N;
+    s_w[(c >> 3) * (8 * N + 4) + (c & 7) * N + n] = n < Cout ? __ldg(wf + (size_t)c * Cout + n) : 0.f;
+  }
+  __syncthreads();
   float wreg[8][N];
 #pragma unroll
   for (int c = 0; c < 8; c++)
 #pragma unroll
-    for (int n = 0; n < N; n++) wreg[c][n] = n < Cout ? __ldg(wf + (size_t)(lane * 8 + c) * Cout + n) : 0.f;
+    for (int n = 0; n < N; n++) wreg[c][n] = s_w[lane * (8 * N + 4) + c * N + n];
   for (int pos = warp; pos < M; pos += nwarps) {
     const float4* xp = reinterpret_cast<const float4*>(x + (size_t)pos * 256 + lane * 8);
     const float4 u = __ldg(xp), v = __ldg(xp + 1);
@@ -456,7 +543,10 @@ int ms_small_conv_fwd(const float* x, const float* wf, const float* bias, float*
   }
   if (d->Cout <= 8 && d->Cin == 256 && p.taps == 1 && d->sh == 1 && d->sw == 1 && d->ph == 0 && d->pw == 0 &&
       ((uintptr_t)x & 15) == 0) {
-    fwd_small_n_k1c256<8><<<blocks_for((long long)M * 32, 256), 256, 0, st>>>(M, d->Cout, x, wf, bias, y, act, slope);
+    // >= 4 pixels per warp: the weight staging is paid once per CTA
+    int blocks = (M + 31) / 32;
+    if (blocks > ms_num_sms() * 4) blocks = ms_num_sms() * 4;
+    fwd_small_n_k1c256<8><<<blocks, 256, 0, st>>>(M, d->Cout, x, wf, bias, y, act, slope);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   if (d->Cout <= NMAX) {
@@ -509,6 +599,14 @@ int ms_small_conv_wgrad(const float* x, const float* dy, float* dwf, const ms_co
   const int M = d->B * d->Ho * d->Wo;
   if (d->Cin == 1 && p.taps * d->Cout <= 1024) {
     if (cudaMemsetAsync(dwf, 0, sizeof(float) * (size_t)p.taps * d->Cout, st) != cudaSuccess) return -1;
+    if (d->kh == 3 && d->kw == 3 && d->sh == 1 && d->sw == 1 && d->ph == 1 && d->pw == 1 && d->Cout == 64 &&
+        !(((uintptr_t)dy) & 15)) {
+      const long long units = (long long)d->B * d->H * ((d->W + CIN1_SEG - 1) / CIN1_SEG);
+      long long blocks = (units + 15) / 16;
+      if (blocks > (long long)ms_num_sms() * 6) blocks = (long long)ms_num_sms() * 6;
+      wgrad_cin1_k3c64<<<(unsigned)blocks, 256, 0, st>>>(d->B, d->H, d->W, x, dy, dwf);
+      return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     const int rows_total = d->B * d->Ho;
     int chunks = rows_total;
     if (chunks > ms_num_sms() * 8) chunks = ms_num_sms() * 8;

@@ -69,6 +69,8 @@ CONVS += [
     (2, 1, 64, 96, 64, 1, 4, 1, 2, 0, 1, 1),        # D.conv1
     (3, 5, 7, 1, 16, 3, 3, 1, 1, 1, 1, 1),          # C_in=1 3x3 row kernel: odd width, short height, 2 channel groups
     (1, 1, 300, 256, 5, 1, 1, 1, 1, 0, 0, 1),       # 1x1 over 256 channels, N=5 (< 8), rows not a multiple of the grid
+    (3, 5, 37, 1, 64, 3, 3, 1, 1, 1, 1, 1),         # C_in=1 3x3, 64 channels (register-accumulator wgrad): ragged 16-pixel segments
+    (2, 1, 16, 1, 64, 3, 3, 1, 1, 1, 1, 1),         # the same with a single row (no row above or below)
 ]
 
 
@@ -131,7 +133,8 @@ def test_conv_cin1_bnact(c, fmt):
         assert float((rec - yg).abs().max()) <= 2 ** -15 * float(yc.abs().max()) + 1e-7
 
 
-@pytest.mark.parametrize("rows,C,L,up2", [(1024, 256, 64, 0), (64, 256, 2, 1), (32, 25, 1, 0), (2048, 2048, 64, 0), (8192, 64, 64, 0)])
+@pytest.mark.parametrize("rows,C,L,up2", [(1024, 256, 64, 0), (64, 256, 2, 1), (32, 25, 1, 0), (2048, 2048, 64, 0), (8192, 64, 64, 0),
+                                               (4100, 128, 4100, 0), (4097, 256, 4097, 0)])
 def test_batchnorm_chain(rows, C, L, up2):
     torch.manual_seed(1)
     x = torch.randn(rows, C) * 1.7 + 0.3

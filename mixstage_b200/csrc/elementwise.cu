@@ -1180,7 +1180,7 @@ extern "C" int ms_style_concat_bwd_f32(const float* dout, int64_t rows, int C, c
   if (!dout || (!idx && !soft) || rows < 1 || rep < 1 || rows % rep || S < 1 || sd < 1) return MS_EINVAL;
   if (idx && !soft && C % 128 == 0 && sd <= 32 && (C + sd) % 2 == 0 && !(((uintptr_t)dout) & 7) && !(((uintptr_t)dx) & 15) &&
       (size_t)S * sd * sizeof(float) <= 40 * 1024) {
-    int64_t blocks = ms_cdiv(rows, 8 * 8);
+    int64_t blocks = ms_cdiv(rows, 8 * 2);          // two rows per warp at least (eight left 16 CTAs for the 1024 rows of batch 16)
     const int64_t cap = (int64_t)ms_num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;

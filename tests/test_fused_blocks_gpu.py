@@ -268,6 +268,8 @@ def test_chain_equals_block_by_block(which, mode):
             worst = (k, e)
         # forward quantities agree to the order of the fp32 reductions (and, for the UNet, to the 16-bit skip planes the
         # chain adds instead of fp32 skips); gradients additionally see a few flipped LeakyReLU masks (see the test above)
-        tol = 2e-4 if (k == "y" or k.startswith("b:")) else 5e-3
+        # (which elements flip depends on the arrival order of the split-K reductions: 2e-3 .. 7e-3 from run to run on the
+        # UNet's BatchNorm bias gradients, sums of 1024 terms that cancel; the bound leaves a factor 3)
+        tol = 2e-4 if (k == "y" or k.startswith("b:")) else 2e-2
         assert e < tol, (which, mode, k, e)
     print({"case": "chain_vs_blocks", "which": which, "mode": mode, "worst": worst})

@@ -408,6 +408,17 @@ int ms_l1_bwd_f32(const float* sgn, const float* g, int64_t n, float* da, void* 
 int ms_l1_bwd_ab_f32(const float* a, const float* b, float c, const float* g, int64_t n, float* da, void* stream);
 /* out[0] = (float)(scale * in[0]) : turns a double accumulator into a loss scalar. */
 int ms_scalar_finish(const double* in, double scale, float* out, void* stream);
+/* The loss bookkeeping of one train step (trainer.py:1268-1285: `loss = sum(internal_losses)` after gan.py:113-135 scaled the
+ * terms by lambda_D / lambda_gan and jlcss.py:197-205 by lambda_id) in ONE launch instead of ~20 scalar casts, multiplies and
+ * adds: losses = HOST array of n (<= MS_LOSS_MAX_TERMS) device pointers to fp32 scalars, weights / lam_idx = host arrays;
+ *   w_i = weights[i] * (lam_idx[i] >= 0 ? lam_dev[lam_idx[i]] : 1);  report[i] = w_i * l_i (fp64, nullable);  total = sum_i.
+ * The host arrays are read at call time (by-value kernel parameters: safe under CUDA-graph capture); lam_dev is read by the
+ * kernel, so a replayed graph follows a lambda schedule.  ms_loss_combine_bwd: g[i] = w_i * gtotal[0]. */
+#define MS_LOSS_MAX_TERMS 8
+int ms_loss_combine(const float* const* losses, const double* weights, const int* lam_idx, int n, const double* lam_dev,
+                    float* total, double* report, void* stream);
+int ms_loss_combine_bwd(const float* gtotal, const double* weights, const int* lam_idx, int n, const double* lam_dev, float* g,
+                        void* stream);
 
 /* ---- fused clip_grad_norm_(params, max_norm) + Adam.step() over flat buffers (trainer.py:1138-1146, :262-287).
  * All parameters of one sub-network live in ONE contiguous buffer of dtype dt (MS_F32 / MS_F64), likewise

@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmixstage_b200.so")
 
 MS_F32, MS_F64, MS_BF16, MS_BF16X2 = 0, 1, 2, 3
+LOSS_MAX_TERMS = 8          # MS_LOSS_MAX_TERMS
 
 
 class ConvDesc(ctypes.Structure):
@@ -147,6 +148,8 @@ PROTOTYPES = {
     "ms_l1_bwd_f32": [_P, _P, _L, _P, _P],
     "ms_l1_bwd_ab_f32": [_P, _P, _F, _P, _L, _P, _P],
     "ms_scalar_finish": [_P, _D, _P, _P],
+    "ms_loss_combine": [_P, _P, _P, _I, _P, _P, _P, _P],
+    "ms_loss_combine_bwd": [_P, _P, _P, _I, _P, _P, _P],
     "ms_grad_sqnorm": [_P, _I, _L, _P, _P, _P],
     "ms_clip_adam": [_P, _P, _P, _P, _I, _L, _P, _P, _D, _D, _D, _D, _D, _P, _P],
     "ms_clip_adam_mixed": [_P, _P, _P, _P, _I, _I, _L, _P, _P, _D, _D, _D, _D, _D, _P, _P],

@@ -926,6 +926,31 @@ __global__ void l1_bwd_kernel(const float* __restrict__ sgn, const float* __rest
 }
 __global__ void scalar_finish_kernel(const double* in, double scale, float* out) { out[0] = (float)(in[0] * scale); }
 
+// The train step's loss bookkeeping in one launch: report[i] = w_i * l_i (w_i = host weight x optional device-resident
+// lambda), total = sum_i report[i]; and its backward, g_i = w_i * gtotal.
+struct LossTerms {
+  const float* l[MS_LOSS_MAX_TERMS];
+  double w[MS_LOSS_MAX_TERMS];
+  int lam[MS_LOSS_MAX_TERMS];
+  int n;
+};
+__global__ void loss_combine_kernel(LossTerms t, const double* __restrict__ lam_dev, float* __restrict__ total,
+                                    double* __restrict__ report) {
+  double s = 0.0;
+  for (int i = 0; i < t.n; i++) {
+    const double w = t.w[i] * (t.lam[i] >= 0 ? lam_dev[t.lam[i]] : 1.0);
+    const double v = w * (double)t.l[i][0];
+    if (report) report[i] = v;
+    s += v;
+  }
+  total[0] = (float)s;
+}
+__global__ void loss_combine_bwd_kernel(LossTerms t, const double* __restrict__ lam_dev, const float* __restrict__ gtotal,
+                                        float* __restrict__ g) {
+  const int i = threadIdx.x;
+  if (i < t.n) g[i] = (float)(t.w[i] * (t.lam[i] >= 0 ? lam_dev[t.lam[i]] : 1.0) * (double)gtotal[0]);
+}
+
 dim3 col_grid(int64_t rows, int C) {
   int gx = (int)ms_cdiv(C, 32);
   int64_t want = ms_cdiv((int64_t)ms_num_sms() * 4, gx);
@@ -1288,6 +1313,36 @@ extern "C" int ms_l1_bwd_f32(const float* sgn, const float* g, int64_t n, float*
 extern "C" int ms_l1_bwd_ab_f32(const float* a, const float* b, float c, const float* g, int64_t n, float* da, void* stream) {
   if (!a || !g || !da || n < 1) return MS_EINVAL;
   l1_bwd_ab_kernel<<<ew_blocks((n + 3) / 4), EW_THREADS, 0, ST>>>(a, b, c, g, n, da);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+static int fill_terms(LossTerms& t, const float* const* losses, const double* weights, const int* lam_idx, int n,
+                      const double* lam_dev) {
+  if (!losses || !weights || !lam_idx || n < 1 || n > MS_LOSS_MAX_TERMS) return MS_EINVAL;
+  t.n = n;
+  for (int i = 0; i < MS_LOSS_MAX_TERMS; i++) {
+    t.l[i] = i < n ? losses[i] : nullptr;
+    t.w[i] = i < n ? weights[i] : 0.0;
+    t.lam[i] = i < n ? lam_idx[i] : -1;
+    if (i < n && (!t.l[i] || (t.lam[i] >= 0 && !lam_dev))) return MS_EINVAL;
+  }
+  return 0;
+}
+extern "C" int ms_loss_combine(const float* const* losses, const double* weights, const int* lam_idx, int n, const double* lam_dev,
+                               float* total, double* report, void* stream) {
+  LossTerms t;
+  if (!total || fill_terms(t, losses, weights, lam_idx, n, lam_dev)) return MS_EINVAL;
+  loss_combine_kernel<<<1, 1, 0, ST>>>(t, lam_dev, total, report);
+  MS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int ms_loss_combine_bwd(const float* gtotal, const double* weights, const int* lam_idx, int n, const double* lam_dev,
+                                   float* g, void* stream) {
+  LossTerms t;
+  const float* dummy[MS_LOSS_MAX_TERMS];
+  for (int i = 0; i < MS_LOSS_MAX_TERMS; i++) dummy[i] = gtotal;
+  if (!gtotal || !g || fill_terms(t, dummy, weights, lam_idx, n, lam_dev)) return MS_EINVAL;
+  loss_combine_bwd_kernel<<<1, 32, 0, ST>>>(t, lam_dev, gtotal, g);
   MS_LAUNCH_CHECK();
   return 0;
 }

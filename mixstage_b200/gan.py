@@ -74,10 +74,17 @@ class GAN(nn.Module):
         return torch.ones(y_pose.shape[0], device=y_pose.device), None
 
     @staticmethod
-    def _l1(a, b=None, const=0.0, dtype=None):
+    def _l1(a, b=None, const=0.0, dtype=None, lam=None, lam_host=None, lam_dev=None):
+        """mean |a - b| (or |a - const|) as a loss entry, optionally times lambda number `lam` (0: lambda_D, 1: lambda_gan):
+        the host value lam_host, or the device-resident lam_dev[lam] under TrainStep."""
         a32 = ops.f32_of(a).contiguous()
         b32 = None if b is None else ops.f32_of(b).contiguous()
-        return ops.cast(ops.l1_mean(a32, b32, const), dtype or a.dtype)
+        l = ops.l1_mean(a32, b32, const)
+        if lam is None:
+            return ops.loss_term(l, dtype or a.dtype)
+        if lam_dev is not None:
+            return ops.loss_term(l, dtype or a.dtype, lam_dev=lam_dev, lam=lam)
+        return ops.loss_term(l, dtype or a.dtype, weight=lam_host)
 
     def _score(self, pose):
         """D(velocity(pose)) without leaving fp32."""
@@ -92,12 +99,15 @@ class GAN(nn.Module):
         if 'input_modalities' not in kwargs:
             kwargs['input_modalities'] = self.input_modalities
         if self.training:
+            ld = None
+            lam_D = lam_gan = None
             if self.lambda_dev is None:
                 self.lambda_D, self.lambda_gan = self.lambda_scheduler.step()
                 lam_D, lam_gan = self.lambda_D, self.lambda_gan
+            elif ops.RAW_LOSSES:
+                ld = self.lambda_dev                   # fp64, read by the loss-combining kernel at replay
             else:
-                ld = self.lambda_dev if self.lambda_dev.dtype == dt else self.lambda_dev.to(dt)
-                lam_D, lam_gan = ld[0], ld[1]          # views: the graph reads the current values at replay
+                ld = self.lambda_dev if self.lambda_dev.dtype == dt else self.lambda_dev.to(dt)     # views: read at replay
             if self.force_step is None:
                 d_step = torch.rand(1).item() < self.D_prob          # gan.py:105
             else:
@@ -114,7 +124,7 @@ class GAN(nn.Module):
                 if f32 is not None:
                     fake_d._ms_f32 = f32.detach()
                 fake_score = self._score(fake_d)
-                fake_D_loss = lam_D * self._l1(fake_score, None, 0.0, dt)
+                fake_D_loss = self._l1(fake_score, None, 0.0, dt, lam=0, lam_host=lam_D, lam_dev=ld)
                 real_score = self._score(y_pose)
                 real_D_loss = self._l1(real_score, None, 1.0, dt)
                 internal_losses.append(real_D_loss)
@@ -129,7 +139,7 @@ class GAN(nn.Module):
                         fake_score = self._score(fake_pose)
                 else:
                     fake_score = self._score(fake_pose)
-                G_gan_loss = lam_gan * self._l1(fake_score, None, 1.0, dt)
+                G_gan_loss = self._l1(fake_score, None, 1.0, dt, lam=1, lam_host=lam_gan, lam_dev=ld)
                 pose_loss = self._l1(fake_pose, y_pose, 0.0, dt)
                 internal_losses.append(pose_loss)
                 internal_losses.append(G_gan_loss)

@@ -258,7 +258,7 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         K = self.num_clusters
         lab = labels.reshape(-1).contiguous()
         soft_c, ce, _ = ops.softmax_ce(score_c.view(Bx * T, K), lab, 1)
-        internal_losses.append(ops.cast(ce, out_dtype))
+        internal_losses.append(ops.loss_term(ce, out_dtype))
         self.labels_cap_soft = ops.cast(soft_c.view(Bx, T, K), out_dtype)
 
         # K sub-decoders (grouped) + grouped 1x1 logits + soft mixture (jlcss.py:190-194)
@@ -284,8 +284,8 @@ class JointLateClusterSoftStyle4_G(nn.Module):
         else:
             id_out_loss = torch.zeros((), dtype=torch.float32, device=h.device)
 
-        internal_losses.append(ops.cast(id_in_loss, out_dtype) * self.lambda_id)
-        internal_losses.append(ops.cast(id_out_loss, out_dtype) * self.lambda_id)
+        internal_losses.append(ops.loss_term(id_in_loss, out_dtype, weight=self.lambda_id))
+        internal_losses.append(ops.loss_term(id_out_loss, out_dtype, weight=self.lambda_id))
         out = ops.cast(pose, out_dtype)
         if out is not pose:
             out._ms_f32 = pose            # consumers that compute in fp32 (GAN: velocity + D, L1) take it from here

@@ -1403,6 +1403,70 @@ def l1_mean(a, b=None, const=0.0):
     return _L1Mean.apply(a, b, const)
 
 
+# ---------------------------------------------------------------------------- loss bookkeeping of a train step
+class LossTerm:
+    """A loss of the step before scaling and widening: the fp32 scalar (connected to the autograd graph), a host weight
+    and, optionally, the index of a device-resident lambda (TrainStep.lambda_dev) it is multiplied by."""
+    __slots__ = ("value", "weight", "lam")
+
+    def __init__(self, value, weight=1.0, lam=None):
+        self.value, self.weight, self.lam = value, float(weight), lam
+
+
+RAW_LOSSES = False           # TrainStep: the modules hand back LossTerm objects; ONE launch scales, widens and sums them
+
+
+def loss_term(value32, dtype, weight=None, lam_dev=None, lam=None):
+    """A module's loss entry.  Default: the reference's tensor -- `value` in the model dtype, times `weight` (a host number)
+    or times lam_dev[lam] (a device scalar).  Under TrainStep (RAW_LOSSES): the unscaled fp32 scalar and how to scale it."""
+    if RAW_LOSSES:
+        return LossTerm(value32, 1.0 if weight is None else weight, lam if lam_dev is not None else None)
+    out = cast(value32, dtype)
+    if lam_dev is not None:
+        return lam_dev[lam] * out
+    if weight is not None:
+        return out * weight
+    return out
+
+
+class _CombineLosses(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, *values):
+        weights, lam_idx, lam_dev = spec
+        n = len(values)
+        vals = [_f32c(v) for v in values]
+        dev = vals[0].device
+        P = (ctypes.c_void_p * n)(*[v.data_ptr() for v in vals])
+        W = (ctypes.c_double * n)(*weights)
+        L = (ctypes.c_int * n)(*lam_idx)
+        total = torch.empty((), dtype=torch.float32, device=dev)
+        report = torch.empty(n, dtype=torch.float64, device=dev)
+        call("ms_loss_combine", P, W, L, n, ptr(lam_dev), ptr(total), ptr(report), stream())
+        ctx.spec = (W, L, n, lam_dev)
+        ctx.mark_non_differentiable(report)
+        return total, report
+
+    @staticmethod
+    def backward(ctx, gtotal, _greport):
+        W, L, n, lam_dev = ctx.spec
+        g = torch.empty(n, dtype=torch.float32, device=gtotal.device)
+        call("ms_loss_combine_bwd", ptr(gtotal.to(torch.float32).contiguous()), W, L, n, ptr(lam_dev), ptr(g), stream())
+        return (None,) + tuple(g[i] if ctx.needs_input_grad[i + 1] else None for i in range(n))
+
+
+def combine_losses(terms, lam_dev=None):
+    """(sum_i w_i * l_i as an fp32 scalar to call backward() on, the n scaled terms as a detached fp64 vector)."""
+    if not terms or len(terms) > _lib.LOSS_MAX_TERMS:
+        raise MixStageError("combine_losses takes 1..%d terms" % _lib.LOSS_MAX_TERMS)
+    for t in terms:
+        if not isinstance(t, LossTerm):
+            raise MixStageError("combine_losses: a module returned a finished loss tensor while RAW_LOSSES is set")
+    if any(t.lam is not None for t in terms) and (lam_dev is None or lam_dev.dtype != torch.float64):
+        raise MixStageError("combine_losses: device-resident lambdas must be an fp64 tensor")
+    spec = ([t.weight for t in terms], [-1 if t.lam is None else int(t.lam) for t in terms], lam_dev)
+    return _CombineLosses.apply(spec, *[t.value for t in terms])
+
+
 # ---------------------------------------------------------------------------- chains of blocks in one launch
 # At batch 16 the train step is bound by the number of dependent launches, not by their arithmetic: a conv stack (UNet1D,
 # ClusterClassify, the grouped sub-decoders, AudioEncoder.conv.1-7, PoseStyleEncoder) runs as ONE cooperative launch per

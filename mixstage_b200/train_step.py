@@ -217,7 +217,7 @@ class TrainStep:
         self.check_agreement = bool(check_agreement)
         # [lambda_D, lambda_gan] in device memory: the GAN forward multiplies by these (captured graphs read the current
         # values at replay); the injectable scheduler (gan.lambda_scheduler) is stepped once per real iteration below
-        self.lambda_dev = torch.tensor([float(gan.lambda_D), float(gan.lambda_gan)], dtype=self.fG.dtype, device=dev)
+        self.lambda_dev = torch.tensor([float(gan.lambda_D), float(gan.lambda_gan)], dtype=torch.float64, device=dev)
         self._lam_host = [float(gan.lambda_D), float(gan.lambda_gan)]
         # persistent weight-gradient accumulators, one set per kind of step (a G-step also produces the discriminator's
         # -- unused -- weight gradients, a D-step only the discriminator's), and the device tables of their conversion
@@ -288,6 +288,7 @@ class TrainStep:
         ops.CAST_CACHE = {}
         ops.SIDE = self.side
         ops.WACC = wacc
+        ops.RAW_LOSSES = True
         overlap = self.overlap and kind == "G" and self._world() > 1
         self._reduced, self._works = [], []
         self._flushed = set()
@@ -298,7 +299,9 @@ class TrainStep:
         try:
             fake, losses, _ = gan([audio, labels], pose, input_modalities=self.mod, style=style, sample_flag=0,
                                   description=self.description, desc=self.description)
-            loss = sum(losses)
+            # one launch scales the terms (lambda_id, the device-resident GAN lambdas), widens them for the report and sums
+            # them; its backward hands every loss its fp32 seed (instead of ~20 scalar casts, multiplies and adds)
+            loss, report = ops.combine_losses(losses, self.lambda_dev)
             if pre:
                 torch.cuda.current_stream().wait_stream(self.side.stream)
             loss.backward()
@@ -307,6 +310,7 @@ class TrainStep:
             G.grad_ready_hook = None
             gan.force_step, gan.lambda_dev = old_force, old_lam       # a direct gan(...) call draws its own coin again
             ops.DIRECT_GRADS = False
+            ops.RAW_LOSSES = False
             ops.CAST_CACHE = None
             ops.SIDE = None
             ops.WACC = None
@@ -339,7 +343,7 @@ class TrainStep:
             # keep every packed copy (bf16 re-tilings, fp32 biases, folded eval BatchNorm) of the sub-network that just
             # stepped in sync with its parameters, so that no forward has to re-pack anything
             self._refresh(kind, "fwd" if (kind == "G" and self.defer_dgrad_pack) else "all")
-        return fake.detach(), torch.stack([l.detach().to(fake.dtype) for l in losses])
+        return fake.detach(), report if report.dtype == fake.dtype else report.to(fake.dtype)
 
     # ------------------------------------------------------------------ overlapped gradient exchange (opt-in)
     def _world(self):

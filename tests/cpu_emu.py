@@ -651,6 +651,31 @@ def ms_unpack_igemm_wgrad(dwp, Cout, Cin_g, taps_total, ntaps, kpad, dw, pdt, ns
     _store(dw, G.numel(), pdt, G, accumulate)
 
 
+def _loss_weights(weights, lam_idx, n, lam_dev):
+    import ctypes
+    out = []
+    for i in range(n):
+        w = float(weights[i])
+        if lam_idx[i] >= 0:
+            w *= float(f64(lam_dev, lam_idx[i] + 1)[lam_idx[i]])
+        out.append(w)
+    return out
+
+
+def ms_loss_combine(losses, weights, lam_idx, n, lam_dev, total, report, st):
+    ws = _loss_weights(weights, lam_idx, n, lam_dev)
+    vals = [w * float(f32(int(losses[i]), 1)[0]) for i, w in enumerate(ws)]
+    if report:
+        f64(report, n).copy_(torch.tensor(vals, dtype=torch.float64))
+    f32(total, 1)[0] = sum(vals)
+
+
+def ms_loss_combine_bwd(gtotal, weights, lam_idx, n, lam_dev, g, st):
+    ws = _loss_weights(weights, lam_idx, n, lam_dev)
+    gt = float(f32(gtotal, 1)[0])
+    f32(g, n).copy_(torch.tensor([w * gt for w in ws], dtype=torch.float32))
+
+
 def ms_grad_sqnorm(g, dt, n, acc, step, st):
     G = param(g, n, dt).double()
     f64(acc, 1).copy_((G * G).sum().reshape(1))

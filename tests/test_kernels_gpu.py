@@ -394,3 +394,32 @@ def test_unpack_wgrad_multi_layouts():
         outs.append([s.cpu() for s in s_])
     for i, (g, c) in enumerate(zip(*outs)):
         assert torch.equal(g, c), cases[i]
+
+
+@pytest.mark.gpu
+def test_loss_combine_and_backward():
+    """ops.combine_losses on the device against the host specification: scaled terms, their sum, the seeds of backward,
+    with a device-resident lambda that changes between two calls (what a replayed graph sees)."""
+    torch.manual_seed(9)
+    vals = [torch.randn((), device=DEV, requires_grad=(i != 3)) for i in range(5)]
+    lam = torch.tensor([0.25, 3.0], dtype=torch.float64, device=DEV)
+    terms = [ops.LossTerm(vals[0]), ops.LossTerm(vals[1], 1.0, 1), ops.LossTerm(vals[2]), ops.LossTerm(vals[3], 0.1),
+             ops.LossTerm(vals[4], 0.1, 0)]
+    for lam_now in ([0.25, 3.0], [0.5, 7.0]):
+        lam.copy_(torch.tensor(lam_now, dtype=torch.float64))
+        total, report = ops.combine_losses(terms, lam)
+        w = [1.0, lam_now[1], 1.0, 0.1, 0.1 * lam_now[0]]
+        want = torch.tensor([wi * float(v) for wi, v in zip(w, vals)], dtype=torch.float64)
+        assert report.dtype == torch.float64 and not report.requires_grad
+        assert torch.allclose(report.cpu(), want, rtol=1e-12, atol=0)
+        assert abs(float(total) - float(want.sum())) <= 1e-6 * max(1.0, float(want.abs().sum()))
+        for v in vals:
+            v.grad = None
+        (2.0 * total).backward()
+        for i, v in enumerate(vals):
+            if i == 3:
+                assert v.grad is None
+            else:
+                assert abs(float(v.grad) - 2.0 * w[i]) <= 1e-6 * max(1.0, abs(2.0 * w[i])), i
+    with pytest.raises(ops.MixStageError):
+        ops.combine_losses([torch.zeros((), device=DEV)], lam)

@@ -205,6 +205,7 @@ class TrainStep:
         if dev.type == "cuda" and free > 0:
             n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
             call("ms_set_chain_sm_budget", max(16, n_sm - free))
+        self._cap_stream = None
         self._reduced, self._works = [], []
         self._flushed = set()
         # tensor-core modes: the conv weight gradients are exchanged as their fp32 accumulators (see _exchange_acc)
@@ -637,7 +638,12 @@ class TrainStep:
         # eager warm-up on a side stream (allocator + lazy kernel attributes), with parameters / moments / BN buffers
         # restored afterwards so that capture does not advance the training state
         snap = self._snapshot()
-        side = torch.cuda.Stream(device=dev)
+        # warm-up and capture share ONE stream for the life of the TrainStep: autograd's AccumulateGrad nodes (the few
+        # parameters whose gradients are not written into the flat buffers by the kernels) remember the stream they were
+        # created on, and a different capture stream would make every captured backward synchronise with it
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream(device=dev)
+        side = self._cap_stream
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             if not self.graphs:
@@ -656,7 +662,7 @@ class TrainStep:
         # the warm-up bodies ended with _refresh(): every packed copy is valid and stays at its address, so the captured
         # forward launches no re-packing; the captured step ends with the same refresh for the sub-network it updates
         l0 = _lib.LAUNCHES
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):
             fake, losses = self._body(kind, use_pose, *self.static)
         n_launch = _lib.LAUNCHES - l0                         # C-ABI launches recorded in this graph
         torch.cuda.synchronize(dev)

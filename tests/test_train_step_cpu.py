@@ -187,3 +187,42 @@ def test_own_generator_isolates_the_coin_flips_from_the_global_rng():
         torch.rand(extra)                      # another consumer of the global generator on "this rank"
         kinds.append([ts._decide(None) for _ in range(16)])
     assert kinds[0] == kinds[1] and {k for k, _ in kinds[0]} == {"G", "D"}
+
+
+def test_moment_dtype_and_loss_report():
+    """TrainStep keeps Adam's moments in fp32 by default (fp64 parameters, fp64 arithmetic in the update) -- the trajectory
+    stays on the native-moment one to rounding -- and its loss report is the list the modules return to a direct caller:
+    same order, same scaling (lambda_id on the two id losses, the GAN lambdas), model dtype."""
+    spec = O.Spec(num_speakers=4)
+    audio, pose, labels, style = O.synth_inputs(2, 64, spec)
+    out = {}
+    for md in ("fp32", "native"):
+        torch.manual_seed(0)
+        G, D, gan = build(spec, 64, "cpu", torch.float64)
+        G.thresh.value, G.thresh.iters = 1.0, 1000
+        ts = M.TrainStep(gan, use_graphs=False, moment_dtype=md)
+        assert ts.fG.m.dtype == (torch.float32 if md == "fp32" else torch.float64) and ts.fG.p.dtype == torch.float64
+        rep = []
+        for kind in ("G", "D", "G"):
+            _, losses = ts.step(audio, labels, pose, style, kind=kind)
+            assert losses.dtype == torch.float64 and losses.shape == (5,)
+            rep.append(losses.clone())
+        out[md] = (ts.fG.p.clone(), ts.fD.p.clone(), rep)
+        if md == "native":
+            # a direct call of the module (no TrainStep): finished loss tensors, the reference's contract
+            gan.train()
+            gan.force_step = "G"
+            G.force_branch = "audio"
+            try:
+                _, il, _ = gan([audio, labels], pose, input_modalities=ts.mod, style=style, sample_flag=0, description="train",
+                               desc="train")
+            finally:
+                gan.force_step, G.force_branch = None, None
+            assert len(il) == 5 and all(torch.is_tensor(l) and l.dtype == torch.float64 and l.dim() == 0 for l in il)
+    pa, da, ra = out["fp32"]
+    pb, db, rb = out["native"]
+    assert float((pa - pb).abs().max()) < 1e-9 and float((da - db).abs().max()) < 1e-9
+    for a, b in zip(ra, rb):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-9)
+    with pytest.raises(M._lib.MixStageError):
+        M.TrainStep(gan, use_graphs=False, moment_dtype="bf16")

@@ -1149,23 +1149,36 @@ __global__ void pack_igemm_weight_kernel(const void* __restrict__ w, int pdt, Pa
 // the optimiser update instead of ~80 separate launches).  Work units of ~PACK_UNIT packed elements are spread over the
 // entries in proportion to their size; a thread converts two adjacent k positions and stores bf16 pairs.
 constexpr int PACK_UNIT = 16384;
+constexpr int PACK_UNIT_MIN = 2048;
 constexpr int PACK_MAX_ENTRIES = 256;
+// sum of a table in shared memory by warp 0 (the caller synchronised after filling it); every thread gets the result
+__device__ __forceinline__ long long pack_table_sum(const int* __restrict__ v, int n, long long* s_out) {
+  if (threadIdx.x < 32) {
+    long long a = 0;
+    for (int i = threadIdx.x; i < n; i += 32) a += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) *s_out = a;
+  }
+  __syncthreads();
+  const long long r = *s_out;
+  __syncthreads();
+  return r;
+}
 __global__ void __launch_bounds__(256) pack_igemm_weight_multi_kernel(const ms_pack_entry* __restrict__ table, int n_entries) {
   __shared__ int s_units[PACK_MAX_ENTRIES];
-  __shared__ int s_total;
+  __shared__ long long s_sum;
   const int tid = threadIdx.x;
-  for (int i = tid; i < n_entries; i += blockDim.x) {
-    const long long tot = (long long)table[i].num_classes * table[i].class_n * table[i].ntaps * table[i].kpad;
-    s_units[i] = (int)((tot + PACK_UNIT - 1) / PACK_UNIT);
-  }
+  for (int i = tid; i < n_entries; i += blockDim.x)
+    s_units[i] = table[i].num_classes * table[i].class_n * table[i].ntaps * table[i].kpad;      // packed elements (< 2^31)
   __syncthreads();
-  if (tid == 0) {
-    int tot = 0;
-    for (int i = 0; i < n_entries; i++) tot += s_units[i];
-    s_total = tot;
-  }
+  // unit size: ~half a unit per CTA, between PACK_UNIT_MIN and PACK_UNIT elements (small tables spread over more CTAs)
+  const long long elems = pack_table_sum(s_units, n_entries, &s_sum);
+  long long unit_ll = 2 * elems / gridDim.x;
+  const unsigned unit = (unsigned)(unit_ll < PACK_UNIT_MIN ? PACK_UNIT_MIN : (unit_ll > PACK_UNIT ? PACK_UNIT : unit_ll));
+  for (int i = tid; i < n_entries; i += blockDim.x) s_units[i] = (int)(((unsigned)s_units[i] + unit - 1) / unit);
   __syncthreads();
-  const int total_units = s_total;
+  const int total_units = (int)pack_table_sum(s_units, n_entries, &s_sum);
   for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
     int ei = 0, local = u;
     while (ei < n_entries && local >= s_units[ei]) { local -= s_units[ei]; ei++; }

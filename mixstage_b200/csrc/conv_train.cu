@@ -1349,10 +1349,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_acc_multi_kernel(const _
 // the same unit -> (entry, output-channel range) map from the table), and every output channel goes through shared memory:
 // its accumulator row [tap][kpad] is read contiguously, its gradient row [c][tap] written contiguously.
 constexpr int MULTI_UNIT = 16384;
+constexpr int MULTI_UNIT_MIN = 2048;
 constexpr int MULTI_MAX_ENTRIES = 256;
 constexpr int UNPACK_SMEM_FLOATS = 10240;      // 40 KB: rows of up to 48 taps x 192 padded channels; longer rows go direct
 
-__device__ __forceinline__ int multi_units(long long elems) { return (int)((elems + MULTI_UNIT - 1) / MULTI_UNIT); }
+// Sum of a table in shared memory by warp 0 (the caller synchronised after filling it); every thread gets the result.
+__device__ __forceinline__ long long multi_table_sum(const int* __restrict__ v, int n, long long* s_out) {
+  if (threadIdx.x < 32) {
+    long long a = 0;
+    for (int i = threadIdx.x; i < n; i += 32) a += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) *s_out = a;
+  }
+  __syncthreads();
+  const long long r = *s_out;
+  __syncthreads();
+  return r;
+}
 
 // unit u -> entry index and the unit's position inside the entry; *nu = units of that entry.  All threads get the same answer.
 __device__ __forceinline__ int multi_find(const int* __restrict__ s_units, int n_entries, int u, int* local, int* nu) {
@@ -1365,18 +1379,19 @@ __device__ __forceinline__ int multi_find(const int* __restrict__ s_units, int n
 
 __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const ms_wgrad_entry* __restrict__ table, int n_entries) {
   __shared__ int s_units[MULTI_MAX_ENTRIES];
-  __shared__ int s_total;
+  __shared__ long long s_sum;
   __shared__ __align__(16) float s_row[UNPACK_SMEM_FLOATS];
   const int t = threadIdx.x;
-  for (int i = t; i < n_entries; i += blockDim.x) s_units[i] = multi_units((long long)table[i].Cout * table[i].Cin_g * table[i].taps);
+  for (int i = t; i < n_entries; i += blockDim.x) s_units[i] = table[i].Cout * table[i].Cin_g * table[i].taps;      // elements (< 2^31)
   __syncthreads();
-  if (t == 0) {
-    int tot = 0;
-    for (int i = 0; i < n_entries; i++) tot += s_units[i];
-    s_total = tot;
-  }
+  // unit size: ~half a unit per CTA, between MULTI_UNIT_MIN and MULTI_UNIT elements (a small table -- the discriminator's
+  // 0.4 M elements -- would otherwise keep 25 CTAs busy for eight serial passes each while 1159 idle)
+  const long long elems = multi_table_sum(s_units, n_entries, &s_sum);
+  long long unit_ll = 2 * elems / gridDim.x;
+  const unsigned unit = (unsigned)(unit_ll < MULTI_UNIT_MIN ? MULTI_UNIT_MIN : (unit_ll > MULTI_UNIT ? MULTI_UNIT : unit_ll));
+  for (int i = t; i < n_entries; i += blockDim.x) s_units[i] = (int)(((unsigned)s_units[i] + unit - 1) / unit);
   __syncthreads();
-  const int total = s_total;
+  const int total = (int)multi_table_sum(s_units, n_entries, &s_sum);
   for (int u = blockIdx.x; u < total; u += gridDim.x) {
     int local, nu;
     const int ei = multi_find(s_units, n_entries, u, &local, &nu);

@@ -226,3 +226,43 @@ def test_moment_dtype_and_loss_report():
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-9)
     with pytest.raises(M._lib.MixStageError):
         M.TrainStep(gan, use_graphs=False, moment_dtype="bf16")
+
+
+def test_conversion_in_two_launches_equals_one():
+    """Data-parallel tail (train_step.py): the accumulators reduced from hooks are converted while the last bucket is still
+    travelling, the rest by a second launch.  Both launches together must write exactly what the single launch writes,
+    whatever subset is held back, and neither may touch an accumulator twice."""
+    spec = O.Spec(num_speakers=4)
+    torch.manual_seed(0)
+    M.set_precision("bf16x3")
+    try:
+        G, D, gan = build(spec, 64, "cpu", torch.float64)
+        G.thresh.value, G.thresh.iters = 1.0, 1000
+        ts = M.TrainStep(gan, use_graphs=False)
+        audio, pose, labels, style = O.synth_inputs(2, 64, spec)
+        ts.step(audio, labels, pose, style, kind="G")           # leaves this step's sums in the accumulators
+        wacc = ts.wacc["G"]
+        assert len(wacc.entries) > 20
+        ts._step_key = ("G", False)
+        ts._flushed = set()
+        ts.fG.g.zero_()
+        ts._flush_wgrads("G")
+        one = ts.fG.g.clone()
+        assert float(one.abs().sum()) > 0
+        ptrs = sorted({k[0] for k in wacc.entries})
+        for held in (set(ptrs[::3]), set(ptrs[:1]), set(ptrs)):
+            ts._flushed = set()
+            ts.fG.g.zero_()
+            ts._flush_wgrads("G", None, ("early", "G", False), exclude=held)
+            part = ts.fG.g.clone()
+            n_early = len(ts._flushed)
+            assert n_early == len([k for k in wacc.entries if k[0] not in held])
+            ts._flush_wgrads("G", None, ("late", "G", False))
+            assert len(ts._flushed) == len(wacc.entries)
+            assert torch.equal(ts.fG.g, one)
+            if held and n_early:
+                assert not torch.equal(part, one)              # something was really left for the second launch
+            ts._flush_wgrads("G", None, ("late", "G", False))   # nothing left: no launch, no change
+            assert torch.equal(ts.fG.g, one)
+    finally:
+        M.set_precision("fp32")

